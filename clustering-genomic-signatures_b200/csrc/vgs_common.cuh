@@ -1,0 +1,218 @@
+// vgs_common.cuh -- internal declarations shared by the libvgs.so translation units.
+//
+// Device data layout (all per handle, resident in HBM for the life of the model set):
+//   key[total]     u32   (1 << 2*len) | code, dict order            (ctx_id = index - ctx_off[m])
+//   prob32[total]  float4 transition rows cast to fp32               (Frobenius / Projection)
+//   prob64[total*4] f64  transition rows                             (Estimate, sampler)
+//   logp[total*4]  f64   host-libm ln p, -1000 where p == 0          (NLL)
+//   hash[...]      uint2 {key, ctx_id} open addressing, load <= 0.5  (every exact-context probe)
+//   nll blob arena: per model either
+//       tier 1 (order <= 6): dense table  f64[4^(order+1)]  indexed by (history << 2 | symbol)
+//       tier 2 (order  > 6): [u32 L1 map over 6-mers | uint2 deep hash (len > 6) | f64 logp rows]
+//   sequences: 2-bit packed, 16 symbols / u32, first symbol in the top bits, 16-byte aligned starts
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vgs.h"
+
+#define VGS_MAX_ORDER 15
+#define VGS_DENSE_MAX_ORDER 6   // tier 1 limit: 4^7 * 8 B = 128 KB of shared memory
+#define VGS_L1_DEPTH 6          // tier 2 first-level map covers the last 6 symbols
+#define VGS_NO_CTX 0x7FFFFFFFu
+
+struct ModelMeta {
+    int64_t ctx_off;      // first context of this model in key/prob arrays
+    int64_t hash_off;     // first slot of this model's hash
+    int64_t nll_off;      // byte offset of the NLL blob in the arena (256-byte aligned)
+    int32_t n_ctx;
+    int32_t order;
+    uint32_t hash_mask;   // capacity - 1
+    int32_t hash_shift;   // 32 - log2(capacity)
+    int32_t tier;         // 1 dense, 2 two-level
+    int32_t nll_bytes;    // blob size, multiple of 16
+    uint32_t deep_mask;   // tier 2: deep hash capacity - 1 (0 if no deep contexts)
+    int32_t deep_shift;
+    int32_t deep_off;     // byte offset of the deep hash inside the blob
+    int32_t logp_off;     // byte offset of the logp rows inside the blob
+};
+
+struct vgs_context {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    int max_smem_optin = 0;
+    int64_t launches = 0;
+
+    // models
+    int64_t n_models = 0, total_ctx = 0;
+    std::vector<int64_t> h_ctx_off;
+    std::vector<ModelMeta> h_meta;
+    std::vector<double> h_logp;
+    int max_order = 0;
+    int64_t max_nll_bytes_t1 = 0, max_nll_bytes_t2 = 0;
+    int64_t max_pair_bytes = 0;  // hash + fp32 rows of the largest model
+    ModelMeta *d_meta = nullptr;
+    uint32_t *d_key = nullptr;
+    uint8_t *d_len = nullptr;
+    uint32_t *d_code = nullptr;
+    float4 *d_prob32 = nullptr;
+    double *d_prob64 = nullptr;
+    double *d_logp = nullptr;
+    uint2 *d_hash = nullptr;
+    int64_t hash_slots = 0;
+    uint8_t *d_nll = nullptr;
+    int64_t nll_bytes = 0;
+
+    // sequences
+    int64_t n_seq = 0, total_symbols = 0, total_words = 0;
+    std::vector<int64_t> h_seq_off, h_seq_len;
+    uint32_t *d_seq = nullptr;
+    int64_t *d_seq_off = nullptr, *d_seq_len = nullptr;
+
+    // scratch
+    double *d_M = nullptr;      // [n_seq][n_models] score matrix
+    int64_t M_elems = 0;
+    void *d_scratch = nullptr;  // generic scratch (pair partials, payloads, count tables)
+    int64_t scratch_bytes = 0;
+    void *d_scratch2 = nullptr;
+    int64_t scratch2_bytes = 0;
+    int *d_err = nullptr;       // device error flag (bit 0: no context, bit 1: bad symbol)
+    cudaStream_t own_stream = nullptr;
+};
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void vgs_set_error(const char *fmt, ...);
+int vgs_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define VGS_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) return vgs_cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+#define VGS_CHECK_ARG(cond, msg)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            vgs_set_error("%s", msg);       \
+            return VGS_ERR_INVALID;         \
+        }                                   \
+    } while (0)
+#define VGS_LAUNCH_CHECK(h)                                                          \
+    do {                                                                             \
+        (h)->launches++;                                                             \
+        cudaError_t _e = cudaGetLastError();                                         \
+        if (_e != cudaSuccess) return vgs_cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+int vgs_ensure_scratch(vgs_context *h, int64_t bytes);
+int vgs_ensure_scratch2(vgs_context *h, int64_t bytes);
+int vgs_ensure_M(vgs_context *h);
+int vgs_read_error_flag(vgs_context *h, cudaStream_t s);  // syncs s, returns a vgs_status
+template <typename T>
+int vgs_dev_alloc(T **p, int64_t n) {
+    if (n <= 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)p, (size_t)n * sizeof(T));
+    if (e != cudaSuccess) {
+        vgs_set_error("cudaMalloc of %lld bytes failed: %s", (long long)(n * (int64_t)sizeof(T)), cudaGetErrorString(e));
+        *p = nullptr;
+        return VGS_ERR_MEMORY;
+    }
+    return VGS_OK;
+}
+
+// tile bookkeeping shared by host and device
+struct TilePlan {
+    int64_t n, tile, nt;   // matrix size, tile edge, tiles per side
+    int world, symmetric;
+    int64_t n_tiles, slots;  // total tiles, slots per rank
+};
+__host__ __device__ inline int64_t vgs_tri_index(int64_t I, int64_t J, int64_t nt) {  // I <= J, row-major upper triangle
+    return I * nt - I * (I - 1) / 2 + (J - I);
+}
+void vgs_make_plan(TilePlan *p, int64_t n, int64_t tile, int world, int symmetric);
+// tile k -> (I, J)
+void vgs_tile_coords(const TilePlan &p, int64_t k, int64_t *I, int64_t *J);
+
+// launchers implemented in the kernel translation units
+int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &seq_lists_per_block, int64_t block,
+                        int64_t m_begin, int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld,
+                        cudaStream_t s);
+int vgs_assemble_impl(vgs_context *h, const TilePlan &p, const float *gathered32, const double *gathered64,
+                      float *D32, double *D64, cudaStream_t s);
+
+#ifdef __CUDACC__
+// ---- device helpers ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t vgs_key(int len, uint32_t code) { return (1u << (2 * len)) | code; }
+__host__ __device__ __forceinline__ uint32_t vgs_lowmask(int len) {  // 2*len low bits set, len <= 16
+    return len >= 16 ? 0xFFFFFFFFu : ((1u << (2 * len)) - 1u);
+}
+__host__ __device__ __forceinline__ uint32_t vgs_hash_slot(uint32_t key, int shift) { return (key * 0x9E3779B1u) >> shift; }
+
+// exact-context probe: ctx_id or -1
+__device__ __forceinline__ int vgs_hash_find(const uint2 *__restrict__ slots, uint32_t mask, int shift, uint32_t key) {
+    uint32_t s = vgs_hash_slot(key, shift);
+    while (true) {
+        uint2 e = slots[s];
+        if (e.x == key) return (int)e.y;
+        if (e.x == 0u) return -1;
+        s = (s + 1) & mask;
+    }
+}
+
+// longest suffix of (hist_code, hist_len) of length <= order that is a context (vlmc.pyx:131-141)
+__device__ __forceinline__ int vgs_longest_suffix(const uint2 *__restrict__ slots, uint32_t mask, int shift, int order,
+                                                  uint32_t hist_code, int hist_len) {
+    int top = hist_len < order ? hist_len : order;
+    for (int ln = top; ln >= 0; --ln) {
+        int id = vgs_hash_find(slots, mask, shift, vgs_key(ln, hist_code & vgs_lowmask(ln)));
+        if (id >= 0) return id;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ double vgs_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ---- mbarrier + 1-D bulk async copy (TMA without a tensor map; SASS: UBLKCP) --------------------
+__device__ __forceinline__ uint32_t vgs_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void vgs_mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vgs_smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void vgs_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vgs_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vgs_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(vgs_smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void vgs_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     vgs_smem_addr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(vgs_smem_addr(bar))
+                 : "memory");
+}
+// one thread issues the copies for `bytes` (multiple of 16) in <= 32 KB pieces; the caller has armed
+// the barrier with vgs_mbar_expect_tx for the total of all pieces it is about to issue
+__device__ __forceinline__ void vgs_copy_pieces(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    const uint32_t piece = 32768u;
+    for (uint32_t o = 0; o < bytes; o += piece) {
+        uint32_t n = bytes - o < piece ? bytes - o : piece;
+        vgs_bulk_g2s((char *)smem_dst + o, (const char *)gmem_src + o, n, bar);
+    }
+}
+__device__ __forceinline__ void vgs_stage(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    vgs_mbar_expect_tx(bar, bytes);  // one arrival (barrier count is 1) + the byte count
+    vgs_copy_pieces(smem_dst, gmem_src, bytes, bar);
+}
+#endif  // __CUDACC__

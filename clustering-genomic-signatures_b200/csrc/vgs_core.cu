@@ -1,0 +1,703 @@
+// vgs_core.cu -- handle lifetime, model-table construction (K1), longest-suffix lookup, sequences.
+//
+// Reference behaviour restated here (paths relative to the reference repository):
+//   src/vlmc/vlmc.pyx:8-22,179-180   VLMC data model, order = max context length
+//   src/vlmc/vlmc.pyx:131-154        get_context / get_all_contexts (longest / all suffix contexts)
+//   src/vlmc/vlmc.pyx:94-99          ln p on the host (libm log == math.log), -1000 where p == 0
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <thread>
+
+#include "vgs_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+void vgs_set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int vgs_cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    vgs_set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return VGS_ERR_CUDA;
+}
+
+extern "C" const char *vgs_last_error(void) { return g_last_error.c_str(); }
+extern "C" int vgs_version(void) { return 100; }
+
+static int ensure_buf(void **p, int64_t *have, int64_t need) {
+    if (need <= *have) return VGS_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    int64_t want = need + need / 8 + 256;
+    cudaError_t e = cudaMalloc(p, (size_t)want);
+    if (e != cudaSuccess) {
+        vgs_set_error("cudaMalloc of %lld scratch bytes failed: %s", (long long)want, cudaGetErrorString(e));
+        return VGS_ERR_MEMORY;
+    }
+    *have = want;
+    return VGS_OK;
+}
+int vgs_ensure_scratch(vgs_context *h, int64_t bytes) { return ensure_buf(&h->d_scratch, &h->scratch_bytes, bytes); }
+int vgs_ensure_scratch2(vgs_context *h, int64_t bytes) { return ensure_buf(&h->d_scratch2, &h->scratch2_bytes, bytes); }
+int vgs_ensure_M(vgs_context *h) {
+    int64_t need = h->n_seq * h->n_models;
+    if (need <= h->M_elems && h->d_M) return VGS_OK;
+    if (h->d_M) cudaFree(h->d_M);
+    h->d_M = nullptr;
+    h->M_elems = 0;
+    int rc = vgs_dev_alloc(&h->d_M, need);
+    if (rc) return rc;
+    h->M_elems = need;
+    return VGS_OK;
+}
+
+int vgs_read_error_flag(vgs_context *h, cudaStream_t s) {
+    int flag = 0;
+    VGS_CUDA(cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGS_CUDA(cudaStreamSynchronize(s));
+    if (flag) {
+        VGS_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), s));
+        VGS_CUDA(cudaStreamSynchronize(s));
+    }
+    if (flag & 2) {
+        vgs_set_error("sequence holds a symbol outside A,C,G,T");
+        return VGS_ERR_SYMBOL;
+    }
+    if (flag & 1) {
+        vgs_set_error("get_context vlmc.pyx");  // the reference's RuntimeError text (src/vlmc/vlmc.pyx:141)
+        return VGS_ERR_NO_CONTEXT;
+    }
+    return VGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int vgs_create(int device, vgs_handle *out) {
+    VGS_CHECK_ARG(out != nullptr, "vgs_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        vgs_set_error("no CUDA device available (%s); libvgs has no CPU fallback",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return VGS_ERR_CUDA;
+    }
+    VGS_CHECK_ARG(device >= 0 && device < n, "vgs_create: bad device index");
+    VGS_CUDA(cudaSetDevice(device));
+    vgs_context *h = new vgs_context();
+    h->device = device;
+    cudaDeviceProp prop;
+    VGS_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->cc_major = prop.major;
+    h->cc_minor = prop.minor;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (prop.major < 10) {
+        vgs_set_error("libvgs is built for sm_100a (Blackwell); device %d is sm_%d%d", device, prop.major, prop.minor);
+        delete h;
+        return VGS_ERR_UNSUPPORTED;
+    }
+    VGS_CUDA(cudaMalloc((void **)&h->d_err, sizeof(int)));
+    VGS_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+    VGS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    *out = h;
+    return VGS_OK;
+}
+
+static void free_models(vgs_context *h) {
+    cudaFree(h->d_meta); cudaFree(h->d_key); cudaFree(h->d_len); cudaFree(h->d_code);
+    cudaFree(h->d_prob32); cudaFree(h->d_prob64); cudaFree(h->d_logp); cudaFree(h->d_hash); cudaFree(h->d_nll);
+    h->d_meta = nullptr; h->d_key = nullptr; h->d_len = nullptr; h->d_code = nullptr; h->d_prob32 = nullptr;
+    h->d_prob64 = nullptr; h->d_logp = nullptr; h->d_hash = nullptr; h->d_nll = nullptr;
+    h->n_models = 0; h->total_ctx = 0;
+    if (h->d_M) { cudaFree(h->d_M); h->d_M = nullptr; h->M_elems = 0; }
+}
+static void free_sequences(vgs_context *h) {
+    cudaFree(h->d_seq); cudaFree(h->d_seq_off); cudaFree(h->d_seq_len);
+    h->d_seq = nullptr; h->d_seq_off = nullptr; h->d_seq_len = nullptr;
+    h->n_seq = 0; h->total_symbols = 0; h->total_words = 0;
+    if (h->d_M) { cudaFree(h->d_M); h->d_M = nullptr; h->M_elems = 0; }
+}
+
+extern "C" int vgs_destroy(vgs_handle h) {
+    if (!h) return VGS_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_models(h);
+    free_sequences(h);
+    cudaFree(h->d_scratch);
+    cudaFree(h->d_scratch2);
+    cudaFree(h->d_err);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return VGS_OK;
+}
+
+extern "C" int vgs_device_info(vgs_handle h, int *sm_count, int *cc_major, int *cc_minor, int64_t *free_bytes) {
+    VGS_CHECK_ARG(h, "null handle");
+    VGS_CUDA(cudaSetDevice(h->device));
+    if (sm_count) *sm_count = h->sm_count;
+    if (cc_major) *cc_major = h->cc_major;
+    if (cc_minor) *cc_minor = h->cc_minor;
+    if (free_bytes) {
+        size_t f = 0, t = 0;
+        VGS_CUDA(cudaMemGetInfo(&f, &t));
+        *free_bytes = (int64_t)f;
+    }
+    return VGS_OK;
+}
+
+extern "C" int64_t vgs_launch_count(vgs_handle h) { return h ? h->launches : 0; }
+
+extern "C" int vgs_poll_error(vgs_handle h, void *stream) {
+    VGS_CHECK_ARG(h, "null handle");
+    VGS_CUDA(cudaSetDevice(h->device));
+    return vgs_read_error_flag(h, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: device-side table construction
+// ---------------------------------------------------------------------------------------------
+__global__ void k_build_keys(int64_t total, const uint8_t *__restrict__ len, const uint32_t *__restrict__ code,
+                             const double *__restrict__ prob, uint32_t *__restrict__ key, float4 *__restrict__ prob32) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    key[i] = vgs_key(len[i], code[i]);
+    const double *p = prob + 4 * i;
+    prob32[i] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);  // round-to-nearest like numpy's float32 store
+}
+
+// one block per model: insert the model's contexts into its open-addressing hash
+__global__ void k_build_hash(const ModelMeta *__restrict__ meta, const uint32_t *__restrict__ key, uint2 *__restrict__ hash) {
+    const ModelMeta mm = meta[blockIdx.x];
+    unsigned long long *slots = (unsigned long long *)(hash + mm.hash_off);
+    for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
+        uint32_t k = key[mm.ctx_off + c];
+        uint32_t s = vgs_hash_slot(k, mm.hash_shift);
+        // uint2 {x = key, y = id} viewed as u64: x is the low word
+        unsigned long long want = ((unsigned long long)(uint32_t)c << 32) | k;
+        while (true) {
+            unsigned long long old = atomicCAS(&slots[s], 0ull, want);
+            if (old == 0ull) break;
+            if ((uint32_t)old == k) {  // duplicate key cannot come from a dict; keep the smaller id
+                atomicMin(&slots[s], want);
+                break;
+            }
+            s = (s + 1) & mm.hash_mask;
+        }
+    }
+}
+
+// tier 1: dense[(h << 2) | x] = logp[longest_suffix(h)][x] for every order-mer h; NaN if none
+__global__ void k_build_dense(const ModelMeta *__restrict__ meta, const uint2 *__restrict__ hash,
+                              const double *__restrict__ logp, uint8_t *__restrict__ arena) {
+    const ModelMeta mm = meta[blockIdx.y];
+    if (mm.tier != 1) return;
+    const uint32_t n_hist = 1u << (2 * mm.order);
+    double *dense = (double *)(arena + mm.nll_off);
+    const uint2 *slots = hash + mm.hash_off;
+    for (uint32_t hcode = blockIdx.x * blockDim.x + threadIdx.x; hcode < n_hist; hcode += gridDim.x * blockDim.x) {
+        int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, hcode, mm.order);
+        double4 v;
+        if (id >= 0) {
+            const double *r = logp + 4 * (mm.ctx_off + id);
+            v = make_double4(r[0], r[1], r[2], r[3]);
+        } else {
+            v = make_double4(vgs_nan(), vgs_nan(), vgs_nan(), vgs_nan());
+        }
+        double *o = dense + 4 * (size_t)hcode;
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+}
+
+// tier 2: L1 map over 6-mers (bit 31 = some longer context ends in this 6-mer), deep hash, logp rows
+__global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint2 *__restrict__ hash,
+                                  const uint32_t *__restrict__ key, const uint8_t *__restrict__ len,
+                                  const uint32_t *__restrict__ code, const double *__restrict__ logp,
+                                  uint8_t *__restrict__ arena) {
+    const ModelMeta mm = meta[blockIdx.x];
+    if (mm.tier != 2) return;
+    uint32_t *l1 = (uint32_t *)(arena + mm.nll_off);
+    unsigned long long *deep = (unsigned long long *)(arena + mm.nll_off + mm.deep_off);
+    double *rows = (double *)(arena + mm.nll_off + mm.logp_off);
+    const uint2 *slots = hash + mm.hash_off;
+    const uint32_t n1 = 1u << (2 * VGS_L1_DEPTH);
+    for (uint32_t hc = threadIdx.x; hc < n1; hc += blockDim.x) {
+        int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, VGS_L1_DEPTH, hc, VGS_L1_DEPTH);
+        l1[hc] = id >= 0 ? (uint32_t)id : VGS_NO_CTX;
+    }
+    for (int i = threadIdx.x; i < 4 * mm.n_ctx; i += blockDim.x) rows[i] = logp[4 * mm.ctx_off + i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
+        int ln = len[mm.ctx_off + c];
+        if (ln <= VGS_L1_DEPTH) continue;
+        uint32_t cd = code[mm.ctx_off + c];
+        atomicOr(&l1[cd & (n1 - 1)], 0x80000000u);
+        uint32_t k = key[mm.ctx_off + c];
+        uint32_t s = vgs_hash_slot(k, mm.deep_shift);
+        unsigned long long want = ((unsigned long long)(uint32_t)c << 32) | k;
+        while (true) {
+            unsigned long long old = atomicCAS(&deep[s], 0ull, want);
+            if (old == 0ull) break;
+            if ((uint32_t)old == k) { atomicMin(&deep[s], want); break; }
+            s = (s + 1) & mm.deep_mask;
+        }
+    }
+}
+
+static int log2_ceil_pow2(int64_t v, int64_t *cap_out) {
+    int64_t cap = 8;
+    int lg = 3;
+    while (cap < v) { cap <<= 1; ++lg; }
+    *cap_out = cap;
+    return lg;
+}
+
+extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h, const uint8_t *ctx_len_h,
+                               const uint32_t *ctx_code_h, const double *prob_h, const double *logp_h) {
+    VGS_CHECK_ARG(h, "null handle");
+    VGS_CHECK_ARG(n_models > 0 && ctx_offsets_h && ctx_len_h && ctx_code_h && prob_h, "vgs_load_models: null/empty input");
+    VGS_CUDA(cudaSetDevice(h->device));
+    free_models(h);
+    const int64_t total = ctx_offsets_h[n_models];
+    VGS_CHECK_ARG(ctx_offsets_h[0] == 0 && total > 0, "vgs_load_models: ctx_offsets must start at 0");
+    VGS_CHECK_ARG(total < (int64_t)1 << 31, "vgs_load_models: more than 2^31 contexts in one set");
+
+    h->h_ctx_off.assign(ctx_offsets_h, ctx_offsets_h + n_models + 1);
+    h->h_meta.assign((size_t)n_models, ModelMeta());
+    h->max_order = 0;
+    h->max_nll_bytes_t1 = h->max_nll_bytes_t2 = h->max_pair_bytes = 0;
+    int64_t hash_slots = 0, nll_bytes = 0;
+    for (int64_t m = 0; m < n_models; ++m) {
+        ModelMeta &mm = h->h_meta[(size_t)m];
+        int64_t a = ctx_offsets_h[m], n = ctx_offsets_h[m + 1] - a;
+        VGS_CHECK_ARG(n > 0, "vgs_load_models: a VLMC needs at least one context");
+        VGS_CHECK_ARG(n < (int64_t)1 << 30, "vgs_load_models: too many contexts in one model");
+        int order = 0, n_deep = 0;
+        for (int64_t c = a; c < a + n; ++c) {
+            int ln = ctx_len_h[c];
+            if (ln > VGS_MAX_ORDER) {
+                vgs_set_error("context longer than %d symbols is not supported (model %lld)", VGS_MAX_ORDER, (long long)m);
+                return VGS_ERR_UNSUPPORTED;
+            }
+            if (ln < 16 && (ctx_code_h[c] >> (2 * ln)) != 0) {
+                vgs_set_error("context code has bits above its length (model %lld, context %lld)", (long long)m, (long long)(c - a));
+                return VGS_ERR_INVALID;
+            }
+            order = std::max(order, ln);
+            n_deep += ln > VGS_L1_DEPTH;
+        }
+        mm.ctx_off = a;
+        mm.n_ctx = (int32_t)n;
+        mm.order = order;
+        int64_t cap;
+        int lg = log2_ceil_pow2(2 * n, &cap);
+        mm.hash_off = hash_slots;
+        mm.hash_mask = (uint32_t)(cap - 1);
+        mm.hash_shift = 32 - lg;
+        hash_slots += cap;
+        h->max_pair_bytes = std::max(h->max_pair_bytes, cap * 8 + n * 16);
+        h->max_order = std::max(h->max_order, order);
+        mm.nll_off = nll_bytes;
+        if (order <= VGS_DENSE_MAX_ORDER) {
+            mm.tier = 1;
+            mm.nll_bytes = (int32_t)(((int64_t)1 << (2 * (order + 1))) * 8);
+            if (mm.nll_bytes < 16) mm.nll_bytes = 32;  // order 0: 4 doubles
+            mm.deep_mask = 0; mm.deep_shift = 0; mm.deep_off = 0; mm.logp_off = 0;
+            h->max_nll_bytes_t1 = std::max<int64_t>(h->max_nll_bytes_t1, mm.nll_bytes);
+        } else {
+            mm.tier = 2;
+            int64_t dcap;
+            int dlg = log2_ceil_pow2(2 * std::max(n_deep, 1), &dcap);
+            int64_t l1_bytes = ((int64_t)1 << (2 * VGS_L1_DEPTH)) * 4;
+            mm.deep_off = (int32_t)l1_bytes;
+            mm.deep_mask = (uint32_t)(dcap - 1);
+            mm.deep_shift = 32 - dlg;
+            mm.logp_off = (int32_t)(l1_bytes + dcap * 8);
+            int64_t bytes = mm.logp_off + n * 32;
+            if (bytes >= ((int64_t)1 << 31)) {
+                vgs_set_error("model %lld is too large for the two-level NLL table", (long long)m);
+                return VGS_ERR_UNSUPPORTED;
+            }
+            mm.nll_bytes = (int32_t)bytes;
+            h->max_nll_bytes_t2 = std::max<int64_t>(h->max_nll_bytes_t2, bytes);
+        }
+        nll_bytes += ((int64_t)mm.nll_bytes + 255) / 256 * 256;
+    }
+
+    // host: ln p with libm (bit-identical to CPython's math.log on this host), threaded
+    h->h_logp.resize((size_t)total * 4);
+    if (logp_h) {
+        memcpy(h->h_logp.data(), logp_h, sizeof(double) * (size_t)total * 4);
+    } else {
+        for (int64_t i = 0; i < total * 4; ++i)
+            if (prob_h[i] < 0) {
+                vgs_set_error("math domain error: negative transition probability (entry %lld)", (long long)i);
+                return VGS_ERR_INVALID;
+            }
+        unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        if (total * 4 < 200000) nt = 1;
+        std::vector<std::thread> th;
+        double *out = h->h_logp.data();
+        for (unsigned t = 0; t < nt; ++t) {
+            int64_t b = total * 4 * t / nt, e = total * 4 * (t + 1) / nt;
+            th.emplace_back([=]() {
+                for (int64_t i = b; i < e; ++i) {
+                    double p = prob_h[i];
+                    out[i] = (p == 0) ? -1000.0 : log(p);
+                }
+            });
+        }
+        for (auto &x : th) x.join();
+    }
+
+    int rc;
+    if ((rc = vgs_dev_alloc(&h->d_meta, n_models))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_key, total))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_len, total))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_code, total))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_prob32, total))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_prob64, total * 4))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_logp, total * 4))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_hash, hash_slots))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_nll, nll_bytes))) return rc;
+    h->hash_slots = hash_slots;
+    h->nll_bytes = nll_bytes;
+    h->n_models = n_models;
+    h->total_ctx = total;
+
+    cudaStream_t s = h->own_stream;
+    VGS_CUDA(cudaMemcpyAsync(h->d_meta, h->h_meta.data(), sizeof(ModelMeta) * (size_t)n_models, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_len, ctx_len_h, (size_t)total, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_code, ctx_code_h, sizeof(uint32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_prob64, prob_h, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_logp, h->h_logp.data(), sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemsetAsync(h->d_hash, 0, sizeof(uint2) * (size_t)hash_slots, s));
+    VGS_CUDA(cudaMemsetAsync(h->d_nll, 0, (size_t)nll_bytes, s));
+
+    k_build_keys<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(total, h->d_len, h->d_code, h->d_prob64, h->d_key, h->d_prob32);
+    VGS_LAUNCH_CHECK(h);
+    k_build_hash<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_key, h->d_hash);
+    VGS_LAUNCH_CHECK(h);
+    if (h->max_nll_bytes_t1 > 0) {
+        // grid.x covers up to 4^6 histories with 256-thread blocks
+        dim3 grid(16, (unsigned)std::min<int64_t>(n_models, 65535));
+        for (int64_t m0 = 0; m0 < n_models; m0 += 65535) {
+            grid.y = (unsigned)std::min<int64_t>(n_models - m0, 65535);
+            k_build_dense<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->d_logp, h->d_nll);
+            VGS_LAUNCH_CHECK(h);
+        }
+    }
+    if (h->max_nll_bytes_t2 > 0) {
+        k_build_two_level<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_hash, h->d_key, h->d_len, h->d_code, h->d_logp, h->d_nll);
+        VGS_LAUNCH_CHECK(h);
+    }
+    VGS_CUDA(cudaStreamSynchronize(s));
+    return VGS_OK;
+}
+
+extern "C" int vgs_model_count(vgs_handle h, int64_t *n_models, int64_t *total_contexts) {
+    VGS_CHECK_ARG(h, "null handle");
+    if (n_models) *n_models = h->n_models;
+    if (total_contexts) *total_contexts = h->total_ctx;
+    return VGS_OK;
+}
+
+extern "C" int vgs_model_info(vgs_handle h, int64_t model, int *order, int64_t *n_ctx, int *tier) {
+    VGS_CHECK_ARG(h && model >= 0 && model < h->n_models, "vgs_model_info: bad model index");
+    const ModelMeta &mm = h->h_meta[(size_t)model];
+    if (order) *order = mm.order;
+    if (n_ctx) *n_ctx = mm.n_ctx;
+    if (tier) *tier = mm.tier;
+    return VGS_OK;
+}
+
+extern "C" int vgs_get_logp(vgs_handle h, double *logp_out_h) {
+    VGS_CHECK_ARG(h && logp_out_h && h->n_models > 0, "vgs_get_logp: no models loaded");
+    VGS_CUDA(cudaSetDevice(h->device));
+    // read back from the device so the test sees what the kernels see
+    VGS_CUDA(cudaMemcpy(logp_out_h, h->d_logp, sizeof(double) * (size_t)h->total_ctx * 4, cudaMemcpyDeviceToHost));
+    return VGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lookup (a3 / a4)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_lookup(int64_t n, const ModelMeta *__restrict__ meta, const uint2 *__restrict__ hash,
+                         const int32_t *__restrict__ model, const uint32_t *__restrict__ hcode,
+                         const uint8_t *__restrict__ hlen, int32_t *__restrict__ out, uint32_t *__restrict__ all_mask) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const ModelMeta mm = meta[model[q]];
+    const uint2 *slots = hash + mm.hash_off;
+    int hl = hlen[q];
+    uint32_t hc = hcode[q];
+    int top = hl < mm.order ? hl : mm.order;
+    int best = -1;
+    uint32_t mask = 0;
+    for (int ln = top; ln >= 0; --ln) {
+        int id = vgs_hash_find(slots, mm.hash_mask, mm.hash_shift, vgs_key(ln, hc & vgs_lowmask(ln)));
+        if (id >= 0) {
+            mask |= 1u << ln;
+            if (best < 0) best = id;
+        }
+    }
+    out[q] = best;
+    if (all_mask) all_mask[q] = mask;
+}
+
+extern "C" int vgs_lookup(vgs_handle h, int64_t n, const int32_t *model_h, const uint32_t *hist_code_h,
+                          const uint8_t *hist_len_h, int32_t *ctx_id_out_h, uint32_t *all_mask_out_h) {
+    VGS_CHECK_ARG(h && h->n_models > 0, "vgs_lookup: no models loaded");
+    VGS_CHECK_ARG(n >= 0 && (n == 0 || (model_h && hist_code_h && hist_len_h && ctx_id_out_h)), "vgs_lookup: null input");
+    if (n == 0) return VGS_OK;
+    for (int64_t q = 0; q < n; ++q) {
+        VGS_CHECK_ARG(model_h[q] >= 0 && model_h[q] < h->n_models, "vgs_lookup: model index out of range");
+        VGS_CHECK_ARG(hist_len_h[q] <= 16, "vgs_lookup: history longer than 16 symbols (pass its last 16)");
+    }
+    VGS_CUDA(cudaSetDevice(h->device));
+    int64_t bytes = n * (4 + 4 + 1 + 4 + 4) + 64;
+    int rc = vgs_ensure_scratch(h, bytes);
+    if (rc) return rc;
+    char *base = (char *)h->d_scratch;
+    int32_t *d_model = (int32_t *)base;
+    uint32_t *d_code = (uint32_t *)(base + 4 * n);
+    int32_t *d_out = (int32_t *)(base + 8 * n);
+    uint32_t *d_mask = (uint32_t *)(base + 12 * n);
+    uint8_t *d_len = (uint8_t *)(base + 16 * n);
+    cudaStream_t s = h->own_stream;
+    VGS_CUDA(cudaMemcpyAsync(d_model, model_h, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(d_code, hist_code_h, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(d_len, hist_len_h, (size_t)n, cudaMemcpyHostToDevice, s));
+    k_lookup<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, h->d_meta, h->d_hash, d_model, d_code, d_len, d_out, d_mask);
+    VGS_LAUNCH_CHECK(h);
+    VGS_CUDA(cudaMemcpyAsync(ctx_id_out_h, d_out, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (all_mask_out_h) VGS_CUDA(cudaMemcpyAsync(all_mask_out_h, d_mask, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    VGS_CUDA(cudaStreamSynchronize(s));
+    return VGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sequences
+// ---------------------------------------------------------------------------------------------
+static int set_sequence_layout(vgs_context *h, int64_t n_seq, const int64_t *lengths) {
+    h->h_seq_len.assign(lengths, lengths + n_seq);
+    h->h_seq_off.assign((size_t)n_seq + 1, 0);
+    int64_t total = 0;
+    for (int64_t i = 0; i < n_seq; ++i) {
+        if (lengths[i] < 0) { vgs_set_error("negative sequence length"); return VGS_ERR_INVALID; }
+        int64_t words = ((lengths[i] + 15) / 16 + 3) / 4 * 4;
+        h->h_seq_off[(size_t)i + 1] = h->h_seq_off[(size_t)i] + words;
+        total += lengths[i];
+    }
+    h->n_seq = n_seq;
+    h->total_symbols = total;
+    h->total_words = h->h_seq_off[(size_t)n_seq];
+    int rc;
+    if ((rc = vgs_dev_alloc(&h->d_seq, h->total_words + 4))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_seq_off, n_seq + 1))) return rc;
+    if ((rc = vgs_dev_alloc(&h->d_seq_len, n_seq))) return rc;
+    return VGS_OK;
+}
+
+// one thread packs one output word from 16 ASCII symbols
+__global__ void k_pack_ascii(int64_t n_seq, const uint8_t *__restrict__ ascii, const int64_t *__restrict__ in_off,
+                             const int64_t *__restrict__ word_off, uint32_t *__restrict__ words, int *__restrict__ err) {
+    int64_t s = blockIdx.y;
+    int64_t len = in_off[s + 1] - in_off[s];
+    int64_t nw = word_off[s + 1] - word_off[s];
+    const uint8_t *src = ascii + in_off[s];
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        for (int j = 0; j < 16; ++j) {
+            int64_t t = w * 16 + j;
+            uint32_t c = 0;
+            if (t < len) {
+                uint8_t ch = src[t];
+                if (ch == 'A') c = 0; else if (ch == 'C') c = 1; else if (ch == 'G') c = 2; else if (ch == 'T') c = 3;
+                else atomicOr(err, 2);
+            }
+            v |= c << (30 - 2 * j);
+        }
+        words[word_off[s] + w] = v;
+    }
+}
+
+extern "C" int vgs_load_sequences_ascii(vgs_handle h, int64_t n_seq, const uint8_t *ascii_h, const int64_t *offsets_h) {
+    VGS_CHECK_ARG(h && n_seq > 0 && ascii_h && offsets_h, "vgs_load_sequences_ascii: null/empty input");
+    VGS_CUDA(cudaSetDevice(h->device));
+    free_sequences(h);
+    std::vector<int64_t> lens((size_t)n_seq);
+    for (int64_t i = 0; i < n_seq; ++i) lens[(size_t)i] = offsets_h[i + 1] - offsets_h[i];
+    int rc = set_sequence_layout(h, n_seq, lens.data());
+    if (rc) return rc;
+    int64_t total = offsets_h[n_seq] - offsets_h[0];
+    rc = vgs_ensure_scratch(h, total + (n_seq + 1) * 8 + 64);
+    if (rc) return rc;
+    cudaStream_t s = h->own_stream;
+    int64_t *d_in_off = (int64_t *)h->d_scratch;
+    uint8_t *d_ascii = (uint8_t *)h->d_scratch + (n_seq + 1) * 8;
+    std::vector<int64_t> rel((size_t)n_seq + 1);
+    for (int64_t i = 0; i <= n_seq; ++i) rel[(size_t)i] = offsets_h[i] - offsets_h[0];
+    VGS_CUDA(cudaMemcpyAsync(d_in_off, rel.data(), 8 * (size_t)(n_seq + 1), cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(d_ascii, ascii_h + offsets_h[0], (size_t)total, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_seq_off, h->h_seq_off.data(), 8 * (size_t)(n_seq + 1), cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_seq_len, h->h_seq_len.data(), 8 * (size_t)n_seq, cudaMemcpyHostToDevice, s));
+    int64_t max_words = 1;
+    for (int64_t i = 0; i < n_seq; ++i) max_words = std::max(max_words, h->h_seq_off[(size_t)i + 1] - h->h_seq_off[(size_t)i]);
+    for (int64_t s0 = 0; s0 < n_seq; s0 += 65535) {
+        dim3 grid((unsigned)std::min<int64_t>((max_words + 127) / 128, 1024), (unsigned)std::min<int64_t>(n_seq - s0, 65535));
+        k_pack_ascii<<<grid, 128, 0, s>>>(n_seq - s0, d_ascii, d_in_off + s0, h->d_seq_off + s0, h->d_seq, h->d_err);
+        VGS_LAUNCH_CHECK(h);
+    }
+    return vgs_read_error_flag(h, s);
+}
+
+extern "C" int vgs_load_sequences_packed(vgs_handle h, int64_t n_seq, const uint32_t *words_h, const int64_t *word_offsets_h,
+                                         const int64_t *lengths_h) {
+    VGS_CHECK_ARG(h && n_seq > 0 && words_h && word_offsets_h && lengths_h, "vgs_load_sequences_packed: null/empty input");
+    VGS_CUDA(cudaSetDevice(h->device));
+    free_sequences(h);
+    int rc = set_sequence_layout(h, n_seq, lengths_h);
+    if (rc) return rc;
+    for (int64_t i = 0; i <= n_seq; ++i)
+        if (word_offsets_h[i] != h->h_seq_off[(size_t)i]) {
+            vgs_set_error("vgs_load_sequences_packed: word_offsets must be 16-byte aligned starts, ceil(len/16) words rounded up to 4");
+            return VGS_ERR_INVALID;
+        }
+    cudaStream_t s = h->own_stream;
+    VGS_CUDA(cudaMemcpyAsync(h->d_seq, words_h, 4 * (size_t)h->total_words, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_seq_off, h->h_seq_off.data(), 8 * (size_t)(n_seq + 1), cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_seq_len, h->h_seq_len.data(), 8 * (size_t)n_seq, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaStreamSynchronize(s));
+    return VGS_OK;
+}
+
+extern "C" int vgs_sequence_count(vgs_handle h, int64_t *n_seq, int64_t *total_symbols) {
+    VGS_CHECK_ARG(h, "null handle");
+    if (n_seq) *n_seq = h->n_seq;
+    if (total_symbols) *total_symbols = h->total_symbols;
+    return VGS_OK;
+}
+
+extern "C" int vgs_get_sequence(vgs_handle h, int64_t sidx, uint8_t *codes_out_h, int64_t capacity) {
+    VGS_CHECK_ARG(h && sidx >= 0 && sidx < h->n_seq && codes_out_h, "vgs_get_sequence: bad index");
+    int64_t len = h->h_seq_len[(size_t)sidx];
+    VGS_CHECK_ARG(capacity >= len, "vgs_get_sequence: output buffer too small");
+    VGS_CUDA(cudaSetDevice(h->device));
+    int64_t nw = h->h_seq_off[(size_t)sidx + 1] - h->h_seq_off[(size_t)sidx];
+    std::vector<uint32_t> w((size_t)nw);
+    VGS_CUDA(cudaMemcpy(w.data(), h->d_seq + h->h_seq_off[(size_t)sidx], 4 * (size_t)nw, cudaMemcpyDeviceToHost));
+    for (int64_t t = 0; t < len; ++t) codes_out_h[t] = (uint8_t)((w[(size_t)(t >> 4)] >> (30 - 2 * (t & 15))) & 3u);
+    return VGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampler (a12 / f2): src/vlmc/vlmc.pyx:156-177 with random.choices spelled out:
+//   cum = accumulate(p_A, p_C, p_G, p_T); total = cum[3] + 0.0; x = bisect_right(cum, random()*total, 0, 3)
+// The MT19937 stream is advanced on the host exactly as CPython does (genrand_res53); the sequential
+// chain (symbol t depends on symbols < t) runs one thread per model on the device.
+// ---------------------------------------------------------------------------------------------
+struct HostMT {
+    uint32_t mt[624];
+    int idx;
+    uint32_t next() {
+        if (idx >= 624) {
+            int kk;
+            for (kk = 0; kk < 624 - 397; kk++) {
+                uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            for (; kk < 623; kk++) {
+                uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    double random() {
+        uint32_t a = next() >> 5, b = next() >> 6;
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    }
+};
+
+__global__ void k_sample(int64_t n_models, const ModelMeta *__restrict__ meta, const uint2 *__restrict__ hash,
+                         const double *__restrict__ prob64, const double *__restrict__ uniforms, int64_t length,
+                         int64_t pre, const int64_t *__restrict__ word_off, uint32_t *__restrict__ words, int *__restrict__ err) {
+    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_models) return;
+    const ModelMeta mm = meta[m];
+    const uint2 *slots = hash + mm.hash_off;
+    const double *u = uniforms + m * (length + pre);
+    uint32_t *out = words + word_off[m];
+    uint32_t hist = 0, omask = vgs_lowmask(mm.order);
+    uint32_t cur = 0;
+    for (int64_t t = 0; t < length + pre; ++t) {
+        int hl = t < mm.order ? (int)t : mm.order;
+        int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, hist, hl);
+        if (id < 0) { atomicOr(err, 1); return; }
+        const double *p = prob64 + 4 * (mm.ctx_off + id);
+        double c0 = p[0];
+        double c1 = __dadd_rn(c0, p[1]);
+        double c2 = __dadd_rn(c1, p[2]);
+        double c3 = __dadd_rn(c2, p[3]);
+        double x = __dmul_rn(u[t], __dadd_rn(c3, 0.0));
+        uint32_t sym = (x < c0) ? 0u : (x < c1) ? 1u : (x < c2) ? 2u : 3u;
+        if (t >= pre) {
+            int64_t k = t - pre;
+            cur |= sym << (30 - 2 * (int)(k & 15));
+            if ((k & 15) == 15 || k == length - 1) { out[k >> 4] = cur; cur = 0; }
+        }
+        hist = ((hist << 2) | sym) & omask;
+    }
+}
+
+extern "C" int vgs_sample_sequences(vgs_handle h, int64_t length, int64_t pre_sample, uint32_t *mt_state_h) {
+    VGS_CHECK_ARG(h && h->n_models > 0, "vgs_sample_sequences: no models loaded");
+    VGS_CHECK_ARG(length > 0 && pre_sample >= 0 && mt_state_h, "vgs_sample_sequences: bad arguments");
+    VGS_CHECK_ARG(mt_state_h[624] <= 624, "vgs_sample_sequences: bad MT19937 position");
+    VGS_CUDA(cudaSetDevice(h->device));
+    free_sequences(h);
+    const int64_t n = h->n_models, per = length + pre_sample;
+    std::vector<int64_t> lens((size_t)n, length);
+    int rc = set_sequence_layout(h, n, lens.data());
+    if (rc) return rc;
+    std::vector<double> u((size_t)(n * per));
+    HostMT mt;
+    memcpy(mt.mt, mt_state_h, sizeof(mt.mt));
+    mt.idx = (int)mt_state_h[624];
+    for (int64_t i = 0; i < n * per; ++i) u[(size_t)i] = mt.random();
+    rc = vgs_ensure_scratch(h, 8 * n * per);
+    if (rc) return rc;
+    cudaStream_t s = h->own_stream;
+    VGS_CUDA(cudaMemcpyAsync(h->d_scratch, u.data(), 8 * (size_t)(n * per), cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_seq_off, h->h_seq_off.data(), 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_seq_len, h->h_seq_len.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemsetAsync(h->d_seq, 0, 4 * (size_t)(h->total_words + 4), s));
+    k_sample<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, h->d_meta, h->d_hash, h->d_prob64, (const double *)h->d_scratch,
+                                                     length, pre_sample, h->d_seq_off, h->d_seq, h->d_err);
+    VGS_LAUNCH_CHECK(h);
+    rc = vgs_read_error_flag(h, s);
+    if (rc) return rc;
+    memcpy(mt_state_h, mt.mt, sizeof(mt.mt));
+    mt_state_h[624] = (uint32_t)mt.idx;
+    return VGS_OK;
+}

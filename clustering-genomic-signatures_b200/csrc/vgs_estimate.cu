@@ -1,0 +1,234 @@
+// vgs_estimate.cu -- K6: EstimateVLMC for all (left model, right sequence) pairs.
+//
+// Reference behaviour restated (src/distance/estimate.pyx, paths relative to the reference repository):
+//   :53-71  _count_events: for every position t of the right model's sequence S and every suffix c of
+//           S[:t] (length <= min(t, order_left)) that is a context of the LEFT model, counts[c][S[t]] += 1,
+//           i.e. counts[c][x] = number of occurrences of the substring c.x in S;
+//   :73-78  pseudo-counts: if a visited context has a zero count, add 1 to all four;
+//   :40-51  estimated probabilities = counts / total;
+//   :80-108 Pearson statistic sum (obs - exp)^2 / exp over visited contexts, over the symbols with
+//           p_left > 0 except the last such symbol (scipy.stats.power_divergence, lambda_ = "pearson").
+//
+// Device formulation.  The counts depend on the left model only through WHICH substrings are counted, so
+// per right sequence we build dense k-mer count tables for k = 1 .. K (K = max order + 1) once:
+//   level K by a histogram pass over the packed sequence (atomics into L2), level k < K by summing the
+//   four (k+1)-mers that extend a k-mer to the left, plus the one k-mer that starts the sequence.
+// A warp then handles one (left, right) pair: lanes walk the left model's contexts (coalesced keys and
+// fp64 rows), fetch the four counts of c.A, c.C, c.G, c.T with one 16-byte load, form the Pearson terms
+// in fp64 and shuffle-reduce.
+#include <algorithm>
+
+#include "vgs_common.cuh"
+
+__host__ __device__ inline int64_t level_off(int k) { return ((((int64_t)1) << (2 * k)) - 4) / 3; }  // u32 units, k >= 1
+
+// level K histogram: grid (chunks, sequences-in-batch)
+__global__ void k_est_count_top(int K, int64_t first_seq, const uint32_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
+                                const int64_t *__restrict__ seq_len, uint32_t *__restrict__ tables, int64_t per_seq) {
+    const int64_t s = first_seq + blockIdx.y;
+    const int64_t L = seq_len[s];
+    const uint32_t *w = seq + seq_off[s];
+    uint32_t *top = tables + (int64_t)blockIdx.y * per_seq + level_off(K);
+    const uint32_t kmask = vgs_lowmask(K);
+    const int64_t span = 256;  // positions per thread
+    const int64_t n_threads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * span; a < L; a += n_threads * span) {
+        const int64_t e = min(L, a + span);
+        int64_t t = max((int64_t)0, a - (K - 1));
+        uint32_t code = 0;
+        for (; t < e; ++t) {
+            const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
+            code = ((code << 2) | x) & kmask;
+            if (t >= a && t >= K - 1) atomicAdd(&top[code], 1u);
+        }
+    }
+}
+
+// level k from level k+1: cnt_k[c] = sum_a cnt_{k+1}[(a << 2k) | c] + [c == S[0:k]]
+__global__ void k_est_count_down(int k, int64_t first_seq, const uint32_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
+                                 const int64_t *__restrict__ seq_len, uint32_t *__restrict__ tables, int64_t per_seq) {
+    const int64_t s = first_seq + blockIdx.y;
+    const int64_t L = seq_len[s];
+    uint32_t *base = tables + (int64_t)blockIdx.y * per_seq;
+    const uint32_t *up = base + level_off(k + 1);
+    uint32_t *cur = base + level_off(k);
+    const int64_t n = (int64_t)1 << (2 * k);
+    uint32_t prefix = 0xFFFFFFFFu;
+    if (L >= k) {
+        const uint32_t *w = seq + seq_off[s];
+        prefix = 0;
+        for (int t = 0; t < k; ++t) prefix = (prefix << 2) | ((w[t >> 4] >> (30 - 2 * (t & 15))) & 3u);
+    }
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = up[c] + up[n + c] + up[2 * n + c] + up[3 * n + c];
+        if ((uint32_t)c == prefix) v += 1u;
+        cur[c] = v;
+    }
+}
+
+struct EstParams {
+    const ModelMeta *meta;
+    const uint32_t *key;
+    const double *prob64;
+    const uint32_t *tables;  // count tables of the J-block's sequences
+    int64_t per_seq;
+    TilePlan pl;
+    int64_t q, I, J;         // slot and tile
+    float *pay32;
+    double *pay64;
+};
+
+__global__ void k_est_pairs(const EstParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t T = p.pl.tile;
+    if (warp >= T * T) return;
+    const int64_t ii = warp / T, jj = warp % T;
+    const int64_t i = p.I * T + ii, j = p.J * T + jj;
+    double acc = 0.0;
+    if (i < p.pl.n && j < p.pl.n) {
+        const ModelMeta mm = p.meta[i];
+        const uint32_t *tab = p.tables + jj * p.per_seq;
+        for (int ci = lane; ci < mm.n_ctx; ci += 32) {
+            const uint32_t key = __ldg(p.key + mm.ctx_off + ci);
+            const int len = (31 - __clz(key)) >> 1;
+            const uint32_t code = key ^ (1u << (2 * len));
+            const uint4 cn = *(const uint4 *)(tab + level_off(len + 1) + 4 * (int64_t)code);
+            int64_t c0 = cn.x, c1 = cn.y, c2 = cn.z, c3 = cn.w;
+            int64_t tot = c0 + c1 + c2 + c3;
+            if (tot != 0 && (c0 == 0 || c1 == 0 || c2 == 0 || c3 == 0)) { c0++; c1++; c2++; c3++; tot += 4; }
+            if (tot > 0) {
+                const double *pr = p.prob64 + 4 * (mm.ctx_off + ci);
+                const double pv[4] = {pr[0], pr[1], pr[2], pr[3]};
+                const int64_t cv[4] = {c0, c1, c2, c3};
+                int last = -1;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) if (pv[x] > 0) last = x;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    if (pv[x] > 0 && x != last) {
+                        const double obs = __ddiv_rn((double)cv[x], (double)tot);
+                        const double d = __dsub_rn(obs, pv[x]);
+                        acc = __dadd_rn(acc, __ddiv_rn(__dmul_rn(d, d), pv[x]));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (lane == 0) {
+        const int64_t e = p.q * T * T + warp;
+        p.pay32[e] = (float)acc;
+        if (p.pay64) p.pay64[e] = acc;
+    }
+}
+
+static int est_tiles_impl(vgs_context *h, const TilePlan &pl, int rank, float *pay32, double *pay64, cudaStream_t s) {
+    const int K = h->max_order + 1;
+    const int64_t per_seq = level_off(K + 1);  // u32 entries for levels 1..K
+    size_t free_b = 0, total_b = 0;
+    VGS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const int64_t need = per_seq * 4 * pl.tile;
+    if (need > (int64_t)(free_b / 2) + h->scratch_bytes) {
+        vgs_set_error("EstimateVLMC count tables for order %d need %lld bytes per tile column; reduce the tile size", h->max_order,
+                      (long long)need);
+        return VGS_ERR_UNSUPPORTED;
+    }
+    int rc = vgs_ensure_scratch2(h, need + 256);
+    if (rc) return rc;
+    uint32_t *tables = (uint32_t *)h->d_scratch2;
+    if (pl.slots > 0) VGS_CUDA(cudaMemsetAsync(pay32, 0, (size_t)(pl.slots * pl.tile * pl.tile * 4), s));
+    if (pay64 && pl.slots > 0) VGS_CUDA(cudaMemsetAsync(pay64, 0, (size_t)(pl.slots * pl.tile * pl.tile * 8), s));
+    for (int64_t J = 0; J < pl.nt; ++J) {
+        // owned tiles in this column
+        bool any = false;
+        for (int64_t I = 0; I < pl.nt && !any; ++I) any = ((I * pl.nt + J) % pl.world) == rank;
+        if (!any) continue;
+        const int64_t j0 = J * pl.tile, nj = std::min(pl.n, (J + 1) * pl.tile) - j0;
+        VGS_CUDA(cudaMemsetAsync(tables, 0, (size_t)(per_seq * 4 * nj), s));
+        int64_t max_len = 1;
+        for (int64_t j = j0; j < j0 + nj; ++j) max_len = std::max(max_len, h->h_seq_len[(size_t)j]);
+        dim3 gtop((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_len + 256 * 128 - 1) / (256 * 128), 64)), (unsigned)nj);
+        k_est_count_top<<<gtop, 128, 0, s>>>(K, j0, h->d_seq, h->d_seq_off, h->d_seq_len, tables, per_seq);
+        VGS_LAUNCH_CHECK(h);
+        for (int k = K - 1; k >= 1; --k) {
+            const int64_t n = (int64_t)1 << (2 * k);
+            dim3 g((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 4096)), (unsigned)nj);
+            k_est_count_down<<<g, 256, 0, s>>>(k, j0, h->d_seq, h->d_seq_off, h->d_seq_len, tables, per_seq);
+            VGS_LAUNCH_CHECK(h);
+        }
+        for (int64_t I = 0; I < pl.nt; ++I) {
+            const int64_t k = I * pl.nt + J;
+            if (k % pl.world != rank) continue;
+            EstParams p;
+            p.meta = h->d_meta; p.key = h->d_key; p.prob64 = h->d_prob64; p.tables = tables; p.per_seq = per_seq;
+            p.pl = pl; p.q = k / pl.world; p.I = I; p.J = J; p.pay32 = pay32; p.pay64 = pay64;
+            const int64_t n_warps = pl.tile * pl.tile;
+            k_est_pairs<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, s>>>(p);
+            VGS_LAUNCH_CHECK(h);
+        }
+    }
+    return VGS_OK;
+}
+
+static int check_est(vgs_context *h) {
+    VGS_CHECK_ARG(h, "null handle");
+    VGS_CHECK_ARG(h->n_models > 0, "no models loaded (vgs_load_models)");
+    VGS_CHECK_ARG(h->n_seq == h->n_models, "EstimateVLMC needs exactly one sequence per model (sequence j sampled from model j)");
+    if (h->max_order + 1 > 13) {
+        vgs_set_error("EstimateVLMC dense counting supports order <= 12 (got %d)", h->max_order);
+        return VGS_ERR_UNSUPPORTED;
+    }
+    return VGS_OK;
+}
+
+extern "C" int vgs_estimate_tiles(vgs_handle h, int64_t tile, int rank, int world, float *payload_d, void *stream) {
+    int rc = check_est(h);
+    if (rc) return rc;
+    VGS_CHECK_ARG(tile > 0 && world > 0 && rank >= 0 && rank < world && payload_d, "vgs_estimate_tiles: bad arguments");
+    VGS_CUDA(cudaSetDevice(h->device));
+    TilePlan pl;
+    vgs_make_plan(&pl, h->n_models, tile, world, 0);
+    return est_tiles_impl(h, pl, rank, payload_d, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int vgs_estimate_matrix(vgs_handle h, float *D32_d, double *D64_d, void *stream) {
+    int rc = check_est(h);
+    if (rc) return rc;
+    VGS_CHECK_ARG(D32_d, "vgs_estimate_matrix: null output");
+    VGS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    TilePlan pl;
+    const int64_t n = h->n_models;
+    int64_t tile = 64;
+    const int K = h->max_order + 1;
+    while (tile > 4 && level_off(K + 1) * 4 * tile > ((int64_t)4 << 30)) tile /= 2;  // keep the count tables under 4 GB
+    vgs_make_plan(&pl, n, tile, 1, 0);
+    const int64_t pay_elems = pl.slots * pl.tile * pl.tile;
+    if ((rc = vgs_ensure_scratch(h, pay_elems * (D64_d ? 12 : 4) + 256))) return rc;
+    float *pay32 = (float *)h->d_scratch;
+    double *pay64 = D64_d ? (double *)((char *)h->d_scratch + (pay_elems * 4 + 255) / 256 * 256) : nullptr;
+    if ((rc = est_tiles_impl(h, pl, 0, pay32, pay64, s))) return rc;
+    return vgs_assemble_impl(h, pl, pay32, pay64, D32_d, D64_d, s);
+}
+
+extern "C" int vgs_estimate_matrix_h(vgs_handle h, float *D32_out_h, double *D64_out_h) {
+    int rc = check_est(h);
+    if (rc) return rc;
+    VGS_CHECK_ARG(D32_out_h || D64_out_h, "vgs_estimate_matrix_h: no output");
+    VGS_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->n_models;
+    float *d32 = nullptr;
+    double *d64 = nullptr;
+    if ((rc = vgs_dev_alloc(&d32, n * n))) return rc;
+    if (D64_out_h && (rc = vgs_dev_alloc(&d64, n * n))) { cudaFree(d32); return rc; }
+    cudaStream_t s = h->own_stream;
+    rc = vgs_estimate_matrix(h, d32, d64, s);
+    if (!rc && D32_out_h) rc = cudaMemcpyAsync(D32_out_h, d32, 4 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
+    if (!rc && D64_out_h) rc = cudaMemcpyAsync(D64_out_h, d64, 8 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
+    cudaStreamSynchronize(s);
+    cudaFree(d32);
+    if (d64) cudaFree(d64);
+    return rc;
+}

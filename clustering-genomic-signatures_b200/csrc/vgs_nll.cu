@@ -1,0 +1,450 @@
+// vgs_nll.cu -- K2 (log-likelihood score matrix M[s][m]) and K3 (NegativeLogLikelihood combine).
+//
+// Reference behaviour restated (paths relative to the reference repository):
+//   src/vlmc/vlmc.pyx:79-101   _log_likelihood: sum_{t >= skip} f(p_t), f(p) = -1000 if p == 0 else ln p,
+//                              fp64, strictly left to right; p_t from the longest-suffix context (:122-141)
+//   src/distance/negloglikelihood.pyx:17-26   D = ((M_ii - M_ij)/L + (M_jj - M_ji)/L) / 2
+//
+// Kernel shape.  A persistent CTA owns a contiguous run of work units (model m, up to 512 sequences).
+// The model's NLL table ("blob") is staged into shared memory with 1-D bulk async copies (TMA, UBLKCP)
+// completing on an mbarrier; it is re-staged only when the model changes.  Two accumulation modes:
+//   VGS_NLL_SEQUENTIAL  one lane per (sequence, model); the lane walks its sequence with 128-bit loads and
+//                       adds the terms strictly in order -> bit-identical to the reference's fp64 sum;
+//   VGS_NLL_WARP        one warp per (sequence, model); lane l takes 64-symbol chunks l, l+32, ...;
+//                       4 partial sums per chunk, fixed-order shuffle reduction (north_star's layout).
+// Per scored base: one funnel shift + mask (the (order+1)-mer ending at the base is a contiguous bit
+// field of the packed sequence), one 8-byte shared-memory gather, one DADD.
+#include <algorithm>
+#include <type_traits>
+
+#include "vgs_common.cuh"
+
+#define NLL_THREADS 512
+
+struct NllUnit {
+    int32_t model;
+    int32_t list_off;  // offset into seq_list, or first sequence index when seq_list == nullptr
+    int32_t count;     // <= NLL_THREADS
+    int32_t extra;     // extra sequence index scored by lane `count` (the diagonal M[m][m]) or -1
+};
+
+struct NllParams {
+    const ModelMeta *meta;
+    const uint8_t *arena;
+    const uint2 *hash;
+    const double *logp;
+    const uint32_t *seq;
+    const int64_t *seq_off;
+    const int64_t *seq_len;
+    const int32_t *seq_list;
+    const NllUnit *units;
+    int n_units;
+    int skip_none;
+    double *M;
+    int64_t ld;
+};
+
+// ---- table views -----------------------------------------------------------------------------
+struct DenseTable {  // tier 1
+    const double *tab;
+    uint32_t fmask;
+    __device__ __forceinline__ void bind(const uint8_t *blob, const ModelMeta &mm) {
+        tab = (const double *)blob;
+        fmask = vgs_lowmask(mm.order + 1);
+    }
+    __device__ __forceinline__ double term(uint32_t f) const { return tab[f & fmask]; }
+};
+
+struct TwoLevelTable {  // tier 2
+    const uint32_t *l1;
+    const uint2 *deep;
+    const double *rows;
+    uint32_t deep_mask;
+    int deep_shift, order;
+    __device__ __forceinline__ void bind(const uint8_t *blob, const ModelMeta &mm) {
+        l1 = (const uint32_t *)blob;
+        deep = (const uint2 *)(blob + mm.deep_off);
+        rows = (const double *)(blob + mm.logp_off);
+        deep_mask = mm.deep_mask;
+        deep_shift = mm.deep_shift;
+        order = mm.order;
+    }
+    __device__ __forceinline__ double term(uint32_t f) const {
+        const uint32_t x = f & 3u, hist = f >> 2;
+        const uint32_t e = l1[hist & ((1u << (2 * VGS_L1_DEPTH)) - 1u)];
+        uint32_t id = e & 0x7FFFFFFFu;
+        if (e & 0x80000000u) {
+            for (int ln = order; ln > VGS_L1_DEPTH; --ln) {
+                int r = vgs_hash_find(deep, deep_mask, deep_shift, vgs_key(ln, hist & vgs_lowmask(ln)));
+                if (r >= 0) { id = (uint32_t)r; break; }
+            }
+        }
+        return id == VGS_NO_CTX ? vgs_nan() : rows[4 * id + x];
+    }
+};
+
+// 64 symbols (one uint4) starting at position t0; `prev` is the word before the chunk.
+template <class TAB, bool SEQ>
+__device__ __forceinline__ void scan_chunk(const TAB &T, const uint4 q, uint32_t prev, int64_t t0, int64_t skip, int64_t L,
+                                           double &acc) {
+    const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t cur = ws[k];
+        const int64_t tw = t0 + 16 * k;
+        if (tw >= skip && tw + 16 <= L) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const double v = T.term(__funnelshift_r(cur, prev, 30 - 2 * j));
+                if (SEQ) acc += v; else part[k] += v;
+            }
+        } else if (tw < L && tw + 16 > skip) {
+#pragma unroll 1
+            for (int j = 0; j < 16; ++j) {
+                const int64_t t = tw + j;
+                if (t >= skip && t < L) {
+                    const double v = T.term(__funnelshift_r(cur, prev, 30 - 2 * j));
+                    if (SEQ) acc += v; else part[k] += v;
+                }
+            }
+        }
+        prev = cur;
+    }
+    if (!SEQ) acc += (part[0] + part[1]) + (part[2] + part[3]);
+}
+
+// first min(order, L) positions of log_likelihood (skip = 0): short histories, generic hash lookup
+__device__ double nll_prologue(const NllParams &p, const ModelMeta &mm, const uint32_t *w, int64_t L) {
+    const uint2 *slots = p.hash + mm.hash_off;
+    double acc = 0.0;
+    uint32_t hist = 0;
+    const int64_t top = L < mm.order ? L : mm.order;
+    for (int64_t t = 0; t < top; ++t) {
+        const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
+        const int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, hist, (int)t);
+        acc += id < 0 ? vgs_nan() : p.logp[4 * (mm.ctx_off + id) + x];
+        hist = (hist << 2) | x;
+    }
+    return acc;
+}
+
+template <int TIER, int MODE, bool STAGED>
+__global__ void __launch_bounds__(NLL_THREADS, 1) k_nll_scores(const NllParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const int u0 = (int)((int64_t)blockIdx.x * p.n_units / gridDim.x);
+    const int u1 = (int)((int64_t)(blockIdx.x + 1) * p.n_units / gridDim.x);
+    if (STAGED) {
+        if (tid == 0) vgs_mbar_init(&bar, 1);
+        __syncthreads();
+    }
+    uint32_t parity = 0;
+    int cur_model = -1;
+    typename std::conditional<TIER == 1, DenseTable, TwoLevelTable>::type T;
+    ModelMeta mm;
+    for (int u = u0; u < u1; ++u) {
+        const NllUnit un = p.units[u];
+        if (un.model != cur_model) {
+            mm = p.meta[un.model];
+            cur_model = un.model;
+            const uint8_t *blob = p.arena + mm.nll_off;
+            if (STAGED) {
+                __syncthreads();  // every lane is done reading the previous table
+                if (tid == 0) vgs_stage(smem, blob, (uint32_t)mm.nll_bytes, &bar);
+                vgs_mbar_wait(&bar, parity);
+                parity ^= 1u;
+                T.bind(smem, mm);
+            } else {
+                T.bind(blob, mm);
+            }
+        }
+        const int64_t skip = mm.order;
+        const int n_items = un.count + (un.extra >= 0 ? 1 : 0);
+        if (MODE == VGS_NLL_SEQUENTIAL) {
+            if (tid < n_items) {
+                const int s = tid < un.count ? (p.seq_list ? p.seq_list[un.list_off + tid] : un.list_off + tid) : un.extra;
+                const uint32_t *w = p.seq + p.seq_off[s];
+                const int64_t L = p.seq_len[s];
+                double acc = p.skip_none ? nll_prologue(p, mm, w, L) : 0.0;
+                const int64_t n_chunks = (L + 63) >> 6;
+                uint32_t prev = 0;
+                const uint4 *w4 = (const uint4 *)w;
+                for (int64_t c = 0; c < n_chunks; ++c) {
+                    const uint4 q = __ldg(w4 + c);
+                    scan_chunk<decltype(T), true>(T, q, prev, c << 6, skip, L, acc);
+                    prev = q.w;
+                }
+                p.M[(int64_t)s * p.ld + un.model] = acc;
+            }
+        } else {
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int it = warp; it < n_items; it += NLL_THREADS / 32) {
+                const int s = it < un.count ? (p.seq_list ? p.seq_list[un.list_off + it] : un.list_off + it) : un.extra;
+                const uint32_t *w = p.seq + p.seq_off[s];
+                const int64_t L = p.seq_len[s];
+                const int64_t n_chunks = (L + 63) >> 6;
+                const uint4 *w4 = (const uint4 *)w;
+                double acc = 0.0;
+                for (int64_t c = lane; c < n_chunks; c += 32) {
+                    const uint4 q = __ldg(w4 + c);
+                    const uint32_t prev = c ? __ldg(w + 4 * c - 1) : 0u;
+                    scan_chunk<decltype(T), false>(T, q, prev, c << 6, skip, L, acc);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) {
+                    if (p.skip_none) acc = nll_prologue(p, mm, w, L) + acc;
+                    p.M[(int64_t)s * p.ld + un.model] = acc;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: build the unit list and launch per tier
+// ---------------------------------------------------------------------------------------------
+template <int TIER, int MODE, bool STAGED>
+static int launch_nll(vgs_context *h, const NllParams &p, int smem_bytes, cudaStream_t s) {
+    auto kern = k_nll_scores<TIER, MODE, STAGED>;
+    if (STAGED) VGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int per_sm = 1;
+    VGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NLL_THREADS, STAGED ? smem_bytes : 0));
+    if (per_sm < 1) per_sm = 1;
+    int grid = std::min(p.n_units, h->sm_count * per_sm);
+    kern<<<grid, NLL_THREADS, STAGED ? smem_bytes : 0, s>>>(p);
+    VGS_LAUNCH_CHECK(h);
+    return VGS_OK;
+}
+
+template <int TIER>
+static int launch_nll_tier(vgs_context *h, const NllParams &p, int mode, int64_t max_bytes, cudaStream_t s) {
+    const bool staged = max_bytes + 1024 <= (int64_t)h->max_smem_optin;
+    const int smem = (int)((max_bytes + 127) / 128 * 128);
+    if (mode == VGS_NLL_SEQUENTIAL) {
+        return staged ? launch_nll<TIER, VGS_NLL_SEQUENTIAL, true>(h, p, smem, s) : launch_nll<TIER, VGS_NLL_SEQUENTIAL, false>(h, p, 0, s);
+    }
+    return staged ? launch_nll<TIER, VGS_NLL_WARP, true>(h, p, smem, s) : launch_nll<TIER, VGS_NLL_WARP, false>(h, p, 0, s);
+}
+
+// seq_lists_per_block[B] = sequences to score against every model of model-block B (models
+// B*block .. min(n, (B+1)*block)-1); an empty outer vector means "all sequences, contiguous".
+int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &lists, int64_t block, int64_t m_begin,
+                        int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld, cudaStream_t s) {
+    std::vector<NllUnit> units[2];
+    std::vector<int32_t> flat;
+    std::vector<int64_t> list_off(lists.size() + 1, 0);
+    for (size_t b = 0; b < lists.size(); ++b) {
+        list_off[b + 1] = list_off[b] + (int64_t)lists[b].size();
+        flat.insert(flat.end(), lists[b].begin(), lists[b].end());
+    }
+    for (int64_t m = m_begin; m < m_end; ++m) {
+        const size_t b = (size_t)(m / block);
+        if (b >= lists.size()) break;
+        const std::vector<int32_t> &L = lists[b];
+        const int t = h->h_meta[(size_t)m].tier - 1;
+        bool diag_needed = add_diagonal && m < h->n_seq && !std::binary_search(L.begin(), L.end(), (int32_t)m);
+        int64_t cnt = (int64_t)L.size();
+        if (cnt == 0 && !diag_needed) continue;
+        // even split into ceil(cnt / NLL_THREADS) units
+        int64_t n_u = std::max<int64_t>(1, (cnt + (diag_needed ? 1 : 0) + NLL_THREADS - 1) / NLL_THREADS);
+        for (int64_t k = 0; k < n_u; ++k) {
+            int64_t a = cnt * k / n_u, e = cnt * (k + 1) / n_u;
+            NllUnit un;
+            un.model = (int32_t)m;
+            un.list_off = (int32_t)(list_off[b] + a);
+            un.count = (int32_t)(e - a);
+            un.extra = (k == n_u - 1 && diag_needed) ? (int32_t)m : -1;
+            units[t].push_back(un);
+        }
+    }
+    if (units[0].empty() && units[1].empty()) return VGS_OK;
+    const int64_t n_units_total = (int64_t)(units[0].size() + units[1].size());
+    int64_t bytes = n_units_total * (int64_t)sizeof(NllUnit) + (int64_t)flat.size() * 4 + 256;
+    int rc = vgs_ensure_scratch2(h, bytes);
+    if (rc) return rc;
+    NllUnit *d_units = (NllUnit *)h->d_scratch2;
+    int32_t *d_list = (int32_t *)((char *)h->d_scratch2 + (n_units_total * sizeof(NllUnit) + 127) / 128 * 128);
+    if (!units[0].empty())
+        VGS_CUDA(cudaMemcpyAsync(d_units, units[0].data(), units[0].size() * sizeof(NllUnit), cudaMemcpyHostToDevice, s));
+    if (!units[1].empty())
+        VGS_CUDA(cudaMemcpyAsync(d_units + units[0].size(), units[1].data(), units[1].size() * sizeof(NllUnit), cudaMemcpyHostToDevice, s));
+    if (!flat.empty()) VGS_CUDA(cudaMemcpyAsync(d_list, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, s));
+    // pageable sources: the copies above have consumed the host vectors when they return
+    NllParams p;
+    p.meta = h->d_meta; p.arena = h->d_nll; p.hash = h->d_hash; p.logp = h->d_logp;
+    p.seq = h->d_seq; p.seq_off = h->d_seq_off; p.seq_len = h->d_seq_len;
+    p.seq_list = d_list;
+    p.skip_none = skip_mode == VGS_SKIP_NONE;
+    p.M = M; p.ld = ld;
+    if (!units[0].empty()) {
+        p.units = d_units; p.n_units = (int)units[0].size();
+        if ((rc = launch_nll_tier<1>(h, p, mode, h->max_nll_bytes_t1, s))) return rc;
+    }
+    if (!units[1].empty()) {
+        p.units = d_units + units[0].size(); p.n_units = (int)units[1].size();
+        if ((rc = launch_nll_tier<2>(h, p, mode, h->max_nll_bytes_t2, s))) return rc;
+    }
+    return VGS_OK;
+}
+
+static int check_nll_ready(vgs_context *h) {
+    VGS_CHECK_ARG(h, "null handle");
+    VGS_CHECK_ARG(h->n_models > 0, "no models loaded (vgs_load_models)");
+    VGS_CHECK_ARG(h->n_seq > 0, "no sequences loaded (vgs_load_sequences_* / vgs_sample_sequences)");
+    return VGS_OK;
+}
+
+extern "C" int vgs_nll_scores(vgs_handle h, int64_t s_begin, int64_t s_end, int64_t m_begin, int64_t m_end, int skip_mode,
+                              int mode, double *M_d, int64_t ld, void *stream) {
+    int rc = check_nll_ready(h);
+    if (rc) return rc;
+    VGS_CHECK_ARG(0 <= s_begin && s_begin <= s_end && s_end <= h->n_seq, "vgs_nll_scores: bad sequence range");
+    VGS_CHECK_ARG(0 <= m_begin && m_begin <= m_end && m_end <= h->n_models, "vgs_nll_scores: bad model range");
+    VGS_CHECK_ARG(M_d && ld >= h->n_models, "vgs_nll_scores: bad output");
+    VGS_CHECK_ARG(mode == VGS_NLL_SEQUENTIAL || mode == VGS_NLL_WARP, "vgs_nll_scores: bad mode");
+    VGS_CHECK_ARG(skip_mode == VGS_SKIP_ORDER || skip_mode == VGS_SKIP_NONE, "vgs_nll_scores: bad skip mode");
+    VGS_CUDA(cudaSetDevice(h->device));
+    if (s_begin == s_end || m_begin == m_end) return VGS_OK;
+    std::vector<int32_t> seqs((size_t)(s_end - s_begin));
+    for (int64_t i = s_begin; i < s_end; ++i) seqs[(size_t)(i - s_begin)] = (int32_t)i;
+    std::vector<std::vector<int32_t>> lists(1, seqs);
+    return vgs_nll_score_lists(h, lists, h->n_models, m_begin, m_end, false, skip_mode, mode, M_d, ld, (cudaStream_t)stream);
+}
+
+extern "C" int vgs_nll_scores_h(vgs_handle h, int skip_mode, int mode, double *M_out_h) {
+    int rc = check_nll_ready(h);
+    if (rc) return rc;
+    VGS_CHECK_ARG(M_out_h, "vgs_nll_scores_h: null output");
+    VGS_CUDA(cudaSetDevice(h->device));
+    if ((rc = vgs_ensure_M(h))) return rc;
+    cudaStream_t s = h->own_stream;
+    std::vector<int32_t> all((size_t)h->n_seq);
+    for (int64_t i = 0; i < h->n_seq; ++i) all[(size_t)i] = (int32_t)i;
+    std::vector<std::vector<int32_t>> lists(1, all);
+    VGS_CHECK_ARG(mode == VGS_NLL_SEQUENTIAL || mode == VGS_NLL_WARP, "bad mode");
+    if ((rc = vgs_nll_score_lists(h, lists, h->n_models, 0, h->n_models, false, skip_mode, mode, h->d_M, h->n_models, s))) return rc;
+    VGS_CUDA(cudaMemcpyAsync(M_out_h, h->d_M, 8 * (size_t)(h->n_seq * h->n_models), cudaMemcpyDeviceToHost, s));
+    VGS_CUDA(cudaStreamSynchronize(s));
+    return VGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: combine scores into distances, tile by tile
+// ---------------------------------------------------------------------------------------------
+__global__ void k_nll_combine(TilePlan pl, int rank, const double *__restrict__ M, int64_t ld, double length,
+                              float *__restrict__ pay32, double *__restrict__ pay64, int *__restrict__ err) {
+    const int64_t q = blockIdx.x;
+    const int64_t k = q * pl.world + rank;
+    const int64_t T = pl.tile;
+    float *o32 = pay32 + q * T * T;
+    double *o64 = pay64 ? pay64 + q * T * T : nullptr;
+    __shared__ int64_t sI, sJ;
+    if (threadIdx.x == 0) {
+        int64_t I = 0, J = 0;
+        if (k < pl.n_tiles) {
+            int64_t rem = k;
+            while (rem >= pl.nt - I) { rem -= pl.nt - I; ++I; }
+            J = I + rem;
+        }
+        sI = I; sJ = J;
+    }
+    __syncthreads();
+    const int64_t I = sI, J = sJ;
+    for (int64_t e = threadIdx.x; e < T * T; e += blockDim.x) {
+        const int64_t i = I * T + e / T, j = J * T + e % T;
+        double d = 0.0;
+        if (k < pl.n_tiles && i < pl.n && j < pl.n) {
+            const double mii = M[i * ld + i], mij = M[i * ld + j], mjj = M[j * ld + j], mji = M[j * ld + i];
+            const double lr = __ddiv_rn(__dsub_rn(mii, mij), length);
+            const double rl = __ddiv_rn(__dsub_rn(mjj, mji), length);
+            d = __ddiv_rn(__dadd_rn(lr, rl), 2.0);
+            if (d != d) atomicOr(err, 1);
+        }
+        o32[e] = (float)d;
+        if (o64) o64[e] = d;
+    }
+}
+
+static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePlan &pl, int rank, float *pay32, double *pay64,
+                          cudaStream_t s) {
+    int rc = vgs_ensure_M(h);
+    if (rc) return rc;
+    // which sequence blocks does this rank need against each model block?
+    std::vector<std::vector<int32_t>> lists((size_t)pl.nt);
+    std::vector<std::vector<char>> need((size_t)pl.nt, std::vector<char>((size_t)pl.nt, 0));
+    for (int64_t k = rank; k < pl.n_tiles; k += pl.world) {
+        int64_t I, J;
+        vgs_tile_coords(pl, k, &I, &J);
+        need[(size_t)J][(size_t)I] = 1;  // model block J scores sequence block I ...
+        need[(size_t)I][(size_t)J] = 1;  // ... and model block I scores sequence block J
+    }
+    for (int64_t B = 0; B < pl.nt; ++B)
+        for (int64_t S = 0; S < pl.nt; ++S)
+            if (need[(size_t)B][(size_t)S])
+                for (int64_t x = S * pl.tile; x < std::min(pl.n, (S + 1) * pl.tile); ++x) lists[(size_t)B].push_back((int32_t)x);
+    // models whose block touches no owned tile need nothing; the diagonal score M[m][m] rides along
+    rc = vgs_nll_score_lists(h, lists, pl.tile, 0, h->n_models, true, VGS_SKIP_ORDER, mode, h->d_M, h->n_models, s);
+    if (rc) return rc;
+    if (pl.slots > 0) {
+        k_nll_combine<<<(unsigned)pl.slots, 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
+        VGS_LAUNCH_CHECK(h);
+    }
+    return VGS_OK;
+}
+
+extern "C" int vgs_nll_tiles(vgs_handle h, int64_t length, int mode, int64_t tile, int rank, int world, float *payload_d,
+                             void *stream) {
+    int rc = check_nll_ready(h);
+    if (rc) return rc;
+    VGS_CHECK_ARG(h->n_seq == h->n_models, "vgs_nll_tiles: need exactly one sequence per model (sequence i sampled from model i)");
+    VGS_CHECK_ARG(length > 0 && tile > 0 && world > 0 && rank >= 0 && rank < world && payload_d, "vgs_nll_tiles: bad arguments");
+    VGS_CHECK_ARG(mode == VGS_NLL_SEQUENTIAL || mode == VGS_NLL_WARP, "vgs_nll_tiles: bad mode");
+    VGS_CUDA(cudaSetDevice(h->device));
+    TilePlan pl;
+    vgs_make_plan(&pl, h->n_models, tile, world, 1);
+    return nll_tiles_impl(h, length, mode, pl, rank, payload_d, nullptr, (cudaStream_t)stream);
+}
+
+static int64_t default_tile(int64_t n) { return n <= 2048 ? 64 : (n <= 8192 ? 128 : 256); }
+
+extern "C" int vgs_nll_matrix(vgs_handle h, int64_t length, int mode, float *D32_d, double *D64_d, void *stream) {
+    int rc = check_nll_ready(h);
+    if (rc) return rc;
+    VGS_CHECK_ARG(h->n_seq == h->n_models, "vgs_nll_matrix: need exactly one sequence per model (sequence i sampled from model i)");
+    VGS_CHECK_ARG(length > 0 && D32_d, "vgs_nll_matrix: bad arguments");
+    VGS_CHECK_ARG(mode == VGS_NLL_SEQUENTIAL || mode == VGS_NLL_WARP, "vgs_nll_matrix: bad mode");
+    VGS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    TilePlan pl;
+    vgs_make_plan(&pl, h->n_models, default_tile(h->n_models), 1, 1);
+    const int64_t pay_elems = pl.slots * pl.tile * pl.tile;
+    if ((rc = vgs_ensure_scratch(h, pay_elems * (D64_d ? 12 : 4) + 256))) return rc;
+    float *pay32 = (float *)h->d_scratch;
+    double *pay64 = D64_d ? (double *)((char *)h->d_scratch + (pay_elems * 4 + 255) / 256 * 256) : nullptr;
+    if ((rc = nll_tiles_impl(h, length, mode, pl, 0, pay32, pay64, s))) return rc;
+    return vgs_assemble_impl(h, pl, pay32, pay64, D32_d, D64_d, s);
+}
+
+extern "C" int vgs_nll_matrix_h(vgs_handle h, int64_t length, int mode, float *D32_out_h, double *D64_out_h) {
+    int rc = check_nll_ready(h);
+    if (rc) return rc;
+    VGS_CHECK_ARG(D32_out_h || D64_out_h, "vgs_nll_matrix_h: no output");
+    VGS_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->n_models;
+    float *d32 = nullptr;
+    double *d64 = nullptr;
+    if ((rc = vgs_dev_alloc(&d32, n * n))) return rc;
+    if (D64_out_h && (rc = vgs_dev_alloc(&d64, n * n))) { cudaFree(d32); return rc; }
+    cudaStream_t s = h->own_stream;
+    rc = vgs_nll_matrix(h, length, mode, d32, d64, s);
+    if (!rc) rc = vgs_read_error_flag(h, s);
+    if (!rc && D32_out_h) rc = cudaMemcpyAsync(D32_out_h, d32, 4 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
+    if (!rc && D64_out_h) rc = cudaMemcpyAsync(D64_out_h, d64, 8 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
+    cudaStreamSynchronize(s);
+    cudaFree(d32);
+    if (d64) cudaFree(d64);
+    return rc;
+}

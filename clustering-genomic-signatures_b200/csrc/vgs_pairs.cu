@@ -1,0 +1,306 @@
+// vgs_pairs.cu -- K4: FrobeniusNorm (intersection / union) and Projection for all pairs.
+//
+// Reference behaviour restated (paths relative to the reference repository):
+//   src/distance/frobenius.pyx:21-53   C = keys_l ∩ keys_r (default) or ∪; a context missing from a model
+//        takes the row of its longest suffix present there (:47-50); rows are float32; the difference is a
+//        float32 subtraction; d = ||P_l - P_r||_F / sqrt(|C|)
+//   src/distance/projection.pyx:7-36   every model embedded over the union universe with zero rows for
+//        absent contexts; d = ||v_l - v_r||_2 (not normalised)
+// Here the float32 subtraction is kept and the sum of squares is accumulated in fp64 (each square of a
+// float32 difference is exact in fp64), so results agree with the oracle to fp64 rounding and with the
+// reference's float32 BLAS dot to ~1e-7 relative (its own rounding).
+//
+// Kernel shape.  One CTA = (tile slot, direction, group of JG "staged" models y).  The staged models'
+// exact-context hashes and fp32 rows are copied into shared memory with bulk async copies (TMA, UBLKCP);
+// each warp then streams the contexts of one "streamed" model x at a time (coalesced key + float4 row
+// loads, 32 contexts per step) and probes all JG staged hashes with the same registers.  Directed
+// partial results go to scratch:  S[x][y] = sum over shared contexts of |a_x - a_y|^2,
+// U[x][y] = sum over contexts of x missing from y (vs. y's fallback row, or vs. zero for Projection),
+// C[x][y] = number of shared contexts.  A second small kernel combines the two directions per entry.
+#include <algorithm>
+
+#include "vgs_common.cuh"
+
+#define PAIR_THREADS 256
+#define PAIR_MAX_JG 8
+
+struct PairParams {
+    const ModelMeta *meta;
+    const uint32_t *key;
+    const float4 *prob32;
+    const uint2 *hash;
+    TilePlan pl;
+    int rank, kind, jg, n_groups, n_dir;
+    double *S, *U;
+    int32_t *C;
+    int *err;
+};
+
+__device__ __forceinline__ void tile_of_slot(const TilePlan &pl, int64_t k, int64_t *I, int64_t *J) {
+    if (!pl.symmetric) { *I = k / pl.nt; *J = k % pl.nt; return; }
+    int64_t i = 0, rem = k;
+    while (rem >= pl.nt - i) { rem -= pl.nt - i; ++i; }
+    *I = i; *J = i + rem;
+}
+
+__device__ __forceinline__ double sq4(const float4 a, const float4 b) {
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;  // float32 subtraction (frobenius.pyx:34)
+    double r = (double)dx * (double)dx;
+    r += (double)dy * (double)dy;
+    r += (double)dz * (double)dz;
+    r += (double)dw * (double)dw;
+    return r;
+}
+
+template <bool STAGED>
+__global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ int64_t sI, sJ;
+    __shared__ ModelMeta ymeta[PAIR_MAX_JG];
+    __shared__ uint32_t yoff_h[PAIR_MAX_JG], yoff_r[PAIR_MAX_JG];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t w = blockIdx.x;
+    const int g = (int)(w % p.n_groups); w /= p.n_groups;
+    const int dir = (int)(w % p.n_dir);
+    const int64_t q = w / p.n_dir;
+    const int64_t k = q * p.pl.world + p.rank;
+    if (k >= p.pl.n_tiles) return;
+    if (tid == 0) {
+        int64_t I, J;
+        tile_of_slot(p.pl, k, &I, &J);
+        sI = I; sJ = J;
+        if (STAGED) vgs_mbar_init(&bar, 1);
+    }
+    __syncthreads();
+    const int64_t T = p.pl.tile;
+    const int64_t I = sI, J = sJ;
+    if (dir == 1 && I == J) return;  // a diagonal tile holds every ordered pair already
+    const int64_t Xb = dir ? J : I, Yb = dir ? I : J;
+    const int64_t y0 = Yb * T + (int64_t)g * p.jg;
+    const int64_t y_end = min(p.pl.n, (Yb + 1) * T);
+    const int ny = (int)min((int64_t)p.jg, y_end - y0);
+    if (ny <= 0) return;
+    const int64_t x0 = Xb * T;
+    const int nx = (int)(min(p.pl.n, (Xb + 1) * T) - x0);
+
+    if (tid < ny) ymeta[tid] = p.meta[y0 + tid];
+    __syncthreads();
+    if (STAGED) {
+        if (tid == 0) {
+            uint32_t off = 0, total = 0;
+            for (int yy = 0; yy < ny; ++yy) {
+                const uint32_t hb = (ymeta[yy].hash_mask + 1u) * 8u, rb = (uint32_t)ymeta[yy].n_ctx * 16u;
+                yoff_h[yy] = off; off += hb;
+                yoff_r[yy] = off; off += rb;
+                total += hb + rb;
+            }
+            vgs_mbar_expect_tx(&bar, total);
+            for (int yy = 0; yy < ny; ++yy) {
+                vgs_copy_pieces(smem + yoff_h[yy], p.hash + ymeta[yy].hash_off, (ymeta[yy].hash_mask + 1u) * 8u, &bar);
+                vgs_copy_pieces(smem + yoff_r[yy], p.prob32 + ymeta[yy].ctx_off, (uint32_t)ymeta[yy].n_ctx * 16u, &bar);
+            }
+        }
+        __syncthreads();
+        vgs_mbar_wait(&bar, 0);
+    }
+
+    const uint2 *yh[PAIR_MAX_JG];
+    const float4 *yr[PAIR_MAX_JG];
+#pragma unroll
+    for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
+        if (yy < ny) {
+            yh[yy] = STAGED ? (const uint2 *)(smem + yoff_h[yy]) : p.hash + ymeta[yy].hash_off;
+            yr[yy] = STAGED ? (const float4 *)(smem + yoff_r[yy]) : p.prob32 + ymeta[yy].ctx_off;
+        } else {
+            yh[yy] = nullptr; yr[yy] = nullptr;
+        }
+    }
+
+    const int64_t part_base = ((q * 2 + dir) * T) * T;
+    for (int xx = warp; xx < nx; xx += PAIR_THREADS / 32) {
+        const ModelMeta xm = p.meta[x0 + xx];
+        double s[PAIR_MAX_JG], u[PAIR_MAX_JG];
+        int c[PAIR_MAX_JG];
+#pragma unroll
+        for (int yy = 0; yy < PAIR_MAX_JG; ++yy) { s[yy] = 0.0; u[yy] = 0.0; c[yy] = 0; }
+        for (int ci = lane; ci < xm.n_ctx; ci += 32) {
+            const uint32_t key = __ldg(p.key + xm.ctx_off + ci);
+            const float4 px = __ldg(p.prob32 + xm.ctx_off + ci);
+            const int len = (31 - __clz(key)) >> 1;
+            const uint32_t code = key ^ (1u << (2 * len));
+#pragma unroll
+            for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
+                if (yy >= ny) break;
+                const uint32_t mask = ymeta[yy].hash_mask;
+                const int shift = ymeta[yy].hash_shift;
+                int id = vgs_hash_find(yh[yy], mask, shift, key);
+                if (id >= 0) {
+                    s[yy] += sq4(px, yr[yy][id]);
+                    c[yy] += 1;
+                } else if (p.kind == VGS_PAIR_FROBENIUS_UNION) {
+                    int top = len - 1 < ymeta[yy].order ? len - 1 : ymeta[yy].order;
+                    for (int ln = top; ln >= 0 && id < 0; --ln) id = vgs_hash_find(yh[yy], mask, shift, vgs_key(ln, code & vgs_lowmask(ln)));
+                    if (id < 0) atomicOr(p.err, 1);
+                    else u[yy] += sq4(px, yr[yy][id]);
+                } else if (p.kind == VGS_PAIR_PROJECTION) {
+                    u[yy] += sq4(px, make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+            }
+        }
+#pragma unroll
+        for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
+            if (yy >= ny) break;
+            double sv = s[yy], uv = u[yy];
+            int cv = c[yy];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                uv += __shfl_xor_sync(0xffffffffu, uv, o);
+                cv += __shfl_xor_sync(0xffffffffu, cv, o);
+            }
+            if (lane == 0) {
+                const int64_t e = part_base + (int64_t)xx * T + (g * p.jg + yy);
+                p.S[e] = sv; p.U[e] = uv; p.C[e] = cv;
+            }
+        }
+    }
+}
+
+__global__ void k_pair_combine(PairParams p, float *__restrict__ pay32, double *__restrict__ pay64) {
+    const int64_t q = blockIdx.x;
+    const int64_t k = q * p.pl.world + p.rank;
+    const int64_t T = p.pl.tile;
+    __shared__ int64_t sI, sJ;
+    if (threadIdx.x == 0) {
+        int64_t I = 0, J = 0;
+        if (k < p.pl.n_tiles) tile_of_slot(p.pl, k, &I, &J);
+        sI = I; sJ = J;
+    }
+    __syncthreads();
+    const int64_t I = sI, J = sJ;
+    const double *S0 = p.S + (q * 2) * T * T, *U0 = p.U + (q * 2) * T * T, *U1 = p.U + (q * 2 + 1) * T * T;
+    const int32_t *C0 = p.C + (q * 2) * T * T;
+    for (int64_t e = threadIdx.x; e < T * T; e += blockDim.x) {
+        const int64_t ii = e / T, jj = e % T, i = I * T + ii, j = J * T + jj;
+        double d = 0.0;
+        if (k < p.pl.n_tiles && i < p.pl.n && j < p.pl.n) {
+            const double s = S0[e];
+            const int cnt = C0[e];
+            if (p.kind == VGS_PAIR_FROBENIUS_INTERSECTION) {
+                d = cnt > 0 ? sqrt(s) / sqrt((double)cnt) : vgs_nan();  // empty intersection: 0/0 in the reference
+            } else {
+                const double u_ij = U0[e];
+                const double u_ji = (I == J) ? U0[jj * T + ii] : U1[jj * T + ii];
+                const double ssq = s + u_ij + u_ji;
+                if (p.kind == VGS_PAIR_FROBENIUS_UNION) {
+                    const int n_union = p.meta[i].n_ctx + p.meta[j].n_ctx - cnt;
+                    d = sqrt(ssq) / sqrt((double)n_union);
+                } else {
+                    d = sqrt(ssq);
+                }
+            }
+        }
+        pay32[q * T * T + e] = (float)d;
+        if (pay64) pay64[q * T * T + e] = d;
+    }
+}
+
+static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int rank, float *pay32, double *pay64, cudaStream_t s) {
+    PairParams p;
+    p.meta = h->d_meta; p.key = h->d_key; p.prob32 = h->d_prob32; p.hash = h->d_hash;
+    p.pl = pl; p.rank = rank; p.kind = kind; p.err = h->d_err;
+    p.n_dir = kind == VGS_PAIR_FROBENIUS_INTERSECTION ? 1 : 2;
+    // how many staged models fit?  prefer >= 2 CTAs per SM
+    const int64_t per_model = (h->max_pair_bytes + 127) / 128 * 128;
+    const int64_t cap = (int64_t)h->max_smem_optin - 2048;
+    bool staged = per_model <= cap;
+    int jg = 4;
+    if (staged) {
+        int64_t budget = cap / 2;
+        jg = (int)std::min<int64_t>(PAIR_MAX_JG, budget / per_model);
+        if (jg < 2) jg = (int)std::min<int64_t>(PAIR_MAX_JG, cap / per_model);
+        if (jg < 1) jg = 1;
+    }
+    jg = (int)std::min<int64_t>(jg, pl.tile);
+    p.jg = jg;
+    p.n_groups = (int)((pl.tile + jg - 1) / jg);
+    const int64_t part = pl.slots * 2 * pl.tile * pl.tile;
+    int rc = vgs_ensure_scratch2(h, part * 20 + 1024);
+    if (rc) return rc;
+    p.S = (double *)h->d_scratch2;
+    p.U = p.S + part;
+    p.C = (int32_t *)(p.U + part);
+    if (pl.slots == 0) return VGS_OK;
+    VGS_CUDA(cudaMemsetAsync(h->d_scratch2, 0, (size_t)(part * 20), s));
+    const int64_t n_cta = pl.slots * p.n_dir * p.n_groups;
+    VGS_CHECK_ARG(n_cta < ((int64_t)1 << 31), "pair kernel grid too large");
+    if (staged) {
+        const int smem = (int)(per_model * jg);
+        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_pair_partials<true><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
+    } else {
+        k_pair_partials<false><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
+    }
+    VGS_LAUNCH_CHECK(h);
+    k_pair_combine<<<(unsigned)pl.slots, 256, 0, s>>>(p, pay32, pay64);
+    VGS_LAUNCH_CHECK(h);
+    return VGS_OK;
+}
+
+static int check_pair_args(vgs_context *h, int kind) {
+    VGS_CHECK_ARG(h, "null handle");
+    VGS_CHECK_ARG(h->n_models > 0, "no models loaded (vgs_load_models)");
+    VGS_CHECK_ARG(kind == VGS_PAIR_FROBENIUS_INTERSECTION || kind == VGS_PAIR_FROBENIUS_UNION || kind == VGS_PAIR_PROJECTION,
+                  "bad pair-distance kind");
+    return VGS_OK;
+}
+
+extern "C" int vgs_pair_tiles(vgs_handle h, int kind, int64_t tile, int rank, int world, float *payload_d, void *stream) {
+    int rc = check_pair_args(h, kind);
+    if (rc) return rc;
+    VGS_CHECK_ARG(tile > 0 && world > 0 && rank >= 0 && rank < world && payload_d, "vgs_pair_tiles: bad arguments");
+    VGS_CUDA(cudaSetDevice(h->device));
+    TilePlan pl;
+    vgs_make_plan(&pl, h->n_models, tile, world, 1);
+    return pair_tiles_impl(h, kind, pl, rank, payload_d, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int vgs_pair_matrix(vgs_handle h, int kind, float *D32_d, double *D64_d, void *stream) {
+    int rc = check_pair_args(h, kind);
+    if (rc) return rc;
+    VGS_CHECK_ARG(D32_d, "vgs_pair_matrix: null output");
+    VGS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    TilePlan pl;
+    const int64_t n = h->n_models;
+    vgs_make_plan(&pl, n, n <= 2048 ? 64 : 128, 1, 1);
+    const int64_t pay_elems = pl.slots * pl.tile * pl.tile;
+    if ((rc = vgs_ensure_scratch(h, pay_elems * (D64_d ? 12 : 4) + 256))) return rc;
+    float *pay32 = (float *)h->d_scratch;
+    double *pay64 = D64_d ? (double *)((char *)h->d_scratch + (pay_elems * 4 + 255) / 256 * 256) : nullptr;
+    if ((rc = pair_tiles_impl(h, kind, pl, 0, pay32, pay64, s))) return rc;
+    return vgs_assemble_impl(h, pl, pay32, pay64, D32_d, D64_d, s);
+}
+
+extern "C" int vgs_pair_matrix_h(vgs_handle h, int kind, float *D32_out_h, double *D64_out_h) {
+    int rc = check_pair_args(h, kind);
+    if (rc) return rc;
+    VGS_CHECK_ARG(D32_out_h || D64_out_h, "vgs_pair_matrix_h: no output");
+    VGS_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->n_models;
+    float *d32 = nullptr;
+    double *d64 = nullptr;
+    if ((rc = vgs_dev_alloc(&d32, n * n))) return rc;
+    if (D64_out_h && (rc = vgs_dev_alloc(&d64, n * n))) { cudaFree(d32); return rc; }
+    cudaStream_t s = h->own_stream;
+    rc = vgs_pair_matrix(h, kind, d32, d64, s);
+    if (!rc) rc = vgs_read_error_flag(h, s);
+    if (!rc && D32_out_h) rc = cudaMemcpyAsync(D32_out_h, d32, 4 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
+    if (!rc && D64_out_h) rc = cudaMemcpyAsync(D64_out_h, d64, 8 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
+    cudaStreamSynchronize(s);
+    cudaFree(d32);
+    if (d64) cudaFree(d64);
+    return rc;
+}

@@ -1,0 +1,268 @@
+"""ctypes binding of ``libvgs.so`` (the C-ABI CUDA library, ``include/vgs.h``).
+
+This is the only module that touches the shared library.  There is no CPU fallback: if the
+library has not been built, or no CUDA device is present, the calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libvgs.so")
+
+PAIR_KINDS = {"frobenius_intersection": 0, "frobenius_union": 1, "projection": 2}
+NLL_MODES = {"sequential": 0, "warp": 1}
+SKIP_ORDER, SKIP_NONE = 0, 1
+
+_lib = None
+
+c_i64, c_i32, c_int, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_int, ctypes.c_void_p
+_P = ctypes.POINTER
+
+# (name, restype, argtypes) -- one entry per declaration in include/vgs.h
+SIGNATURES = [
+    ("vgs_version", c_int, []),
+    ("vgs_last_error", ctypes.c_char_p, []),
+    ("vgs_create", c_int, [c_int, _P(c_vp)]),
+    ("vgs_destroy", c_int, [c_vp]),
+    ("vgs_device_info", c_int, [c_vp, _P(c_int), _P(c_int), _P(c_int), _P(c_i64)]),
+    ("vgs_launch_count", c_i64, [c_vp]),
+    ("vgs_poll_error", c_int, [c_vp, c_vp]),
+    ("vgs_load_models", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    ("vgs_model_count", c_int, [c_vp, _P(c_i64), _P(c_i64)]),
+    ("vgs_model_info", c_int, [c_vp, c_i64, _P(c_int), _P(c_i64), _P(c_int)]),
+    ("vgs_get_logp", c_int, [c_vp, c_vp]),
+    ("vgs_lookup", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    ("vgs_load_sequences_ascii", c_int, [c_vp, c_i64, c_vp, c_vp]),
+    ("vgs_load_sequences_packed", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    ("vgs_sequence_count", c_int, [c_vp, _P(c_i64), _P(c_i64)]),
+    ("vgs_get_sequence", c_int, [c_vp, c_i64, c_vp, c_i64]),
+    ("vgs_sample_sequences", c_int, [c_vp, c_i64, c_i64, c_vp]),
+    ("vgs_nll_scores", c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp]),
+    ("vgs_nll_scores_h", c_int, [c_vp, c_int, c_int, c_vp]),
+    ("vgs_nll_matrix", c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
+    ("vgs_nll_matrix_h", c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    ("vgs_pair_matrix", c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
+    ("vgs_pair_matrix_h", c_int, [c_vp, c_int, c_vp, c_vp]),
+    ("vgs_estimate_matrix", c_int, [c_vp, c_vp, c_vp, c_vp]),
+    ("vgs_estimate_matrix_h", c_int, [c_vp, c_vp, c_vp]),
+    ("vgs_tile_plan", c_int, [c_i64, c_i64, c_int, c_int, _P(c_i64), _P(c_i64)]),
+    ("vgs_nll_tiles", c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_int, c_vp, c_vp]),
+    ("vgs_pair_tiles", c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp]),
+    ("vgs_estimate_tiles", c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
+    ("vgs_assemble", c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    ("vgs_matrix_to_triples", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+]
+
+
+def lib():
+    """Load libvgs.so (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libvgs.so is missing (%s): build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C clustering-genomic-signatures_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, res, args in SIGNATURES:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class VgsError(RuntimeError):
+    pass
+
+
+def _raise(status):
+    msg = lib().vgs_last_error().decode("utf-8", "replace")
+    if status == 1:
+        raise ValueError(msg)
+    if status == 3:
+        raise RuntimeError(msg)  # "get_context vlmc.pyx", same text as the reference
+    if status == 4:
+        raise KeyError(msg)
+    if status == 5:
+        raise NotImplementedError(msg)
+    if status == 6:
+        raise MemoryError(msg)
+    raise VgsError(msg)
+
+
+def _check(status):
+    if status != 0:
+        _raise(status)
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(c_vp)
+
+
+def _dev_ptr(t):
+    """torch CUDA tensor (or None / raw int) -> void*."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return c_vp(t)
+    return c_vp(t.data_ptr())
+
+
+def tile_plan(n, tile, world, symmetric=True):
+    nt, slots = c_i64(), c_i64()
+    _check(lib().vgs_tile_plan(n, tile, world, int(bool(symmetric)), ctypes.byref(nt), ctypes.byref(slots)))
+    return nt.value, slots.value
+
+
+class Handle:
+    """One device context: model tables + sequences resident in HBM, kernels on demand."""
+
+    def __init__(self, device=0):
+        self._h = c_vp()
+        self.device = int(device)
+        _check(lib().vgs_create(self.device, ctypes.byref(self._h)))
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().vgs_destroy(self._h)
+            self._h = c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- info
+    def device_info(self):
+        sm, ma, mi, fr = c_int(), c_int(), c_int(), c_i64()
+        _check(lib().vgs_device_info(self._h, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(fr)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "free_bytes": fr.value}
+
+    def launch_count(self):
+        return int(lib().vgs_launch_count(self._h))
+
+    def poll_error(self, stream):
+        """Synchronise `stream` and raise what the kernels flagged (RuntimeError / KeyError)."""
+        _check(lib().vgs_poll_error(self._h, c_vp(stream)))
+
+    # ---- models
+    def load_models(self, fm, logp=None):
+        off = np.ascontiguousarray(fm.ctx_offsets, dtype=np.int64)
+        ln = np.ascontiguousarray(fm.ctx_len, dtype=np.uint8)
+        code = np.ascontiguousarray(fm.ctx_code, dtype=np.uint32)
+        prob = np.ascontiguousarray(fm.prob, dtype=np.float64)
+        lp = None if logp is None else np.ascontiguousarray(logp, dtype=np.float64)
+        _check(lib().vgs_load_models(self._h, fm.n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), _np_ptr(lp)))
+        self.n_models = fm.n_models
+        self.total_contexts = fm.total_contexts
+
+    def load_models_raw(self, n_models, off, ln, code, prob):
+        """Same as load_models but from already-contiguous (e.g. pinned) arrays; no conversions."""
+        _check(lib().vgs_load_models(self._h, n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), None))
+        self.n_models = n_models
+        self.total_contexts = int(off[-1])
+
+    def model_info(self, m):
+        order, n_ctx, tier = c_int(), c_i64(), c_int()
+        _check(lib().vgs_model_info(self._h, m, ctypes.byref(order), ctypes.byref(n_ctx), ctypes.byref(tier)))
+        return {"order": order.value, "n_ctx": n_ctx.value, "tier": tier.value}
+
+    def get_logp(self):
+        out = np.zeros((self.total_contexts, 4), dtype=np.float64)
+        _check(lib().vgs_get_logp(self._h, _np_ptr(out)))
+        return out
+
+    def lookup(self, models, codes, lengths, want_all=False):
+        models = np.ascontiguousarray(models, dtype=np.int32)
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint8)
+        n = len(models)
+        ids = np.zeros(n, dtype=np.int32)
+        masks = np.zeros(n, dtype=np.uint32) if want_all else None
+        _check(lib().vgs_lookup(self._h, n, _np_ptr(models), _np_ptr(codes), _np_ptr(lengths), _np_ptr(ids), _np_ptr(masks)))
+        return (ids, masks) if want_all else ids
+
+    # ---- sequences
+    def load_sequences_ascii(self, buf, offsets):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        _check(lib().vgs_load_sequences_ascii(self._h, len(offsets) - 1, _np_ptr(buf), _np_ptr(offsets)))
+        self.n_seq = len(offsets) - 1
+
+    def load_sequences_packed(self, words, word_offsets, lengths):
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        word_offsets = np.ascontiguousarray(word_offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        _check(lib().vgs_load_sequences_packed(self._h, len(lengths), _np_ptr(words), _np_ptr(word_offsets), _np_ptr(lengths)))
+        self.n_seq = len(lengths)
+
+    def get_sequence(self, s, length):
+        out = np.zeros(length, dtype=np.uint8)
+        _check(lib().vgs_get_sequence(self._h, s, _np_ptr(out), length))
+        return out
+
+    def sample_sequences(self, length, pre_sample, mt_state):
+        """mt_state: uint32[625] view of random.getstate()[1]; advanced in place."""
+        assert mt_state.dtype == np.uint32 and mt_state.size == 625 and mt_state.flags["C_CONTIGUOUS"]
+        _check(lib().vgs_sample_sequences(self._h, length, pre_sample, _np_ptr(mt_state)))
+        self.n_seq = self.n_models
+
+    # ---- host-buffer entry points (copies inside)
+    def nll_scores_h(self, skip_mode=SKIP_ORDER, mode="sequential"):
+        M = np.zeros((self.n_seq, self.n_models), dtype=np.float64)
+        _check(lib().vgs_nll_scores_h(self._h, skip_mode, NLL_MODES[mode], _np_ptr(M)))
+        return M
+
+    def nll_matrix_h(self, length, mode="sequential", want_f64=True, out32=None):
+        n = self.n_models
+        D32 = out32 if out32 is not None else np.zeros((n, n), dtype=np.float32)
+        D64 = np.zeros((n, n), dtype=np.float64) if want_f64 else None
+        _check(lib().vgs_nll_matrix_h(self._h, length, NLL_MODES[mode], _np_ptr(D32), _np_ptr(D64)))
+        return D32, D64
+
+    def pair_matrix_h(self, kind, want_f64=True, out32=None):
+        n = self.n_models
+        D32 = out32 if out32 is not None else np.zeros((n, n), dtype=np.float32)
+        D64 = np.zeros((n, n), dtype=np.float64) if want_f64 else None
+        _check(lib().vgs_pair_matrix_h(self._h, PAIR_KINDS[kind], _np_ptr(D32), _np_ptr(D64)))
+        return D32, D64
+
+    def estimate_matrix_h(self, want_f64=True):
+        n = self.n_models
+        D32 = np.zeros((n, n), dtype=np.float32)
+        D64 = np.zeros((n, n), dtype=np.float64) if want_f64 else None
+        _check(lib().vgs_estimate_matrix_h(self._h, _np_ptr(D32), _np_ptr(D64)))
+        return D32, D64
+
+    # ---- device-pointer entry points (torch tensors; enqueue on `stream`)
+    def nll_scores(self, M, s_range, m_range, skip_mode, mode, stream):
+        _check(lib().vgs_nll_scores(self._h, s_range[0], s_range[1], m_range[0], m_range[1], skip_mode, NLL_MODES[mode],
+                                    _dev_ptr(M), M.shape[1], c_vp(stream)))
+
+    def nll_matrix(self, length, mode, D32, D64, stream):
+        _check(lib().vgs_nll_matrix(self._h, length, NLL_MODES[mode], _dev_ptr(D32), _dev_ptr(D64), c_vp(stream)))
+
+    def pair_matrix(self, kind, D32, D64, stream):
+        _check(lib().vgs_pair_matrix(self._h, PAIR_KINDS[kind], _dev_ptr(D32), _dev_ptr(D64), c_vp(stream)))
+
+    def estimate_matrix(self, D32, D64, stream):
+        _check(lib().vgs_estimate_matrix(self._h, _dev_ptr(D32), _dev_ptr(D64), c_vp(stream)))
+
+    def nll_tiles(self, length, mode, tile, rank, world, payload, stream):
+        _check(lib().vgs_nll_tiles(self._h, length, NLL_MODES[mode], tile, rank, world, _dev_ptr(payload), c_vp(stream)))
+
+    def pair_tiles(self, kind, tile, rank, world, payload, stream):
+        _check(lib().vgs_pair_tiles(self._h, PAIR_KINDS[kind], tile, rank, world, _dev_ptr(payload), c_vp(stream)))
+
+    def estimate_tiles(self, tile, rank, world, payload, stream):
+        _check(lib().vgs_estimate_tiles(self._h, tile, rank, world, _dev_ptr(payload), c_vp(stream)))
+
+    def assemble(self, n, tile, world, symmetric, gathered, D32, stream):
+        _check(lib().vgs_assemble(self._h, n, tile, world, int(bool(symmetric)), _dev_ptr(gathered), _dev_ptr(D32), c_vp(stream)))
+
+    def matrix_to_triples(self, n, D32, triples, stream):
+        _check(lib().vgs_matrix_to_triples(self._h, n, _dev_ptr(D32), _dev_ptr(triples), c_vp(stream)))

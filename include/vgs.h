@@ -1,0 +1,153 @@
+/*
+ * vgs.h -- C ABI of libvgs.so: B200-native (sm_100a) all-pairs VLMC distance matrices.
+ *
+ * This is the drop-in boundary for the one hot path of Kalior/clustering-genomic-signatures that
+ * this repository accelerates: everything a `d.distance(left_vlmc, right_vlmc)` call does, for all
+ * (left, right), plus the matrix hand-off to the clustering code.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference repository root).  The reference
+ * is Python/Cython, so the reference-side binding is a ctypes stub.
+ *
+ * Conventions
+ *   - plain C types only; every size / index is int64_t unless noted;
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_h` (host memory; pinned
+ *     host memory makes the copies asynchronous);
+ *   - `stream` is a cudaStream_t passed as void* (e.g. torch.cuda.current_stream().cuda_stream);
+ *     functions taking a stream only enqueue work on it; `_h` functions synchronise before return;
+ *   - every function returns a vgs_status; vgs_last_error() gives the message (thread local);
+ *   - a handle owns device copies of the model tables and sequences it was given; the caller owns
+ *     every buffer it passes in.  Calls on one handle must be serialised by the caller.
+ *   - there is no CPU fallback: without a CUDA device vgs_create fails with VGS_ERR_CUDA.
+ *
+ * Encoding (same as the Python `flat` module): symbols A,C,G,T = 0..3 (src/vlmc/vlmc.pyx:21); a
+ * context of length l is (len, code) with two bits per symbol, NEWEST symbol in the two lowest bits;
+ * ctx_id = position of the context in the reference's `tree` dict iteration order; packed sequences
+ * hold 16 symbols per uint32 with the FIRST symbol in the two HIGHEST bits, every sequence starting on
+ * a 16-byte boundary.
+ */
+#ifndef VGS_H
+#define VGS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vgs_context *vgs_handle;
+
+typedef enum {
+    VGS_OK = 0,
+    VGS_ERR_INVALID = 1,      /* bad argument (ValueError) */
+    VGS_ERR_CUDA = 2,         /* CUDA runtime failure / no device (RuntimeError) */
+    VGS_ERR_NO_CONTEXT = 3,   /* a history matched no context, not even "": the reference raises
+                                 RuntimeError("get_context vlmc.pyx") (src/vlmc/vlmc.pyx:141) */
+    VGS_ERR_SYMBOL = 4,       /* non-ACGT symbol: KeyError in the reference (src/vlmc/vlmc.pyx:125) */
+    VGS_ERR_UNSUPPORTED = 5,  /* shape outside what this build handles (e.g. order > 15) */
+    VGS_ERR_MEMORY = 6        /* device or host allocation failed */
+} vgs_status;
+
+/* distance kinds for vgs_pair_* (src/distance/frobenius.pyx, src/distance/projection.pyx) */
+#define VGS_PAIR_FROBENIUS_INTERSECTION 0
+#define VGS_PAIR_FROBENIUS_UNION 1
+#define VGS_PAIR_PROJECTION 2
+
+/* NLL accumulation modes for vgs_nll_* */
+#define VGS_NLL_SEQUENTIAL 0 /* one lane per (sequence, model), strictly left-to-right fp64: bit-exact */
+#define VGS_NLL_WARP 1       /* one warp per (sequence, model), 128-bit loads, shuffle reduction     */
+
+/* skip modes (src/vlmc/vlmc.pyx:79-85) */
+#define VGS_SKIP_ORDER 0 /* log_likelihood_ignore_initial_bias: first `order` symbols not scored */
+#define VGS_SKIP_NONE 1  /* log_likelihood: every symbol scored                                   */
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int vgs_version(void);
+const char *vgs_last_error(void);
+int vgs_create(int device, vgs_handle *out);
+int vgs_destroy(vgs_handle h);
+int vgs_device_info(vgs_handle h, int *sm_count, int *cc_major, int *cc_minor, int64_t *free_bytes);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t vgs_launch_count(vgs_handle h);
+/* device-pointer entry points only enqueue work: this synchronises `stream` and reports what the kernels
+ * flagged (VGS_ERR_NO_CONTEXT, VGS_ERR_SYMBOL) -- the errors the reference raises from get_context */
+int vgs_poll_error(vgs_handle h, void *stream);
+
+/* ---- model tables: replaces VLMC.__init__/from_json table construction (src/vlmc/vlmc.pyx:8-60,
+ *      :179-180).  prob_h is [total][4] fp64 in A,C,G,T order, bit-identical to the dict values.  The
+ *      library derives on the host ln p with libm log() (== CPython math.log, src/vlmc/vlmc.pyx:99;
+ *      -1000.0 where p == 0, :94-97) unless logp_h is given, and on the device the per-model hash, the
+ *      longest-suffix maps and the fp32 rows. ---------------------------------------------------- */
+int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h, const uint8_t *ctx_len_h,
+                    const uint32_t *ctx_code_h, const double *prob_h, const double *logp_h /* nullable */);
+int vgs_model_count(vgs_handle h, int64_t *n_models, int64_t *total_contexts);
+/* order (src/vlmc/vlmc.pyx:179-180), number of contexts and NLL table tier of one model */
+int vgs_model_info(vgs_handle h, int64_t model, int *order, int64_t *n_ctx, int *tier);
+/* copy back the host-computed ln p table [total][4] (parity hook against math.log) */
+int vgs_get_logp(vgs_handle h, double *logp_out_h);
+
+/* ---- longest-suffix lookup: VLMC.get_context / get_all_contexts (src/vlmc/vlmc.pyx:131-154).
+ *      ctx_id_out_h[q] = ctx_id of the longest suffix (length <= order) of the history that is a
+ *      context, or -1 (reference: RuntimeError).  all_mask_out_h[q] (nullable): bit l set <=> the
+ *      length-l suffix is a context.  Runs on the device. ------------------------------------------ */
+int vgs_lookup(vgs_handle h, int64_t n_queries, const int32_t *model_h, const uint32_t *hist_code_h,
+               const uint8_t *hist_len_h, int32_t *ctx_id_out_h, uint32_t *all_mask_out_h);
+
+/* ---- sequences: the strings VLMC.generate_sequence returns / log_likelihood takes
+ *      (src/vlmc/vlmc.pyx:79-101, :156-163) ------------------------------------------------------- */
+int vgs_load_sequences_ascii(vgs_handle h, int64_t n_seq, const uint8_t *ascii_h, const int64_t *offsets_h);
+int vgs_load_sequences_packed(vgs_handle h, int64_t n_seq, const uint32_t *words_h, const int64_t *word_offsets_h,
+                              const int64_t *lengths_h);
+int vgs_sequence_count(vgs_handle h, int64_t *n_seq, int64_t *total_symbols);
+/* copy sequence s back as symbol codes 0..3 */
+int vgs_get_sequence(vgs_handle h, int64_t s, uint8_t *codes_out_h, int64_t capacity);
+
+/* ---- sampler: VLMC.generate_sequence / generate_sequence_from / _generate_next_letter
+ *      (src/vlmc/vlmc.pyx:156-177) for every loaded model at once.  mt_state_h is CPython's
+ *      random.getstate()[1] (624 MT19937 words + position), advanced in place exactly as
+ *      n_models * (length + pre_sample) calls of random.random() would; model m consumes the
+ *      m-th block of that stream (list order, as the reference's N^2 loop does).  The sampled
+ *      sequences replace the handle's sequence set. --------------------------------------------- */
+int vgs_sample_sequences(vgs_handle h, int64_t length, int64_t pre_sample, uint32_t *mt_state_h);
+
+/* ---- log-likelihood scores: VLMC.log_likelihood / log_likelihood_ignore_initial_bias
+ *      (src/vlmc/vlmc.pyx:79-101).  M[s * ld + m] for s in [s_begin, s_end), m in [m_begin, m_end);
+ *      NaN marks a failed lookup.  M_d is a device pointer to the full [n_seq][ld] matrix. ----------- */
+int vgs_nll_scores(vgs_handle h, int64_t s_begin, int64_t s_end, int64_t m_begin, int64_t m_end, int skip_mode,
+                   int mode, double *M_d, int64_t ld, void *stream);
+int vgs_nll_scores_h(vgs_handle h, int skip_mode, int mode, double *M_out_h /* [n_seq][n_models] */);
+
+/* ---- NegativeLogLikelihood.distance for all pairs (src/distance/negloglikelihood.pyx:17-26) and
+ *      the float32 [N,N] matrix of src/clustering/util.pyx:23-33.  Sequence i belongs to model i.
+ *      D32_d float32 [N][N]; D64_d nullable fp64 [N][N]. ------------------------------------------ */
+int vgs_nll_matrix(vgs_handle h, int64_t length, int mode, float *D32_d, double *D64_d, void *stream);
+int vgs_nll_matrix_h(vgs_handle h, int64_t length, int mode, float *D32_out_h, double *D64_out_h);
+
+/* ---- FrobeniusNorm.distance (src/distance/frobenius.pyx:17-53) and Projection.distance
+ *      (src/distance/projection.pyx:7-36) for all pairs; `kind` is a VGS_PAIR_* value. ------------- */
+int vgs_pair_matrix(vgs_handle h, int kind, float *D32_d, double *D64_d, void *stream);
+int vgs_pair_matrix_h(vgs_handle h, int kind, float *D32_out_h, double *D64_out_h);
+
+/* ---- EstimateVLMC.distance for all (left, right) (src/distance/estimate.pyx:19-108):
+ *      D[i][j] = statistic of model i's contexts counted along sequence j (asymmetric). ------------- */
+int vgs_estimate_matrix(vgs_handle h, float *D32_d, double *D64_d, void *stream);
+int vgs_estimate_matrix_h(vgs_handle h, float *D32_out_h, double *D64_out_h);
+
+/* ---- multi-GPU tiling (north_star (c)): the N x N matrix is cut into T x T tiles; the upper
+ *      triangle of the tile grid (symmetric kinds) or the whole grid (Estimate) is enumerated row-major
+ *      as k = 0..n_tiles-1 and tile k belongs to rank k % world.  A rank computes its tiles into a
+ *      payload of slots [slots][T][T] float32 (slot q <-> tile k = q * world + rank, zero padded);
+ *      the payloads are all-gathered (NCCL) and vgs_assemble scatters / mirrors them into [N][N]. -- */
+int vgs_tile_plan(int64_t n, int64_t tile, int world, int symmetric, int64_t *n_tiles, int64_t *slots_per_rank);
+int vgs_nll_tiles(vgs_handle h, int64_t length, int mode, int64_t tile, int rank, int world, float *payload_d,
+                  void *stream);
+int vgs_pair_tiles(vgs_handle h, int kind, int64_t tile, int rank, int world, float *payload_d, void *stream);
+int vgs_estimate_tiles(vgs_handle h, int64_t tile, int rank, int world, float *payload_d, void *stream);
+int vgs_assemble(vgs_handle h, int64_t n, int64_t tile, int world, int symmetric, const float *gathered_d,
+                 float *D32_d, void *stream);
+
+/* ---- matrix hand-off layouts of src/clustering/util.pyx:6-21: float32 [N*N][3] rows (i, j, d) ---- */
+int vgs_matrix_to_triples(vgs_handle h, int64_t n, const float *D32_d, float *triples_d, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGS_H */
