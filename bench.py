@@ -1,0 +1,482 @@
+#!/usr/bin/env python
+"""bench.py -- VLMC pair-distances/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload nll|frobenius|frobenius_union|projection|estimate]
+    python bench.py --impl reference ...        # the reference's own CPU implementation (oracle/_ref)
+
+Default workload: BASELINE configs[2] -- 1,000 synthetic VLMCs (depth <= 6, ~500 contexts, SURVEY.md
+§8d recipe, seed 2) x 10 kbp sequences sampled from the models, negative-log-likelihood distance
+(10^6 pair scorings, 499,500 unordered pair-distances), the configuration the metric "pair-distances/
+sec at 1/2/4/8 B200" is quoted on.  ``--workload frobenius`` is BASELINE configs[1].
+
+A step = one full N x N float32 distance matrix:
+  value  tables and packed sequences already resident in HBM -> matrix resident on every GPU
+         (N > 1: upper-triangular tile space sharded over ranks, NCCL all-gather, local assemble);
+  e2e    the same matrix through the C-ABI with HOST buffers: H2D of the flat model tables and packed
+         sequences (pinned), table construction, kernels, D2H of the float32 matrix (pinned).
+Timing: CUDA events on the launching stream, one pair per step, L2 flushed (256 MiB memset) between
+steps outside the timed pairs, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, n_models, seq_len, depth, ctx, description)
+    "nll": ("nll", 1000, 10000, 6, 500, "cfg3: 1000 VLMCs (depth<=6, ~500 ctx) x 10 kbp, NLL distance"),
+    "frobenius": ("frobenius_intersection", 1000, 0, 6, 500, "cfg2: 1000 VLMCs (depth<=6, ~500 ctx), Frobenius intersection"),
+    "frobenius_union": ("frobenius_union", 1000, 0, 6, 500, "cfg2: 1000 VLMCs, Frobenius union"),
+    "projection": ("projection", 1000, 0, 6, 500, "cfg2: 1000 VLMCs, Projection"),
+    "estimate": ("estimate", 1000, 100000, 6, 500, "1000 VLMCs x 100 kbp, EstimateVLMC"),
+    "nll_deep": ("nll", 2000, 1000, 9, 2000, "cfg4 slice: 2000 VLMCs (depth<=9, ~2000 ctx) x 1 kbp, NLL"),
+    "frobenius_deep": ("frobenius_intersection", 2000, 0, 9, 2000, "cfg4 slice: 2000 VLMCs (depth<=9, ~2000 ctx), Frobenius"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="nll", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-models", type=int, default=0)
+    ap.add_argument("--seq-len", type=int, default=0)
+    ap.add_argument("--mode", default="sequential", choices=["sequential", "warp"])
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="models in the CPU-baseline sample")
+    return ap.parse_args()
+
+
+def make_inputs(kind, n, L, depth, ctx):
+    from clustering_genomic_signatures_b200 import synthetic
+    fm, fam = synthetic.make_family_models(n, 2 if depth == 6 else 4, depth, ctx, max(1, n // 50))
+    seqs = None
+    if kind in ("nll", "estimate"):
+        seqs = synthetic.sample_sequences(fm, L, 3)
+    return fm, fam, seqs
+
+
+# ---------------------------------------------------------------------------------------------
+def algorithmic_bytes(kind, fm, L, orders):
+    """SURVEY.md §8(d) per-unit figures evaluated on the actual set.  Returns (bytes per step of the
+    dominant kernel, description)."""
+    n = fm.n_models
+    n_ctx = np.diff(fm.ctx_offsets).astype(np.float64)
+    if kind == "nll":
+        T_m = 32.0 * n_ctx + 2.0 * 4.0 ** orders
+        per_scoring = np.ceil(L / 4.0) + np.minimum(T_m, L * 10.0) + 8.0
+        return float(n * per_scoring.sum()), "N scorings per model x (ceil(L/4) + min(32 n_ctx + 2*4^order, 10 L) + 8) B"
+    if kind == "estimate":
+        per = np.ceil(L / 4.0) + n_ctx * 36.0 + 8.0
+        return float(n * per.sum()), "N^2 x (ceil(L/4) + 36 n_ctx + 8) B"
+    # pair kinds: unordered pairs, (n_i + n_j) * 20 + 4
+    s = n_ctx.sum()
+    return float(20.0 * (n - 1) * s + 4.0 * n * (n - 1) / 2), "P x ((n_ctx_i + n_ctx_j) x 20 + 4) B"
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7 or not (t0 - 0.05 <= t <= t1 + 0.1):
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:  # timed region shorter than the sampling period: use every sample we have
+            for t, line in self.rows:
+                parts = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(parts[0])); mx.append(float(parts[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline(kind, fm, seqs, L, sample_n, threads=1):
+    """Bounded CPU sample of the same workload.  Returns the cpu_baseline dict.
+    Uses the compiled reference (oracle/_ref) when present, else the C oracle port."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    from clustering_genomic_signatures_b200 import synthetic
+    n = min(sample_n, fm.n_models)
+    if ref_loader.available():
+        ns = ref_loader.load()
+        vl = [ns.VLMC(fm.tree(m), fm.names[m], {}) for m in range(n)]
+        if kind == "nll":
+            d = ns.NegativeLogLikelihood(L)
+            for v, s in zip(vl, synthetic.codes_to_strings(seqs[:n])):
+                v.sequence = s
+        elif kind == "estimate":
+            d = ns.EstimateVLMC()
+            for v, s in zip(vl, synthetic.codes_to_strings(seqs[:n])):
+                v.sequence = s
+        elif kind == "projection":
+            d = ns.Projection()
+            d.set_vlmcs(vl)
+        else:
+            d = ns.FrobeniusNorm(kind == "frobenius_union")
+        t0 = time.perf_counter()
+        if kind == "estimate":
+            with ref_loader.patched_power_divergence():
+                ns.calculate_distances_within_vlmcs(vl, d)
+        else:
+            ns.calculate_distances_within_vlmcs(vl, d)
+        dt = time.perf_counter() - t0
+        return {"value": n * n / dt, "unit": "pair-distances/s", "cores": 1, "kind": "reference",
+                "sample": "compiled reference (oracle/_ref), calculate_distances_within_vlmcs on the first %d models "
+                          "= %d distance() calls in %.2f s, single thread" % (n, n * n, dt)}
+    import c_oracle
+    co = c_oracle.COracle(fm.subset(range(n)))
+    t0 = time.perf_counter()
+    if kind == "nll":
+        co.nll_matrix(seqs[:n])
+    elif kind == "estimate":
+        co.estimate_matrix(seqs[:n])
+    else:
+        co.pair_matrix({"frobenius_intersection": "intersection", "frobenius_union": "union", "projection": "projection"}[kind])
+    dt = time.perf_counter() - t0
+    return {"value": n * n / dt, "unit": "pair-distances/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "C oracle port (oracle/vgs_oracle.c, OpenMP) on the first %d models = %d distances in %.2f s" % (n, n * n, dt)}
+
+
+def _ref_worker(args):
+    kind, trees, names, seq_strs, L, rows = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    ns = ref_loader.load()
+    vl = [ns.VLMC(t, nm, {}) for t, nm in zip(trees, names)]
+    if kind in ("nll", "estimate"):
+        for v, s in zip(vl, seq_strs):
+            v.sequence = s
+    if kind == "nll":
+        d = ns.NegativeLogLikelihood(L)
+    elif kind == "estimate":
+        d = ns.EstimateVLMC()
+    elif kind == "projection":
+        d = ns.Projection(); d.set_vlmcs(vl)
+    else:
+        d = ns.FrobeniusNorm(kind == "frobenius_union")
+    out = 0
+    ctx = ref_loader.patched_power_divergence() if kind == "estimate" else None
+    if ctx:
+        ctx.__enter__()
+    for i in rows:
+        for j in range(len(vl)):
+            d.distance(vl[i], vl[j])
+            out += 1
+    if ctx:
+        ctx.__exit__(None, None, None)
+    return out
+
+
+def run_reference(args, kind, n, L, depth, ctx, desc):
+    """--impl reference: the reference's own CPU implementation with every host core (row-sharded
+    multiprocessing, the only parallelism the reference itself uses), on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import multiprocessing as mp
+    import ref_loader
+    from clustering_genomic_signatures_b200 import synthetic
+    cores = os.cpu_count() or 1
+    sample_n = args.cpu_sample or {"nll": max(24, min(96, 2 * cores)), "estimate": max(6, min(32, cores)),
+                                   "frobenius_union": 400, "projection": 400}.get(kind, 600)
+    sample_n = min(sample_n, n)
+    fm, fam, seqs = make_inputs(kind, n, L, depth, ctx)  # the same set as our arm; the sample is its first models
+    fm = fm.subset(range(sample_n))
+    seq_strs = synthetic.codes_to_strings(seqs[:sample_n]) if seqs is not None else None
+    trees = [fm.tree(m) for m in range(sample_n)]
+    if not ref_loader.available():
+        cb = cpu_baseline(kind, fm, seqs, L, sample_n)
+        ms = 1000.0 * sample_n * sample_n / cb["value"]
+        line = {"impl": "reference", "metric": "pair-distances/sec", "value": cb["value"], "unit": "pair-distances/s",
+                "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "sample_models": sample_n},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "pair-distances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+    workers = min(cores, sample_n)
+    shards = [list(range(w, sample_n, workers)) for w in range(workers)]
+    jobs = [(kind, trees, fm.names, seq_strs, L, rows) for rows in shards]
+    times = []
+    with mp.get_context("fork").Pool(workers) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            total = sum(pool.map(_ref_worker, jobs))
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+            if sum(times) > 150:  # keep the whole run within a few minutes
+                break
+    steps = len(times)
+    ms = 1000.0 * sum(times) / steps
+    value = sample_n * sample_n / (ms / 1000.0)
+    cb = {"value": value, "unit": "pair-distances/s", "cores": workers, "kind": "reference",
+          "sample": "compiled reference (oracle/_ref): all %d x %d distance() calls of the first %d models per step, "
+                    "row-sharded over %d processes" % (sample_n, sample_n, sample_n, workers)}
+    line = {"impl": "reference", "metric": "pair-distances/sec", "value": value, "unit": "pair-distances/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64" if kind in ("nll", "estimate") else "f32", "data": "synthetic",
+            "config": {"workload": desc, "sample_models": sample_n, "seq_len": L},
+            "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "pair-distances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    kind, n, L, depth, ctx, desc = WORKLOADS[args.workload]
+    n = args.n_models or n
+    L = args.seq_len or L
+    if args.impl == "reference":
+        run_reference(args, kind, n, L, depth, ctx, desc)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from clustering_genomic_signatures_b200 import native
+    from clustering_genomic_signatures_b200.flat import pack_sequences
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    fm, fam, seqs = make_inputs(kind, n, L, depth, ctx)
+    h = native.Handle(local_rank)
+    sm_count = h.device_info()["sm_count"]
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    keep = []
+    host = {}
+    for name, arr in (("off", fm.ctx_offsets.astype(np.int64)), ("len", fm.ctx_len.astype(np.uint8)),
+                      ("code", fm.ctx_code.astype(np.uint32)), ("prob", fm.prob.astype(np.float64))):
+        t, a = pinned(arr); keep.append(t); host[name] = a
+    h2d = sum(a.nbytes for a in host.values())
+    if seqs is not None:
+        words, woff, lens = pack_sequences(seqs)
+        for name, arr in (("words", words), ("woff", woff), ("lens", lens)):
+            t, a = pinned(arr); keep.append(t); host[name] = a
+        h2d += host["words"].nbytes + host["woff"].nbytes + host["lens"].nbytes
+    out_t = torch.empty((n, n), dtype=torch.float32).pin_memory()
+    out_h = out_t.numpy()
+    d2h = out_h.nbytes
+
+    def load_all():
+        h.load_models_raw(n, host["off"], host["len"], host["code"], host["prob"])
+        if seqs is not None:
+            h.load_sequences_packed(host["words"], host["woff"], host["lens"])
+
+    load_all()
+    stream = torch.cuda.current_stream().cuda_stream
+    D32 = torch.empty((n, n), dtype=torch.float32, device=dev)
+    symmetric = kind != "estimate"
+    tile = args.tile or (32 if n <= 1024 else 64 if n <= 4096 else 128)
+    if world > 1:
+        nt, slots = native.tile_plan(n, tile, world, symmetric)
+        payload = torch.zeros(slots * tile * tile, dtype=torch.float32, device=dev)
+        gathered = torch.empty(world * slots * tile * tile, dtype=torch.float32, device=dev)
+
+    def device_step():
+        if world == 1:
+            if kind == "nll":
+                h.nll_matrix(L, args.mode, D32, None, stream)
+            elif kind == "estimate":
+                h.estimate_matrix(D32, None, stream)
+            else:
+                h.pair_matrix(kind, D32, None, stream)
+        else:
+            if kind == "nll":
+                h.nll_tiles(L, args.mode, tile, rank, world, payload, stream)
+            elif kind == "estimate":
+                h.estimate_tiles(tile, rank, world, payload, stream)
+            else:
+                h.pair_tiles(kind, tile, rank, world, payload, stream)
+            dist.all_gather_into_tensor(gathered, payload)
+            h.assemble(n, tile, world, symmetric, gathered, D32, stream)
+
+    def e2e_step():
+        load_all()
+        if world == 1:
+            if kind == "nll":
+                h.nll_matrix_h(L, args.mode, want_f64=False, out32=out_h)
+            elif kind == "estimate":
+                device_step(); out_t.copy_(D32, non_blocking=True); torch.cuda.synchronize()
+            else:
+                h.pair_matrix_h(kind, want_f64=False, out32=out_h)
+        else:
+            device_step()
+            out_t.copy_(D32, non_blocking=True)
+            torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, use_events):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        total_ms = 0.0
+        t_begin = time.time()
+        for _ in range(steps):
+            flush.zero_()
+            if world > 1:
+                torch.cuda.synchronize(); dist.barrier()
+            if use_events:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); b.synchronize()
+                total_ms += a.elapsed_time(b)
+            else:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+                total_ms += (time.perf_counter() - t0) * 1000.0
+        barrier()
+        t_end = time.time()
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms / steps, t_begin, t_end
+
+    pairs = n * n if kind == "estimate" else n * (n - 1) // 2
+    unit = "pair-distances/s"
+
+    # ---- device-resident throughput (value) + per-kernel roofline
+    prof_id = {"nll": 0, "estimate": 2}.get(kind, 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        device_step()
+    torch.cuda.synchronize()
+    h.profile_enable(True)
+    h.profile_read(prof_id)
+    l0 = h.launch_count()
+    ms_step, tb, te = timed(device_step, args.steps, 0, True)
+    launches = h.launch_count() - l0
+    k_ms, k_n = h.profile_read(prof_id)
+    h.profile_enable(False)
+    clocks = sampler.stop(tb, te) if rank == 0 else None
+    h.poll_error(stream)
+
+    # ---- end to end through the host-buffer C-ABI
+    e2e_ms, _, _ = timed(e2e_step, max(3, args.steps // 4), 1, False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    orders = fm.orders().astype(np.float64)
+    alg_bytes, alg_desc = algorithmic_bytes(kind, fm, L, orders)
+    alg_bytes_rank = alg_bytes / world  # each rank's launch covers its share of the units
+    k_avg_ms = k_ms / max(k_n, 1)
+    launches_per_step = max(1, k_n // args.steps)
+    achieved = alg_bytes_rank / launches_per_step / (k_avg_ms / 1000.0) / 1e9 if k_avg_ms > 0 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": (achieved / peak_gbs) if achieved else None, "traffic": None,
+                "kernel": {0: "k_nll_scores", 1: "k_pair_partials", 2: "k_est_pairs"}[prof_id],
+                "kernel_ms_per_launch": k_avg_ms, "kernel_launches_per_step": launches_per_step,
+                "kernel_share_of_step": (k_ms / args.steps) / ms_step if ms_step > 0 else None,
+                "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_formula": alg_desc, "peak_source": peak_src}
+    # ncu dram bytes per launch of the dominant kernel, when a committed profile summary provides it
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            roofline["traffic"] = json.load(fh).get(args.workload)
+    except Exception:
+        pass
+
+    line = {
+        "metric": "pair-distances/sec", "value": pairs / (ms_step / 1000.0), "unit": unit, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if kind in ("nll", "estimate") else "f32 rows, f64 accumulate", "data": "synthetic",
+        "config": {"workload": desc, "n_models": n, "seq_len": L, "pairs_per_step": pairs, "total_contexts": fm.total_contexts,
+                   "nll_mode": args.mode if kind == "nll" else None, "tile": tile if world > 1 else None,
+                   "l2": "flushed between steps (256 MiB memset outside the timed events)",
+                   "parallelism": "tile-sharded upper triangle + NCCL all-gather" if world > 1 else "single GPU",
+                   "sm_count": sm_count},
+        "e2e": {"value": pairs / (e2e_ms / 1000.0), "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h),
+                "includes": "vgs_load_models (H2D + host ln p + device table build), vgs_load_sequences_packed, kernels, D2H"},
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sample_n = args.cpu_sample or {"nll": 24, "estimate": 6, "frobenius_union": 150, "projection": 150}.get(kind, 400)
+        line["cpu_baseline"] = cpu_baseline(kind, fm, seqs, L, sample_n)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/vgs.h"
@@ -82,7 +83,25 @@ struct vgs_context {
     int64_t scratch2_bytes = 0;
     int *d_err = nullptr;       // device error flag (bit 0: no context, bit 1: bad symbol)
     cudaStream_t own_stream = nullptr;
+
+    // optional per-kernel event timing (vgs_profile_*)
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[4];
 };
+
+// RAII-less helpers: bracket a kernel launch with events when profiling is on
+inline void vgs_prof_begin(vgs_context *h, int id, cudaStream_t s) {
+    if (!h->profile) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    h->prof[id].push_back({a, b});
+}
+inline void vgs_prof_end(vgs_context *h, int id, cudaStream_t s) {
+    if (!h->profile || h->prof[id].empty()) return;
+    cudaEventRecord(h->prof[id].back().second, s);
+}
 
 // ---- error plumbing ---------------------------------------------------------------------------
 void vgs_set_error(const char *fmt, ...);

@@ -159,6 +159,32 @@ extern "C" int vgs_device_info(vgs_handle h, int *sm_count, int *cc_major, int *
 
 extern "C" int64_t vgs_launch_count(vgs_handle h) { return h ? h->launches : 0; }
 
+extern "C" int vgs_profile_enable(vgs_handle h, int on) {
+    VGS_CHECK_ARG(h, "null handle");
+    h->profile = on != 0;
+    return VGS_OK;
+}
+
+extern "C" int vgs_profile_read(vgs_handle h, int kernel_id, double *total_ms, int64_t *launches) {
+    VGS_CHECK_ARG(h && kernel_id >= 0 && kernel_id < 4, "vgs_profile_read: bad kernel id");
+    VGS_CUDA(cudaSetDevice(h->device));
+    double sum = 0.0;
+    int64_t n = 0;
+    for (auto &pr : h->prof[kernel_id]) {
+        VGS_CUDA(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        VGS_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        sum += ms;
+        ++n;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    h->prof[kernel_id].clear();
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = n;
+    return VGS_OK;
+}
+
 extern "C" int vgs_poll_error(vgs_handle h, void *stream) {
     VGS_CHECK_ARG(h, "null handle");
     VGS_CUDA(cudaSetDevice(h->device));

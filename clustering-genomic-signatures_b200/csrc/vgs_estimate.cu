@@ -150,6 +150,7 @@ static int est_tiles_impl(vgs_context *h, const TilePlan &pl, int rank, float *p
         int64_t max_len = 1;
         for (int64_t j = j0; j < j0 + nj; ++j) max_len = std::max(max_len, h->h_seq_len[(size_t)j]);
         dim3 gtop((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_len + 256 * 128 - 1) / (256 * 128), 64)), (unsigned)nj);
+        vgs_prof_begin(h, VGS_PROF_ESTIMATE_COUNTS, s);
         k_est_count_top<<<gtop, 128, 0, s>>>(K, j0, h->d_seq, h->d_seq_off, h->d_seq_len, tables, per_seq);
         VGS_LAUNCH_CHECK(h);
         for (int k = K - 1; k >= 1; --k) {
@@ -158,6 +159,7 @@ static int est_tiles_impl(vgs_context *h, const TilePlan &pl, int rank, float *p
             k_est_count_down<<<g, 256, 0, s>>>(k, j0, h->d_seq, h->d_seq_off, h->d_seq_len, tables, per_seq);
             VGS_LAUNCH_CHECK(h);
         }
+        vgs_prof_end(h, VGS_PROF_ESTIMATE_COUNTS, s);
         for (int64_t I = 0; I < pl.nt; ++I) {
             const int64_t k = I * pl.nt + J;
             if (k % pl.world != rank) continue;
@@ -165,7 +167,9 @@ static int est_tiles_impl(vgs_context *h, const TilePlan &pl, int rank, float *p
             p.meta = h->d_meta; p.key = h->d_key; p.prob64 = h->d_prob64; p.tables = tables; p.per_seq = per_seq;
             p.pl = pl; p.q = k / pl.world; p.I = I; p.J = J; p.pay32 = pay32; p.pay64 = pay64;
             const int64_t n_warps = pl.tile * pl.tile;
+            vgs_prof_begin(h, VGS_PROF_ESTIMATE_PAIRS, s);
             k_est_pairs<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, s>>>(p);
+            vgs_prof_end(h, VGS_PROF_ESTIMATE_PAIRS, s);
             VGS_LAUNCH_CHECK(h);
         }
     }

@@ -214,7 +214,9 @@ static int launch_nll(vgs_context *h, const NllParams &p, int smem_bytes, cudaSt
     VGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NLL_THREADS, STAGED ? smem_bytes : 0));
     if (per_sm < 1) per_sm = 1;
     int grid = std::min(p.n_units, h->sm_count * per_sm);
+    vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
     kern<<<grid, NLL_THREADS, STAGED ? smem_bytes : 0, s>>>(p);
+    vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
     VGS_LAUNCH_CHECK(h);
     return VGS_OK;
 }

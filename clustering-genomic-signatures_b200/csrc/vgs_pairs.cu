@@ -236,6 +236,7 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
     VGS_CUDA(cudaMemsetAsync(h->d_scratch2, 0, (size_t)(part * 20), s));
     const int64_t n_cta = pl.slots * p.n_dir * p.n_groups;
     VGS_CHECK_ARG(n_cta < ((int64_t)1 << 31), "pair kernel grid too large");
+    vgs_prof_begin(h, VGS_PROF_PAIR_PARTIALS, s);
     if (staged) {
         const int smem = (int)(per_model * jg);
         VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -243,6 +244,7 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
     } else {
         k_pair_partials<false><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
     }
+    vgs_prof_end(h, VGS_PROF_PAIR_PARTIALS, s);
     VGS_LAUNCH_CHECK(h);
     k_pair_combine<<<(unsigned)pl.slots, 256, 0, s>>>(p, pay32, pay64);
     VGS_LAUNCH_CHECK(h);

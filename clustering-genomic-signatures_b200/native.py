@@ -29,6 +29,8 @@ SIGNATURES = [
     ("vgs_device_info", c_int, [c_vp, _P(c_int), _P(c_int), _P(c_int), _P(c_i64)]),
     ("vgs_launch_count", c_i64, [c_vp]),
     ("vgs_poll_error", c_int, [c_vp, c_vp]),
+    ("vgs_profile_enable", c_int, [c_vp, c_int]),
+    ("vgs_profile_read", c_int, [c_vp, c_int, _P(ctypes.c_double), _P(c_i64)]),
     ("vgs_load_models", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     ("vgs_model_count", c_int, [c_vp, _P(c_i64), _P(c_i64)]),
     ("vgs_model_info", c_int, [c_vp, c_i64, _P(c_int), _P(c_i64), _P(c_int)]),
@@ -144,6 +146,15 @@ class Handle:
 
     def launch_count(self):
         return int(lib().vgs_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        _check(lib().vgs_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self, kernel_id):
+        """(total device ms, launches) of one kernel kind since the last read."""
+        ms, n = ctypes.c_double(), c_i64()
+        _check(lib().vgs_profile_read(self._h, kernel_id, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     def poll_error(self, stream):
         """Synchronise `stream` and raise what the kernels flagged (RuntimeError / KeyError)."""

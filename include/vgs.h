@@ -71,6 +71,16 @@ int64_t vgs_launch_count(vgs_handle h);
  * flagged (VGS_ERR_NO_CONTEXT, VGS_ERR_SYMBOL) -- the errors the reference raises from get_context */
 int vgs_poll_error(vgs_handle h, void *stream);
 
+/* ---- per-kernel timing for bench.py's roofline: when enabled, the dominant kernel of each path is
+ *      bracketed by CUDA events on its own stream; vgs_profile_read synchronises, returns the summed device
+ *      time and number of launches since the last read, and resets.  kernel ids: VGS_PROF_* ------------ */
+#define VGS_PROF_NLL_SCORES 0
+#define VGS_PROF_PAIR_PARTIALS 1
+#define VGS_PROF_ESTIMATE_PAIRS 2
+#define VGS_PROF_ESTIMATE_COUNTS 3
+int vgs_profile_enable(vgs_handle h, int on);
+int vgs_profile_read(vgs_handle h, int kernel_id, double *total_ms, int64_t *launches);
+
 /* ---- model tables: replaces VLMC.__init__/from_json table construction (src/vlmc/vlmc.pyx:8-60,
  *      :179-180).  prob_h is [total][4] fp64 in A,C,G,T order, bit-identical to the dict values.  The
  *      library derives on the host ln p with libm log() (== CPython math.log, src/vlmc/vlmc.pyx:99;
