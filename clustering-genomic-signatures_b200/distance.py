@@ -1,0 +1,180 @@
+"""Drop-in distance classes: same names, constructors and ``distance(left, right)`` method as the
+reference's ``src/distance`` package, computed on the B200 through ``libvgs.so``.
+
+    NegativeLogLikelihood(sequence_length)      src/distance/negloglikelihood.pyx:13-26
+    FrobeniusNorm(use_union=False)              src/distance/frobenius.pyx:14-53
+    Projection()  (+ set_vlmcs)                 src/distance/projection.pyx:7-36
+    EstimateVLMC(d=None)                        src/distance/estimate.pyx:16-108
+
+The reference evaluates ``d.distance`` once per ordered pair inside Python loops
+(``src/clustering/util.pyx:12-14``, ``src/test_distance_function.py:102``).  Here the whole N x N
+matrix is one device job: ``set_vlmcs(vlmcs)`` (the reference's own batch hook, honoured by
+``test_distance_function_`` for Projection, ``src/test_distance_function.py:63-64``) or
+``distance_matrix(vlmcs)`` runs it, and ``distance(left, right)`` then indexes the result.  A
+``distance`` call on models that were not batched computes that pair on the device as a 2-model set.
+"""
+import numpy as np
+
+from . import native
+from .flat import sequences_to_ascii
+from .vlmc import _default_device, sample_missing_sequences, vlmcs_to_flat
+
+
+class _DeviceDistance(object):
+    """Shared batching / caching logic.  Subclasses implement
+    ``_compute(handle, vlmcs, pair_only=False) -> (D32, D64)``."""
+
+    def __init__(self):
+        self._index = None     # id(vlmc) -> row
+        self._names = None     # name -> row (the reference's equality is by name, vlmc.pyx:27-31)
+        self._D64 = None
+        self._D32 = None
+        self.device = None
+
+    # -- batch hook (same name as Projection.set_vlmcs in the reference)
+    def set_vlmcs(self, vlmcs):
+        self.distance_matrix(vlmcs)
+
+    def distance_matrix(self, vlmcs):
+        """float32 [N, N] matrix of ``distance(vlmcs[i], vlmcs[j])`` (src/clustering/util.pyx:23-33 layout)."""
+        vlmcs = list(vlmcs)
+        h = native.Handle(_default_device() if self.device is None else self.device)
+        try:
+            h.load_models(vlmcs_to_flat(vlmcs))
+            D32, D64 = self._compute(h, vlmcs)
+        finally:
+            h.close()
+        self._D32, self._D64 = D32, D64
+        self._index = {id(v): i for i, v in enumerate(vlmcs)}
+        self._names = {}
+        for i, v in enumerate(vlmcs):
+            self._names.setdefault(v.name, i)
+        return D32
+
+    def _row(self, v):
+        if self._index is None:
+            return None
+        r = self._index.get(id(v))
+        if r is None:
+            r = self._names.get(getattr(v, "name", None))
+        return r
+
+    def _value(self, i, j):
+        return float(self._D64[i, j])
+
+    def distance(self, left_vlmc, right_vlmc):
+        i, j = self._row(left_vlmc), self._row(right_vlmc)
+        if i is not None and j is not None and self._still_valid(left_vlmc, right_vlmc):
+            return self._value(i, j)
+        # not batched: this pair alone, still on the device
+        pair = [left_vlmc, right_vlmc]
+        h = native.Handle(_default_device() if self.device is None else self.device)
+        try:
+            h.load_models(vlmcs_to_flat(pair))
+            D32, D64 = self._compute(h, pair, pair_only=True)
+        finally:
+            h.close()
+        return self._scalar(D32, D64)
+
+    def _scalar(self, D32, D64):
+        return float(D64[0, 1])
+
+    def _still_valid(self, left, right):
+        return True
+
+
+class NegativeLogLikelihood(_DeviceDistance):
+    """D(l, r) = (CE(l, r) + CE(r, l)) / 2 with CE(x, y) = (ln Pr(S_x|x) - ln Pr(S_x|y)) / L on a sequence
+    S_x of L symbols sampled from x (cached on the model), src/distance/negloglikelihood.pyx:17-26."""
+
+    length_of_pregenerated_sequence = 500  # src/distance/negloglikelihood.pyx:12
+
+    def __init__(self, sequence_length, mode="sequential"):
+        super().__init__()
+        self.generated_sequence_length = sequence_length
+        self.mode = mode  # "sequential" is bit-identical to the reference's fp64 sum; "warp" is within 1e-12
+        self._seq_ids = None
+
+    def _compute(self, h, vlmcs, pair_only=False):
+        L = self.generated_sequence_length
+        sample_missing_sequences(vlmcs, L, self.length_of_pregenerated_sequence, h.device)
+        buf, off = sequences_to_ascii([v.sequence for v in vlmcs])
+        h.load_sequences_ascii(buf, off)
+        self._seq_ids = {id(v): v.sequence for v in vlmcs}
+        return h.nll_matrix_h(L, self.mode)
+
+    def _still_valid(self, left, right):
+        # the reference re-samples when a model's cached sequence was reset or has another length
+        return self._seq_ids.get(id(left)) is left.sequence and self._seq_ids.get(id(right)) is right.sequence
+
+
+class FrobeniusNorm(_DeviceDistance):
+    """||P_l - P_r||_F / sqrt(#C) over the shared (default) or united context set, src/distance/frobenius.pyx:21-36."""
+
+    def __init__(self, use_union=False):
+        super().__init__()
+        self.use_union = use_union
+
+    def _compute(self, h, vlmcs, pair_only=False):
+        return h.pair_matrix_h("frobenius_union" if self.use_union else "frobenius_intersection")
+
+
+class Projection(_DeviceDistance):
+    """Euclidean distance between the models embedded over the union of all context sets,
+    src/distance/projection.pyx:7-36.  ``distance`` returns ``numpy.float32`` like the reference."""
+
+    def __init__(self):
+        super().__init__()
+        self.vlmcs = None
+        self.dimension = 0
+        self.context_transition_to_array_index = None
+
+    def set_vlmcs(self, vlmcs):
+        self.vlmcs = list(vlmcs)
+        universe = {}
+        for v in self.vlmcs:
+            for c in v.tree.keys():
+                universe.setdefault(c, len(universe))
+        self.context_transition_to_array_index = {c: {ch: 4 * i + k for k, ch in enumerate("ACGT")} for c, i in universe.items()}
+        self.dimension = 4 * len(universe)
+        self.distance_matrix(self.vlmcs)
+
+    def _compute(self, h, vlmcs, pair_only=False):
+        return h.pair_matrix_h("projection")
+
+    def _value(self, i, j):
+        return np.float32(self._D64[i, j])
+
+    def _scalar(self, D32, D64):
+        return np.float32(D64[0, 1])
+
+
+class EstimateVLMC(_DeviceDistance):
+    """Pearson statistic between the left model and its re-estimation from a 100 000-symbol sequence of
+    the right model; asymmetric, src/distance/estimate.pyx:19-38.  ``d`` is accepted and ignored exactly
+    as in the reference (its use is commented out there, :36)."""
+
+    pre_sample_length = 500      # src/distance/estimate.pyx:27
+    sequence_length = 100000     # src/distance/estimate.pyx:28
+
+    def __init__(self, d=None):
+        super().__init__()
+        self.d = d
+        self._seq_ids = None
+
+    def _compute(self, h, vlmcs, pair_only=False):
+        if pair_only:
+            # distance(left, right) samples only the RIGHT model's sequence (estimate.pyx:30); the left
+            # slot just needs a sequence of some kind for the (unused) other direction
+            sample_missing_sequences([vlmcs[1]], self.sequence_length, self.pre_sample_length, h.device)
+            seqs = [vlmcs[1].sequence, vlmcs[1].sequence]
+        else:
+            sample_missing_sequences(vlmcs, self.sequence_length, self.pre_sample_length, h.device)
+            seqs = [v.sequence for v in vlmcs]
+        buf, off = sequences_to_ascii(seqs)
+        h.load_sequences_ascii(buf, off)
+        self._seq_ids = {id(v): v.sequence for v in vlmcs}
+        return h.estimate_matrix_h()
+
+    def _still_valid(self, left, right):
+        return self._seq_ids.get(id(right)) is right.sequence

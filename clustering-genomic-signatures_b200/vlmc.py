@@ -1,0 +1,201 @@
+"""Host-side mirror of the reference's ``VLMC`` class (``src/vlmc/vlmc.pyx``) for the device path.
+
+Same constructor, attributes and method names as the reference so that the reference's drivers
+(``test_distance_function_``, ``AverageLinkClustering`` ...) accept these objects unchanged:
+
+    VLMC(tree, name, occurrence_probability)      .tree .name .order .sequence .alphabet
+    VLMC.from_json / from_json_dir / strip_parameters_from_name / to_json
+    get_context / get_all_contexts                (src/vlmc/vlmc.pyx:131-154)   -> device lookup kernel
+    log_likelihood / log_likelihood_ignore_initial_bias   (:79-101)             -> device scoring kernel
+    generate_sequence / reset_sequence            (:156-177, :208-209)          -> device sampler, CPython MT stream
+
+Nothing here computes on the CPU: every method that the reference implements with dict lookups
+goes through ``libvgs.so`` and raises if the library or a CUDA device is missing.
+"""
+import json
+import os
+import random
+
+import numpy as np
+
+from . import native
+from .flat import ALPHABET, FlatModels, decode_context, encode_history, sequences_to_ascii
+
+_CODE_TO_CHAR = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _default_device():
+    try:
+        import torch
+        return torch.cuda.current_device() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+def take_mt_state():
+    """CPython's global MT19937 state as uint32[625] (random.getstate()[1])."""
+    version, state, gauss = random.getstate()
+    return np.array(state, dtype=np.uint32), (version, gauss)
+
+
+def put_mt_state(arr, tag):
+    version, gauss = tag
+    random.setstate((version, tuple(int(x) for x in arr), gauss))
+
+
+class VLMC(object):
+    def __init__(self, tree, name, occurrence_probability):
+        self.tree = tree
+        self.name = name
+        self.order = max(len(k) for k in tree.keys())  # src/vlmc/vlmc.pyx:179-180
+        self.sequence = ""
+        self.alphabet = list(ALPHABET)
+        self.occurrence_probabilites = occurrence_probability
+        self._handle = None
+        self._keys = None
+
+    # identity is by name, as in the reference (src/vlmc/vlmc.pyx:24-31)
+    def __str__(self):
+        return self.name
+
+    def __hash__(self):
+        return hash(self.name)
+
+    def __eq__(self, other):
+        return other is not None and self.name == getattr(other, "name", None)
+
+    # ---- construction (src/vlmc/vlmc.pyx:33-70)
+    @classmethod
+    def from_json(cls, s, name=""):
+        info = json.loads(s)
+        if "tree" in info and "occurrence_probability" in info:
+            return cls(info["tree"], name, info["occurrence_probability"])
+        return cls(info, name, {})  # old format: the json is the bare tree
+
+    @classmethod
+    def from_json_dir(cls, directory):
+        out = []
+        for file in [f for f in os.listdir(directory) if f.endswith(".json")]:
+            stem, _ = os.path.splitext(file)
+            with open(os.path.join(directory, file)) as fh:
+                d = json.load(fh)
+            out.append(cls(d["tree"], cls.strip_parameters_from_name(stem), d["occurrence_probability"]))
+        return out
+
+    @classmethod
+    def strip_parameters_from_name(cls, signature_name):
+        parts = signature_name.split("_")
+        return "_".join(p for p in parts[1:len(parts) - 2] if p != "")
+
+    def to_json(self):
+        return json.dumps({"tree": self.tree, "occurrence_probability": self.occurrence_probabilites})
+
+    def occurrence_probability(self, state):
+        if len(self.occurrence_probabilites) == 0:
+            raise RuntimeError("No information about occurrence probabilites")
+        return self.occurrence_probabilites[state]
+
+    # ---- device plumbing
+    def flat(self):
+        return FlatModels.from_trees([self.tree], [self.name])
+
+    def _device(self):
+        if self._handle is None:
+            h = native.Handle(_default_device())
+            h.load_models(self.flat())
+            self._handle = h
+            self._keys = list(self.tree.keys())
+        return self._handle
+
+    # ---- lookups (src/vlmc/vlmc.pyx:131-154)
+    def _lookup(self, sequence, want_all):
+        for ch in sequence:
+            if ch not in ("A", "C", "G", "T"):
+                raise KeyError(ch)
+        ln, code = encode_history(sequence)
+        return self._device().lookup([0], [code], [ln], want_all=want_all)
+
+    def get_context(self, sequence):
+        ids = self._lookup(sequence, False)
+        if ids[0] < 0:
+            raise RuntimeError("get_context vlmc.pyx")
+        return self._keys[int(ids[0])]
+
+    def get_all_contexts(self, sequence):
+        ids, masks = self._lookup(sequence, True)
+        out = []
+        for ln in range(min(len(sequence), self.order), -1, -1):
+            if int(masks[0]) >> ln & 1:
+                out.append(sequence[len(sequence) - ln:] if ln else "")
+        return out
+
+    # ---- scoring (src/vlmc/vlmc.pyx:79-101)
+    def _score(self, sequence, skip_mode):
+        if len(sequence) == 0:
+            return 0.0
+        h = self._device()
+        try:
+            buf, off = sequences_to_ascii([sequence])
+        except UnicodeEncodeError:
+            raise KeyError(sequence)
+        h.load_sequences_ascii(buf, off)
+        M = h.nll_scores_h(skip_mode, "sequential")
+        if np.isnan(M[0, 0]):
+            raise RuntimeError("get_context vlmc.pyx")
+        return float(M[0, 0])
+
+    def log_likelihood_ignore_initial_bias(self, sequence):
+        return self._score(sequence, native.SKIP_ORDER)
+
+    def log_likelihood(self, sequence):
+        return self._score(sequence, native.SKIP_NONE)
+
+    # ---- sampling (src/vlmc/vlmc.pyx:156-177)
+    def generate_sequence(self, sequence_length, pre_sample_length):
+        if len(self.sequence) == sequence_length:
+            return self.sequence
+        h = self._device()
+        state, tag = take_mt_state()
+        h.sample_sequences(sequence_length, pre_sample_length, state)
+        put_mt_state(state, tag)  # the global stream advanced by length + pre doubles, like the reference
+        self.sequence = _CODE_TO_CHAR[h.get_sequence(0, sequence_length)].tobytes().decode("ascii")
+        return self.sequence
+
+    def generate_sequence_from(self, sequence_length, context):
+        if context != "":
+            raise NotImplementedError("device sampler starts from the empty history (the only way the hot path calls it)")
+        saved = self.sequence
+        self.sequence = ""
+        try:
+            return self.generate_sequence(sequence_length, 0)
+        finally:
+            self.sequence = saved
+
+    def reset_sequence(self):
+        self.sequence = ""
+
+
+def vlmcs_to_flat(vlmcs):
+    return FlatModels.from_trees([v.tree for v in vlmcs], [v.name for v in vlmcs])
+
+
+def sample_missing_sequences(vlmcs, sequence_length, pre_sample_length, device=None):
+    """Give every VLMC whose cached ``.sequence`` has another length a freshly sampled one, consuming
+    CPython's global MT19937 stream in list order exactly as the reference's N^2 loop does on first use
+    (``src/distance/negloglikelihood.pyx:22-24``, ``src/vlmc/vlmc.pyx:156-163``)."""
+    todo = [v for v in vlmcs if len(v.sequence) != sequence_length]
+    seen, uniq = set(), []
+    for v in todo:  # equal names alias one object in the reference's dict/index based code
+        if id(v) not in seen:
+            seen.add(id(v))
+            uniq.append(v)
+    if not uniq:
+        return
+    h = native.Handle(_default_device() if device is None else device)
+    h.load_models(vlmcs_to_flat(uniq))
+    state, tag = take_mt_state()
+    h.sample_sequences(sequence_length, pre_sample_length, state)
+    put_mt_state(state, tag)
+    for i, v in enumerate(uniq):
+        v.sequence = _CODE_TO_CHAR[h.get_sequence(i, sequence_length)].tobytes().decode("ascii")
+    h.close()

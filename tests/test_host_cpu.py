@@ -1,0 +1,203 @@
+"""Host-side logic that needs no GPU: flat encoding, packing, tile plan (vs the C library), the
+.tree ingest, the C-ABI export list, loud failure without a device, gloo world_size-2 sharding."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import golden_io
+import tiling_ref
+from clustering_genomic_signatures_b200 import flat, native, parse_trees_to_json, synthetic
+from clustering_genomic_signatures_b200.vlmc import VLMC
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_context_encoding_round_trip():
+    assert flat.encode_context("") == (0, 0)
+    assert flat.encode_context("CAA") == (3, 0b010000)
+    for ctx in ["A", "T", "ACGTACGT", "TTTTTTTTTTTTTTT", "GATTACA"]:
+        assert flat.decode_context(*flat.encode_context(ctx)) == ctx
+    with pytest.raises(KeyError):
+        flat.encode_context("ACN")
+    # rolling history: the length-k suffix code is h & (4**k - 1)
+    h = 0
+    s = "GATTACAGATTACA"
+    for ch in s:
+        h = (h << 2) | flat.SYMBOL_CODE[ch]
+    for k in range(1, 8):
+        assert flat.encode_context(s[-k:])[1] == h & (4 ** k - 1)
+
+
+def test_flat_models_from_trees_and_back():
+    g = golden_io.fixtures()
+    fm = golden_io.fixture_flat(g)
+    assert fm.n_models == 5 and fm.orders().tolist() == g["orders"]
+    for m in range(5):
+        assert fm.tree(m) == g["trees"][m] and list(fm.tree(m)) == list(g["trees"][m])
+    sub = fm.subset([3, 1])
+    assert sub.tree(0) == g["trees"][3] and sub.tree(1) == g["trees"][1]
+    with pytest.raises(ValueError):
+        flat.FlatModels.from_trees([{"A" * 16: {"A": 1.0, "C": 0.0, "G": 0.0, "T": 0.0}}])
+    with pytest.raises(ValueError):
+        flat.FlatModels.from_trees([{"": {"A": -0.1, "C": 0.5, "G": 0.3, "T": 0.3}}])
+
+
+def test_pack_sequences_layout():
+    rng = np.random.default_rng(0)
+    seqs = [rng.integers(0, 4, size=L).astype(np.uint8) for L in (0, 1, 15, 16, 17, 64, 65, 1000)]
+    words, offs, lens = flat.pack_sequences(seqs)
+    assert np.all(offs % 4 == 0) and lens.tolist() == [len(s) for s in seqs]
+    for i, s in enumerate(seqs):
+        assert np.array_equal(golden_io.unpack(words, offs, lens, i), s)
+    # first symbol in the two highest bits
+    w, _, _ = flat.pack_sequences([np.array([3, 0, 1], dtype=np.uint8)])
+    assert w[0] == (3 << 30) | (0 << 28) | (1 << 26)
+    buf, off = flat.sequences_to_ascii(["ACGT", "", "TT"])
+    assert buf.tobytes() == b"ACGTTT" and off.tolist() == [0, 4, 4, 6]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "vgs.h")).read()
+    declared = sorted(set(re.findall(r"\b(vgs_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    L = native.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(s[0] for s in native.SIGNATURES) == declared
+    out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (vgs_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        native.Handle(0)
+    v = VLMC({"": {"A": 0.25, "C": 0.25, "G": 0.25, "T": 0.25}}, "x", {})
+    with pytest.raises(RuntimeError):
+        v.get_context("ACG")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "clustering-genomic-signatures_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "vlmc_oracle" not in text and "c_oracle" not in text and "ref_loader" not in text, f
+                assert "oracle/" not in text, f
+
+
+@pytest.mark.parametrize("n,tile,world,sym", [(5, 2, 1, True), (10, 3, 2, True), (33, 8, 4, True), (1000, 64, 8, True),
+                                              (7, 2, 3, False), (20, 5, 8, False)])
+def test_tile_plan_matches_c_library_and_round_trips(n, tile, world, sym):
+    nt, n_tiles, slots = tiling_ref.plan(n, tile, world, sym)
+    assert native.tile_plan(n, tile, world, sym) == (n_tiles, slots)
+    rng = np.random.default_rng(n)
+    D = rng.random((n, n)).astype(np.float32)
+    if sym:
+        D = ((D + D.T) / 2).astype(np.float32)
+    gathered = np.stack([tiling_ref.payload_of_rank(D, tile, r, world, sym) for r in range(world)])
+    assert np.array_equal(tiling_ref.assemble(gathered, n, tile, world, sym), D)
+    # every tile is owned exactly once
+    owned = [k for r in range(world) for k in range(r, n_tiles, world)]
+    assert sorted(owned) == list(range(n_tiles))
+
+
+def test_tree_ingest_matches_reference_parser():
+    with open(os.path.join(golden_io.GOLD, "tree_parse_golden.json")) as fh:
+        gold = json.load(fh)
+    for name, item in gold.items():
+        got = parse_trees_to_json.parse_tree_lines(item["text"].splitlines(True))
+        assert list(got["tree"]) == list(item["json"]["tree"])
+        assert got == item["json"]
+    ref_dir = "/root/reference/original_test_trees"
+    if os.path.isdir(ref_dir):  # full files, against the shipped .json (same keys, order and doubles)
+        for f in os.listdir(ref_dir):
+            if f.endswith(".tree"):
+                got = parse_trees_to_json.parse_file(os.path.join(ref_dir, f))
+                want = json.load(open(os.path.join(ref_dir, f[:-5] + ".json")))
+                assert got["tree"] == want and list(got["tree"]) == list(want)
+
+
+def test_vlmc_host_mirror_construction():
+    assert VLMC.strip_parameters_from_name("PST_AB026117.1_10229_34094") == "AB026117.1"
+    assert VLMC.strip_parameters_from_name("pst_vlmc_name_23_23") == "vlmc_name"
+    assert VLMC.strip_parameters_from_name("pst_acgtacgt__") == "acgtacgt"
+    old = '{"":{"A":0.5,"C":0.5,"G":0,"T":0},"AC":{"A":0.25,"C":0.25,"G":0.25,"T":0.25}}'
+    v = VLMC.from_json(old, "x")
+    assert v.order == 2 and v.sequence == "" and v.alphabet == ["A", "C", "G", "T"] and str(v) == "x"
+    new = json.dumps({"tree": json.loads(old), "occurrence_probability": {"": 1.0, "AC": 0.1}})
+    w = VLMC.from_json(new, "x")
+    assert w == v and hash(w) == hash(v) and w.occurrence_probability("AC") == 0.1
+    with pytest.raises(RuntimeError):
+        v.occurrence_probability("")
+    assert json.loads(w.to_json())["tree"] == w.tree
+
+
+def test_matrix_layouts_host():
+    from clustering_genomic_signatures_b200.clustering import util
+
+    class Fake:
+        def distance_matrix(self, vlmcs):
+            n = len(vlmcs)
+            return (np.arange(n * n, dtype=np.float32).reshape(n, n) / 7).astype(np.float32)
+
+    tri = util.calculate_distances_within_vlmcs([1, 2, 3], Fake())
+    assert tri.dtype == np.float32 and tri.shape == (9, 3)
+    assert tri[:, 0].tolist() == [0, 0, 0, 1, 1, 1, 2, 2, 2] and tri[:, 1].tolist() == [0, 1, 2] * 3
+    assert np.array_equal(util.index_distances([1, 2, 3], tri), Fake().distance_matrix([1, 2, 3]))
+    with pytest.raises(TypeError):
+        util.calculate_distances_within_vlmcs([1, 2], object())
+
+
+def test_synthetic_sets_are_suffix_closed_and_normalised():
+    fm, fam = synthetic.make_family_models(20, 5, 9, 200, 4)
+    assert fm.orders().max() <= 9 and abs(fm.prob.sum(axis=1) - 1).max() < 1e-12
+    for m in (0, 7, 19):
+        t = fm.tree(m)
+        assert "" in t and all(c[1:] in t for c in t if c)
+    fc, _ = synthetic.make_full_chains(3, 1, 3)
+    assert fc.n_ctx(0) == 1 + 4 + 16 + 64
+    seqs = synthetic.sample_sequences(fm, 50, 1)
+    assert seqs.shape == (20, 50) and seqs.max() <= 3
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import tiling_ref
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), 2
+for n, tile, sym in ((37, 8, True), (21, 4, False)):
+    rng = np.random.default_rng(3)
+    D = rng.random((n, n)).astype(np.float32)
+    if sym:
+        D = ((D + D.T) / 2).astype(np.float32)
+    mine = torch.from_numpy(tiling_ref.payload_of_rank(D, tile, rank, world, sym).ravel().copy())
+    gathered = torch.empty(world * mine.numel(), dtype=torch.float32)
+    dist.all_gather_into_tensor(gathered, mine)
+    out = tiling_ref.assemble(gathered.numpy(), n, tile, world, sym)
+    assert np.array_equal(out, D), "rank %d: assembled matrix differs" % rank
+dist.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world2_sharding_round_trip(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "rank %d ok" % r in o, o
