@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -84,6 +85,12 @@ struct vgs_context {
     int *d_err = nullptr;       // device error flag (bit 0: no context, bit 1: bad symbol)
     cudaStream_t own_stream = nullptr;
 
+    // capacity of every handle-owned device buffer (keyed by the address of the pointer member):
+    // buffers are reused across vgs_load_* calls and only re-allocated when they must grow
+    std::map<void *, int64_t> caps;
+    float *d_out32 = nullptr;   // staging for the *_h entry points
+    double *d_out64 = nullptr;
+
     // optional per-kernel event timing (vgs_profile_*)
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[4];
@@ -138,6 +145,26 @@ int vgs_dev_alloc(T **p, int64_t n) {
         *p = nullptr;
         return VGS_ERR_MEMORY;
     }
+    return VGS_OK;
+}
+
+// grow-only reservation of a handle-owned device buffer of n elements
+template <typename T>
+int vgs_reserve(vgs_context *h, T **p, int64_t n) {
+    if (n <= 0) n = 1;
+    const int64_t bytes = n * (int64_t)sizeof(T);
+    auto it = h->caps.find((void *)p);
+    if (*p && it != h->caps.end() && it->second >= bytes) return VGS_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    h->caps.erase((void *)p);
+    cudaError_t e = cudaMalloc((void **)p, (size_t)bytes);
+    if (e != cudaSuccess) {
+        vgs_set_error("cudaMalloc of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+        *p = nullptr;
+        return VGS_ERR_MEMORY;
+    }
+    h->caps[(void *)p] = bytes;
     return VGS_OK;
 }
 

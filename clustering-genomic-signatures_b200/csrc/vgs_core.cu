@@ -52,11 +52,7 @@ int vgs_ensure_scratch(vgs_context *h, int64_t bytes) { return ensure_buf(&h->d_
 int vgs_ensure_scratch2(vgs_context *h, int64_t bytes) { return ensure_buf(&h->d_scratch2, &h->scratch2_bytes, bytes); }
 int vgs_ensure_M(vgs_context *h) {
     int64_t need = h->n_seq * h->n_models;
-    if (need <= h->M_elems && h->d_M) return VGS_OK;
-    if (h->d_M) cudaFree(h->d_M);
-    h->d_M = nullptr;
-    h->M_elems = 0;
-    int rc = vgs_dev_alloc(&h->d_M, need);
+    int rc = vgs_reserve(h, &h->d_M, need);
     if (rc) return rc;
     h->M_elems = need;
     return VGS_OK;
@@ -114,27 +110,23 @@ extern "C" int vgs_create(int device, vgs_handle *out) {
     return VGS_OK;
 }
 
-static void free_models(vgs_context *h) {
-    cudaFree(h->d_meta); cudaFree(h->d_key); cudaFree(h->d_len); cudaFree(h->d_code);
-    cudaFree(h->d_prob32); cudaFree(h->d_prob64); cudaFree(h->d_logp); cudaFree(h->d_hash); cudaFree(h->d_nll);
-    h->d_meta = nullptr; h->d_key = nullptr; h->d_len = nullptr; h->d_code = nullptr; h->d_prob32 = nullptr;
-    h->d_prob64 = nullptr; h->d_logp = nullptr; h->d_hash = nullptr; h->d_nll = nullptr;
-    h->n_models = 0; h->total_ctx = 0;
-    if (h->d_M) { cudaFree(h->d_M); h->d_M = nullptr; h->M_elems = 0; }
-}
-static void free_sequences(vgs_context *h) {
-    cudaFree(h->d_seq); cudaFree(h->d_seq_off); cudaFree(h->d_seq_len);
-    h->d_seq = nullptr; h->d_seq_off = nullptr; h->d_seq_len = nullptr;
-    h->n_seq = 0; h->total_symbols = 0; h->total_words = 0;
-    if (h->d_M) { cudaFree(h->d_M); h->d_M = nullptr; h->M_elems = 0; }
+// the device buffers stay allocated (grow-only, vgs_reserve); only the logical contents are dropped
+static void free_models(vgs_context *h) { h->n_models = 0; h->total_ctx = 0; }
+static void free_sequences(vgs_context *h) { h->n_seq = 0; h->total_symbols = 0; h->total_words = 0; }
+static void free_all_buffers(vgs_context *h) {
+    for (auto &kv : h->caps) {
+        void **p = (void **)kv.first;
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    h->caps.clear();
 }
 
 extern "C" int vgs_destroy(vgs_handle h) {
     if (!h) return VGS_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    free_models(h);
-    free_sequences(h);
+    free_all_buffers(h);
     cudaFree(h->d_scratch);
     cudaFree(h->d_scratch2);
     cudaFree(h->d_err);
@@ -388,15 +380,15 @@ extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ct
     }
 
     int rc;
-    if ((rc = vgs_dev_alloc(&h->d_meta, n_models))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_key, total))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_len, total))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_code, total))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_prob32, total))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_prob64, total * 4))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_logp, total * 4))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_hash, hash_slots))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_nll, nll_bytes))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_meta, n_models))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_key, total))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_len, total))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_code, total))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_prob32, total))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_prob64, total * 4))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_logp, total * 4))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_hash, hash_slots))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_nll, nll_bytes))) return rc;
     h->hash_slots = hash_slots;
     h->nll_bytes = nll_bytes;
     h->n_models = n_models;
@@ -530,9 +522,9 @@ static int set_sequence_layout(vgs_context *h, int64_t n_seq, const int64_t *len
     h->total_symbols = total;
     h->total_words = h->h_seq_off[(size_t)n_seq];
     int rc;
-    if ((rc = vgs_dev_alloc(&h->d_seq, h->total_words + 4))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_seq_off, n_seq + 1))) return rc;
-    if ((rc = vgs_dev_alloc(&h->d_seq_len, n_seq))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_seq, h->total_words + 4))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_seq_off, n_seq + 1))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_seq_len, n_seq))) return rc;
     return VGS_OK;
 }
 

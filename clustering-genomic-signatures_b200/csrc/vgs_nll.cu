@@ -436,17 +436,15 @@ extern "C" int vgs_nll_matrix_h(vgs_handle h, int64_t length, int mode, float *D
     VGS_CHECK_ARG(D32_out_h || D64_out_h, "vgs_nll_matrix_h: no output");
     VGS_CUDA(cudaSetDevice(h->device));
     const int64_t n = h->n_models;
-    float *d32 = nullptr;
-    double *d64 = nullptr;
-    if ((rc = vgs_dev_alloc(&d32, n * n))) return rc;
-    if (D64_out_h && (rc = vgs_dev_alloc(&d64, n * n))) { cudaFree(d32); return rc; }
+    if ((rc = vgs_reserve(h, &h->d_out32, n * n))) return rc;
+    if (D64_out_h && (rc = vgs_reserve(h, &h->d_out64, n * n))) return rc;
+    float *d32 = h->d_out32;
+    double *d64 = D64_out_h ? h->d_out64 : nullptr;
     cudaStream_t s = h->own_stream;
     rc = vgs_nll_matrix(h, length, mode, d32, d64, s);
     if (!rc) rc = vgs_read_error_flag(h, s);
     if (!rc && D32_out_h) rc = cudaMemcpyAsync(D32_out_h, d32, 4 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
     if (!rc && D64_out_h) rc = cudaMemcpyAsync(D64_out_h, d64, 8 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
     cudaStreamSynchronize(s);
-    cudaFree(d32);
-    if (d64) cudaFree(d64);
     return rc;
 }
