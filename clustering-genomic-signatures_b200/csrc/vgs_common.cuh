@@ -25,6 +25,8 @@
 #define VGS_DENSE_MAX_ORDER 6   // tier 1 limit: 4^7 * 8 B = 128 KB of shared memory
 #define VGS_L1_DEPTH 6          // tier 2 first-level map covers the last 6 symbols
 #define VGS_NO_CTX 0x7FFFFFFFu
+#define VGS_UMAP_MAX_ORDER 7    // dense "universe" maps for the pair kernels: (4^8 - 1) / 3 = 21845 u16 entries
+#define VGS_UMAP_NONE 0x7FFFu
 
 struct ModelMeta {
     int64_t ctx_off;      // first context of this model in key/prob arrays
@@ -68,6 +70,12 @@ struct vgs_context {
     int64_t hash_slots = 0;
     uint8_t *d_nll = nullptr;
     int64_t nll_bytes = 0;
+    // pair kernels, shallow sets (max_order <= VGS_UMAP_MAX_ORDER): per model a dense map over EVERY string of
+    // length <= max_order (index (4^len - 1) / 3 + code) -> u16: low 15 bits = ctx_id of the longest suffix that is
+    // a context (VGS_UMAP_NONE if none), bit 15 = the string itself is a context
+    uint16_t *d_umap = nullptr;
+    int64_t umap_stride = 0;     // entries per model (multiple of 8), 0 = not built
+    int max_n_ctx = 0;
 
     // sequences
     int64_t n_seq = 0, total_symbols = 0, total_words = 0;

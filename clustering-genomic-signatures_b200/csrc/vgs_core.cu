@@ -273,6 +273,30 @@ __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint
     }
 }
 
+// dense universe map for the pair kernels (shallow sets)
+__global__ void k_build_umap(const ModelMeta *__restrict__ meta, const uint2 *__restrict__ hash, int depth, int64_t stride,
+                             uint16_t *__restrict__ umap) {
+    const ModelMeta mm = meta[blockIdx.y];
+    const uint2 *slots = hash + mm.hash_off;
+    uint16_t *out = umap + (int64_t)blockIdx.y * stride;
+    const int64_t total = ((((int64_t)1) << (2 * (depth + 1))) - 1) / 3;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < stride; u += (int64_t)gridDim.x * blockDim.x) {
+        uint16_t v = VGS_UMAP_NONE;
+        if (u < total) {
+            int len = 0;
+            int64_t base = 0;
+            while (base + (((int64_t)1) << (2 * len)) <= u) { base += ((int64_t)1) << (2 * len); ++len; }
+            const uint32_t code = (uint32_t)(u - base);
+            const int top = len < mm.order ? len : mm.order;
+            for (int ln = top; ln >= 0; --ln) {
+                int id = vgs_hash_find(slots, mm.hash_mask, mm.hash_shift, vgs_key(ln, code & vgs_lowmask(ln)));
+                if (id >= 0) { v = (uint16_t)(id | (ln == len ? 0x8000 : 0)); break; }
+            }
+        }
+        out[u] = v;
+    }
+}
+
 static int log2_ceil_pow2(int64_t v, int64_t *cap_out) {
     int64_t cap = 8;
     int lg = 3;
@@ -295,6 +319,8 @@ extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ct
     h->h_meta.assign((size_t)n_models, ModelMeta());
     h->max_order = 0;
     h->max_nll_bytes_t1 = h->max_nll_bytes_t2 = h->max_pair_bytes = 0;
+    h->max_n_ctx = 0;
+    h->umap_stride = 0;
     int64_t hash_slots = 0, nll_bytes = 0;
     for (int64_t m = 0; m < n_models; ++m) {
         ModelMeta &mm = h->h_meta[(size_t)m];
@@ -325,6 +351,7 @@ extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ct
         mm.hash_shift = 32 - lg;
         hash_slots += cap;
         h->max_pair_bytes = std::max(h->max_pair_bytes, cap * 8 + n * 16);
+        h->max_n_ctx = std::max<int>(h->max_n_ctx, (int)n);
         h->max_order = std::max(h->max_order, order);
         mm.nll_off = nll_bytes;
         if (order <= VGS_DENSE_MAX_ORDER) {
@@ -419,6 +446,19 @@ extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ct
     if (h->max_nll_bytes_t2 > 0) {
         k_build_two_level<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_hash, h->d_key, h->d_len, h->d_code, h->d_logp, h->d_nll);
         VGS_LAUNCH_CHECK(h);
+    }
+    if (h->max_order <= VGS_UMAP_MAX_ORDER && h->max_n_ctx < 0x7FFF) {
+        const int64_t total_u = ((((int64_t)1) << (2 * (h->max_order + 1))) - 1) / 3;
+        const int64_t stride = (total_u + 7) / 8 * 8;
+        if (stride * n_models * 2 <= ((int64_t)8 << 30)) {  // at most 8 GB of maps
+            if ((rc = vgs_reserve(h, &h->d_umap, stride * n_models))) return rc;
+            for (int64_t m0 = 0; m0 < n_models; m0 += 65535) {
+                dim3 grid((unsigned)std::min<int64_t>((stride + 255) / 256, 64), (unsigned)std::min<int64_t>(n_models - m0, 65535));
+                k_build_umap<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->max_order, stride, h->d_umap + m0 * stride);
+                VGS_LAUNCH_CHECK(h);
+            }
+            h->umap_stride = stride;
+        }
     }
     VGS_CUDA(cudaStreamSynchronize(s));
     return VGS_OK;

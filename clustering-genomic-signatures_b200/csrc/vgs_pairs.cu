@@ -29,6 +29,8 @@ struct PairParams {
     const uint32_t *key;
     const float4 *prob32;
     const uint2 *hash;
+    const uint16_t *umap;
+    int64_t umap_stride;
     TilePlan pl;
     int rank, kind, jg, n_groups, n_dir;
     double *S, *U;
@@ -45,14 +47,18 @@ __device__ __forceinline__ void tile_of_slot(const TilePlan &pl, int64_t k, int6
 
 __device__ __forceinline__ double sq4(const float4 a, const float4 b) {
     const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;  // float32 subtraction (frobenius.pyx:34)
-    double r = (double)dx * (double)dx;
-    r += (double)dy * (double)dy;
-    r += (double)dz * (double)dz;
-    r += (double)dw * (double)dw;
+    // each product of two float32 values is exact in fp64, so the fused form rounds exactly like mul-then-add
+    double r = __dmul_rn((double)dx, (double)dx);
+    r = __fma_rn((double)dy, (double)dy, r);
+    r = __fma_rn((double)dz, (double)dz, r);
+    r = __fma_rn((double)dw, (double)dw, r);
     return r;
 }
 
-template <bool STAGED>
+// UMAP = true : shallow sets; each staged model carries a dense map over every string of length <= max order
+//               (one u16 gather gives presence AND the longest-suffix fallback row: no probing loop, no divergence)
+// UMAP = false: deep sets; exact-context hash probes, and for the union a probe per shorter suffix
+template <bool STAGED, bool UMAP>
 __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -87,18 +93,20 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
 
     if (tid < ny) ymeta[tid] = p.meta[y0 + tid];
     __syncthreads();
+    const uint32_t map_bytes = UMAP ? (uint32_t)p.umap_stride * 2u : 0u;
     if (STAGED) {
         if (tid == 0) {
             uint32_t off = 0, total = 0;
             for (int yy = 0; yy < ny; ++yy) {
-                const uint32_t hb = (ymeta[yy].hash_mask + 1u) * 8u, rb = (uint32_t)ymeta[yy].n_ctx * 16u;
+                const uint32_t hb = UMAP ? map_bytes : (ymeta[yy].hash_mask + 1u) * 8u, rb = (uint32_t)ymeta[yy].n_ctx * 16u;
                 yoff_h[yy] = off; off += hb;
                 yoff_r[yy] = off; off += rb;
                 total += hb + rb;
             }
             vgs_mbar_expect_tx(&bar, total);
             for (int yy = 0; yy < ny; ++yy) {
-                vgs_copy_pieces(smem + yoff_h[yy], p.hash + ymeta[yy].hash_off, (ymeta[yy].hash_mask + 1u) * 8u, &bar);
+                if (UMAP) vgs_copy_pieces(smem + yoff_h[yy], p.umap + (y0 + yy) * p.umap_stride, map_bytes, &bar);
+                else vgs_copy_pieces(smem + yoff_h[yy], p.hash + ymeta[yy].hash_off, (ymeta[yy].hash_mask + 1u) * 8u, &bar);
                 vgs_copy_pieces(smem + yoff_r[yy], p.prob32 + ymeta[yy].ctx_off, (uint32_t)ymeta[yy].n_ctx * 16u, &bar);
             }
         }
@@ -106,12 +114,13 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
         vgs_mbar_wait(&bar, 0);
     }
 
-    const uint2 *yh[PAIR_MAX_JG];
+    const void *yh[PAIR_MAX_JG];
     const float4 *yr[PAIR_MAX_JG];
 #pragma unroll
     for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
         if (yy < ny) {
-            yh[yy] = STAGED ? (const uint2 *)(smem + yoff_h[yy]) : p.hash + ymeta[yy].hash_off;
+            if (STAGED) yh[yy] = smem + yoff_h[yy];
+            else yh[yy] = UMAP ? (const void *)(p.umap + (y0 + yy) * p.umap_stride) : (const void *)(p.hash + ymeta[yy].hash_off);
             yr[yy] = STAGED ? (const float4 *)(smem + yoff_r[yy]) : p.prob32 + ymeta[yy].ctx_off;
         } else {
             yh[yy] = nullptr; yr[yy] = nullptr;
@@ -119,6 +128,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
     }
 
     const int64_t part_base = ((q * 2 + dir) * T) * T;
+    const int kind = p.kind;
     for (int xx = warp; xx < nx; xx += PAIR_THREADS / 32) {
         const ModelMeta xm = p.meta[x0 + xx];
         double s[PAIR_MAX_JG], u[PAIR_MAX_JG];
@@ -130,22 +140,44 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
             const float4 px = __ldg(p.prob32 + xm.ctx_off + ci);
             const int len = (31 - __clz(key)) >> 1;
             const uint32_t code = key ^ (1u << (2 * len));
+            if (UMAP) {
+                const uint32_t uidx = (((1u << (2 * len)) - 1u) / 3u) + code;
 #pragma unroll
-            for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
-                if (yy >= ny) break;
-                const uint32_t mask = ymeta[yy].hash_mask;
-                const int shift = ymeta[yy].hash_shift;
-                int id = vgs_hash_find(yh[yy], mask, shift, key);
-                if (id >= 0) {
-                    s[yy] += sq4(px, yr[yy][id]);
-                    c[yy] += 1;
-                } else if (p.kind == VGS_PAIR_FROBENIUS_UNION) {
-                    int top = len - 1 < ymeta[yy].order ? len - 1 : ymeta[yy].order;
-                    for (int ln = top; ln >= 0 && id < 0; --ln) id = vgs_hash_find(yh[yy], mask, shift, vgs_key(ln, code & vgs_lowmask(ln)));
-                    if (id < 0) atomicOr(p.err, 1);
-                    else u[yy] += sq4(px, yr[yy][id]);
-                } else if (p.kind == VGS_PAIR_PROJECTION) {
-                    u[yy] += sq4(px, make_float4(0.f, 0.f, 0.f, 0.f));
+                for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
+                    if (yy >= ny) break;
+                    const uint32_t e = ((const uint16_t *)yh[yy])[uidx];
+                    const uint32_t id = e & 0x7FFFu;
+                    const bool exact = (e & 0x8000u) != 0u;
+                    if (kind == VGS_PAIR_FROBENIUS_INTERSECTION) {
+                        if (exact) { s[yy] += sq4(px, yr[yy][id]); c[yy] += 1; }
+                    } else if (kind == VGS_PAIR_FROBENIUS_UNION) {
+                        if (id == VGS_UMAP_NONE) { atomicOr(p.err, 1); continue; }
+                        const double v = sq4(px, yr[yy][id]);
+                        if (exact) { s[yy] += v; c[yy] += 1; } else { u[yy] += v; }
+                    } else {
+                        if (exact) { s[yy] += sq4(px, yr[yy][id]); c[yy] += 1; }
+                        else u[yy] += sq4(px, make_float4(0.f, 0.f, 0.f, 0.f));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
+                    if (yy >= ny) break;
+                    const uint2 *slots = (const uint2 *)yh[yy];
+                    const uint32_t mask = ymeta[yy].hash_mask;
+                    const int shift = ymeta[yy].hash_shift;
+                    int id = vgs_hash_find(slots, mask, shift, key);
+                    if (id >= 0) {
+                        s[yy] += sq4(px, yr[yy][id]);
+                        c[yy] += 1;
+                    } else if (kind == VGS_PAIR_FROBENIUS_UNION) {
+                        int top = len - 1 < ymeta[yy].order ? len - 1 : ymeta[yy].order;
+                        for (int ln = top; ln >= 0 && id < 0; --ln) id = vgs_hash_find(slots, mask, shift, vgs_key(ln, code & vgs_lowmask(ln)));
+                        if (id < 0) atomicOr(p.err, 1);
+                        else u[yy] += sq4(px, yr[yy][id]);
+                    } else if (kind == VGS_PAIR_PROJECTION) {
+                        u[yy] += sq4(px, make_float4(0.f, 0.f, 0.f, 0.f));
+                    }
                 }
             }
         }
@@ -186,13 +218,18 @@ __global__ void k_pair_combine(PairParams p, float *__restrict__ pay32, double *
         const int64_t ii = e / T, jj = e % T, i = I * T + ii, j = J * T + jj;
         double d = 0.0;
         if (k < p.pl.n_tiles && i < p.pl.n && j < p.pl.n) {
-            const double s = S0[e];
-            const int cnt = C0[e];
+            // canonical orientation (a, b): inside a diagonal tile both (i, j) and (j, i) were accumulated, in
+            // different context orders; reading the a <= b copy for both makes the matrix exactly symmetric
+            int64_t a = ii, b = jj;
+            if (I == J && ii > jj) { a = jj; b = ii; }
+            const int64_t ab = a * T + b, ba = b * T + a;
+            const double s = S0[ab];
+            const int cnt = C0[ab];
             if (p.kind == VGS_PAIR_FROBENIUS_INTERSECTION) {
                 d = cnt > 0 ? sqrt(s) / sqrt((double)cnt) : vgs_nan();  // empty intersection: 0/0 in the reference
             } else {
-                const double u_ij = U0[e];
-                const double u_ji = (I == J) ? U0[jj * T + ii] : U1[jj * T + ii];
+                const double u_ij = U0[ab];
+                const double u_ji = (I == J) ? U0[ba] : U1[ba];
                 const double ssq = s + u_ij + u_ji;
                 if (p.kind == VGS_PAIR_FROBENIUS_UNION) {
                     const int n_union = p.meta[i].n_ctx + p.meta[j].n_ctx - cnt;
@@ -213,7 +250,10 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
     p.pl = pl; p.rank = rank; p.kind = kind; p.err = h->d_err;
     p.n_dir = kind == VGS_PAIR_FROBENIUS_INTERSECTION ? 1 : 2;
     // how many staged models fit?  prefer >= 2 CTAs per SM
-    const int64_t per_model = (h->max_pair_bytes + 127) / 128 * 128;
+    const bool umap = h->umap_stride > 0;
+    p.umap = h->d_umap; p.umap_stride = h->umap_stride;
+    const int64_t per_model_raw = umap ? h->umap_stride * 2 + (int64_t)h->max_n_ctx * 16 : h->max_pair_bytes;
+    const int64_t per_model = (per_model_raw + 127) / 128 * 128;
     const int64_t cap = (int64_t)h->max_smem_optin - 2048;
     bool staged = per_model <= cap;
     int jg = 4;
@@ -236,13 +276,18 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
     VGS_CUDA(cudaMemsetAsync(h->d_scratch2, 0, (size_t)(part * 20), s));
     const int64_t n_cta = pl.slots * p.n_dir * p.n_groups;
     VGS_CHECK_ARG(n_cta < ((int64_t)1 << 31), "pair kernel grid too large");
+    const int smem = staged ? (int)(per_model * jg) : 0;
     vgs_prof_begin(h, VGS_PROF_PAIR_PARTIALS, s);
-    if (staged) {
-        const int smem = (int)(per_model * jg);
-        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_pair_partials<true><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
+    if (staged && umap) {
+        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_pair_partials<true, true><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
+    } else if (staged) {
+        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_pair_partials<true, false><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
+    } else if (umap) {
+        k_pair_partials<false, true><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
     } else {
-        k_pair_partials<false><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
+        k_pair_partials<false, false><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
     }
     vgs_prof_end(h, VGS_PROF_PAIR_PARTIALS, s);
     VGS_LAUNCH_CHECK(h);
