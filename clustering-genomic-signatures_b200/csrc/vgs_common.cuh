@@ -96,6 +96,7 @@ struct vgs_context {
     // capacity of every handle-owned device buffer (keyed by the address of the pointer member):
     // buffers are reused across vgs_load_* calls and only re-allocated when they must grow
     std::map<void *, int64_t> caps;
+    int *d_counters = nullptr;  // dynamic-scheduler counters
     float *d_out32 = nullptr;   // staging for the *_h entry points
     double *d_out64 = nullptr;
 

@@ -14,17 +14,19 @@
 //                       4 partial sums per chunk, fixed-order shuffle reduction (north_star's layout).
 // Per scored base: one funnel shift + mask (the (order+1)-mer ending at the base is a contiguous bit
 // field of the packed sequence), one 8-byte shared-memory gather, one DADD.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
 #include "vgs_common.cuh"
 
-#define NLL_THREADS 512
+#define NLL_MAX_THREADS 1024
 
 struct NllUnit {
     int32_t model;
     int32_t list_off;  // offset into seq_list, or first sequence index when seq_list == nullptr
-    int32_t count;     // <= NLL_THREADS
+    int32_t count;     // <= threads per CTA
     int32_t extra;     // extra sequence index scored by lane `count` (the diagonal M[m][m]) or -1
 };
 
@@ -42,6 +44,7 @@ struct NllParams {
     int skip_none;
     double *M;
     int64_t ld;
+    int *counter;      // dynamic unit scheduler (zeroed before the launch)
 };
 
 // ---- table views -----------------------------------------------------------------------------
@@ -130,28 +133,29 @@ __device__ double nll_prologue(const NllParams &p, const ModelMeta &mm, const ui
 }
 
 template <int TIER, int MODE, bool STAGED>
-__global__ void __launch_bounds__(NLL_THREADS, 1) k_nll_scores(const NllParams p) {
+__global__ void __launch_bounds__(NLL_MAX_THREADS, 1) k_nll_scores(const NllParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
+    __shared__ int s_unit;
     const int tid = threadIdx.x;
-    const int u0 = (int)((int64_t)blockIdx.x * p.n_units / gridDim.x);
-    const int u1 = (int)((int64_t)(blockIdx.x + 1) * p.n_units / gridDim.x);
-    if (STAGED) {
-        if (tid == 0) vgs_mbar_init(&bar, 1);
-        __syncthreads();
-    }
+    if (STAGED && tid == 0) vgs_mbar_init(&bar, 1);
     uint32_t parity = 0;
     int cur_model = -1;
     typename std::conditional<TIER == 1, DenseTable, TwoLevelTable>::type T;
     ModelMeta mm;
-    for (int u = u0; u < u1; ++u) {
+    // units are handed out dynamically (they are sorted by model, so a CTA mostly keeps its staged table)
+    for (;;) {
+        __syncthreads();  // every lane is done with the previous unit (and with the previous table)
+        if (tid == 0) s_unit = atomicAdd(p.counter, 1);
+        __syncthreads();
+        const int u = s_unit;
+        if (u >= p.n_units) break;
         const NllUnit un = p.units[u];
         if (un.model != cur_model) {
             mm = p.meta[un.model];
             cur_model = un.model;
             const uint8_t *blob = p.arena + mm.nll_off;
             if (STAGED) {
-                __syncthreads();  // every lane is done reading the previous table
                 if (tid == 0) vgs_stage(smem, blob, (uint32_t)mm.nll_bytes, &bar);
                 vgs_mbar_wait(&bar, parity);
                 parity ^= 1u;
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(NLL_THREADS, 1) k_nll_scores(const NllParams p
             }
         } else {
             const int lane = tid & 31, warp = tid >> 5;
-            for (int it = warp; it < n_items; it += NLL_THREADS / 32) {
+            for (int it = warp; it < n_items; it += (int)(blockDim.x >> 5)) {
                 const int s = it < un.count ? (p.seq_list ? p.seq_list[un.list_off + it] : un.list_off + it) : un.extra;
                 const uint32_t *w = p.seq + p.seq_off[s];
                 const int64_t L = p.seq_len[s];
@@ -206,16 +210,47 @@ __global__ void __launch_bounds__(NLL_THREADS, 1) k_nll_scores(const NllParams p
 // ---------------------------------------------------------------------------------------------
 // host side: build the unit list and launch per tier
 // ---------------------------------------------------------------------------------------------
+// threads per CTA = sequences per unit.  512 is ~1% faster than 256 when the units are full (measured,
+// B200, cfg 3); 256 wastes fewer lanes when the per-model sequence lists are not multiples of 512 (multi-GPU
+// tilings).  VGS_NLL_THREADS overrides for experiments.
+static int g_nll_threads = 512;
+static int vgs_nll_threads() { return g_nll_threads; }
+static void vgs_choose_nll_threads(const std::vector<int64_t> &list_sizes) {
+    const char *e = getenv("VGS_NLL_THREADS");
+    if (e) {
+        int t = atoi(e);
+        if (t < 32) t = 32;
+        if (t > NLL_MAX_THREADS) t = NLL_MAX_THREADS;
+        g_nll_threads = t / 32 * 32;
+        return;
+    }
+    double used[2] = {0, 0}, alloc[2] = {0, 0};
+    const int cand[2] = {512, 256};
+    for (int64_t c : list_sizes) {
+        if (c <= 0) continue;
+        for (int k = 0; k < 2; ++k) {
+            const int64_t units = (c + cand[k] - 1) / cand[k];
+            const int64_t warps = ((c + units - 1) / units + 31) / 32;  // warps a unit keeps busy
+            used[k] += (double)c;
+            alloc[k] += (double)(units * warps * 32);
+        }
+    }
+    const double e512 = alloc[0] > 0 ? used[0] / alloc[0] : 1.0, e256 = alloc[1] > 0 ? used[1] / alloc[1] : 1.0;
+    g_nll_threads = (e256 > e512 + 0.03) ? 256 : 512;
+}
+
 template <int TIER, int MODE, bool STAGED>
 static int launch_nll(vgs_context *h, const NllParams &p, int smem_bytes, cudaStream_t s) {
     auto kern = k_nll_scores<TIER, MODE, STAGED>;
     if (STAGED) VGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 1;
-    VGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NLL_THREADS, STAGED ? smem_bytes : 0));
+    const int threads = vgs_nll_threads();
+    VGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, STAGED ? smem_bytes : 0));
     if (per_sm < 1) per_sm = 1;
     int grid = std::min(p.n_units, h->sm_count * per_sm);
+    VGS_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(int), s));
     vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
-    kern<<<grid, NLL_THREADS, STAGED ? smem_bytes : 0, s>>>(p);
+    kern<<<grid, threads, STAGED ? smem_bytes : 0, s>>>(p);
     vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
     VGS_LAUNCH_CHECK(h);
     return VGS_OK;
@@ -242,6 +277,15 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
         list_off[b + 1] = list_off[b] + (int64_t)lists[b].size();
         flat.insert(flat.end(), lists[b].begin(), lists[b].end());
     }
+    {
+        std::vector<int64_t> sizes;
+        for (int64_t m = m_begin; m < m_end; ++m) {
+            const size_t b = (size_t)(m / block);
+            if (b >= lists.size()) break;
+            sizes.push_back((int64_t)lists[b].size() + (add_diagonal ? 1 : 0));
+        }
+        vgs_choose_nll_threads(sizes);
+    }
     for (int64_t m = m_begin; m < m_end; ++m) {
         const size_t b = (size_t)(m / block);
         if (b >= lists.size()) break;
@@ -250,8 +294,9 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
         bool diag_needed = add_diagonal && m < h->n_seq && !std::binary_search(L.begin(), L.end(), (int32_t)m);
         int64_t cnt = (int64_t)L.size();
         if (cnt == 0 && !diag_needed) continue;
-        // even split into ceil(cnt / NLL_THREADS) units
-        int64_t n_u = std::max<int64_t>(1, (cnt + (diag_needed ? 1 : 0) + NLL_THREADS - 1) / NLL_THREADS);
+        // even split into ceil(cnt / threads) units
+        const int64_t per_unit = vgs_nll_threads();
+        int64_t n_u = std::max<int64_t>(1, (cnt + (diag_needed ? 1 : 0) + per_unit - 1) / per_unit);
         for (int64_t k = 0; k < n_u; ++k) {
             int64_t a = cnt * k / n_u, e = cnt * (k + 1) / n_u;
             NllUnit un;
@@ -281,11 +326,14 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
     p.seq_list = d_list;
     p.skip_none = skip_mode == VGS_SKIP_NONE;
     p.M = M; p.ld = ld;
+    if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
     if (!units[0].empty()) {
+        p.counter = h->d_counters;
         p.units = d_units; p.n_units = (int)units[0].size();
         if ((rc = launch_nll_tier<1>(h, p, mode, h->max_nll_bytes_t1, s))) return rc;
     }
     if (!units[1].empty()) {
+        p.counter = h->d_counters + 1;
         p.units = d_units + units[0].size(); p.n_units = (int)units[1].size();
         if ((rc = launch_nll_tier<2>(h, p, mode, h->max_nll_bytes_t2, s))) return rc;
     }
