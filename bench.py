@@ -319,7 +319,7 @@ def main():
     d2h = out_h.nbytes
 
     def load_all():
-        h.load_models_raw(n, host["off"], host["len"], host["code"], host["prob"])
+        h.load_models_raw(n, host["off"], host["len"], host["code"], host["prob"], skip_nll=(kind != "nll"))
         if seqs is not None:
             h.load_sequences_packed(host["words"], host["woff"], host["lens"])
 

@@ -55,7 +55,9 @@ struct vgs_context {
     int64_t n_models = 0, total_ctx = 0;
     std::vector<int64_t> h_ctx_off;
     std::vector<ModelMeta> h_meta;
-    std::vector<double> h_logp;
+    double *h_logp = nullptr;   // pinned staging of the host-computed ln p table
+    int64_t h_logp_cap = 0;
+    bool nll_ready = false;     // false when loaded with VGS_LOAD_SKIP_NLL
     int max_order = 0;
     int64_t max_nll_bytes_t1 = 0, max_nll_bytes_t2 = 0;
     int64_t max_pair_bytes = 0;  // hash + fp32 rows of the largest model

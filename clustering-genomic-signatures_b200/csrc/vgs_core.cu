@@ -130,6 +130,7 @@ extern "C" int vgs_destroy(vgs_handle h) {
     cudaFree(h->d_scratch);
     cudaFree(h->d_scratch2);
     cudaFree(h->d_err);
+    if (h->h_logp) cudaFreeHost(h->h_logp);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return VGS_OK;
@@ -307,6 +308,11 @@ static int log2_ceil_pow2(int64_t v, int64_t *cap_out) {
 
 extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h, const uint8_t *ctx_len_h,
                                const uint32_t *ctx_code_h, const double *prob_h, const double *logp_h) {
+    return vgs_load_models_ex(h, n_models, ctx_offsets_h, ctx_len_h, ctx_code_h, prob_h, logp_h, 0);
+}
+
+extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h, const uint8_t *ctx_len_h,
+                                  const uint32_t *ctx_code_h, const double *prob_h, const double *logp_h, int flags) {
     VGS_CHECK_ARG(h, "null handle");
     VGS_CHECK_ARG(n_models > 0 && ctx_offsets_h && ctx_len_h && ctx_code_h && prob_h, "vgs_load_models: null/empty input");
     VGS_CUDA(cudaSetDevice(h->device));
@@ -380,32 +386,6 @@ extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ct
         nll_bytes += ((int64_t)mm.nll_bytes + 255) / 256 * 256;
     }
 
-    // host: ln p with libm (bit-identical to CPython's math.log on this host), threaded
-    h->h_logp.resize((size_t)total * 4);
-    if (logp_h) {
-        memcpy(h->h_logp.data(), logp_h, sizeof(double) * (size_t)total * 4);
-    } else {
-        for (int64_t i = 0; i < total * 4; ++i)
-            if (prob_h[i] < 0) {
-                vgs_set_error("math domain error: negative transition probability (entry %lld)", (long long)i);
-                return VGS_ERR_INVALID;
-            }
-        unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-        if (total * 4 < 200000) nt = 1;
-        std::vector<std::thread> th;
-        double *out = h->h_logp.data();
-        for (unsigned t = 0; t < nt; ++t) {
-            int64_t b = total * 4 * t / nt, e = total * 4 * (t + 1) / nt;
-            th.emplace_back([=]() {
-                for (int64_t i = b; i < e; ++i) {
-                    double p = prob_h[i];
-                    out[i] = (p == 0) ? -1000.0 : log(p);
-                }
-            });
-        }
-        for (auto &x : th) x.join();
-    }
-
     int rc;
     if ((rc = vgs_reserve(h, &h->d_meta, n_models))) return rc;
     if ((rc = vgs_reserve(h, &h->d_key, total))) return rc;
@@ -413,40 +393,26 @@ extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ct
     if ((rc = vgs_reserve(h, &h->d_code, total))) return rc;
     if ((rc = vgs_reserve(h, &h->d_prob32, total))) return rc;
     if ((rc = vgs_reserve(h, &h->d_prob64, total * 4))) return rc;
-    if ((rc = vgs_reserve(h, &h->d_logp, total * 4))) return rc;
     if ((rc = vgs_reserve(h, &h->d_hash, hash_slots))) return rc;
-    if ((rc = vgs_reserve(h, &h->d_nll, nll_bytes))) return rc;
     h->hash_slots = hash_slots;
     h->nll_bytes = nll_bytes;
     h->n_models = n_models;
     h->total_ctx = total;
+    const bool want_nll = !(flags & VGS_LOAD_SKIP_NLL);
+    h->nll_ready = false;
 
+    // 1. upload what the caller gave us (asynchronous when its buffers are pinned) and build everything that
+    //    does not need ln p: keys, fp32 rows, hashes, universe maps
     cudaStream_t s = h->own_stream;
     VGS_CUDA(cudaMemcpyAsync(h->d_meta, h->h_meta.data(), sizeof(ModelMeta) * (size_t)n_models, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemcpyAsync(h->d_len, ctx_len_h, (size_t)total, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemcpyAsync(h->d_code, ctx_code_h, sizeof(uint32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemcpyAsync(h->d_prob64, prob_h, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
-    VGS_CUDA(cudaMemcpyAsync(h->d_logp, h->h_logp.data(), sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemsetAsync(h->d_hash, 0, sizeof(uint2) * (size_t)hash_slots, s));
-    VGS_CUDA(cudaMemsetAsync(h->d_nll, 0, (size_t)nll_bytes, s));
-
     k_build_keys<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(total, h->d_len, h->d_code, h->d_prob64, h->d_key, h->d_prob32);
     VGS_LAUNCH_CHECK(h);
     k_build_hash<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_key, h->d_hash);
     VGS_LAUNCH_CHECK(h);
-    if (h->max_nll_bytes_t1 > 0) {
-        // grid.x covers up to 4^6 histories with 256-thread blocks
-        dim3 grid(16, (unsigned)std::min<int64_t>(n_models, 65535));
-        for (int64_t m0 = 0; m0 < n_models; m0 += 65535) {
-            grid.y = (unsigned)std::min<int64_t>(n_models - m0, 65535);
-            k_build_dense<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->d_logp, h->d_nll);
-            VGS_LAUNCH_CHECK(h);
-        }
-    }
-    if (h->max_nll_bytes_t2 > 0) {
-        k_build_two_level<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_hash, h->d_key, h->d_len, h->d_code, h->d_logp, h->d_nll);
-        VGS_LAUNCH_CHECK(h);
-    }
     if (h->max_order <= VGS_UMAP_MAX_ORDER && h->max_n_ctx < 0x7FFF) {
         const int64_t total_u = ((((int64_t)1) << (2 * (h->max_order + 1))) - 1) / 3;
         const int64_t stride = (total_u + 7) / 8 * 8;
@@ -460,6 +426,74 @@ extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ct
             h->umap_stride = stride;
         }
     }
+    if (!want_nll) {
+        // negative probabilities are still rejected (the reference fails on them at scoring time)
+        for (int64_t i = 0; i < total * 4; ++i)
+            if (prob_h[i] < 0) {
+                cudaStreamSynchronize(s);
+                vgs_set_error("math domain error: negative transition probability (entry %lld)", (long long)i);
+                return VGS_ERR_INVALID;
+            }
+        VGS_CUDA(cudaStreamSynchronize(s));
+        return VGS_OK;
+    }
+
+    // 2. meanwhile on the host: ln p with libm (bit-identical to CPython's math.log on this host), threaded,
+    //    into a pinned staging buffer
+    if (h->h_logp_cap < total * 4) {
+        if (h->h_logp) cudaFreeHost(h->h_logp);
+        h->h_logp = nullptr;
+        h->h_logp_cap = 0;
+        VGS_CUDA(cudaHostAlloc((void **)&h->h_logp, sizeof(double) * (size_t)total * 4, cudaHostAllocDefault));
+        h->h_logp_cap = total * 4;
+    }
+    if (logp_h) {
+        memcpy(h->h_logp, logp_h, sizeof(double) * (size_t)total * 4);
+    } else {
+        unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        if (total * 4 < 200000) nt = 1;
+        std::vector<std::thread> th;
+        double *out = h->h_logp;
+        std::vector<int64_t> bad(nt, -1);
+        for (unsigned t = 0; t < nt; ++t) {
+            int64_t b0 = total * 4 * t / nt, e0 = total * 4 * (t + 1) / nt;
+            int64_t *badp = &bad[t];
+            th.emplace_back([=]() {
+                for (int64_t i = b0; i < e0; ++i) {
+                    double p = prob_h[i];
+                    if (p < 0 && *badp < 0) *badp = i;
+                    out[i] = (p == 0) ? -1000.0 : log(p);
+                }
+            });
+        }
+        for (auto &x : th) x.join();
+        for (unsigned t = 0; t < nt; ++t)
+            if (bad[t] >= 0) {
+                cudaStreamSynchronize(s);
+                vgs_set_error("math domain error: negative transition probability (entry %lld)", (long long)bad[t]);
+                return VGS_ERR_INVALID;
+            }
+    }
+
+    // 3. upload ln p and build the NLL tables
+    if ((rc = vgs_reserve(h, &h->d_logp, total * 4))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_nll, nll_bytes))) return rc;
+    VGS_CUDA(cudaMemcpyAsync(h->d_logp, h->h_logp, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    if (h->max_nll_bytes_t2 > 0) VGS_CUDA(cudaMemsetAsync(h->d_nll, 0, (size_t)nll_bytes, s));  // deep hashes start empty
+    if (h->max_nll_bytes_t1 > 0) {
+        // grid.x covers up to 4^6 histories with 256-thread blocks
+        dim3 grid(16, (unsigned)std::min<int64_t>(n_models, 65535));
+        for (int64_t m0 = 0; m0 < n_models; m0 += 65535) {
+            grid.y = (unsigned)std::min<int64_t>(n_models - m0, 65535);
+            k_build_dense<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->d_logp, h->d_nll);
+            VGS_LAUNCH_CHECK(h);
+        }
+    }
+    if (h->max_nll_bytes_t2 > 0) {
+        k_build_two_level<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_hash, h->d_key, h->d_len, h->d_code, h->d_logp, h->d_nll);
+        VGS_LAUNCH_CHECK(h);
+    }
+    h->nll_ready = true;
     VGS_CUDA(cudaStreamSynchronize(s));
     return VGS_OK;
 }
@@ -482,6 +516,7 @@ extern "C" int vgs_model_info(vgs_handle h, int64_t model, int *order, int64_t *
 
 extern "C" int vgs_get_logp(vgs_handle h, double *logp_out_h) {
     VGS_CHECK_ARG(h && logp_out_h && h->n_models > 0, "vgs_get_logp: no models loaded");
+    VGS_CHECK_ARG(h->nll_ready, "vgs_get_logp: models were loaded with VGS_LOAD_SKIP_NLL");
     VGS_CUDA(cudaSetDevice(h->device));
     // read back from the device so the test sees what the kernels see
     VGS_CUDA(cudaMemcpy(logp_out_h, h->d_logp, sizeof(double) * (size_t)h->total_ctx * 4, cudaMemcpyDeviceToHost));

@@ -343,6 +343,7 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
 static int check_nll_ready(vgs_context *h) {
     VGS_CHECK_ARG(h, "null handle");
     VGS_CHECK_ARG(h->n_models > 0, "no models loaded (vgs_load_models)");
+    VGS_CHECK_ARG(h->nll_ready, "models were loaded with VGS_LOAD_SKIP_NLL: no NLL tables");
     VGS_CHECK_ARG(h->n_seq > 0, "no sequences loaded (vgs_load_sequences_* / vgs_sample_sequences)");
     return VGS_OK;
 }

@@ -24,6 +24,8 @@ class _DeviceDistance(object):
     """Shared batching / caching logic.  Subclasses implement
     ``_compute(handle, vlmcs, pair_only=False) -> (D32, D64)``."""
 
+    needs_nll_tables = False   # only NegativeLogLikelihood needs ln p and the NLL tables on the device
+
     def __init__(self):
         self._index = None     # id(vlmc) -> row
         self._names = None     # name -> row (the reference's equality is by name, vlmc.pyx:27-31)
@@ -40,7 +42,7 @@ class _DeviceDistance(object):
         vlmcs = list(vlmcs)
         h = native.Handle(_default_device() if self.device is None else self.device)
         try:
-            h.load_models(vlmcs_to_flat(vlmcs))
+            h.load_models(vlmcs_to_flat(vlmcs), skip_nll=not self.needs_nll_tables)
             D32, D64 = self._compute(h, vlmcs)
         finally:
             h.close()
@@ -70,7 +72,7 @@ class _DeviceDistance(object):
         pair = [left_vlmc, right_vlmc]
         h = native.Handle(_default_device() if self.device is None else self.device)
         try:
-            h.load_models(vlmcs_to_flat(pair))
+            h.load_models(vlmcs_to_flat(pair), skip_nll=not self.needs_nll_tables)
             D32, D64 = self._compute(h, pair, pair_only=True)
         finally:
             h.close()
@@ -88,6 +90,7 @@ class NegativeLogLikelihood(_DeviceDistance):
     S_x of L symbols sampled from x (cached on the model), src/distance/negloglikelihood.pyx:17-26."""
 
     length_of_pregenerated_sequence = 500  # src/distance/negloglikelihood.pyx:12
+    needs_nll_tables = True
 
     def __init__(self, sequence_length, mode="sequential"):
         super().__init__()

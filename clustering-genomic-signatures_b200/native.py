@@ -32,6 +32,7 @@ SIGNATURES = [
     ("vgs_profile_enable", c_int, [c_vp, c_int]),
     ("vgs_profile_read", c_int, [c_vp, c_int, _P(ctypes.c_double), _P(c_i64)]),
     ("vgs_load_models", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    ("vgs_load_models_ex", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]),
     ("vgs_model_count", c_int, [c_vp, _P(c_i64), _P(c_i64)]),
     ("vgs_model_info", c_int, [c_vp, c_i64, _P(c_int), _P(c_i64), _P(c_int)]),
     ("vgs_get_logp", c_int, [c_vp, c_vp]),
@@ -161,19 +162,21 @@ class Handle:
         _check(lib().vgs_poll_error(self._h, c_vp(stream)))
 
     # ---- models
-    def load_models(self, fm, logp=None):
+    def load_models(self, fm, logp=None, skip_nll=False):
         off = np.ascontiguousarray(fm.ctx_offsets, dtype=np.int64)
         ln = np.ascontiguousarray(fm.ctx_len, dtype=np.uint8)
         code = np.ascontiguousarray(fm.ctx_code, dtype=np.uint32)
         prob = np.ascontiguousarray(fm.prob, dtype=np.float64)
         lp = None if logp is None else np.ascontiguousarray(logp, dtype=np.float64)
-        _check(lib().vgs_load_models(self._h, fm.n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), _np_ptr(lp)))
+        _check(lib().vgs_load_models_ex(self._h, fm.n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), _np_ptr(lp),
+                                        1 if skip_nll else 0))
         self.n_models = fm.n_models
         self.total_contexts = fm.total_contexts
 
-    def load_models_raw(self, n_models, off, ln, code, prob):
+    def load_models_raw(self, n_models, off, ln, code, prob, skip_nll=False):
         """Same as load_models but from already-contiguous (e.g. pinned) arrays; no conversions."""
-        _check(lib().vgs_load_models(self._h, n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), None))
+        _check(lib().vgs_load_models_ex(self._h, n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), None,
+                                        1 if skip_nll else 0))
         self.n_models = n_models
         self.total_contexts = int(off[-1])
 

@@ -88,6 +88,11 @@ int vgs_profile_read(vgs_handle h, int kernel_id, double *total_ms, int64_t *lau
  *      longest-suffix maps and the fp32 rows. ---------------------------------------------------- */
 int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h, const uint8_t *ctx_len_h,
                     const uint32_t *ctx_code_h, const double *prob_h, const double *logp_h /* nullable */);
+/* same, with flags: VGS_LOAD_SKIP_NLL skips ln p and the NLL tables (enough for Frobenius / Projection /
+ * Estimate / sampling / lookups; the vgs_nll_* entry points then return VGS_ERR_INVALID) */
+#define VGS_LOAD_SKIP_NLL 1
+int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h, const uint8_t *ctx_len_h,
+                       const uint32_t *ctx_code_h, const double *prob_h, const double *logp_h /* nullable */, int flags);
 int vgs_model_count(vgs_handle h, int64_t *n_models, int64_t *total_contexts);
 /* order (src/vlmc/vlmc.pyx:179-180), number of contexts and NLL table tier of one model */
 int vgs_model_info(vgs_handle h, int64_t model, int *order, int64_t *n_ctx, int *tier);
