@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--workload", default="nll", choices=sorted(WORKLOADS))
     ap.add_argument("--n-models", type=int, default=0)
     ap.add_argument("--seq-len", type=int, default=0)
-    ap.add_argument("--mode", default="sequential", choices=["sequential", "warp"])
+    ap.add_argument("--mode", default="sequential", choices=["sequential", "warp", "kmer"])
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="models in the CPU-baseline sample")
@@ -328,6 +328,8 @@ def main():
     D32 = torch.empty((n, n), dtype=torch.float32, device=dev)
     symmetric = kind != "estimate"
     tile = args.tile or (32 if n <= 1024 else 64 if n <= 4096 else 128)
+    if kind == "nll" and args.mode == "kmer":
+        tile = max(128, tile // 128 * 128)
     if world > 1:
         nt, slots = native.tile_plan(n, tile, world, symmetric)
         payload = torch.zeros(slots * tile * tile, dtype=torch.float32, device=dev)

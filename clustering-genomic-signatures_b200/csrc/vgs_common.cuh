@@ -99,6 +99,9 @@ struct vgs_context {
     // buffers are reused across vgs_load_* calls and only re-allocated when they must grow
     std::map<void *, int64_t> caps;
     int *d_counters = nullptr;  // dynamic-scheduler counters
+    // k-mer contraction mode (vgs_kmer.cu)
+    double *d_kmer_T = nullptr, *d_kmer_C = nullptr, *d_kmer_partial = nullptr;
+    bool kmer_tables_ready = false, kmer_counts_ready = false, kmer_has_nan = false;
     float *d_out32 = nullptr;   // staging for the *_h entry points
     double *d_out64 = nullptr;
 
@@ -196,6 +199,9 @@ void vgs_tile_coords(const TilePlan &p, int64_t k, int64_t *I, int64_t *J);
 int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &seq_lists_per_block, int64_t block,
                         int64_t m_begin, int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld,
                         cudaStream_t s);
+bool vgs_kmer_applicable(vgs_context *h);
+// returns VGS_OK, an error, or -1 when the set needs the scan kernel (a model without a root context)
+int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, double *M, int64_t ld, cudaStream_t s);
 int vgs_assemble_impl(vgs_context *h, const TilePlan &p, const float *gathered32, const double *gathered64,
                       float *D32, double *D64, cudaStream_t s);
 

@@ -111,8 +111,8 @@ extern "C" int vgs_create(int device, vgs_handle *out) {
 }
 
 // the device buffers stay allocated (grow-only, vgs_reserve); only the logical contents are dropped
-static void free_models(vgs_context *h) { h->n_models = 0; h->total_ctx = 0; }
-static void free_sequences(vgs_context *h) { h->n_seq = 0; h->total_symbols = 0; h->total_words = 0; }
+static void free_models(vgs_context *h) { h->n_models = 0; h->total_ctx = 0; h->kmer_tables_ready = false; }
+static void free_sequences(vgs_context *h) { h->n_seq = 0; h->total_symbols = 0; h->total_words = 0; h->kmer_counts_ready = false; }
 static void free_all_buffers(vgs_context *h) {
     for (auto &kv : h->caps) {
         void **p = (void **)kv.first;

@@ -1,0 +1,328 @@
+// vgs_kmer.cu -- NLL "k-mer contraction" mode (VGS_NLL_KMER): the score matrix as an fp64 contraction.
+//
+// Same quantity as K2 (src/vlmc/vlmc.pyx:79-101): M[s][m] = sum_{t >= order_m} f(p_m(S_s[t] | history)).
+// With D = the largest order of the set, every term with t >= D depends on S_s only through the (D+1)-mer
+// ending at t, so
+//
+//     M[s][m] = sum_k  C[s][k] * T[m][k]  +  head(s, m)
+//
+//   C[s][k]  number of positions t >= D of sequence s whose (D+1)-mer is k      -- one histogram per sequence,
+//                                                                                  reused for EVERY model
+//   T[m][k]  = logp_m[longest_suffix_m(history of k)][symbol of k]               -- the tier-1 dense table at depth D
+//   head     the terms t in [order_m, D) of models shallower than D              -- a few direct look-ups
+//
+// The scan kernel performs L random 8-byte shared-memory gathers per (s, m); it is bound by shared-memory
+// bank conflicts (6.4 wavefronts per warp-wide LDS.64, profiles/).  The contraction replaces them by
+// 4^(D+1) fused multiply-adds per (s, m) from conflict-free operand tiles, which is cheaper on B200 whenever
+// 4^(D+1) is below ~10 L (64 fp64 FMA lanes per SM vs ~4.6 gathers per SM per clock).  It is an fp64 CUDA-core
+// kernel: the counts are exact small integers but ln p needs all 53 bits, so no tensor-core format applies.
+// Summation order differs from the reference's left-to-right order (parity: <= 1e-12 relative on scores);
+// the bit-exact path remains VGS_NLL_SEQUENTIAL.
+#include <algorithm>
+
+#include "vgs_common.cuh"
+
+#define KG_BLOCK 128   // scores per CTA tile edge (sequences x models)
+#define KG_BK 8        // k-mers per shared-memory stage
+#define KG_THREADS 256 // 16 x 16 threads, 8 x 8 scores each
+
+// ---- uniform-depth dense tables: Tu[m][k], NaN (no matching context) replaced by 0 and flagged ------------
+__global__ void k_kmer_tables(const ModelMeta *__restrict__ meta, const uint2 *__restrict__ hash, const double *__restrict__ logp,
+                              int depth, double *__restrict__ Tu, int *__restrict__ nan_flag) {
+    const ModelMeta mm = meta[blockIdx.y];
+    const uint32_t n_hist = 1u << (2 * depth);
+    const uint2 *slots = hash + mm.hash_off;
+    double *out = Tu + (int64_t)blockIdx.y * 4 * n_hist;
+    for (uint32_t hc = blockIdx.x * blockDim.x + threadIdx.x; hc < n_hist; hc += gridDim.x * blockDim.x) {
+        const int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, hc, depth);
+        double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (id >= 0) {
+            const double *r = logp + 4 * (mm.ctx_off + id);
+            v = make_double4(r[0], r[1], r[2], r[3]);
+        } else {
+            atomicOr(nan_flag, 1);
+        }
+        double *o = out + 4 * (size_t)hc;
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+}
+
+// ---- per-sequence (D+1)-mer histogram, one CTA per sequence, shared-memory atomics -----------------------
+__global__ void k_kmer_hist(int depth, const uint32_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
+                            const int64_t *__restrict__ seq_len, double *__restrict__ C) {
+    extern __shared__ uint32_t hist[];
+    const int64_t s = blockIdx.x;
+    const int64_t K = (int64_t)1 << (2 * (depth + 1));
+    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0u;
+    __syncthreads();
+    const int64_t L = seq_len[s];
+    const uint32_t *w = seq + seq_off[s];
+    const uint32_t kmask = vgs_lowmask(depth + 1);
+    const int64_t span = (L + blockDim.x - 1) / blockDim.x;
+    const int64_t a = (int64_t)threadIdx.x * span, e = min(L, a + span);
+    if (a < e) {
+        int64_t t = max((int64_t)0, a - depth);
+        uint32_t code = 0;
+        for (; t < e; ++t) {
+            const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
+            code = ((code << 2) | x) & kmask;
+            if (t >= a && t >= depth) atomicAdd(&hist[code], 1u);
+        }
+    }
+    __syncthreads();
+    double *out = C + s * K;
+    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) out[k] = (double)hist[k];
+}
+
+// ---- fp64 contraction -----------------------------------------------------------------------------------
+struct KgUnit {
+    int32_t sb, mb;      // 128-blocks of sequences / models
+    int32_t k0, k1;      // k range [k0, k1), multiples of KG_BK
+    int32_t slot;        // partial-sum slot (block pair index * split + split index)
+};
+
+struct KgParams {
+    const double *C;     // [n_seq][K]
+    const double *Tu;    // [n_models][K]
+    const KgUnit *units;
+    int n_units;
+    int64_t K, n_seq, n_models;
+    double *partial;     // [slots][128][128]
+    int *counter;
+};
+
+__global__ void __launch_bounds__(KG_THREADS, 1) k_kmer_gemm(const KgParams p) {
+    __shared__ __align__(16) double As[2][KG_BK][KG_BLOCK];
+    __shared__ __align__(16) double Bs[2][KG_BK][KG_BLOCK];
+    __shared__ int s_unit;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;            // 16 x 16 thread grid
+    // global -> shared loader: thread t moves KG_BK/2 consecutive k of one row of each operand
+    const int lrow = tid & 127, lk = (tid >> 7) * (KG_BK / 2);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_unit = atomicAdd(p.counter, 1);
+        __syncthreads();
+        const int u = s_unit;
+        if (u >= p.n_units) break;
+        const KgUnit un = p.units[u];
+        const int64_t srow = (int64_t)un.sb * KG_BLOCK + lrow, mrow = (int64_t)un.mb * KG_BLOCK + lrow;
+        const bool s_ok = srow < p.n_seq, m_ok = mrow < p.n_models;
+        const double *ga = p.C + (s_ok ? srow : 0) * p.K + lk;
+        const double *gb = p.Tu + (m_ok ? mrow : 0) * p.K + lk;
+        double acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+        double2 ra[KG_BK / 4], rb[KG_BK / 4];
+        // prologue: first stage
+        {
+            const int k = un.k0;
+#pragma unroll
+            for (int q = 0; q < KG_BK / 4; ++q) {
+                ra[q] = s_ok ? __ldg((const double2 *)(ga + k) + q) : make_double2(0.0, 0.0);
+                rb[q] = m_ok ? __ldg((const double2 *)(gb + k) + q) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int q = 0; q < KG_BK / 4; ++q) {
+                As[0][lk + 2 * q][lrow] = ra[q].x; As[0][lk + 2 * q + 1][lrow] = ra[q].y;
+                Bs[0][lk + 2 * q][lrow] = rb[q].x; Bs[0][lk + 2 * q + 1][lrow] = rb[q].y;
+            }
+        }
+        __syncthreads();
+        int buf = 0;
+        for (int k = un.k0; k < un.k1; k += KG_BK) {
+            const bool more = k + KG_BK < un.k1;
+            if (more) {
+#pragma unroll
+                for (int q = 0; q < KG_BK / 4; ++q) {
+                    ra[q] = s_ok ? __ldg((const double2 *)(ga + k + KG_BK) + q) : make_double2(0.0, 0.0);
+                    rb[q] = m_ok ? __ldg((const double2 *)(gb + k + KG_BK) + q) : make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < KG_BK; ++kk) {
+                // thread (ty, tx) owns rows {16 i2 + 2 ty + r} and columns {16 j2 + 2 tx + r}: every 128-bit shared
+                // load of a quarter-warp covers 128 contiguous bytes (no bank conflicts)
+                double a[8], b[8];
+#pragma unroll
+                for (int i2 = 0; i2 < 4; ++i2) {
+                    const double2 v = *(const double2 *)&As[buf][kk][16 * i2 + 2 * ty];
+                    a[2 * i2] = v.x; a[2 * i2 + 1] = v.y;
+                    const double2 w = *(const double2 *)&Bs[buf][kk][16 * i2 + 2 * tx];
+                    b[2 * i2] = w.x; b[2 * i2 + 1] = w.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = __fma_rn(a[i], b[j], acc[i][j]);
+            }
+            if (more) {
+#pragma unroll
+                for (int q = 0; q < KG_BK / 4; ++q) {
+                    As[buf ^ 1][lk + 2 * q][lrow] = ra[q].x; As[buf ^ 1][lk + 2 * q + 1][lrow] = ra[q].y;
+                    Bs[buf ^ 1][lk + 2 * q][lrow] = rb[q].x; Bs[buf ^ 1][lk + 2 * q + 1][lrow] = rb[q].y;
+                }
+            }
+            __syncthreads();
+            buf ^= 1;
+        }
+        double *out = p.partial + (int64_t)un.slot * KG_BLOCK * KG_BLOCK;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 16 * (i >> 1) + 2 * ty + (i & 1);
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) {
+                const int c = 16 * j2 + 2 * tx;
+                *(double2 *)&out[r * KG_BLOCK + c] = make_double2(acc[i][2 * j2], acc[i][2 * j2 + 1]);
+            }
+        }
+    }
+}
+
+// ---- epilogue: fixed-order sum of the k-splits + head terms of models shallower than D ---------------------
+struct KgEpi {
+    const double *partial;
+    const int32_t *pairs;   // [n_pairs][2] (sb, mb)
+    int n_pairs, split, depth;
+    const ModelMeta *meta;
+    const uint8_t *arena;   // per-model tier-1 tables (their own order)
+    const uint32_t *seq;
+    const int64_t *seq_off, *seq_len;
+    int64_t n_seq, n_models, ld;
+    double *M;
+};
+
+__global__ void k_kmer_epilogue(const KgEpi p) {
+    const int pair = blockIdx.x;
+    const int sb = p.pairs[2 * pair], mb = p.pairs[2 * pair + 1];
+    for (int e = threadIdx.x; e < KG_BLOCK * KG_BLOCK; e += blockDim.x) {
+        const int r = e / KG_BLOCK, c = e % KG_BLOCK;
+        const int64_t s = (int64_t)sb * KG_BLOCK + r, m = (int64_t)mb * KG_BLOCK + c;
+        if (s >= p.n_seq || m >= p.n_models) continue;
+        double v = 0.0;
+        for (int q = 0; q < p.split; ++q) v += p.partial[((int64_t)pair * p.split + q) * KG_BLOCK * KG_BLOCK + e];
+        const ModelMeta mm = p.meta[m];
+        if (mm.order < p.depth) {
+            const double *tab = (const double *)(p.arena + mm.nll_off);
+            const uint32_t fmask = vgs_lowmask(mm.order + 1);
+            const uint32_t *w = p.seq + p.seq_off[s];
+            const int64_t L = p.seq_len[s];
+            const int64_t top = L < p.depth ? L : p.depth;
+            uint32_t code = 0;
+            double head = 0.0;
+            for (int64_t t = 0; t < top; ++t) {
+                const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
+                code = (code << 2) | x;
+                if (t >= mm.order) head += tab[code & fmask];
+            }
+            v = head + v;
+        }
+        p.M[s * p.ld + m] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------------
+bool vgs_kmer_applicable(vgs_context *h) {
+    if (h->max_nll_bytes_t2 > 0 || h->max_order > VGS_DENSE_MAX_ORDER) return false;
+    return true;
+}
+
+static int ensure_kmer_tables(vgs_context *h, cudaStream_t s) {
+    const int D = h->max_order;
+    const int64_t K = (int64_t)1 << (2 * (D + 1));
+    if (h->kmer_tables_ready) return VGS_OK;
+    int rc;
+    if ((rc = vgs_reserve(h, &h->d_kmer_T, h->n_models * K))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
+    VGS_CUDA(cudaMemsetAsync(h->d_counters + 8, 0, sizeof(int), s));
+    const uint32_t n_hist = 1u << (2 * D);
+    for (int64_t m0 = 0; m0 < h->n_models; m0 += 65535) {
+        dim3 grid((unsigned)std::min<uint32_t>((n_hist + 255) / 256, 16), (unsigned)std::min<int64_t>(h->n_models - m0, 65535));
+        k_kmer_tables<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->d_logp, D, h->d_kmer_T + m0 * K, h->d_counters + 8);
+        VGS_LAUNCH_CHECK(h);
+    }
+    int flag = 0;
+    VGS_CUDA(cudaMemcpyAsync(&flag, h->d_counters + 8, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGS_CUDA(cudaStreamSynchronize(s));
+    h->kmer_has_nan = flag != 0;
+    h->kmer_tables_ready = true;
+    return VGS_OK;
+}
+
+// scores for the needed (sequence-block, model-block) pairs at 128-granularity; need[sb * nb_m + mb] != 0
+int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, double *M, int64_t ld, cudaStream_t s) {
+    int rc = ensure_kmer_tables(h, s);
+    if (rc) return rc;
+    if (h->kmer_has_nan) return -1;  // caller falls back to the scan kernel
+    const int D = h->max_order;
+    const int64_t K = (int64_t)1 << (2 * (D + 1));
+    // 1. histograms (cached per sequence set)
+    if (!h->kmer_counts_ready) {
+        if ((rc = vgs_reserve(h, &h->d_kmer_C, h->n_seq * K))) return rc;
+        const int smem = (int)(K * 4);
+        VGS_CUDA(cudaFuncSetAttribute(k_kmer_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_kmer_hist<<<(unsigned)h->n_seq, 256, smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, h->d_kmer_C);
+        VGS_LAUNCH_CHECK(h);
+        h->kmer_counts_ready = true;
+    }
+    // 2. unit list
+    std::vector<int32_t> pairs;
+    for (int64_t sb = 0; sb < nb_s; ++sb)
+        for (int64_t mb = 0; mb < nb_m; ++mb)
+            if (need[(size_t)(sb * nb_m + mb)]) { pairs.push_back((int32_t)sb); pairs.push_back((int32_t)mb); }
+    const int n_pairs = (int)(pairs.size() / 2);
+    if (n_pairs == 0) return VGS_OK;
+    const int64_t ksteps = K / KG_BK;
+    // split K so that the number of units is a near-multiple of the SM count (one CTA per SM)
+    int split = 1;
+    {
+        double best = -1.0;
+        const int max_split = (int)std::min<int64_t>(16, ksteps);
+        for (int sp = 1; sp <= max_split; ++sp) {
+            const int64_t units = (int64_t)n_pairs * sp;
+            const int64_t rounds = (units + h->sm_count - 1) / h->sm_count;
+            double eff = (double)units / (double)(rounds * h->sm_count);
+            eff -= 0.004 * sp;  // partial-sum traffic
+            if (eff > best) { best = eff; split = sp; }
+        }
+    }
+    std::vector<KgUnit> units;
+    for (int pi = 0; pi < n_pairs; ++pi)
+        for (int q = 0; q < split; ++q) {
+            KgUnit un;
+            un.sb = pairs[2 * pi]; un.mb = pairs[2 * pi + 1];
+            un.k0 = (int32_t)(ksteps * q / split * KG_BK);
+            un.k1 = (int32_t)(ksteps * (q + 1) / split * KG_BK);
+            un.slot = pi * split + q;
+            units.push_back(un);
+        }
+    const int64_t part_elems = (int64_t)n_pairs * split * KG_BLOCK * KG_BLOCK;
+    if ((rc = vgs_reserve(h, &h->d_kmer_partial, part_elems))) return rc;
+    const int64_t meta_bytes = (int64_t)units.size() * sizeof(KgUnit) + pairs.size() * 4 + 256;
+    if ((rc = vgs_ensure_scratch2(h, meta_bytes))) return rc;
+    KgUnit *d_units = (KgUnit *)h->d_scratch2;
+    int32_t *d_pairs = (int32_t *)((char *)h->d_scratch2 + (units.size() * sizeof(KgUnit) + 127) / 128 * 128);
+    VGS_CUDA(cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(KgUnit), cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
+    VGS_CUDA(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(int), s));
+    KgParams p;
+    p.C = h->d_kmer_C; p.Tu = h->d_kmer_T; p.units = d_units; p.n_units = (int)units.size();
+    p.K = K; p.n_seq = h->n_seq; p.n_models = h->n_models; p.partial = h->d_kmer_partial; p.counter = h->d_counters + 2;
+    const int grid = std::min<int>((int)units.size(), h->sm_count);
+    vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
+    k_kmer_gemm<<<grid, KG_THREADS, 0, s>>>(p);
+    vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
+    VGS_LAUNCH_CHECK(h);
+    KgEpi e;
+    e.partial = h->d_kmer_partial; e.pairs = d_pairs; e.n_pairs = n_pairs; e.split = split; e.depth = D;
+    e.meta = h->d_meta; e.arena = h->d_nll; e.seq = h->d_seq; e.seq_off = h->d_seq_off; e.seq_len = h->d_seq_len;
+    e.n_seq = h->n_seq; e.n_models = h->n_models; e.ld = ld; e.M = M;
+    k_kmer_epilogue<<<n_pairs, 256, 0, s>>>(e);
+    VGS_LAUNCH_CHECK(h);
+    return VGS_OK;
+}

@@ -270,6 +270,7 @@ static int launch_nll_tier(vgs_context *h, const NllParams &p, int mode, int64_t
 // B*block .. min(n, (B+1)*block)-1); an empty outer vector means "all sequences, contiguous".
 int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &lists, int64_t block, int64_t m_begin,
                         int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld, cudaStream_t s) {
+    if (mode == VGS_NLL_KMER) mode = VGS_NLL_WARP;  // the scan kernels have two modes
     std::vector<NllUnit> units[2];
     std::vector<int32_t> flat;
     std::vector<int64_t> list_off(lists.size() + 1, 0);
@@ -355,10 +356,18 @@ extern "C" int vgs_nll_scores(vgs_handle h, int64_t s_begin, int64_t s_end, int6
     VGS_CHECK_ARG(0 <= s_begin && s_begin <= s_end && s_end <= h->n_seq, "vgs_nll_scores: bad sequence range");
     VGS_CHECK_ARG(0 <= m_begin && m_begin <= m_end && m_end <= h->n_models, "vgs_nll_scores: bad model range");
     VGS_CHECK_ARG(M_d && ld >= h->n_models, "vgs_nll_scores: bad output");
-    VGS_CHECK_ARG(mode == VGS_NLL_SEQUENTIAL || mode == VGS_NLL_WARP, "vgs_nll_scores: bad mode");
+    VGS_CHECK_ARG(mode >= VGS_NLL_SEQUENTIAL && mode <= VGS_NLL_KMER, "vgs_nll_scores: bad mode");
     VGS_CHECK_ARG(skip_mode == VGS_SKIP_ORDER || skip_mode == VGS_SKIP_NONE, "vgs_nll_scores: bad skip mode");
     VGS_CUDA(cudaSetDevice(h->device));
     if (s_begin == s_end || m_begin == m_end) return VGS_OK;
+    if (mode == VGS_NLL_KMER && skip_mode == VGS_SKIP_ORDER && vgs_kmer_applicable(h)) {
+        const int64_t nb_s = (h->n_seq + 127) / 128, nb_m = (h->n_models + 127) / 128;
+        std::vector<char> need((size_t)(nb_s * nb_m), 0);
+        for (int64_t sb = s_begin / 128; sb <= (s_end - 1) / 128; ++sb)
+            for (int64_t mb = m_begin / 128; mb <= (m_end - 1) / 128; ++mb) need[(size_t)(sb * nb_m + mb)] = 1;
+        rc = vgs_kmer_scores(h, need, nb_s, nb_m, M_d, ld, (cudaStream_t)stream);
+        if (rc != -1) return rc;
+    }
     std::vector<int32_t> seqs((size_t)(s_end - s_begin));
     for (int64_t i = s_begin; i < s_end; ++i) seqs[(size_t)(i - s_begin)] = (int32_t)i;
     std::vector<std::vector<int32_t>> lists(1, seqs);
@@ -375,8 +384,15 @@ extern "C" int vgs_nll_scores_h(vgs_handle h, int skip_mode, int mode, double *M
     std::vector<int32_t> all((size_t)h->n_seq);
     for (int64_t i = 0; i < h->n_seq; ++i) all[(size_t)i] = (int32_t)i;
     std::vector<std::vector<int32_t>> lists(1, all);
-    VGS_CHECK_ARG(mode == VGS_NLL_SEQUENTIAL || mode == VGS_NLL_WARP, "bad mode");
-    if ((rc = vgs_nll_score_lists(h, lists, h->n_models, 0, h->n_models, false, skip_mode, mode, h->d_M, h->n_models, s))) return rc;
+    VGS_CHECK_ARG(mode >= VGS_NLL_SEQUENTIAL && mode <= VGS_NLL_KMER, "bad mode");
+    rc = -1;
+    if (mode == VGS_NLL_KMER && skip_mode == VGS_SKIP_ORDER && vgs_kmer_applicable(h)) {
+        const int64_t nb_s = (h->n_seq + 127) / 128, nb_m = (h->n_models + 127) / 128;
+        std::vector<char> need((size_t)(nb_s * nb_m), 1);
+        rc = vgs_kmer_scores(h, need, nb_s, nb_m, h->d_M, h->n_models, s);
+        if (rc > 0) return rc;
+    }
+    if (rc == -1 && (rc = vgs_nll_score_lists(h, lists, h->n_models, 0, h->n_models, false, skip_mode, mode, h->d_M, h->n_models, s))) return rc;
     VGS_CUDA(cudaMemcpyAsync(M_out_h, h->d_M, 8 * (size_t)(h->n_seq * h->n_models), cudaMemcpyDeviceToHost, s));
     VGS_CUDA(cudaStreamSynchronize(s));
     return VGS_OK;
@@ -423,6 +439,32 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
                           cudaStream_t s) {
     int rc = vgs_ensure_M(h);
     if (rc) return rc;
+    if (mode == VGS_NLL_KMER && vgs_kmer_applicable(h) && pl.tile % 128 == 0) {
+        // needed (sequence-block, model-block) pairs at the contraction's 128 x 128 granularity; the diagonal
+        // scores M[i][i] of every touched row/column block ride along as diagonal blocks
+        const int64_t nb = (pl.n + 127) / 128, per = pl.tile / 128;
+        std::vector<char> need((size_t)(nb * nb), 0);
+        for (int64_t k = rank; k < pl.n_tiles; k += pl.world) {
+            int64_t I, J;
+            vgs_tile_coords(pl, k, &I, &J);
+            for (int64_t a = I * per; a < std::min(nb, (I + 1) * per); ++a)
+                for (int64_t b = J * per; b < std::min(nb, (J + 1) * per); ++b) {
+                    need[(size_t)(a * nb + b)] = 1;
+                    need[(size_t)(b * nb + a)] = 1;
+                    need[(size_t)(a * nb + a)] = 1;
+                    need[(size_t)(b * nb + b)] = 1;
+                }
+        }
+        rc = vgs_kmer_scores(h, need, nb, nb, h->d_M, h->n_models, s);
+        if (rc > 0) return rc;
+        if (rc == VGS_OK) {
+            if (pl.slots > 0) {
+                k_nll_combine<<<(unsigned)pl.slots, 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
+                VGS_LAUNCH_CHECK(h);
+            }
+            return VGS_OK;
+        }
+    }
     // which sequence blocks does this rank need against each model block?
     std::vector<std::vector<int32_t>> lists((size_t)pl.nt);
     std::vector<std::vector<char>> need((size_t)pl.nt, std::vector<char>((size_t)pl.nt, 0));
@@ -452,7 +494,8 @@ extern "C" int vgs_nll_tiles(vgs_handle h, int64_t length, int mode, int64_t til
     if (rc) return rc;
     VGS_CHECK_ARG(h->n_seq == h->n_models, "vgs_nll_tiles: need exactly one sequence per model (sequence i sampled from model i)");
     VGS_CHECK_ARG(length > 0 && tile > 0 && world > 0 && rank >= 0 && rank < world && payload_d, "vgs_nll_tiles: bad arguments");
-    VGS_CHECK_ARG(mode == VGS_NLL_SEQUENTIAL || mode == VGS_NLL_WARP, "vgs_nll_tiles: bad mode");
+    VGS_CHECK_ARG(mode >= VGS_NLL_SEQUENTIAL && mode <= VGS_NLL_KMER, "vgs_nll_tiles: bad mode");
+    VGS_CHECK_ARG(mode != VGS_NLL_KMER || tile % 128 == 0, "vgs_nll_tiles: the k-mer mode needs a tile edge that is a multiple of 128");
     VGS_CUDA(cudaSetDevice(h->device));
     TilePlan pl;
     vgs_make_plan(&pl, h->n_models, tile, world, 1);
@@ -466,11 +509,11 @@ extern "C" int vgs_nll_matrix(vgs_handle h, int64_t length, int mode, float *D32
     if (rc) return rc;
     VGS_CHECK_ARG(h->n_seq == h->n_models, "vgs_nll_matrix: need exactly one sequence per model (sequence i sampled from model i)");
     VGS_CHECK_ARG(length > 0 && D32_d, "vgs_nll_matrix: bad arguments");
-    VGS_CHECK_ARG(mode == VGS_NLL_SEQUENTIAL || mode == VGS_NLL_WARP, "vgs_nll_matrix: bad mode");
+    VGS_CHECK_ARG(mode >= VGS_NLL_SEQUENTIAL && mode <= VGS_NLL_KMER, "vgs_nll_matrix: bad mode");
     VGS_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     TilePlan pl;
-    vgs_make_plan(&pl, h->n_models, default_tile(h->n_models), 1, 1);
+    vgs_make_plan(&pl, h->n_models, mode == VGS_NLL_KMER ? 128 : default_tile(h->n_models), 1, 1);
     const int64_t pay_elems = pl.slots * pl.tile * pl.tile;
     if ((rc = vgs_ensure_scratch(h, pay_elems * (D64_d ? 12 : 4) + 256))) return rc;
     float *pay32 = (float *)h->d_scratch;

@@ -12,7 +12,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libvgs.so")
 
 PAIR_KINDS = {"frobenius_intersection": 0, "frobenius_union": 1, "projection": 2}
-NLL_MODES = {"sequential": 0, "warp": 1}
+NLL_MODES = {"sequential": 0, "warp": 1, "kmer": 2}
 SKIP_ORDER, SKIP_NONE = 0, 1
 
 _lib = None

@@ -187,6 +187,17 @@ def test_tiling_invariance_1_2_4_8_ranks(kind):
         for tile in (8, 16):
             out = MatrixJob(h, kind, n, length=L, tile=tile).run_emulated(world)
             assert torch.equal(out, base), (world, tile)
+    if kind == "nll":  # the contraction mode shards at 128-granularity
+        n2 = 300
+        fm2, _ = synthetic.make_family_models(n2, 32, 5, 100, 4)
+        seqs2 = synthetic.sample_sequences(fm2, 400, 6)
+        h2 = native.Handle(0)
+        h2.load_models(fm2)
+        h2.load_sequences_packed(*pack_sequences(seqs2))
+        base2 = MatrixJob(h2, "nll", n2, length=400, mode="kmer", tile=128).run().clone()
+        for world in (2, 4):
+            assert torch.equal(MatrixJob(h2, "nll", n2, length=400, mode="kmer", tile=128).run_emulated(world), base2)
+        assert np.allclose(base2.cpu().numpy(), c_oracle.COracle(fm2).nll_matrix(seqs2).astype(np.float32), rtol=2e-7, atol=0)
     co = c_oracle.COracle(fm)
     if kind == "nll":
         want = co.nll_matrix(seqs)
@@ -212,6 +223,10 @@ def test_full_size_properties():
     D32w, D64w = h.nll_matrix_h(10000, "warp")
     off = ~np.eye(1000, dtype=bool)
     assert np.max(np.abs(D64w[off] - D64[off]) / np.abs(D64[off])) < 1e-9
+    D32k, D64k = h.nll_matrix_h(10000, "kmer")
+    assert np.max(np.abs(D64k[off] - D64[off]) / np.abs(D64[off])) < 1e-9 and np.all(np.diag(D64k) == 0)
+    print("float32 entries that differ from the bit-exact mode: warp %d, kmer %d of %d" % (
+        int((D32w != D32).sum()), int((D32k != D32).sum()), D32.size))
     k = 40
     co = c_oracle.COracle(fm.subset(range(k)))
     M = h.nll_scores_h(native.SKIP_ORDER, "sequential")

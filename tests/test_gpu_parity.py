@@ -205,12 +205,15 @@ def test_against_c_oracle_medium(n, depth, ctx, L):
     M_or = co.score_matrix(seqs)
     assert np.array_equal(h.nll_scores_h(native.SKIP_ORDER, "sequential"), M_or)
     assert rel_err(h.nll_scores_h(native.SKIP_ORDER, "warp"), M_or) < 1e-12
+    assert rel_err(h.nll_scores_h(native.SKIP_ORDER, "kmer"), M_or) < 1e-12  # contraction (depth <= 6) or its fallback
     D_or = co.nll_from_scores(M_or, L)
     D32, D64 = h.nll_matrix_h(L, "sequential")
     assert np.array_equal(D64, D_or)
     assert np.array_equal(D32, D_or.astype(np.float32))
     D32w, D64w = h.nll_matrix_h(L, "warp")
     assert rel_err(D64w, D_or) < RTOL
+    D32k, D64k = h.nll_matrix_h(L, "kmer")
+    assert rel_err(D64k, D_or) < RTOL and np.all(np.diag(D64k) == 0) and np.array_equal(D64k, D64k.T)
     for kind, mode in (("frobenius_intersection", "intersection"), ("frobenius_union", "union"), ("projection", "projection")):
         D32, D64 = h.pair_matrix_h(kind)
         assert rel_err(D64, co.pair_matrix(mode)) < RTOL
@@ -224,3 +227,27 @@ def test_against_c_oracle_medium(n, depth, ctx, L):
         hs.load_sequences_packed(w2, o2, l2)
         D32, D64 = hs.estimate_matrix_h()
         assert rel_err(D64, c_oracle.COracle(sub).estimate_matrix(seqs[:k])) < RTOL
+
+
+def test_kmer_mode_mixed_orders_and_short_sequences():
+    """The contraction mode with models of different orders (head terms), ragged block edges and
+    sequences shorter than the deepest order."""
+    fa, _ = synthetic.make_family_models(70, 41, 6, 150, 5)
+    fb, _ = synthetic.make_family_models(40, 42, 3, 30, 4)
+    fc, _ = synthetic.make_family_models(25, 43, 1, 5, 2)
+    trees = [f.tree(m) for f in (fa, fb, fc) for m in range(f.n_models)]
+    order = np.random.default_rng(0).permutation(len(trees))
+    fm = FlatModels.from_trees([trees[i] for i in order])
+    assert sorted(set(fm.orders().tolist())) == [1, 3, 6]
+    for L in (700, 5):
+        seqs = synthetic.sample_sequences(fm, L, 8)
+        h = native.Handle(0)
+        h.load_models(fm)
+        h.load_sequences_packed(*pack_sequences(seqs))
+        co = c_oracle.COracle(fm)
+        M_or = co.score_matrix(seqs)
+        assert np.array_equal(h.nll_scores_h(native.SKIP_ORDER, "sequential"), M_or)
+        Mk = h.nll_scores_h(native.SKIP_ORDER, "kmer")
+        assert rel_err(Mk, M_or) < 1e-12
+        D32, D64 = h.nll_matrix_h(L, "kmer")
+        assert rel_err(D64, co.nll_from_scores(M_or, L)) < RTOL
