@@ -18,6 +18,8 @@
 // kernel: the counts are exact small integers but ln p needs all 53 bits, so no tensor-core format applies.
 // Summation order differs from the reference's left-to-right order (parity: <= 1e-12 relative on scores);
 // the bit-exact path remains VGS_NLL_SEQUENTIAL.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "vgs_common.cuh"
@@ -28,11 +30,11 @@
 
 // ---- uniform-depth dense tables: Tu[m][k], NaN (no matching context) replaced by 0 and flagged ------------
 __global__ void k_kmer_tables(const ModelMeta *__restrict__ meta, const uint2 *__restrict__ hash, const double *__restrict__ logp,
-                              int depth, double *__restrict__ Tu, int *__restrict__ nan_flag) {
+                              int depth, int64_t stride, double *__restrict__ Tu, int *__restrict__ nan_flag) {
     const ModelMeta mm = meta[blockIdx.y];
     const uint32_t n_hist = 1u << (2 * depth);
     const uint2 *slots = hash + mm.hash_off;
-    double *out = Tu + (int64_t)blockIdx.y * 4 * n_hist;
+    double *out = Tu + (int64_t)blockIdx.y * stride;
     for (uint32_t hc = blockIdx.x * blockDim.x + threadIdx.x; hc < n_hist; hc += gridDim.x * blockDim.x) {
         const int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, hc, depth);
         double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -49,7 +51,7 @@ __global__ void k_kmer_tables(const ModelMeta *__restrict__ meta, const uint2 *_
 
 // ---- per-sequence (D+1)-mer histogram, one CTA per sequence, shared-memory atomics -----------------------
 __global__ void k_kmer_hist(int depth, const uint32_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
-                            const int64_t *__restrict__ seq_len, double *__restrict__ C) {
+                            const int64_t *__restrict__ seq_len, int64_t stride, double *__restrict__ C) {
     extern __shared__ uint32_t hist[];
     const int64_t s = blockIdx.x;
     const int64_t K = (int64_t)1 << (2 * (depth + 1));
@@ -70,8 +72,8 @@ __global__ void k_kmer_hist(int depth, const uint32_t *__restrict__ seq, const i
         }
     }
     __syncthreads();
-    double *out = C + s * K;
-    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) out[k] = (double)hist[k];
+    double *out = C + s * stride;
+    for (int64_t k = threadIdx.x; k < stride; k += blockDim.x) out[k] = k < K ? (double)hist[k] : 0.0;
 }
 
 // ---- fp64 contraction -----------------------------------------------------------------------------------
@@ -181,6 +183,101 @@ __global__ void __launch_bounds__(KG_THREADS, 1) k_kmer_gemm(const KgParams p) {
     }
 }
 
+// ---- the same contraction on the fp64 tensor-core path (mma.sync m8n8k4 f64, SASS DMMA) ---------------------
+// The FMA kernel above needs 16 shared-memory doubles per 64 FMAs per lane and ends up L1/shared-bound (41 % of
+// the fp64 peak measured).  With 8x8x4 fp64 MMA tiles a warp computes a 64 x 32 block from 8 + 4 fragment loads
+// per k4-step (32 MMAs, 8192 FMAs): ~8x fewer shared-memory wavefronts per FMA.  Operand tiles keep the global
+// layout (row-major, k contiguous) in k4-slices [slice][row][4], so a half-warp fragment load is 128 contiguous
+// bytes (conflict free) and the global->shared copies are plain 16-byte cp.async (LDGSTS), 3 stages deep.
+#define KD_BK 16
+#define KD_STAGES 3
+#define KD_STAGE_DOUBLES (2 * KD_BK * KG_BLOCK)   // A tile + B tile of one stage
+
+__device__ __forceinline__ void vgs_dmma(double &d0, double &d1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void vgs_cp_async16(void *smem_dst, const void *gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vgs_smem_addr(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void vgs_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void vgs_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(KG_THREADS, 1) k_kmer_dmma(const KgParams p) {
+    extern __shared__ __align__(128) double dsm[];   // [KD_STAGES][A: 4 slices x 128 rows x 4 | B: same]
+    __shared__ int s_unit;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ws = (warp >> 2) * 64, wm = (warp & 3) * 32;   // warp tile origin: 64 sequences x 32 models
+    const int frow = lane >> 2, fk = lane & 3;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_unit = atomicAdd(p.counter, 1);
+        __syncthreads();
+        const int u = s_unit;
+        if (u >= p.n_units) break;
+        const KgUnit un = p.units[u];
+        const int n_steps = (un.k1 - un.k0) / KD_BK;
+
+        auto issue = [&](int step) {
+            double *st = dsm + (size_t)(step % KD_STAGES) * KD_STAGE_DOUBLES;
+            const int64_t k = (int64_t)un.k0 + (int64_t)step * KD_BK;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = tid + KG_THREADS * j;       // 1024 16-byte chunks per operand tile
+                const int row = c >> 3, ck = c & 7;       // chunk ck covers k = 2 ck, 2 ck + 1
+                const int dst = ((ck >> 1) * KG_BLOCK + row) * 4 + (ck & 1) * 2;
+                const int64_t srow = (int64_t)un.sb * KG_BLOCK + row, mrow = (int64_t)un.mb * KG_BLOCK + row;
+                const bool s_ok = srow < p.n_seq, m_ok = mrow < p.n_models;
+                vgs_cp_async16(st + dst, p.C + (s_ok ? srow : 0) * p.K + k + 2 * ck, s_ok ? 16 : 0);
+                vgs_cp_async16(st + KD_BK * KG_BLOCK + dst, p.Tu + (m_ok ? mrow : 0) * p.K + k + 2 * ck, m_ok ? 16 : 0);
+            }
+        };
+
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+#pragma unroll
+        for (int st = 0; st < KD_STAGES - 1; ++st) {
+            if (st < n_steps) issue(st);
+            vgs_cp_async_commit();
+        }
+        for (int step = 0; step < n_steps; ++step) {
+            vgs_cp_async_wait<KD_STAGES - 2>();
+            __syncthreads();
+            if (step + KD_STAGES - 1 < n_steps) issue(step + KD_STAGES - 1);
+            vgs_cp_async_commit();
+            const double *A = dsm + (size_t)(step % KD_STAGES) * KD_STAGE_DOUBLES;
+            const double *B = A + KD_BK * KG_BLOCK;
+#pragma unroll
+            for (int sl = 0; sl < KD_BK / 4; ++sl) {
+                double a[8], b[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = A[(sl * KG_BLOCK + ws + 8 * i + frow) * 4 + fk];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = B[(sl * KG_BLOCK + wm + 8 * j + frow) * 4 + fk];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) vgs_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        vgs_cp_async_wait<0>();
+        double *out = p.partial + (int64_t)un.slot * KG_BLOCK * KG_BLOCK;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = ws + 8 * i + frow, c = wm + 8 * j + 2 * fk;
+                *(double2 *)&out[r * KG_BLOCK + c] = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+    }
+}
+
 // ---- epilogue: fixed-order sum of the k-splits + head terms of models shallower than D ---------------------
 struct KgEpi {
     const double *partial;
@@ -233,16 +330,17 @@ bool vgs_kmer_applicable(vgs_context *h) {
 
 static int ensure_kmer_tables(vgs_context *h, cudaStream_t s) {
     const int D = h->max_order;
-    const int64_t K = (int64_t)1 << (2 * (D + 1));
+    const int64_t K = std::max<int64_t>(16, (int64_t)1 << (2 * (D + 1)));  // row stride, padded to one MMA k-stage
     if (h->kmer_tables_ready) return VGS_OK;
     int rc;
     if ((rc = vgs_reserve(h, &h->d_kmer_T, h->n_models * K))) return rc;
+    if (K != ((int64_t)1 << (2 * (D + 1)))) VGS_CUDA(cudaMemsetAsync(h->d_kmer_T, 0, sizeof(double) * (size_t)(h->n_models * K), s));
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
     VGS_CUDA(cudaMemsetAsync(h->d_counters + 8, 0, sizeof(int), s));
     const uint32_t n_hist = 1u << (2 * D);
     for (int64_t m0 = 0; m0 < h->n_models; m0 += 65535) {
         dim3 grid((unsigned)std::min<uint32_t>((n_hist + 255) / 256, 16), (unsigned)std::min<int64_t>(h->n_models - m0, 65535));
-        k_kmer_tables<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->d_logp, D, h->d_kmer_T + m0 * K, h->d_counters + 8);
+        k_kmer_tables<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->d_logp, D, K, h->d_kmer_T + m0 * K, h->d_counters + 8);
         VGS_LAUNCH_CHECK(h);
     }
     int flag = 0;
@@ -259,13 +357,13 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
     if (rc) return rc;
     if (h->kmer_has_nan) return -1;  // caller falls back to the scan kernel
     const int D = h->max_order;
-    const int64_t K = (int64_t)1 << (2 * (D + 1));
+    const int64_t K = std::max<int64_t>(16, (int64_t)1 << (2 * (D + 1)));
     // 1. histograms (cached per sequence set)
     if (!h->kmer_counts_ready) {
         if ((rc = vgs_reserve(h, &h->d_kmer_C, h->n_seq * K))) return rc;
-        const int smem = (int)(K * 4);
+        const int smem = (int)(((int64_t)1 << (2 * (D + 1))) * 4);
         VGS_CUDA(cudaFuncSetAttribute(k_kmer_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_kmer_hist<<<(unsigned)h->n_seq, 256, smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, h->d_kmer_C);
+        k_kmer_hist<<<(unsigned)h->n_seq, 256, smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K, h->d_kmer_C);
         VGS_LAUNCH_CHECK(h);
         h->kmer_counts_ready = true;
     }
@@ -276,27 +374,19 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
             if (need[(size_t)(sb * nb_m + mb)]) { pairs.push_back((int32_t)sb); pairs.push_back((int32_t)mb); }
     const int n_pairs = (int)(pairs.size() / 2);
     if (n_pairs == 0) return VGS_OK;
-    const int64_t ksteps = K / KG_BK;
-    // split K so that the number of units is a near-multiple of the SM count (one CTA per SM)
-    int split = 1;
-    {
-        double best = -1.0;
-        const int max_split = (int)std::min<int64_t>(16, ksteps);
-        for (int sp = 1; sp <= max_split; ++sp) {
-            const int64_t units = (int64_t)n_pairs * sp;
-            const int64_t rounds = (units + h->sm_count - 1) / h->sm_count;
-            double eff = (double)units / (double)(rounds * h->sm_count);
-            eff -= 0.004 * sp;  // partial-sum traffic
-            if (eff > best) { best = eff; split = sp; }
-        }
-    }
+    const int64_t ksteps = K / KD_BK;   // unit boundaries are multiples of 16 k-mers (one MMA stage; two FMA stages)
+    // split K so that the FULL problem (every block pair) gives >= ~8 units per SM.  The split depends only on the
+    // problem shape, never on which block pairs this call computes, so every entry is summed in the same order
+    // however the tile space is sharded (1/2/4/8-rank matrices stay bit-identical).
+    const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, ksteps),
+                                                                  (8 * 148 + nb_s * nb_m - 1) / (nb_s * nb_m)));
     std::vector<KgUnit> units;
     for (int pi = 0; pi < n_pairs; ++pi)
         for (int q = 0; q < split; ++q) {
             KgUnit un;
             un.sb = pairs[2 * pi]; un.mb = pairs[2 * pi + 1];
-            un.k0 = (int32_t)(ksteps * q / split * KG_BK);
-            un.k1 = (int32_t)(ksteps * (q + 1) / split * KG_BK);
+            un.k0 = (int32_t)(ksteps * q / split * KD_BK);
+            un.k1 = (int32_t)(ksteps * (q + 1) / split * KD_BK);
             un.slot = pi * split + q;
             units.push_back(un);
         }
@@ -314,8 +404,16 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
     p.C = h->d_kmer_C; p.Tu = h->d_kmer_T; p.units = d_units; p.n_units = (int)units.size();
     p.K = K; p.n_seq = h->n_seq; p.n_models = h->n_models; p.partial = h->d_kmer_partial; p.counter = h->d_counters + 2;
     const int grid = std::min<int>((int)units.size(), h->sm_count);
+    static int use_fma = -1;
+    if (use_fma < 0) { const char *e = getenv("VGS_KMER_GEMM"); use_fma = (e && e[0] == 'f') ? 1 : 0; }
     vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
-    k_kmer_gemm<<<grid, KG_THREADS, 0, s>>>(p);
+    if (use_fma) {
+        k_kmer_gemm<<<grid, KG_THREADS, 0, s>>>(p);
+    } else {
+        const int smem = KD_STAGES * KD_STAGE_DOUBLES * 8;
+        VGS_CUDA(cudaFuncSetAttribute(k_kmer_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_kmer_dmma<<<grid, KG_THREADS, smem, s>>>(p);
+    }
     vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
     VGS_LAUNCH_CHECK(h);
     KgEpi e;
