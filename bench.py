@@ -51,7 +51,10 @@ def parse_args():
     ap.add_argument("--workload", default="nll", choices=sorted(WORKLOADS))
     ap.add_argument("--n-models", type=int, default=0)
     ap.add_argument("--seq-len", type=int, default=0)
-    ap.add_argument("--mode", default="sequential", choices=["sequential", "warp", "kmer"])
+    ap.add_argument("--mode", default="kmer", choices=["sequential", "warp", "kmer"],
+                    help="NLL kernel: kmer = histogram + fp64 MMA contraction (<= 1e-9 rel.), sequential = bit-exact scan, "
+                         "warp = warp-per-pair scan")
+    ap.add_argument("--no-mode-sweep", action="store_true", help="skip the short timings of the other NLL modes")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="models in the CPU-baseline sample")
@@ -425,6 +428,24 @@ def main():
     # ---- end to end through the host-buffer C-ABI
     e2e_ms, _, _ = timed(e2e_step, max(3, args.steps // 4), 1, False)
 
+    sweep = None
+    if kind == "nll" and not args.no_mode_sweep:
+        # the other kernels of the same path, 3 timed steps each, for the record (not the headline)
+        sweep = {}
+        main_mode = args.mode
+        for mname in ("sequential", "warp", "kmer"):
+            if mname == main_mode:
+                sweep[mname] = ms_step
+                continue
+            args.mode = mname
+            if world > 1 and mname == "kmer" and tile % 128:
+                continue
+            try:
+                m_ms, _, _ = timed(device_step, 3, 1, True)
+                sweep[mname] = m_ms
+            except Exception as exc:  # e.g. tile not a multiple of 128 for kmer
+                sweep[mname] = "n/a: %s" % str(exc)[:60]
+        args.mode = main_mode
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -446,16 +467,26 @@ def main():
     achieved = alg_bytes_rank / launches_per_step / (k_avg_ms / 1000.0) / 1e9 if k_avg_ms > 0 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": (achieved / peak_gbs) if achieved else None, "traffic": None,
-                "kernel": {0: "k_nll_scores", 1: "k_pair_partials", 2: "k_est_pairs"}[prof_id],
+                "kernel": {0: "k_kmer_dmma" if (kind == "nll" and args.mode == "kmer") else "k_nll_scores",
+                           1: "k_pair_partials", 2: "k_est_pairs"}[prof_id],
                 "kernel_ms_per_launch": k_avg_ms, "kernel_launches_per_step": launches_per_step,
                 "kernel_share_of_step": (k_ms / args.steps) / ms_step if ms_step > 0 else None,
                 "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_formula": alg_desc, "peak_source": peak_src}
     # ncu dram bytes per launch of the dominant kernel, when a committed profile summary provides it
+    traffic_key = args.workload + ("_" + args.mode if kind == "nll" else "")
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            roofline["traffic"] = json.load(fh).get(args.workload)
+            roofline["traffic"] = json.load(fh).get(traffic_key)
     except Exception:
         pass
+    if kind == "nll" and args.mode == "kmer" and k_avg_ms > 0:
+        # the contraction is an fp64 MMA kernel: report it against the fp64 pipe as well
+        # (64 fp64 FMA lanes per SM: 2 * 64 * SMs * max SM clock)
+        flops = 2.0 * n * n * max(16.0, 4.0 ** (orders.max() + 1)) / world
+        peak64 = 2.0 * 64 * sm_count * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+        roofline["fp64"] = {"achieved_tflops": flops / (k_avg_ms / 1e3) / 1e12, "peak_tflops": peak64,
+                            "frac": flops / (k_avg_ms / 1e3) / 1e12 / peak64,
+                            "peak_source": "64 fp64 FMA lanes/SM x %d SMs x sm_max_mhz" % sm_count}
 
     line = {
         "metric": "pair-distances/sec", "value": pairs / (ms_step / 1000.0), "unit": unit, "n_gpus": world,
@@ -472,6 +503,8 @@ def main():
                 "includes": "vgs_load_models (H2D + host ln p + device table build), vgs_load_sequences_packed, kernels, D2H"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
     }
+    if sweep is not None:
+        line["config"]["ms_per_step_by_nll_mode"] = sweep
     if world == 1 and not args.no_cpu_baseline:
         sample_n = args.cpu_sample or {"nll": 24, "estimate": 6, "frobenius_union": 150, "projection": 150}.get(kind, 400)
         line["cpu_baseline"] = cpu_baseline(kind, fm, seqs, L, sample_n)
