@@ -56,6 +56,7 @@ SIGNATURES = [
     ("vgs_estimate_tiles", c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     ("vgs_assemble", c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     ("vgs_matrix_to_triples", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    ("vgs_average_link", c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, _P(c_i64)]),
 ]
 
 
@@ -277,6 +278,15 @@ class Handle:
 
     def assemble(self, n, tile, world, symmetric, gathered, D32, stream):
         _check(lib().vgs_assemble(self._h, n, tile, world, int(bool(symmetric)), _dev_ptr(gathered), _dev_ptr(D32), c_vp(stream)))
+
+    def average_link(self, D32, k):
+        """D32: torch CUDA float32 [n, n].  Returns (labels int32[n], merge distances float64[n - k])."""
+        n = int(D32.shape[0])
+        labels = np.zeros(n, dtype=np.int32)
+        merges = np.zeros(max(n - k, 1), dtype=np.float64)
+        m = c_i64()
+        _check(lib().vgs_average_link(self._h, n, _dev_ptr(D32), k, _np_ptr(labels), _np_ptr(merges), ctypes.byref(m)))
+        return labels, merges[: m.value]
 
     def matrix_to_triples(self, n, D32, triples, stream):
         _check(lib().vgs_matrix_to_triples(self._h, n, _dev_ptr(D32), _dev_ptr(triples), c_vp(stream)))

@@ -165,6 +165,13 @@ int vgs_assemble(vgs_handle h, int64_t n, int64_t tile, int world, int symmetric
 /* ---- matrix hand-off layouts of src/clustering/util.pyx:6-21: float32 [N*N][3] rows (i, j, d) ---- */
 int vgs_matrix_to_triples(vgs_handle h, int64_t n, const float *D32_d, float *triples_d, void *stream);
 
+/* ---- average-link clustering of the float32 [N][N] matrix on the device, with the reference's exact merge order,
+ *      tie-breaking and mixed float32/float64 arithmetic (src/clustering/average_link_clustering.pyx:21-146): merges
+ *      until k clusters remain.  labels_out_h[n]: clusters numbered by their smallest member; merge_dist_out_h[n-k]
+ *      (nullable): the merge distances in order; n_merges_out (nullable). ------------------------------------------- */
+int vgs_average_link(vgs_handle h, int64_t n, const float *D32_d, int64_t k, int32_t *labels_out_h,
+                     double *merge_dist_out_h, int64_t *n_merges_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,7 +47,8 @@ def lib():
         L.vo_mt_uniforms.argtypes = [vp, vp, i64]
         L.vo_sample.restype = ctypes.c_int
         L.vo_sample.argtypes = [vp, i64, vp, i64, i64, vp]
-        L.vo_upgma.argtypes = [vp, i64, i64, vp, vp]
+        L.vo_average_link.restype = i64
+        L.vo_average_link.argtypes = [vp, i64, i64, vp, vp]
         _lib = L
     return _lib
 
@@ -137,10 +138,11 @@ def np_sum(a):
     return lib().vo_np_sum(_p(a), len(a))
 
 
-def upgma(D32, k):
+def average_link(D32, k):
+    """Exact reference semantics (mixed precision, tie-breaking); see vo_average_link."""
     D32 = np.ascontiguousarray(D32, dtype=np.float32)
     n = D32.shape[0]
     labels = np.zeros(n, dtype=np.int64)
     merges = np.zeros(max(n - k, 1), dtype=np.float64)
-    lib().vo_upgma(_p(D32), n, k, _p(labels), _p(merges))
-    return labels, merges[: n - k]
+    m = lib().vo_average_link(_p(D32), n, k, _p(labels), _p(merges))
+    return labels, merges[:m]

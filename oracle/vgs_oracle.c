@@ -342,30 +342,107 @@ int vo_sample(void *h, int64_t model, uint32_t *state, int64_t length, int64_t p
     return 0;
 }
 
-/* Lance-Williams UPGMA on a float32 [n][n] matrix in plain double arithmetic -- the fast oracle for the
- * scalable average-link row (f1).  Strict '<', first pair in (row, column) scan order wins.
- * labels[n] out; merges[n-k] out (merge distances).  The mixed-precision reference semantics are in
- * vlmc_oracle.average_link; this version is its large-N approximation used for throughput only. */
-void vo_upgma(const float *D32, int64_t n, int64_t k, int64_t *labels, double *merges) {
+/* Average-link clustering with the reference's exact semantics (src/clustering/average_link_clustering.pyx:21-146),
+ * in O(n^2) memory and ~O(n^2) time with a nearest-neighbour cache -- the scalable oracle for row f1.
+ *
+ *  - _find_min_edge (:62-80): scan the clusters in dict insertion order (singletons 0..n-1, every merged cluster
+ *    appended at the end); a cluster's candidate is the top of its heap = min over the other clusters of the tuple
+ *    (distance, key); keys are sorted member tuples of disjoint clusters, so the tuple order is the order of the
+ *    smallest member; a candidate replaces the best one only if strictly smaller ('<', :75): first in dict order wins;
+ *  - _new_dist (:119-122) with numpy's scalar promotion (NEP 50) as it runs in this container: entries between two
+ *    never-merged singletons are numpy.float32, entries that came out of an earlier merge are Python floats
+ *    (cdef double return); int * float32 -> float32, float32 + pyfloat -> float32 (the pyfloat is cast first),
+ *    float32 / int -> float32, pyfloat arithmetic -> float64;
+ *  - other clusters' rows are updated from THEIR distances to left/right (_merge_weights :101-117), the merged
+ *    cluster's own row from left's and right's rows (_merge_heaps :124-146): a non-symmetric input stays consistent.
+ * labels[i] = index of i's cluster when clusters are numbered by their smallest member; merges[n-k] = merge distances. */
+static double vo_new_dist(int64_t nl, double ld, int l32, int64_t nr, double rd, int r32) {
+    if (l32 && r32) {
+        float a = (float)nl * (float)ld, b = (float)nr * (float)rd;
+        float s = a + b;
+        s = s / (float)(nl + nr);
+        return (double)s;
+    }
+    if (l32 || r32) {
+        float a = l32 ? (float)nl * (float)ld : (float)((double)nl * ld);
+        float b = r32 ? (float)nr * (float)rd : (float)((double)nr * rd);
+        float s = a + b;
+        s = s / (float)(nl + nr);
+        return (double)s;
+    }
+    double s = (double)nl * ld + (double)nr * rd;
+    return s / (double)(nl + nr);
+}
+
+static void vo_rescan(const double *D, int64_t n, const int *alive, const int64_t *minmem, int64_t i, double *nn_d, int64_t *nn_j) {
+    double bd = INFINITY;
+    int64_t bj = -1, bm = -1;
+    for (int64_t j = 0; j < n; ++j) {
+        if (!alive[j] || j == i) continue;
+        double d = D[i * n + j];
+        if (bj < 0 || d < bd || (d == bd && minmem[j] < bm)) { bd = d; bj = j; bm = minmem[j]; }
+    }
+    *nn_d = bd; *nn_j = bj;
+}
+
+int64_t vo_average_link(const float *D32, int64_t n, int64_t k, int64_t *labels, double *merges) {
     double *D = (double *)malloc(sizeof(double) * (size_t)(n * n));
-    int64_t *size = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
-    int *alive = (int *)malloc(sizeof(int) * (size_t)n);
+    int64_t *size = (int64_t *)malloc(sizeof(int64_t) * (size_t)n), *minmem = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    int64_t *okey = (int64_t *)malloc(sizeof(int64_t) * (size_t)n), *nn_j = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    int64_t *parent = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    int *alive = (int *)malloc(sizeof(int) * (size_t)n), *single = (int *)malloc(sizeof(int) * (size_t)n);
+    double *nn_d = (double *)malloc(sizeof(double) * (size_t)n);
     for (int64_t i = 0; i < n * n; ++i) D[i] = D32[i];
-    for (int64_t i = 0; i < n; ++i) { size[i] = 1; alive[i] = 1; labels[i] = i; }
+    for (int64_t i = 0; i < n; ++i) { size[i] = 1; alive[i] = 1; single[i] = 1; minmem[i] = i; okey[i] = i; parent[i] = i; }
+    for (int64_t i = 0; i < n; ++i) vo_rescan(D, n, alive, minmem, i, &nn_d[i], &nn_j[i]);
+    int64_t n_merges = 0;
     for (int64_t step = 0; step < n - k; ++step) {
         double best = INFINITY;
-        int64_t bi = -1, bj = -1;
-        for (int64_t i = 0; i < n; ++i) if (alive[i])
-            for (int64_t j = 0; j < n; ++j) if (alive[j] && j != i && D[i * n + j] < best) { best = D[i * n + j]; bi = i; bj = j; }
-        if (bi < 0) break;
-        merges[step] = best;
-        for (int64_t x = 0; x < n; ++x) if (alive[x] && x != bi && x != bj) {
-            double v = ((double)size[bi] * D[bi * n + x] + (double)size[bj] * D[bj * n + x]) / (double)(size[bi] + size[bj]);
-            D[bi * n + x] = D[x * n + bi] = v;
+        int64_t bl = -1, bkey = -1;
+        for (int64_t i = 0; i < n; ++i) {
+            if (!alive[i] || nn_j[i] < 0) continue;
+            if (nn_d[i] < best || (nn_d[i] == best && bl >= 0 && okey[i] < bkey && 0)) { best = nn_d[i]; bl = i; bkey = okey[i]; }
         }
-        size[bi] += size[bj];
-        alive[bj] = 0;
-        for (int64_t x = 0; x < n; ++x) if (labels[x] == bj) labels[x] = bi;
+        /* strict '<' with a scan in dict order: among equal distances the smallest dict position wins */
+        for (int64_t i = 0; i < n; ++i)
+            if (alive[i] && nn_j[i] >= 0 && nn_d[i] == best && okey[i] < bkey) { bl = i; bkey = okey[i]; }
+        if (bl < 0 || !(best < INFINITY)) break;
+        const int64_t l = bl, r = nn_j[l];
+        merges[n_merges++] = best;
+        const int64_t nl = size[l], nr = size[r];
+        /* other rows first (they read D[x][l], D[x][r]), then the merged row (reads D[l][x], D[r][x]) */
+        double *newrow = (double *)malloc(sizeof(double) * (size_t)n);
+        for (int64_t x = 0; x < n; ++x) {
+            if (!alive[x] || x == l || x == r) continue;
+            const double vx = vo_new_dist(nl, D[x * n + l], single[x] && single[l], nr, D[x * n + r], single[x] && single[r]);
+            newrow[x] = vo_new_dist(nl, D[l * n + x], single[x] && single[l], nr, D[r * n + x], single[x] && single[r]);
+            D[x * n + l] = vx;
+        }
+        for (int64_t x = 0; x < n; ++x)
+            if (alive[x] && x != l && x != r) D[l * n + x] = newrow[x];
+        free(newrow);
+        alive[r] = 0;
+        single[l] = 0;
+        size[l] = nl + nr;
+        if (minmem[r] < minmem[l]) minmem[l] = minmem[r];
+        okey[l] = n + step;
+        parent[r] = l;
+        for (int64_t x = 0; x < n; ++x) {
+            if (!alive[x]) continue;
+            if (x == l || nn_j[x] == l || nn_j[x] == r) vo_rescan(D, n, alive, minmem, x, &nn_d[x], &nn_j[x]);
+            else {
+                const double d = D[x * n + l];
+                if (d < nn_d[x] || (d == nn_d[x] && minmem[l] < minmem[nn_j[x]])) { nn_d[x] = d; nn_j[x] = l; }
+            }
+        }
     }
-    free(D); free(size); free(alive);
+    /* labels: clusters numbered by smallest member */
+    for (int64_t i = 0; i < n; ++i) { int64_t x = i; while (parent[x] != x) x = parent[x]; labels[i] = minmem[x]; }
+    int64_t next = 0;
+    int64_t *remap = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) remap[i] = -1;
+    for (int64_t i = 0; i < n; ++i) if (remap[labels[i]] < 0 && labels[i] == i) remap[i] = next++;
+    for (int64_t i = 0; i < n; ++i) labels[i] = remap[labels[i]];
+    free(remap); free(D); free(size); free(minmem); free(okey); free(nn_j); free(parent); free(alive); free(single); free(nn_d);
+    return n_merges;
 }

@@ -120,6 +120,26 @@ def test_average_link_restated(g):
         assert merges == ref[k]["merge_distances"][: len(merges)]
 
 
+def test_c_average_link_equals_pinned_restatement(g):
+    """oracle/vgs_oracle.c:vo_average_link (O(n^2), used at large n) == vlmc_oracle.average_link (pinned above)
+    including forced ties and a non-symmetric matrix."""
+    rng = np.random.default_rng(0)
+    for n, k, q, sym in ((12, 3, 0, True), (40, 5, 0, True), (60, 4, 16, True), (50, 1, 4, True), (30, 3, 0, False)):
+        X = rng.random((n, 6))
+        D = np.sqrt(((X[:, None] - X[None]) ** 2).sum(-1)).astype(np.float32)
+        if q:
+            D = (np.round(D * q) / q).astype(np.float32)
+        if not sym:
+            D = rng.random((n, n)).astype(np.float32)
+        np.fill_diagonal(D, 0)
+        l1, m1 = O.average_link(D, k)
+        l2, m2 = c_oracle.average_link(D, k)
+        assert np.array_equal(l1, l2) and np.array_equal(np.array(m1), m2)
+    D32 = np.array(g["frobenius_intersection"]).astype(np.float32)
+    labels, merges = c_oracle.average_link(D32, 3)
+    assert merges.tolist() == g["clustering_AverageLinkClustering"]["3"]["merge_distances"]
+
+
 @pytest.mark.parametrize("name", ["shallow", "deep"])
 def test_synthetic_small(name):
     fm, seqs, est, z = golden_io.synthetic_small(name)
