@@ -5,7 +5,7 @@
 // SURVEY.md §3.4).  Here the state is one fp64 [N][N] matrix plus a nearest-neighbour cache per cluster row:
 //   step = (1) argmin over the cache   (2) Lance-Williams update of one row and one column
 //          (3) bookkeeping             (4) refresh of the cache rows that pointed at the merged clusters.
-// Semantics kept bit for bit (pinned by oracle/vlmc_oracle.average_link on the reference's goldens):
+// Semantics kept bit for bit (checked in tests/ against the reference's own golden runs):
 //   - _find_min_edge (:62-80): clusters are scanned in dict insertion order (singletons in index order, every merged
 //     cluster appended at the end); a cluster's candidate is its heap top = min of (distance, key tuple) -- keys are
 //     sorted member tuples of disjoint clusters, so the tuple order is the order of the smallest member; the global
