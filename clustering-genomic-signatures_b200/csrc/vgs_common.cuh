@@ -42,6 +42,13 @@ struct ModelMeta {
     int32_t deep_shift;
     int32_t deep_off;     // byte offset of the deep hash inside the blob
     int32_t logp_off;     // byte offset of the logp rows inside the blob
+    // perfect hash (hash-and-displace) over the same contexts: exactly two dependent loads per exact-context
+    // probe, no probing loop -> no warp divergence (pair kernels on deep sets)
+    int64_t ph_off;       // byte offset in the ph arena: [u16 disp[2^ph_lgr] (16-byte padded) | uint2 table[capacity]]
+    int32_t ph_lgr;       // log2(number of displacement buckets)
+    int32_t ph_seed;      // which multiplier pair built it (-1: build failed, use the probing hash)
+    int32_t ph_bytes;     // blob size (multiple of 16)
+    int32_t ph_pad;
 };
 
 struct vgs_context {
@@ -75,6 +82,10 @@ struct vgs_context {
     // pair kernels, shallow sets (max_order <= VGS_UMAP_MAX_ORDER): per model a dense map over EVERY string of
     // length <= max_order (index (4^len - 1) / 3 + code) -> u16: low 15 bits = ctx_id of the longest suffix that is
     // a context (VGS_UMAP_NONE if none), bit 15 = the string itself is a context
+    uint8_t *d_ph = nullptr;     // perfect-hash arena
+    int64_t ph_bytes = 0;
+    int64_t max_ph_bytes = 0;    // largest per-model blob
+    bool ph_ready = false;
     uint16_t *d_umap = nullptr;
     int64_t umap_stride = 0;     // entries per model (multiple of 8), 0 = not built
     int max_n_ctx = 0;
@@ -199,6 +210,7 @@ void vgs_tile_coords(const TilePlan &p, int64_t k, int64_t *I, int64_t *J);
 int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &seq_lists_per_block, int64_t block,
                         int64_t m_begin, int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld,
                         cudaStream_t s);
+int vgs_ensure_ph(vgs_context *h, cudaStream_t s);  // builds the perfect hashes on first use
 bool vgs_kmer_applicable(vgs_context *h);
 // returns VGS_OK, an error, or -1 when the set needs the scan kernel (a model without a root context)
 int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, double *M, int64_t ld, cudaStream_t s);
@@ -233,6 +245,29 @@ __device__ __forceinline__ int vgs_longest_suffix(const uint2 *__restrict__ slot
         if (id >= 0) return id;
     }
     return -1;
+}
+
+// ---- hash-and-displace perfect hash -------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t vgs_ph_a2(int seed) {
+    const uint32_t t[8] = {0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u, 0x2545F491u};
+    return t[seed & 7];
+}
+__host__ __device__ __forceinline__ uint32_t vgs_ph_a3(int seed) {
+    const uint32_t t[8] = {0x9E3779B9u, 0x7F4A7C15u, 0x94D049BBu, 0xBF58476Du, 0x1B873593u, 0xCC9E2D51u, 0x38495AB5u, 0x6C8E9CF5u};
+    return t[seed & 7];
+}
+__device__ __forceinline__ uint32_t vgs_ph_slot(uint32_t key, uint32_t disp, int lgcap, int seed) {
+    const uint32_t h2 = (key * vgs_ph_a2(seed)) >> (32 - lgcap);
+    const uint32_t h3 = ((key * vgs_ph_a3(seed)) >> (32 - lgcap)) | 1u;
+    return (h2 + disp * h3) & ((1u << lgcap) - 1u);
+}
+// blob = [u16 disp[1 << lgr] padded to 16 bytes | uint2 table[1 << lgcap]]; returns ctx_id or -1
+__device__ __forceinline__ int vgs_ph_find(const uint8_t *__restrict__ blob, int lgr, int lgcap, int seed, uint32_t key) {
+    const uint16_t *disp = (const uint16_t *)blob;
+    const uint2 *table = (const uint2 *)(blob + (((2u << lgr) + 15u) & ~15u));
+    const uint32_t d = disp[(key * 0x9E3779B1u) >> (32 - lgr)];
+    const uint2 e = table[vgs_ph_slot(key, d, lgcap, seed)];
+    return e.x == key ? (int)e.y : -1;
 }
 
 __device__ __forceinline__ double vgs_nan() { return __longlong_as_double(0x7ff8000000000000LL); }

@@ -298,6 +298,70 @@ __global__ void k_build_umap(const ModelMeta *__restrict__ meta, const uint2 *__
     }
 }
 
+// hash-and-displace build, one thread per model (serial per model, all models in parallel).  Buckets of the first-level
+// hash are placed largest first; a bucket's displacement is the first d for which all its keys fall into free,
+// pairwise distinct slots.  scratch per model: cnt[r] | start[r + 1] | items[n] | order[r]  (ints)
+__global__ void k_build_ph(int64_t n_models, ModelMeta *__restrict__ meta, const uint32_t *__restrict__ key,
+                           uint8_t *__restrict__ arena, int *__restrict__ scratch, const int64_t *__restrict__ scratch_off) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_models) return;
+    ModelMeta mm = meta[m];
+    const int lgcap = 32 - mm.hash_shift, lgr = mm.ph_lgr;
+    const int r = 1 << lgr, n = mm.n_ctx;
+    const uint32_t cap_mask = (1u << lgcap) - 1u;
+    uint8_t *blob = arena + mm.ph_off;
+    uint16_t *disp = (uint16_t *)blob;
+    unsigned long long *table = (unsigned long long *)(blob + (((2u << lgr) + 15u) & ~15u));
+    int *cnt = scratch + scratch_off[m], *start = cnt + r, *items = start + r + 1, *order = items + n;
+    const uint32_t *keys = key + mm.ctx_off;
+    for (int b = 0; b < r; ++b) cnt[b] = 0;
+    for (int c = 0; c < n; ++c) cnt[(keys[c] * 0x9E3779B1u) >> (32 - lgr)]++;
+    start[0] = 0;
+    int max_size = 0;
+    for (int b = 0; b < r; ++b) { start[b + 1] = start[b] + cnt[b]; if (cnt[b] > max_size) max_size = cnt[b]; }
+    for (int b = 0; b < r; ++b) cnt[b] = 0;
+    for (int c = 0; c < n; ++c) {
+        const int b = (int)((keys[c] * 0x9E3779B1u) >> (32 - lgr));
+        items[start[b] + cnt[b]++] = c;
+    }
+    // buckets by decreasing size (selection by size classes; sizes are small)
+    int no = 0;
+    for (int sz = max_size; sz >= 1; --sz)
+        for (int b = 0; b < r; ++b)
+            if (cnt[b] == sz) order[no++] = b;
+    int seed_ok = -1;
+    for (int seed = 0; seed < 8 && seed_ok < 0; ++seed) {
+        for (uint32_t s = 0; s <= cap_mask; ++s) table[s] = 0ull;
+        for (int b = 0; b < r; ++b) disp[b] = 0;
+        bool ok = true;
+        for (int oi = 0; oi < no && ok; ++oi) {
+            const int b = order[oi], sz = cnt[b];
+            const int *it = items + start[b];
+            bool placed = false;
+            for (uint32_t d = 0; d < 65536u && !placed; ++d) {
+                bool fits = true;
+                for (int a = 0; a < sz && fits; ++a) {
+                    const uint32_t sa = vgs_ph_slot(keys[it[a]], d, lgcap, seed);
+                    if (table[sa] != 0ull) { fits = false; break; }
+                    for (int a2 = 0; a2 < a; ++a2)
+                        if (vgs_ph_slot(keys[it[a2]], d, lgcap, seed) == sa) { fits = false; break; }
+                }
+                if (fits) {
+                    for (int a = 0; a < sz; ++a) {
+                        const uint32_t sa = vgs_ph_slot(keys[it[a]], d, lgcap, seed);
+                        table[sa] = ((unsigned long long)(uint32_t)it[a] << 32) | keys[it[a]];
+                    }
+                    disp[b] = (uint16_t)d;
+                    placed = true;
+                }
+            }
+            if (!placed) ok = false;
+        }
+        if (ok) seed_ok = seed;
+    }
+    meta[m].ph_seed = seed_ok;
+}
+
 static int log2_ceil_pow2(int64_t v, int64_t *cap_out) {
     int64_t cap = 8;
     int lg = 3;
@@ -327,7 +391,9 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     h->max_nll_bytes_t1 = h->max_nll_bytes_t2 = h->max_pair_bytes = 0;
     h->max_n_ctx = 0;
     h->umap_stride = 0;
-    int64_t hash_slots = 0, nll_bytes = 0;
+    int64_t hash_slots = 0, nll_bytes = 0, ph_bytes = 0;
+    h->max_ph_bytes = 0;
+    h->ph_ready = false;
     for (int64_t m = 0; m < n_models; ++m) {
         ModelMeta &mm = h->h_meta[(size_t)m];
         int64_t a = ctx_offsets_h[m], n = ctx_offsets_h[m + 1] - a;
@@ -356,6 +422,13 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         mm.hash_mask = (uint32_t)(cap - 1);
         mm.hash_shift = 32 - lg;
         hash_slots += cap;
+        mm.ph_lgr = std::max(1, lg - 2);
+        mm.ph_seed = -1;
+        mm.ph_bytes = (int32_t)((((int64_t)2 << mm.ph_lgr) + 15) / 16 * 16 + cap * 8);
+        mm.ph_off = ph_bytes;
+        mm.ph_pad = 0;
+        ph_bytes += ((int64_t)mm.ph_bytes + 255) / 256 * 256;
+        h->max_ph_bytes = std::max<int64_t>(h->max_ph_bytes, mm.ph_bytes);
         h->max_pair_bytes = std::max(h->max_pair_bytes, cap * 8 + n * 16);
         h->max_n_ctx = std::max<int>(h->max_n_ctx, (int)n);
         h->max_order = std::max(h->max_order, order);
@@ -395,6 +468,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     if ((rc = vgs_reserve(h, &h->d_prob64, total * 4))) return rc;
     if ((rc = vgs_reserve(h, &h->d_hash, hash_slots))) return rc;
     h->hash_slots = hash_slots;
+    h->ph_bytes = ph_bytes;
     h->nll_bytes = nll_bytes;
     h->n_models = n_models;
     h->total_ctx = total;
@@ -495,6 +569,29 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     }
     h->nll_ready = true;
     VGS_CUDA(cudaStreamSynchronize(s));
+    return VGS_OK;
+}
+
+int vgs_ensure_ph(vgs_context *h, cudaStream_t s) {
+    if (h->ph_ready) return VGS_OK;
+    int rc;
+    if ((rc = vgs_reserve(h, &h->d_ph, h->ph_bytes))) return rc;
+    // scratch: per model cnt[r] | start[r + 1] | items[n] | order[r]
+    std::vector<int64_t> off((size_t)h->n_models + 1, 0);
+    for (int64_t m = 0; m < h->n_models; ++m) {
+        const ModelMeta &mm = h->h_meta[(size_t)m];
+        const int64_t r = (int64_t)1 << mm.ph_lgr;
+        off[(size_t)m + 1] = off[(size_t)m] + 3 * r + 1 + mm.n_ctx;
+    }
+    const int64_t off_bytes = ((int64_t)off.size() * 8 + 255) / 256 * 256;
+    if ((rc = vgs_ensure_scratch(h, off_bytes + off.back() * 4 + 256))) return rc;
+    int64_t *d_off = (int64_t *)h->d_scratch;
+    int *d_scr = (int *)((char *)h->d_scratch + off_bytes);
+    VGS_CUDA(cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
+    k_build_ph<<<(unsigned)((h->n_models + 31) / 32), 32, 0, s>>>(h->n_models, h->d_meta, h->d_key, h->d_ph, d_scr, d_off);
+    VGS_LAUNCH_CHECK(h);
+    VGS_CUDA(cudaStreamSynchronize(s));
+    h->ph_ready = true;
     return VGS_OK;
 }
 

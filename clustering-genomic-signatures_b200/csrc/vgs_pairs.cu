@@ -22,7 +22,8 @@
 #include "vgs_common.cuh"
 
 #define PAIR_THREADS 256
-#define PAIR_MAX_JG 8
+#define PAIR_MAX_JG 8   // staged models per CTA, shallow sets (universe maps)
+#define PAIR_DEEP_JG 4  // staged models per CTA, deep sets (perfect hashes)
 
 struct PairParams {
     const ModelMeta *meta;
@@ -31,6 +32,7 @@ struct PairParams {
     const uint2 *hash;
     const uint16_t *umap;
     int64_t umap_stride;
+    const uint8_t *ph;      // perfect-hash arena (deep sets)
     TilePlan pl;
     int rank, kind, jg, n_groups, n_dir;
     double *S, *U;
@@ -58,13 +60,13 @@ __device__ __forceinline__ double sq4(const float4 a, const float4 b) {
 // UMAP = true : shallow sets; each staged model carries a dense map over every string of length <= max order
 //               (one u16 gather gives presence AND the longest-suffix fallback row: no probing loop, no divergence)
 // UMAP = false: deep sets; exact-context hash probes, and for the union a probe per shorter suffix
-template <bool STAGED, bool UMAP>
+template <bool STAGED, bool UMAP, int MAXJ>
 __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ int64_t sI, sJ;
-    __shared__ ModelMeta ymeta[PAIR_MAX_JG];
-    __shared__ uint32_t yoff_h[PAIR_MAX_JG], yoff_r[PAIR_MAX_JG];
+    __shared__ ModelMeta ymeta[MAXJ];
+    __shared__ uint32_t yoff_h[MAXJ], yoff_r[MAXJ];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int64_t w = blockIdx.x;
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
         if (tid == 0) {
             uint32_t off = 0, total = 0;
             for (int yy = 0; yy < ny; ++yy) {
-                const uint32_t hb = UMAP ? map_bytes : (ymeta[yy].hash_mask + 1u) * 8u, rb = (uint32_t)ymeta[yy].n_ctx * 16u;
+                const uint32_t hb = UMAP ? map_bytes : (uint32_t)ymeta[yy].ph_bytes, rb = (uint32_t)ymeta[yy].n_ctx * 16u;
                 yoff_h[yy] = off; off += hb;
                 yoff_r[yy] = off; off += rb;
                 total += hb + rb;
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
             vgs_mbar_expect_tx(&bar, total);
             for (int yy = 0; yy < ny; ++yy) {
                 if (UMAP) vgs_copy_pieces(smem + yoff_h[yy], p.umap + (y0 + yy) * p.umap_stride, map_bytes, &bar);
-                else vgs_copy_pieces(smem + yoff_h[yy], p.hash + ymeta[yy].hash_off, (ymeta[yy].hash_mask + 1u) * 8u, &bar);
+                else vgs_copy_pieces(smem + yoff_h[yy], p.ph + ymeta[yy].ph_off, (uint32_t)ymeta[yy].ph_bytes, &bar);
                 vgs_copy_pieces(smem + yoff_r[yy], p.prob32 + ymeta[yy].ctx_off, (uint32_t)ymeta[yy].n_ctx * 16u, &bar);
             }
         }
@@ -114,13 +116,13 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
         vgs_mbar_wait(&bar, 0);
     }
 
-    const void *yh[PAIR_MAX_JG];
-    const float4 *yr[PAIR_MAX_JG];
+    const void *yh[MAXJ];
+    const float4 *yr[MAXJ];
 #pragma unroll
-    for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
+    for (int yy = 0; yy < MAXJ; ++yy) {
         if (yy < ny) {
             if (STAGED) yh[yy] = smem + yoff_h[yy];
-            else yh[yy] = UMAP ? (const void *)(p.umap + (y0 + yy) * p.umap_stride) : (const void *)(p.hash + ymeta[yy].hash_off);
+            else yh[yy] = UMAP ? (const void *)(p.umap + (y0 + yy) * p.umap_stride) : (const void *)(p.ph + ymeta[yy].ph_off);
             yr[yy] = STAGED ? (const float4 *)(smem + yoff_r[yy]) : p.prob32 + ymeta[yy].ctx_off;
         } else {
             yh[yy] = nullptr; yr[yy] = nullptr;
@@ -131,10 +133,10 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
     const int kind = p.kind;
     for (int xx = warp; xx < nx; xx += PAIR_THREADS / 32) {
         const ModelMeta xm = p.meta[x0 + xx];
-        double s[PAIR_MAX_JG], u[PAIR_MAX_JG];
-        int c[PAIR_MAX_JG];
+        double s[MAXJ], u[MAXJ];
+        int c[MAXJ];
 #pragma unroll
-        for (int yy = 0; yy < PAIR_MAX_JG; ++yy) { s[yy] = 0.0; u[yy] = 0.0; c[yy] = 0; }
+        for (int yy = 0; yy < MAXJ; ++yy) { s[yy] = 0.0; u[yy] = 0.0; c[yy] = 0; }
         for (int ci = lane; ci < xm.n_ctx; ci += 32) {
             const uint32_t key = __ldg(p.key + xm.ctx_off + ci);
             const float4 px = __ldg(p.prob32 + xm.ctx_off + ci);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
             if (UMAP) {
                 const uint32_t uidx = (((1u << (2 * len)) - 1u) / 3u) + code;
 #pragma unroll
-                for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
+                for (int yy = 0; yy < MAXJ; ++yy) {
                     if (yy >= ny) break;
                     const uint32_t e = ((const uint16_t *)yh[yy])[uidx];
                     const uint32_t id = e & 0x7FFFu;
@@ -161,18 +163,25 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
                 }
             } else {
 #pragma unroll
-                for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
+                for (int yy = 0; yy < MAXJ; ++yy) {
                     if (yy >= ny) break;
-                    const uint2 *slots = (const uint2 *)yh[yy];
+                    // exact-context probe: perfect hash (two loads, no loop); a model whose build failed falls
+                    // back to the probing hash in global memory
+                    const uint8_t *blob = (const uint8_t *)yh[yy];
+                    const int lgr = ymeta[yy].ph_lgr, lgcap = 32 - ymeta[yy].hash_shift, seed = ymeta[yy].ph_seed;
+                    const uint2 *gslots = p.hash + ymeta[yy].hash_off;
                     const uint32_t mask = ymeta[yy].hash_mask;
                     const int shift = ymeta[yy].hash_shift;
-                    int id = vgs_hash_find(slots, mask, shift, key);
+                    int id = seed >= 0 ? vgs_ph_find(blob, lgr, lgcap, seed, key) : vgs_hash_find(gslots, mask, shift, key);
                     if (id >= 0) {
                         s[yy] += sq4(px, yr[yy][id]);
                         c[yy] += 1;
                     } else if (kind == VGS_PAIR_FROBENIUS_UNION) {
                         int top = len - 1 < ymeta[yy].order ? len - 1 : ymeta[yy].order;
-                        for (int ln = top; ln >= 0 && id < 0; --ln) id = vgs_hash_find(slots, mask, shift, vgs_key(ln, code & vgs_lowmask(ln)));
+                        for (int ln = top; ln >= 0 && id < 0; --ln) {
+                            const uint32_t k2 = vgs_key(ln, code & vgs_lowmask(ln));
+                            id = seed >= 0 ? vgs_ph_find(blob, lgr, lgcap, seed, k2) : vgs_hash_find(gslots, mask, shift, k2);
+                        }
                         if (id < 0) atomicOr(p.err, 1);
                         else u[yy] += sq4(px, yr[yy][id]);
                     } else if (kind == VGS_PAIR_PROJECTION) {
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
             }
         }
 #pragma unroll
-        for (int yy = 0; yy < PAIR_MAX_JG; ++yy) {
+        for (int yy = 0; yy < MAXJ; ++yy) {
             if (yy >= ny) break;
             double sv = s[yy], uv = u[yy];
             int cv = c[yy];
@@ -252,18 +261,25 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
     // how many staged models fit?  prefer >= 2 CTAs per SM
     const bool umap = h->umap_stride > 0;
     p.umap = h->d_umap; p.umap_stride = h->umap_stride;
-    const int64_t per_model_raw = umap ? h->umap_stride * 2 + (int64_t)h->max_n_ctx * 16 : h->max_pair_bytes;
+    if (!umap) {
+        int rc0 = vgs_ensure_ph(h, s);
+        if (rc0) return rc0;
+    }
+    p.ph = h->d_ph;
+    const int64_t per_model_raw = umap ? h->umap_stride * 2 + (int64_t)h->max_n_ctx * 16 : h->max_ph_bytes + (int64_t)h->max_n_ctx * 16;
     const int64_t per_model = (per_model_raw + 127) / 128 * 128;
     const int64_t cap = (int64_t)h->max_smem_optin - 2048;
     bool staged = per_model <= cap;
     int jg = 4;
     if (staged) {
         int64_t budget = cap / 2;
-        jg = (int)std::min<int64_t>(PAIR_MAX_JG, budget / per_model);
-        if (jg < 2) jg = (int)std::min<int64_t>(PAIR_MAX_JG, cap / per_model);
+        const int64_t max_jg = umap ? PAIR_MAX_JG : PAIR_DEEP_JG;
+        jg = (int)std::min<int64_t>(max_jg, budget / per_model);
+        if (jg < 2) jg = (int)std::min<int64_t>(max_jg, cap / per_model);
         if (jg < 1) jg = 1;
     }
     jg = (int)std::min<int64_t>(jg, pl.tile);
+    if (!umap) jg = std::min(jg, PAIR_DEEP_JG);
     p.jg = jg;
     p.n_groups = (int)((pl.tile + jg - 1) / jg);
     const int64_t part = pl.slots * 2 * pl.tile * pl.tile;
@@ -279,15 +295,15 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
     const int smem = staged ? (int)(per_model * jg) : 0;
     vgs_prof_begin(h, VGS_PROF_PAIR_PARTIALS, s);
     if (staged && umap) {
-        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_pair_partials<true, true><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
+        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, true, PAIR_MAX_JG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_pair_partials<true, true, PAIR_MAX_JG><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
     } else if (staged) {
-        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_pair_partials<true, false><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
+        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, false, PAIR_DEEP_JG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_pair_partials<true, false, PAIR_DEEP_JG><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
     } else if (umap) {
-        k_pair_partials<false, true><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
+        k_pair_partials<false, true, PAIR_MAX_JG><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
     } else {
-        k_pair_partials<false, false><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
+        k_pair_partials<false, false, PAIR_DEEP_JG><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
     }
     vgs_prof_end(h, VGS_PROF_PAIR_PARTIALS, s);
     VGS_LAUNCH_CHECK(h);
