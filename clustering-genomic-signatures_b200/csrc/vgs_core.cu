@@ -583,14 +583,25 @@ int vgs_ensure_ph(vgs_context *h, cudaStream_t s) {
         const int64_t r = (int64_t)1 << mm.ph_lgr;
         off[(size_t)m + 1] = off[(size_t)m] + 3 * r + 1 + mm.n_ctx;
     }
+    // one-off build scratch of its own (callers may be holding pointers into the shared scratch buffers)
     const int64_t off_bytes = ((int64_t)off.size() * 8 + 255) / 256 * 256;
-    if ((rc = vgs_ensure_scratch(h, off_bytes + off.back() * 4 + 256))) return rc;
-    int64_t *d_off = (int64_t *)h->d_scratch;
-    int *d_scr = (int *)((char *)h->d_scratch + off_bytes);
-    VGS_CUDA(cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
-    k_build_ph<<<(unsigned)((h->n_models + 31) / 32), 32, 0, s>>>(h->n_models, h->d_meta, h->d_key, h->d_ph, d_scr, d_off);
-    VGS_LAUNCH_CHECK(h);
-    VGS_CUDA(cudaStreamSynchronize(s));
+    char *tmp = nullptr;
+    cudaError_t e = cudaMalloc((void **)&tmp, (size_t)(off_bytes + off.back() * 4 + 256));
+    if (e != cudaSuccess) {
+        vgs_set_error("cudaMalloc of the perfect-hash build scratch failed: %s", cudaGetErrorString(e));
+        return VGS_ERR_MEMORY;
+    }
+    int64_t *d_off = (int64_t *)tmp;
+    int *d_scr = (int *)(tmp + off_bytes);
+    e = cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        k_build_ph<<<(unsigned)((h->n_models + 31) / 32), 32, 0, s>>>(h->n_models, h->d_meta, h->d_key, h->d_ph, d_scr, d_off);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return vgs_cuda_fail(e, "perfect-hash build", __FILE__, __LINE__);
     h->ph_ready = true;
     return VGS_OK;
 }
