@@ -257,19 +257,25 @@ __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint
     }
     for (int i = threadIdx.x; i < 4 * mm.n_ctx; i += blockDim.x) rows[i] = logp[4 * mm.ctx_off + i];
     __syncthreads();
+    // deep node table: EVERY suffix of length 7..len of every deep context is a node (real or virtual) whose value is
+    // the ctx_id of the longest real context that is a suffix of the node string.  A scan can then walk upwards from
+    // length 7 and stop at the first missing node, whether or not the context set is suffix-closed.
     for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
-        int ln = len[mm.ctx_off + c];
+        const int ln = len[mm.ctx_off + c];
         if (ln <= VGS_L1_DEPTH) continue;
-        uint32_t cd = code[mm.ctx_off + c];
+        const uint32_t cd = code[mm.ctx_off + c];
         atomicOr(&l1[cd & (n1 - 1)], 0x80000000u);
-        uint32_t k = key[mm.ctx_off + c];
-        uint32_t s = vgs_hash_slot(k, mm.deep_shift);
-        unsigned long long want = ((unsigned long long)(uint32_t)c << 32) | k;
-        while (true) {
-            unsigned long long old = atomicCAS(&deep[s], 0ull, want);
-            if (old == 0ull) break;
-            if ((uint32_t)old == k) { atomicMin(&deep[s], want); break; }
-            s = (s + 1) & mm.deep_mask;
+        for (int l2 = VGS_L1_DEPTH + 1; l2 <= ln; ++l2) {
+            const uint32_t sc = cd & vgs_lowmask(l2);
+            const uint32_t k = vgs_key(l2, sc);
+            const int val = l2 == ln ? c : vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, sc, l2);
+            uint32_t s = vgs_hash_slot(k, mm.deep_shift);
+            const unsigned long long want = ((unsigned long long)(uint32_t)val << 32) | k;
+            while (true) {
+                const unsigned long long old = atomicCAS(&deep[s], 0ull, want);
+                if (old == 0ull || (uint32_t)old == k) break;  // same node from another context: same value
+                s = (s + 1) & mm.deep_mask;
+            }
         }
     }
 }
@@ -411,7 +417,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
                 return VGS_ERR_INVALID;
             }
             order = std::max(order, ln);
-            n_deep += ln > VGS_L1_DEPTH;
+            n_deep += ln > VGS_L1_DEPTH ? ln - VGS_L1_DEPTH : 0;  // upper bound on the deep nodes (suffixes of length 7..len)
         }
         mm.ctx_off = a;
         mm.n_ctx = (int32_t)n;

@@ -77,9 +77,12 @@ struct TwoLevelTable {  // tier 2
         const uint32_t e = l1[hist & ((1u << (2 * VGS_L1_DEPTH)) - 1u)];
         uint32_t id = e & 0x7FFFFFFFu;
         if (e & 0x80000000u) {
-            for (int ln = order; ln > VGS_L1_DEPTH; --ln) {
-                int r = vgs_hash_find(deep, deep_mask, deep_shift, vgs_key(ln, hist & vgs_lowmask(ln)));
-                if (r >= 0) { id = (uint32_t)r; break; }
+            // walk up the deep node table from length 7; the first missing node ends the walk (every suffix of a
+            // deep context is a node, and a node's value is already the longest real context below it)
+            for (int ln = VGS_L1_DEPTH + 1; ln <= order; ++ln) {
+                const int r = vgs_hash_find(deep, deep_mask, deep_shift, vgs_key(ln, hist & vgs_lowmask(ln)));
+                if (r < 0) break;
+                id = (uint32_t)r;
             }
         }
         return id == VGS_NO_CTX ? vgs_nan() : rows[4 * id + x];
