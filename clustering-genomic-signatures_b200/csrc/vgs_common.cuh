@@ -23,7 +23,9 @@
 
 #define VGS_MAX_ORDER 15
 #define VGS_DENSE_MAX_ORDER 6   // tier 1 limit: 4^7 * 8 B = 128 KB of shared memory
-#define VGS_L1_DEPTH 6          // tier 2 first-level map covers the last 6 symbols
+#define VGS_L1_DEPTH 6          // tier 2 first-level map: minimum depth (and the depth of 32-bit maps)
+#define VGS_L1_MAX_DEPTH 8      // 4^8 u16 entries = 128 KB
+#define VGS_T2_SMEM_BUDGET (220 * 1024)
 #define VGS_NO_CTX 0x7FFFFFFFu
 #define VGS_UMAP_MAX_ORDER 7    // dense "universe" maps for the pair kernels: (4^8 - 1) / 3 = 21845 u16 entries
 #define VGS_UMAP_NONE 0x7FFFu
@@ -48,7 +50,7 @@ struct ModelMeta {
     int32_t ph_lgr;       // log2(number of displacement buckets)
     int32_t ph_seed;      // which multiplier pair built it (-1: build failed, use the probing hash)
     int32_t ph_bytes;     // blob size (multiple of 16)
-    int32_t ph_pad;
+    int32_t l1_depth;     // tier 2: low byte = depth D1 of the first-level map, bit 8 = 32-bit entries
 };
 
 struct vgs_context {

@@ -250,10 +250,14 @@ __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint
     unsigned long long *deep = (unsigned long long *)(arena + mm.nll_off + mm.deep_off);
     double *rows = (double *)(arena + mm.nll_off + mm.logp_off);
     const uint2 *slots = hash + mm.hash_off;
-    const uint32_t n1 = 1u << (2 * VGS_L1_DEPTH);
+    const int d1 = mm.l1_depth & 0xFF;
+    const bool wide = (mm.l1_depth & 0x100) != 0;
+    uint16_t *l1n = (uint16_t *)l1;
+    const uint32_t n1 = 1u << (2 * d1);
     for (uint32_t hc = threadIdx.x; hc < n1; hc += blockDim.x) {
-        int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, VGS_L1_DEPTH, hc, VGS_L1_DEPTH);
-        l1[hc] = id >= 0 ? (uint32_t)id : VGS_NO_CTX;
+        int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, d1 < mm.order ? d1 : mm.order, hc, d1);
+        if (wide) l1[hc] = id >= 0 ? (uint32_t)id : VGS_NO_CTX;
+        else l1n[hc] = id >= 0 ? (uint16_t)id : (uint16_t)VGS_UMAP_NONE;
     }
     for (int i = threadIdx.x; i < 4 * mm.n_ctx; i += blockDim.x) rows[i] = logp[4 * mm.ctx_off + i];
     __syncthreads();
@@ -262,10 +266,12 @@ __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint
     // length 7 and stop at the first missing node, whether or not the context set is suffix-closed.
     for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
         const int ln = len[mm.ctx_off + c];
-        if (ln <= VGS_L1_DEPTH) continue;
+        if (ln <= d1) continue;
         const uint32_t cd = code[mm.ctx_off + c];
-        atomicOr(&l1[cd & (n1 - 1)], 0x80000000u);
-        for (int l2 = VGS_L1_DEPTH + 1; l2 <= ln; ++l2) {
+        const uint32_t li = cd & (n1 - 1);
+        if (wide) atomicOr(&l1[li], 0x80000000u);
+        else atomicOr(&l1[li >> 1], (li & 1u) ? 0x80000000u : 0x00008000u);  // the u16 flag bit inside its 32-bit word
+        for (int l2 = d1 + 1; l2 <= ln; ++l2) {
             const uint32_t sc = cd & vgs_lowmask(l2);
             const uint32_t k = vgs_key(l2, sc);
             const int val = l2 == ln ? c : vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, sc, l2);
@@ -405,7 +411,8 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         int64_t a = ctx_offsets_h[m], n = ctx_offsets_h[m + 1] - a;
         VGS_CHECK_ARG(n > 0, "vgs_load_models: a VLMC needs at least one context");
         VGS_CHECK_ARG(n < (int64_t)1 << 30, "vgs_load_models: too many contexts in one model");
-        int order = 0, n_deep = 0;
+        int order = 0;
+        int64_t len_hist[VGS_MAX_ORDER + 1] = {0};
         for (int64_t c = a; c < a + n; ++c) {
             int ln = ctx_len_h[c];
             if (ln > VGS_MAX_ORDER) {
@@ -417,7 +424,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
                 return VGS_ERR_INVALID;
             }
             order = std::max(order, ln);
-            n_deep += ln > VGS_L1_DEPTH ? ln - VGS_L1_DEPTH : 0;  // upper bound on the deep nodes (suffixes of length 7..len)
+            len_hist[ln]++;
         }
         mm.ctx_off = a;
         mm.n_ctx = (int32_t)n;
@@ -432,7 +439,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         mm.ph_seed = -1;
         mm.ph_bytes = (int32_t)((((int64_t)2 << mm.ph_lgr) + 15) / 16 * 16 + cap * 8);
         mm.ph_off = ph_bytes;
-        mm.ph_pad = 0;
+        mm.l1_depth = 0;
         ph_bytes += ((int64_t)mm.ph_bytes + 255) / 256 * 256;
         h->max_ph_bytes = std::max<int64_t>(h->max_ph_bytes, mm.ph_bytes);
         h->max_pair_bytes = std::max(h->max_pair_bytes, cap * 8 + n * 16);
@@ -447,9 +454,21 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
             h->max_nll_bytes_t1 = std::max<int64_t>(h->max_nll_bytes_t1, mm.nll_bytes);
         } else {
             mm.tier = 2;
-            int64_t dcap;
-            int dlg = log2_ceil_pow2(2 * std::max(n_deep, 1), &dcap);
-            int64_t l1_bytes = ((int64_t)1 << (2 * VGS_L1_DEPTH)) * 4;
+            // first-level map over the last D1 symbols: as deep as shared memory allows (D1 = order means the map
+            // alone answers every history: two gathers per base, no deep walk).  u16 entries (bit 15 = "a longer
+            // context ends here") unless the model has >= 32767 contexts.
+            const bool wide = n >= 0x7FFF;
+            int d1 = wide ? VGS_L1_DEPTH : std::min(order, VGS_L1_MAX_DEPTH);
+            int64_t dcap = 8, l1_bytes = 0, n_nodes = 0;
+            int dlg = 3;
+            for (;; --d1) {
+                n_nodes = 0;  // deep nodes: every suffix of length d1+1..len of every context longer than d1
+                for (int ln = d1 + 1; ln <= order; ++ln) n_nodes += len_hist[ln] * (ln - d1);
+                dlg = log2_ceil_pow2(2 * std::max<int64_t>(n_nodes, 1), &dcap);
+                l1_bytes = (((int64_t)1 << (2 * d1)) * (wide ? 4 : 2) + 15) / 16 * 16;
+                if (d1 <= VGS_L1_DEPTH || l1_bytes + dcap * 8 + n * 32 <= VGS_T2_SMEM_BUDGET) break;
+            }
+            mm.l1_depth = d1 | (wide ? 0x100 : 0);
             mm.deep_off = (int32_t)l1_bytes;
             mm.deep_mask = (uint32_t)(dcap - 1);
             mm.deep_shift = 32 - dlg;

@@ -59,13 +59,17 @@ struct DenseTable {  // tier 1
 };
 
 struct TwoLevelTable {  // tier 2
-    const uint32_t *l1;
+    const void *l1;
     const uint2 *deep;
     const double *rows;
-    uint32_t deep_mask;
-    int deep_shift, order;
+    uint32_t deep_mask, d1mask;
+    int deep_shift, order, d1;
+    bool wide;
     __device__ __forceinline__ void bind(const uint8_t *blob, const ModelMeta &mm) {
-        l1 = (const uint32_t *)blob;
+        l1 = (const void *)blob;
+        d1 = mm.l1_depth & 0xFF;
+        wide = (mm.l1_depth & 0x100) != 0;
+        d1mask = vgs_lowmask(d1);
         deep = (const uint2 *)(blob + mm.deep_off);
         rows = (const double *)(blob + mm.logp_off);
         deep_mask = mm.deep_mask;
@@ -74,12 +78,21 @@ struct TwoLevelTable {  // tier 2
     }
     __device__ __forceinline__ double term(uint32_t f) const {
         const uint32_t x = f & 3u, hist = f >> 2;
-        const uint32_t e = l1[hist & ((1u << (2 * VGS_L1_DEPTH)) - 1u)];
-        uint32_t id = e & 0x7FFFFFFFu;
-        if (e & 0x80000000u) {
-            // walk up the deep node table from length 7; the first missing node ends the walk (every suffix of a
-            // deep context is a node, and a node's value is already the longest real context below it)
-            for (int ln = VGS_L1_DEPTH + 1; ln <= order; ++ln) {
+        uint32_t id;
+        bool more;
+        if (wide) {
+            const uint32_t e = ((const uint32_t *)l1)[hist & d1mask];
+            id = e & 0x7FFFFFFFu;
+            more = (e & 0x80000000u) != 0u;
+        } else {
+            const uint32_t e = ((const uint16_t *)l1)[hist & d1mask];
+            id = (e & 0x7FFFu) == VGS_UMAP_NONE ? VGS_NO_CTX : (e & 0x7FFFu);
+            more = (e & 0x8000u) != 0u;
+        }
+        if (more) {
+            // walk up the deep node table from length D1 + 1; the first missing node ends the walk (every suffix of
+            // a deep context is a node, and a node's value is already the longest real context below it)
+            for (int ln = d1 + 1; ln <= order; ++ln) {
                 const int r = vgs_hash_find(deep, deep_mask, deep_shift, vgs_key(ln, hist & vgs_lowmask(ln)));
                 if (r < 0) break;
                 id = (uint32_t)r;
