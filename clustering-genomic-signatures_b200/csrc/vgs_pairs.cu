@@ -338,7 +338,16 @@ extern "C" int vgs_pair_matrix(vgs_handle h, int kind, float *D32_d, double *D64
     cudaStream_t s = (cudaStream_t)stream;
     TilePlan pl;
     const int64_t n = h->n_models;
-    vgs_make_plan(&pl, n, n <= 2048 ? 64 : 128, 1, 1);
+    // tile edge: 64/128 normally; a few huge models (tables larger than shared memory, read from L2/HBM) need many
+    // more CTAs than pairs/4096, so the tile shrinks until the grid covers the SMs a few times
+    int64_t tile = n <= 2048 ? 64 : 128;
+    {
+        const int64_t per_model = h->umap_stride > 0 ? h->umap_stride * 2 + (int64_t)h->max_n_ctx * 16
+                                                     : h->max_pair_bytes + (int64_t)h->max_n_ctx * 16;
+        if (per_model > (int64_t)h->max_smem_optin - 2048)
+            while (tile > 4 && ((n + tile - 1) / tile) * ((n + tile - 1) / tile + 1) / 2 * ((tile + 3) / 4) < 4 * h->sm_count) tile /= 2;
+    }
+    vgs_make_plan(&pl, n, tile, 1, 1);
     const int64_t pay_elems = pl.slots * pl.tile * pl.tile;
     if ((rc = vgs_ensure_scratch(h, pay_elems * (D64_d ? 12 : 4) + 256))) return rc;
     float *pay32 = (float *)h->d_scratch;
