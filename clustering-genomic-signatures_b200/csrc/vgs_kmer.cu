@@ -293,8 +293,9 @@ struct KgEpi {
 
 __global__ void k_kmer_epilogue(const KgEpi p) {
     const int pair = blockIdx.x;
+    const int e_begin = blockIdx.y * (KG_BLOCK * KG_BLOCK / 8), e_end = e_begin + KG_BLOCK * KG_BLOCK / 8;
     const int sb = p.pairs[2 * pair], mb = p.pairs[2 * pair + 1];
-    for (int e = threadIdx.x; e < KG_BLOCK * KG_BLOCK; e += blockDim.x) {
+    for (int e = e_begin + threadIdx.x; e < e_end; e += blockDim.x) {
         const int r = e / KG_BLOCK, c = e % KG_BLOCK;
         const int64_t s = (int64_t)sb * KG_BLOCK + r, m = (int64_t)mb * KG_BLOCK + c;
         if (s >= p.n_seq || m >= p.n_models) continue;
@@ -420,7 +421,7 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
     e.partial = h->d_kmer_partial; e.pairs = d_pairs; e.n_pairs = n_pairs; e.split = split; e.depth = D;
     e.meta = h->d_meta; e.arena = h->d_nll; e.seq = h->d_seq; e.seq_off = h->d_seq_off; e.seq_len = h->d_seq_len;
     e.n_seq = h->n_seq; e.n_models = h->n_models; e.ld = ld; e.M = M;
-    k_kmer_epilogue<<<n_pairs, 256, 0, s>>>(e);
+    k_kmer_epilogue<<<dim3((unsigned)n_pairs, 8), 256, 0, s>>>(e);
     VGS_LAUNCH_CHECK(h);
     return VGS_OK;
 }

@@ -436,7 +436,10 @@ __global__ void k_nll_combine(TilePlan pl, int rank, const double *__restrict__ 
     }
     __syncthreads();
     const int64_t I = sI, J = sJ;
-    for (int64_t e = threadIdx.x; e < T * T; e += blockDim.x) {
+    // gridDim.y blocks share one tile slot
+    const int64_t per = (T * T + gridDim.y - 1) / gridDim.y;
+    const int64_t e_end = min(T * T, (int64_t)(blockIdx.y + 1) * per);
+    for (int64_t e = (int64_t)blockIdx.y * per + threadIdx.x; e < e_end; e += blockDim.x) {
         const int64_t i = I * T + e / T, j = J * T + e % T;
         double d = 0.0;
         if (k < pl.n_tiles && i < pl.n && j < pl.n) {
@@ -475,7 +478,7 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
         if (rc > 0) return rc;
         if (rc == VGS_OK) {
             if (pl.slots > 0) {
-                k_nll_combine<<<(unsigned)pl.slots, 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
+                k_nll_combine<<<dim3((unsigned)pl.slots, (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, pl.tile * pl.tile / 2048))), 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
                 VGS_LAUNCH_CHECK(h);
             }
             return VGS_OK;
@@ -498,7 +501,7 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
     rc = vgs_nll_score_lists(h, lists, pl.tile, 0, h->n_models, true, VGS_SKIP_ORDER, mode, h->d_M, h->n_models, s);
     if (rc) return rc;
     if (pl.slots > 0) {
-        k_nll_combine<<<(unsigned)pl.slots, 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
+        k_nll_combine<<<dim3((unsigned)pl.slots, (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, pl.tile * pl.tile / 2048))), 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
         VGS_LAUNCH_CHECK(h);
     }
     return VGS_OK;
