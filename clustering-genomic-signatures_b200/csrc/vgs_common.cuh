@@ -38,7 +38,7 @@ struct ModelMeta {
     int32_t order;
     uint32_t hash_mask;   // capacity - 1
     int32_t hash_shift;   // 32 - log2(capacity)
-    int32_t tier;         // 1 dense, 2 two-level
+    int32_t tier;         // 1 dense, 2 two-level (u16 map), 3 two-level (u32 map, >= 32767 contexts)
     int32_t nll_bytes;    // blob size, multiple of 16
     uint32_t deep_mask;   // tier 2: deep hash capacity - 1 (0 if no deep contexts)
     int32_t deep_shift;
@@ -68,7 +68,7 @@ struct vgs_context {
     int64_t h_logp_cap = 0;
     bool nll_ready = false;     // false when loaded with VGS_LOAD_SKIP_NLL
     int max_order = 0;
-    int64_t max_nll_bytes_t1 = 0, max_nll_bytes_t2 = 0;
+    int64_t max_nll_bytes_t1 = 0, max_nll_bytes_t2 = 0, max_nll_bytes_t3 = 0;
     int64_t max_pair_bytes = 0;  // hash + fp32 rows of the largest model
     ModelMeta *d_meta = nullptr;
     uint32_t *d_key = nullptr;

@@ -245,7 +245,7 @@ __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint
                                   const uint32_t *__restrict__ code, const double *__restrict__ logp,
                                   uint8_t *__restrict__ arena) {
     const ModelMeta mm = meta[blockIdx.x];
-    if (mm.tier != 2) return;
+    if (mm.tier < 2) return;
     uint32_t *l1 = (uint32_t *)(arena + mm.nll_off);
     unsigned long long *deep = (unsigned long long *)(arena + mm.nll_off + mm.deep_off);
     double *rows = (double *)(arena + mm.nll_off + mm.logp_off);
@@ -400,7 +400,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     h->h_ctx_off.assign(ctx_offsets_h, ctx_offsets_h + n_models + 1);
     h->h_meta.assign((size_t)n_models, ModelMeta());
     h->max_order = 0;
-    h->max_nll_bytes_t1 = h->max_nll_bytes_t2 = h->max_pair_bytes = 0;
+    h->max_nll_bytes_t1 = h->max_nll_bytes_t2 = h->max_nll_bytes_t3 = h->max_pair_bytes = 0;
     h->max_n_ctx = 0;
     h->umap_stride = 0;
     int64_t hash_slots = 0, nll_bytes = 0, ph_bytes = 0;
@@ -453,7 +453,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
             mm.deep_mask = 0; mm.deep_shift = 0; mm.deep_off = 0; mm.logp_off = 0;
             h->max_nll_bytes_t1 = std::max<int64_t>(h->max_nll_bytes_t1, mm.nll_bytes);
         } else {
-            mm.tier = 2;
+            mm.tier = n >= 0x7FFF ? 3 : 2;
             // first-level map over the last D1 symbols: as deep as shared memory allows (D1 = order means the map
             // alone answers every history: two gathers per base, no deep walk).  u16 entries (bit 15 = "a longer
             // context ends here") unless the model has >= 32767 contexts.
@@ -479,7 +479,8 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
                 return VGS_ERR_UNSUPPORTED;
             }
             mm.nll_bytes = (int32_t)bytes;
-            h->max_nll_bytes_t2 = std::max<int64_t>(h->max_nll_bytes_t2, bytes);
+            if (mm.tier == 2) h->max_nll_bytes_t2 = std::max<int64_t>(h->max_nll_bytes_t2, bytes);
+            else h->max_nll_bytes_t3 = std::max<int64_t>(h->max_nll_bytes_t3, bytes);
         }
         nll_bytes += ((int64_t)mm.nll_bytes + 255) / 256 * 256;
     }
@@ -578,7 +579,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     if ((rc = vgs_reserve(h, &h->d_logp, total * 4))) return rc;
     if ((rc = vgs_reserve(h, &h->d_nll, nll_bytes))) return rc;
     VGS_CUDA(cudaMemcpyAsync(h->d_logp, h->h_logp, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
-    if (h->max_nll_bytes_t2 > 0) VGS_CUDA(cudaMemsetAsync(h->d_nll, 0, (size_t)nll_bytes, s));  // deep hashes start empty
+    if (h->max_nll_bytes_t2 > 0 || h->max_nll_bytes_t3 > 0) VGS_CUDA(cudaMemsetAsync(h->d_nll, 0, (size_t)nll_bytes, s));  // deep hashes start empty
     if (h->max_nll_bytes_t1 > 0) {
         // grid.x covers up to 4^6 histories with 256-thread blocks
         dim3 grid(16, (unsigned)std::min<int64_t>(n_models, 65535));
@@ -588,7 +589,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
             VGS_LAUNCH_CHECK(h);
         }
     }
-    if (h->max_nll_bytes_t2 > 0) {
+    if (h->max_nll_bytes_t2 > 0 || h->max_nll_bytes_t3 > 0) {
         k_build_two_level<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_hash, h->d_key, h->d_len, h->d_code, h->d_logp, h->d_nll);
         VGS_LAUNCH_CHECK(h);
     }

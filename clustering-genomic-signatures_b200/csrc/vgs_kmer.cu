@@ -325,7 +325,7 @@ __global__ void k_kmer_epilogue(const KgEpi p) {
 // host
 // ---------------------------------------------------------------------------------------------------------
 bool vgs_kmer_applicable(vgs_context *h) {
-    if (h->max_nll_bytes_t2 > 0 || h->max_order > VGS_DENSE_MAX_ORDER) return false;
+    if (h->max_nll_bytes_t2 > 0 || h->max_nll_bytes_t3 > 0 || h->max_order > VGS_DENSE_MAX_ORDER) return false;
     return true;
 }
 

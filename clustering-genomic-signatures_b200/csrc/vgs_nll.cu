@@ -56,19 +56,24 @@ struct DenseTable {  // tier 1
         fmask = vgs_lowmask(mm.order + 1);
     }
     __device__ __forceinline__ double term(uint32_t f) const { return tab[f & fmask]; }
+    // the 16 symbols of one fully scored word, in order
+    template <bool SEQ>
+    __device__ __forceinline__ void word16(uint32_t cur, uint32_t prev, double &acc) const {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += tab[__funnelshift_r(cur, prev, 30 - 2 * j) & fmask];
+    }
 };
 
-struct TwoLevelTable {  // tier 2
+template <bool WIDE>
+struct TwoLevelTable {  // tier 2 (u16 first-level entries) and tier 3 (u32 entries, models with >= 32767 contexts)
     const void *l1;
     const uint2 *deep;
     const double *rows;
     uint32_t deep_mask, d1mask;
     int deep_shift, order, d1;
-    bool wide;
     __device__ __forceinline__ void bind(const uint8_t *blob, const ModelMeta &mm) {
         l1 = (const void *)blob;
         d1 = mm.l1_depth & 0xFF;
-        wide = (mm.l1_depth & 0x100) != 0;
         d1mask = vgs_lowmask(d1);
         deep = (const uint2 *)(blob + mm.deep_off);
         rows = (const double *)(blob + mm.logp_off);
@@ -80,18 +85,20 @@ struct TwoLevelTable {  // tier 2
         const uint32_t x = f & 3u, hist = f >> 2;
         uint32_t id;
         bool more;
-        if (wide) {
+        if (WIDE) {
             const uint32_t e = ((const uint32_t *)l1)[hist & d1mask];
             id = e & 0x7FFFFFFFu;
             more = (e & 0x80000000u) != 0u;
         } else {
             const uint32_t e = ((const uint16_t *)l1)[hist & d1mask];
-            id = (e & 0x7FFFu) == VGS_UMAP_NONE ? VGS_NO_CTX : (e & 0x7FFFu);
+            id = e & 0x7FFFu;
             more = (e & 0x8000u) != 0u;
+            if (id == VGS_UMAP_NONE) id = VGS_NO_CTX;
         }
         if (more) {
-            // walk up the deep node table from length D1 + 1; the first missing node ends the walk (every suffix of
-            // a deep context is a node, and a node's value is already the longest real context below it)
+            // walk up the deep node table from length D1 + 1; the first missing node ends the walk (every suffix of a
+            // deep context is a node, and a node's value is already the longest real context below it)
+#pragma unroll 1
             for (int ln = d1 + 1; ln <= order; ++ln) {
                 const int r = vgs_hash_find(deep, deep_mask, deep_shift, vgs_key(ln, hist & vgs_lowmask(ln)));
                 if (r < 0) break;
@@ -99,6 +106,34 @@ struct TwoLevelTable {  // tier 2
             }
         }
         return id == VGS_NO_CTX ? vgs_nan() : rows[4 * id + x];
+    }
+    // One fully scored word in two phases so that the unrolled code has no branches: (1) the 16 first-level entries;
+    // (2) if none of them asks for the deep table (the common case: < 2 % of the words at D1 = 8) the 16 row gathers
+    // and adds in order, else the word is redone symbol by symbol through term() in a rolled loop.
+    template <bool SEQ>
+    __device__ __forceinline__ void word16(uint32_t cur, uint32_t prev, double &acc) const {
+        uint32_t e[16];
+        uint32_t any = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t hist = __funnelshift_r(cur, prev, 30 - 2 * j) >> 2;
+            if (WIDE) {
+                e[j] = ((const uint32_t *)l1)[hist & d1mask];
+                any |= e[j] & 0x80000000u;
+                any |= (e[j] == VGS_NO_CTX) ? 1u : 0u;
+            } else {
+                e[j] = ((const uint16_t *)l1)[hist & d1mask];
+                any |= e[j] & 0x8000u;
+                any |= (e[j] == VGS_UMAP_NONE) ? 1u : 0u;
+            }
+        }
+        if (any == 0u) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc += rows[4 * e[j] + ((cur >> (30 - 2 * j)) & 3u)];
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < 16; ++j) acc += term(__funnelshift_r(cur, prev, 30 - 2 * j));
+        }
     }
 };
 
@@ -113,11 +148,8 @@ __device__ __forceinline__ void scan_chunk(const TAB &T, const uint4 q, uint32_t
         const uint32_t cur = ws[k];
         const int64_t tw = t0 + 16 * k;
         if (tw >= skip && tw + 16 <= L) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const double v = T.term(__funnelshift_r(cur, prev, 30 - 2 * j));
-                if (SEQ) acc += v; else part[k] += v;
-            }
+            if (SEQ) T.template word16<true>(cur, prev, acc);
+            else T.template word16<false>(cur, prev, part[k]);
         } else if (tw < L && tw + 16 > skip) {
 #pragma unroll 1
             for (int j = 0; j < 16; ++j) {
@@ -157,7 +189,7 @@ __global__ void __launch_bounds__(NLL_MAX_THREADS, 1) k_nll_scores(const NllPara
     if (STAGED && tid == 0) vgs_mbar_init(&bar, 1);
     uint32_t parity = 0;
     int cur_model = -1;
-    typename std::conditional<TIER == 1, DenseTable, TwoLevelTable>::type T;
+    typename std::conditional<TIER == 1, DenseTable, TwoLevelTable<TIER == 3>>::type T;
     ModelMeta mm;
     // units are handed out dynamically (they are sorted by model, so a CTA mostly keeps its staged table)
     for (;;) {
@@ -287,7 +319,7 @@ static int launch_nll_tier(vgs_context *h, const NllParams &p, int mode, int64_t
 int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &lists, int64_t block, int64_t m_begin,
                         int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld, cudaStream_t s) {
     if (mode == VGS_NLL_KMER) mode = VGS_NLL_WARP;  // the scan kernels have two modes
-    std::vector<NllUnit> units[2];
+    std::vector<NllUnit> units[3];
     std::vector<int32_t> flat;
     std::vector<int64_t> list_off(lists.size() + 1, 0);
     for (size_t b = 0; b < lists.size(); ++b) {
@@ -324,8 +356,8 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
             units[t].push_back(un);
         }
     }
-    if (units[0].empty() && units[1].empty()) return VGS_OK;
-    const int64_t n_units_total = (int64_t)(units[0].size() + units[1].size());
+    if (units[0].empty() && units[1].empty() && units[2].empty()) return VGS_OK;
+    const int64_t n_units_total = (int64_t)(units[0].size() + units[1].size() + units[2].size());
     int64_t bytes = n_units_total * (int64_t)sizeof(NllUnit) + (int64_t)flat.size() * 4 + 256;
     int rc = vgs_ensure_scratch2(h, bytes);
     if (rc) return rc;
@@ -335,6 +367,9 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
         VGS_CUDA(cudaMemcpyAsync(d_units, units[0].data(), units[0].size() * sizeof(NllUnit), cudaMemcpyHostToDevice, s));
     if (!units[1].empty())
         VGS_CUDA(cudaMemcpyAsync(d_units + units[0].size(), units[1].data(), units[1].size() * sizeof(NllUnit), cudaMemcpyHostToDevice, s));
+    if (!units[2].empty())
+        VGS_CUDA(cudaMemcpyAsync(d_units + units[0].size() + units[1].size(), units[2].data(), units[2].size() * sizeof(NllUnit),
+                                 cudaMemcpyHostToDevice, s));
     if (!flat.empty()) VGS_CUDA(cudaMemcpyAsync(d_list, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, s));
     // pageable sources: the copies above have consumed the host vectors when they return
     NllParams p;
@@ -353,6 +388,11 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
         p.counter = h->d_counters + 1;
         p.units = d_units + units[0].size(); p.n_units = (int)units[1].size();
         if ((rc = launch_nll_tier<2>(h, p, mode, h->max_nll_bytes_t2, s))) return rc;
+    }
+    if (!units[2].empty()) {
+        p.counter = h->d_counters + 3;
+        p.units = d_units + units[0].size() + units[1].size(); p.n_units = (int)units[2].size();
+        if ((rc = launch_nll_tier<3>(h, p, mode, h->max_nll_bytes_t3, s))) return rc;
     }
     return VGS_OK;
 }
