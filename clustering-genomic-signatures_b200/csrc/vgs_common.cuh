@@ -67,6 +67,7 @@ struct vgs_context {
     double *h_logp = nullptr;   // pinned staging of the host-computed ln p table
     int64_t h_logp_cap = 0;
     bool nll_ready = false;     // false when loaded with VGS_LOAD_SKIP_NLL
+    void *pool = nullptr;       // host thread pool (VgsPool, vgs_core.cu)
     int max_order = 0;
     int64_t max_nll_bytes_t1 = 0, max_nll_bytes_t2 = 0, max_nll_bytes_t3 = 0;
     int64_t max_pair_bytes = 0;  // hash + fp32 rows of the largest model

@@ -10,11 +10,73 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #include "vgs_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
+// small persistent host thread pool (per handle): the host side of vgs_load_models (validation, ln p) runs on it
+class VgsPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::function<void(int)> fn;
+    int gen = 0, pending = 0, n;
+    bool stop = false;
+
+  public:
+    explicit VgsPool(int n_) : n(n_) {
+        for (int i = 0; i < n; ++i)
+            th.emplace_back([this, i]() {
+                int seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return stop || gen != seen; });
+                    if (stop) return;
+                    seen = gen;
+                    std::function<void(int)> f = fn;
+                    lk.unlock();
+                    f(i);
+                    lk.lock();
+                    if (--pending == 0) cv_done.notify_all();
+                }
+            });
+    }
+    ~VgsPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+    }
+    int size() const { return n; }
+    void start(std::function<void(int)> f) {
+        std::lock_guard<std::mutex> lk(mu);
+        fn = std::move(f);
+        pending = n;
+        ++gen;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+
+static VgsPool *get_pool(vgs_context *h) {
+    if (!h->pool) {
+        unsigned hc = std::thread::hardware_concurrency();
+        int n = (int)std::max(1u, std::min(hc > 2 ? hc - 1 : 1u, 24u));
+        h->pool = new VgsPool(n);
+    }
+    return (VgsPool *)h->pool;
+}
+
 static thread_local std::string g_last_error;
 
 void vgs_set_error(const char *fmt, ...) {
@@ -131,6 +193,7 @@ extern "C" int vgs_destroy(vgs_handle h) {
     cudaFree(h->d_scratch2);
     cudaFree(h->d_err);
     if (h->h_logp) cudaFreeHost(h->h_logp);
+    delete (VgsPool *)h->pool;
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return VGS_OK;
@@ -406,6 +469,36 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     int64_t hash_slots = 0, nll_bytes = 0, ph_bytes = 0;
     h->max_ph_bytes = 0;
     h->ph_ready = false;
+    // per-model scan of the context lengths (order, length histogram, validity) on the host pool
+    VgsPool *pool = get_pool(h);
+    std::vector<int32_t> len_hists((size_t)n_models * 16, 0);
+    std::vector<int64_t> bad_model((size_t)pool->size(), -1);
+    std::vector<int> bad_kind((size_t)pool->size(), 0);
+    {
+        const int nt = pool->size();
+        pool->start([&, nt](int tid) {
+            for (int64_t m = tid; m < n_models; m += nt) {
+                const int64_t a = ctx_offsets_h[m], e = ctx_offsets_h[m + 1];
+                int32_t *hist = &len_hists[(size_t)m * 16];
+                for (int64_t c = a; c < e; ++c) {
+                    const int ln = ctx_len_h[c];
+                    if (ln > VGS_MAX_ORDER) { if (bad_model[(size_t)tid] < 0) { bad_model[(size_t)tid] = m; bad_kind[(size_t)tid] = 1; } continue; }
+                    if ((ctx_code_h[c] >> (2 * ln)) != 0 && bad_model[(size_t)tid] < 0) { bad_model[(size_t)tid] = m; bad_kind[(size_t)tid] = 2; }
+                    hist[ln]++;
+                }
+            }
+        });
+        pool->wait();
+        for (int t = 0; t < nt; ++t)
+            if (bad_model[(size_t)t] >= 0) {
+                if (bad_kind[(size_t)t] == 1) {
+                    vgs_set_error("context longer than %d symbols is not supported (model %lld)", VGS_MAX_ORDER, (long long)bad_model[(size_t)t]);
+                    return VGS_ERR_UNSUPPORTED;
+                }
+                vgs_set_error("context code has bits above its length (model %lld)", (long long)bad_model[(size_t)t]);
+                return VGS_ERR_INVALID;
+            }
+    }
     for (int64_t m = 0; m < n_models; ++m) {
         ModelMeta &mm = h->h_meta[(size_t)m];
         int64_t a = ctx_offsets_h[m], n = ctx_offsets_h[m + 1] - a;
@@ -413,18 +506,9 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         VGS_CHECK_ARG(n < (int64_t)1 << 30, "vgs_load_models: too many contexts in one model");
         int order = 0;
         int64_t len_hist[VGS_MAX_ORDER + 1] = {0};
-        for (int64_t c = a; c < a + n; ++c) {
-            int ln = ctx_len_h[c];
-            if (ln > VGS_MAX_ORDER) {
-                vgs_set_error("context longer than %d symbols is not supported (model %lld)", VGS_MAX_ORDER, (long long)m);
-                return VGS_ERR_UNSUPPORTED;
-            }
-            if (ln < 16 && (ctx_code_h[c] >> (2 * ln)) != 0) {
-                vgs_set_error("context code has bits above its length (model %lld, context %lld)", (long long)m, (long long)(c - a));
-                return VGS_ERR_INVALID;
-            }
-            order = std::max(order, ln);
-            len_hist[ln]++;
+        for (int ln = 0; ln <= VGS_MAX_ORDER; ++ln) {
+            len_hist[ln] = len_hists[(size_t)m * 16 + ln];
+            if (len_hist[ln] > 0) order = ln;
         }
         mm.ctx_off = a;
         mm.n_ctx = (int32_t)n;
@@ -547,38 +631,57 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         VGS_CUDA(cudaHostAlloc((void **)&h->h_logp, sizeof(double) * (size_t)total * 4, cudaHostAllocDefault));
         h->h_logp_cap = total * 4;
     }
-    if (logp_h) {
-        memcpy(h->h_logp, logp_h, sizeof(double) * (size_t)total * 4);
-    } else {
-        unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-        if (total * 4 < 200000) nt = 1;
-        std::vector<std::thread> th;
-        double *out = h->h_logp;
-        std::vector<int64_t> bad(nt, -1);
-        for (unsigned t = 0; t < nt; ++t) {
-            int64_t b0 = total * 4 * t / nt, e0 = total * 4 * (t + 1) / nt;
-            int64_t *badp = &bad[t];
-            th.emplace_back([=]() {
-                for (int64_t i = b0; i < e0; ++i) {
-                    double p = prob_h[i];
-                    if (p < 0 && *badp < 0) *badp = i;
-                    out[i] = (p == 0) ? -1000.0 : log(p);
-                }
-            });
-        }
-        for (auto &x : th) x.join();
-        for (unsigned t = 0; t < nt; ++t)
-            if (bad[t] >= 0) {
-                cudaStreamSynchronize(s);
-                vgs_set_error("math domain error: negative transition probability (entry %lld)", (long long)bad[t]);
-                return VGS_ERR_INVALID;
-            }
-    }
-
-    // 3. upload ln p and build the NLL tables
+    if (logp_h) memcpy(h->h_logp, logp_h, sizeof(double) * (size_t)total * 4);
     if ((rc = vgs_reserve(h, &h->d_logp, total * 4))) return rc;
     if ((rc = vgs_reserve(h, &h->d_nll, nll_bytes))) return rc;
-    VGS_CUDA(cudaMemcpyAsync(h->d_logp, h->h_logp, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    if (logp_h) {
+        VGS_CUDA(cudaMemcpyAsync(h->d_logp, h->h_logp, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    } else {
+        // chunks are claimed with an atomic counter; this thread uploads each chunk as soon as it is complete, so the
+        // PCIe transfer of ln p overlaps its computation
+        const int64_t n_elem = total * 4;
+        const int64_t chunk = 1 << 16;
+        const int64_t n_chunks = (n_elem + chunk - 1) / chunk;
+        std::atomic<int64_t> next(0), bad(-1);
+        std::vector<std::atomic<int>> done((size_t)n_chunks);
+        for (auto &d : done) d.store(0);
+        double *out = h->h_logp;
+        pool->start([&](int) {
+            for (;;) {
+                const int64_t c = next.fetch_add(1);
+                if (c >= n_chunks) break;
+                const int64_t b0 = c * chunk, e0 = std::min(n_elem, b0 + chunk);
+                for (int64_t i = b0; i < e0; ++i) {
+                    const double p = prob_h[i];
+                    if (p < 0) { int64_t expect = -1; bad.compare_exchange_strong(expect, i); }
+                    out[i] = (p == 0) ? -1000.0 : log(p);
+                }
+                done[(size_t)c].store(1, std::memory_order_release);
+            }
+        });
+        cudaError_t ce = cudaSuccess;
+        int64_t sent = 0;  // chunks [0, sent) are uploaded; batches of completed consecutive chunks go out together
+        while (sent < n_chunks && ce == cudaSuccess) {
+            int64_t upto = sent;
+            while (upto < n_chunks && done[(size_t)upto].load(std::memory_order_acquire)) ++upto;
+            if (upto - sent >= 8 || (upto == n_chunks && upto > sent)) {
+                const int64_t b0 = sent * chunk, e0 = std::min(n_elem, upto * chunk);
+                ce = cudaMemcpyAsync(h->d_logp + b0, out + b0, sizeof(double) * (size_t)(e0 - b0), cudaMemcpyHostToDevice, s);
+                sent = upto;
+            } else {
+                std::this_thread::yield();
+            }
+        }
+        pool->wait();
+        if (ce != cudaSuccess) return vgs_cuda_fail(ce, "ln p upload", __FILE__, __LINE__);
+        if (bad.load() >= 0) {
+            cudaStreamSynchronize(s);
+            vgs_set_error("math domain error: negative transition probability (entry %lld)", (long long)bad.load());
+            return VGS_ERR_INVALID;
+        }
+    }
+
+    // 3. build the NLL tables
     if (h->max_nll_bytes_t2 > 0 || h->max_nll_bytes_t3 > 0) VGS_CUDA(cudaMemsetAsync(h->d_nll, 0, (size_t)nll_bytes, s));  // deep hashes start empty
     if (h->max_nll_bytes_t1 > 0) {
         // grid.x covers up to 4^6 histories with 256-thread blocks
