@@ -319,10 +319,12 @@ __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint
     const uint32_t n1 = 1u << (2 * d1);
     for (uint32_t hc = threadIdx.x; hc < n1; hc += blockDim.x) {
         int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, d1 < mm.order ? d1 : mm.order, hc, d1);
-        if (wide) l1[hc] = id >= 0 ? (uint32_t)id : VGS_NO_CTX;
-        else l1n[hc] = id >= 0 ? (uint16_t)id : (uint16_t)VGS_UMAP_NONE;
+        // "no context" points at the extra all-NaN row behind the model's rows: no special case in the scan
+        if (wide) l1[hc] = id >= 0 ? (uint32_t)id : (uint32_t)mm.n_ctx;
+        else l1n[hc] = id >= 0 ? (uint16_t)id : (uint16_t)mm.n_ctx;
     }
     for (int i = threadIdx.x; i < 4 * mm.n_ctx; i += blockDim.x) rows[i] = logp[4 * mm.ctx_off + i];
+    if (threadIdx.x < 4) rows[4 * mm.n_ctx + threadIdx.x] = vgs_nan();
     __syncthreads();
     // deep node table: EVERY suffix of length 7..len of every deep context is a node (real or virtual) whose value is
     // the ctx_id of the longest real context that is a suffix of the node string.  A scan can then walk upwards from
@@ -337,7 +339,8 @@ __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint
         for (int l2 = d1 + 1; l2 <= ln; ++l2) {
             const uint32_t sc = cd & vgs_lowmask(l2);
             const uint32_t k = vgs_key(l2, sc);
-            const int val = l2 == ln ? c : vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, sc, l2);
+            int val = l2 == ln ? c : vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, sc, l2);
+            if (val < 0) val = mm.n_ctx;  // no real context below this virtual node: the NaN row
             uint32_t s = vgs_hash_slot(k, mm.deep_shift);
             const unsigned long long want = ((unsigned long long)(uint32_t)val << 32) | k;
             while (true) {
@@ -550,14 +553,14 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
                 for (int ln = d1 + 1; ln <= order; ++ln) n_nodes += len_hist[ln] * (ln - d1);
                 dlg = log2_ceil_pow2(2 * std::max<int64_t>(n_nodes, 1), &dcap);
                 l1_bytes = (((int64_t)1 << (2 * d1)) * (wide ? 4 : 2) + 15) / 16 * 16;
-                if (d1 <= VGS_L1_DEPTH || l1_bytes + dcap * 8 + n * 32 <= VGS_T2_SMEM_BUDGET) break;
+                if (d1 <= VGS_L1_DEPTH || l1_bytes + dcap * 8 + (n + 1) * 32 <= VGS_T2_SMEM_BUDGET) break;
             }
             mm.l1_depth = d1 | (wide ? 0x100 : 0);
             mm.deep_off = (int32_t)l1_bytes;
             mm.deep_mask = (uint32_t)(dcap - 1);
             mm.deep_shift = 32 - dlg;
             mm.logp_off = (int32_t)(l1_bytes + dcap * 8);
-            int64_t bytes = mm.logp_off + n * 32;
+            int64_t bytes = mm.logp_off + (n + 1) * 32;  // + one all-NaN row for histories without any context
             if (bytes >= ((int64_t)1 << 31)) {
                 vgs_set_error("model %lld is too large for the two-level NLL table", (long long)m);
                 return VGS_ERR_UNSUPPORTED;

@@ -64,11 +64,25 @@ struct DenseTable {  // tier 1
     }
 };
 
+// rare path of the two-level table, out of line so that the unrolled per-base code stays small: walk up the deep
+// node table from length D1 + 1; the first missing node ends the walk (every suffix of a deep context is a node, and a
+// node's value is already the longest real context below it)
+__device__ __noinline__ uint32_t nll_deep_walk(const uint2 *deep, uint32_t deep_mask, int deep_shift, int d1, int order,
+                                               uint32_t hist, uint32_t id) {
+#pragma unroll 1
+    for (int ln = d1 + 1; ln <= order; ++ln) {
+        const int r = vgs_hash_find(deep, deep_mask, deep_shift, vgs_key(ln, hist & vgs_lowmask(ln)));
+        if (r < 0) break;
+        id = (uint32_t)r;
+    }
+    return id;
+}
+
 template <bool WIDE>
 struct TwoLevelTable {  // tier 2 (u16 first-level entries) and tier 3 (u32 entries, models with >= 32767 contexts)
     const void *l1;
     const uint2 *deep;
-    const double *rows;
+    const double *rows;   // [n_ctx + 1][4]: the last row is NaN ("no context"), first-level entries point at it
     uint32_t deep_mask, d1mask;
     int deep_shift, order, d1;
     __device__ __forceinline__ void bind(const uint8_t *blob, const ModelMeta &mm) {
@@ -81,59 +95,32 @@ struct TwoLevelTable {  // tier 2 (u16 first-level entries) and tier 3 (u32 entr
         deep_shift = mm.deep_shift;
         order = mm.order;
     }
-    __device__ __forceinline__ double term(uint32_t f) const {
-        const uint32_t x = f & 3u, hist = f >> 2;
-        uint32_t id;
-        bool more;
-        if (WIDE) {
-            const uint32_t e = ((const uint32_t *)l1)[hist & d1mask];
-            id = e & 0x7FFFFFFFu;
-            more = (e & 0x80000000u) != 0u;
-        } else {
-            const uint32_t e = ((const uint16_t *)l1)[hist & d1mask];
-            id = e & 0x7FFFu;
-            more = (e & 0x8000u) != 0u;
-            if (id == VGS_UMAP_NONE) id = VGS_NO_CTX;
-        }
-        if (more) {
-            // walk up the deep node table from length D1 + 1; the first missing node ends the walk (every suffix of a
-            // deep context is a node, and a node's value is already the longest real context below it)
-#pragma unroll 1
-            for (int ln = d1 + 1; ln <= order; ++ln) {
-                const int r = vgs_hash_find(deep, deep_mask, deep_shift, vgs_key(ln, hist & vgs_lowmask(ln)));
-                if (r < 0) break;
-                id = (uint32_t)r;
-            }
-        }
-        return id == VGS_NO_CTX ? vgs_nan() : rows[4 * id + x];
+    // first-level entry of a history -> ctx_id, taking the deep walk when the entry asks for it
+    __device__ __forceinline__ uint32_t resolve(uint32_t e, uint32_t hist) const {
+        const uint32_t flag = WIDE ? 0x80000000u : 0x8000u;
+        uint32_t id = e & (flag - 1u);
+        if (e & flag) id = nll_deep_walk(deep, deep_mask, deep_shift, d1, order, hist, id);
+        return id;
     }
-    // One fully scored word in two phases so that the unrolled code has no branches: (1) the 16 first-level entries;
-    // (2) if none of them asks for the deep table (the common case: < 2 % of the words at D1 = 8) the 16 row gathers
-    // and adds in order, else the word is redone symbol by symbol through term() in a rolled loop.
+    __device__ __forceinline__ uint32_t entry(uint32_t hist) const {
+        return WIDE ? ((const uint32_t *)l1)[hist & d1mask] : (uint32_t)((const uint16_t *)l1)[hist & d1mask];
+    }
+    __device__ __forceinline__ double term(uint32_t f) const {
+        const uint32_t hist = f >> 2;
+        return rows[4 * resolve(entry(hist), hist) + (f & 3u)];
+    }
+    // One fully scored word in three phases, so that the unrolled code is branch-free except for the rare deep walk:
+    // (1) the 16 first-level gathers, (2) entries that ask for the deep table (~0.1 % of the bases at D1 = 8) are
+    // resolved by the out-of-line walk, (3) the 16 row gathers and adds, in order.
     template <bool SEQ>
     __device__ __forceinline__ void word16(uint32_t cur, uint32_t prev, double &acc) const {
         uint32_t e[16];
-        uint32_t any = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const uint32_t hist = __funnelshift_r(cur, prev, 30 - 2 * j) >> 2;
-            if (WIDE) {
-                e[j] = ((const uint32_t *)l1)[hist & d1mask];
-                any |= e[j] & 0x80000000u;
-                any |= (e[j] == VGS_NO_CTX) ? 1u : 0u;
-            } else {
-                e[j] = ((const uint16_t *)l1)[hist & d1mask];
-                any |= e[j] & 0x8000u;
-                any |= (e[j] == VGS_UMAP_NONE) ? 1u : 0u;
-            }
-        }
-        if (any == 0u) {
+        for (int j = 0; j < 16; ++j) e[j] = entry(__funnelshift_r(cur, prev, 30 - 2 * j) >> 2);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc += rows[4 * e[j] + ((cur >> (30 - 2 * j)) & 3u)];
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < 16; ++j) acc += term(__funnelshift_r(cur, prev, 30 - 2 * j));
-        }
+        for (int j = 0; j < 16; ++j) e[j] = resolve(e[j], __funnelshift_r(cur, prev, 30 - 2 * j) >> 2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += rows[4 * e[j] + ((cur >> (30 - 2 * j)) & 3u)];
     }
 };
 
