@@ -317,11 +317,37 @@ __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint
     const bool wide = (mm.l1_depth & 0x100) != 0;
     uint16_t *l1n = (uint16_t *)l1;
     const uint32_t n1 = 1u << (2 * d1);
-    for (uint32_t hc = threadIdx.x; hc < n1; hc += blockDim.x) {
-        int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, d1 < mm.order ? d1 : mm.order, hc, d1);
-        // "no context" points at the extra all-NaN row behind the model's rows: no special case in the scan
-        if (wide) l1[hc] = id >= 0 ? (uint32_t)id : (uint32_t)mm.n_ctx;
-        else l1n[hc] = id >= 0 ? (uint16_t)id : (uint16_t)mm.n_ctx;
+    // "no context" points at the extra all-NaN row behind the model's rows: no special case in the scan
+    if (wide) {
+        for (uint32_t hc = threadIdx.x; hc < n1; hc += blockDim.x) {
+            int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, d1 < mm.order ? d1 : mm.order, hc, d1);
+            l1[hc] = id >= 0 ? (uint32_t)id : (uint32_t)mm.n_ctx;
+        }
+    } else {
+        // u16 map, built in shared memory level by level without any hash probe: every context of length l <= D1
+        // stamps its id on the 4^(D1-l) histories it is a suffix of; longer contexts overwrite shorter ones
+        extern __shared__ uint16_t smap[];
+        for (uint32_t hc = threadIdx.x; hc < n1; hc += blockDim.x) smap[hc] = (uint16_t)mm.n_ctx;
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int l = 0; l <= d1; ++l) {
+            const uint32_t reps = 1u << (2 * (d1 - l));
+            if (reps >= 32u) {
+                for (int c = warp; c < mm.n_ctx; c += nwarps) {
+                    if (len[mm.ctx_off + c] != l) continue;
+                    const uint32_t cd = code[mm.ctx_off + c];
+                    for (uint32_t pfx = lane; pfx < reps; pfx += 32) smap[(pfx << (2 * l)) | cd] = (uint16_t)c;
+                }
+            } else {
+                for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
+                    if (len[mm.ctx_off + c] != l) continue;
+                    const uint32_t cd = code[mm.ctx_off + c];
+                    for (uint32_t pfx = 0; pfx < reps; ++pfx) smap[(pfx << (2 * l)) | cd] = (uint16_t)c;
+                }
+            }
+            __syncthreads();
+        }
+        for (uint32_t hc = threadIdx.x; hc < n1; hc += blockDim.x) l1n[hc] = smap[hc];
     }
     for (int i = threadIdx.x; i < 4 * mm.n_ctx; i += blockDim.x) rows[i] = logp[4 * mm.ctx_off + i];
     if (threadIdx.x < 4) rows[4 * mm.n_ctx + threadIdx.x] = vgs_nan();
@@ -696,7 +722,9 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         }
     }
     if (h->max_nll_bytes_t2 > 0 || h->max_nll_bytes_t3 > 0) {
-        k_build_two_level<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_hash, h->d_key, h->d_len, h->d_code, h->d_logp, h->d_nll);
+        const int l1_smem = 2 << (2 * VGS_L1_MAX_DEPTH);  // u16 map of the deepest first level
+        VGS_CUDA(cudaFuncSetAttribute(k_build_two_level, cudaFuncAttributeMaxDynamicSharedMemorySize, l1_smem));
+        k_build_two_level<<<(unsigned)n_models, 512, l1_smem, s>>>(h->d_meta, h->d_hash, h->d_key, h->d_len, h->d_code, h->d_logp, h->d_nll);
         VGS_LAUNCH_CHECK(h);
     }
     h->nll_ready = true;
