@@ -73,7 +73,8 @@ struct EstParams {
     const uint32_t *tables;  // count tables of the J-block's sequences
     int64_t per_seq;
     TilePlan pl;
-    int64_t q, I, J;         // slot and tile
+    int64_t J;               // tile column; every owned tile (I, J) of the column is done by one launch
+    int rank;
     float *pay32;
     double *pay64;
 };
@@ -82,9 +83,13 @@ __global__ void k_est_pairs(const EstParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t T = p.pl.tile;
-    if (warp >= T * T) return;
-    const int64_t ii = warp / T, jj = warp % T;
-    const int64_t i = p.I * T + ii, j = p.J * T + jj;
+    if (warp >= p.pl.nt * T * T) return;
+    const int64_t I = warp / (T * T), within = warp % (T * T);
+    const int64_t k = I * p.pl.nt + p.J;
+    if (k % p.pl.world != p.rank) return;   // tile (I, J) belongs to another rank
+    const int64_t q = k / p.pl.world;
+    const int64_t ii = within / T, jj = within % T;
+    const int64_t i = I * T + ii, j = p.J * T + jj;
     double acc = 0.0;
     if (i < p.pl.n && j < p.pl.n) {
         const ModelMeta mm = p.meta[i];
@@ -118,7 +123,7 @@ __global__ void k_est_pairs(const EstParams p) {
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     }
     if (lane == 0) {
-        const int64_t e = p.q * T * T + warp;
+        const int64_t e = q * T * T + within;
         p.pay32[e] = (float)acc;
         if (p.pay64) p.pay64[e] = acc;
     }
@@ -160,13 +165,11 @@ static int est_tiles_impl(vgs_context *h, const TilePlan &pl, int rank, float *p
             VGS_LAUNCH_CHECK(h);
         }
         vgs_prof_end(h, VGS_PROF_ESTIMATE_COUNTS, s);
-        for (int64_t I = 0; I < pl.nt; ++I) {
-            const int64_t k = I * pl.nt + J;
-            if (k % pl.world != rank) continue;
+        {
             EstParams p;
             p.meta = h->d_meta; p.key = h->d_key; p.prob64 = h->d_prob64; p.tables = tables; p.per_seq = per_seq;
-            p.pl = pl; p.q = k / pl.world; p.I = I; p.J = J; p.pay32 = pay32; p.pay64 = pay64;
-            const int64_t n_warps = pl.tile * pl.tile;
+            p.pl = pl; p.J = J; p.rank = rank; p.pay32 = pay32; p.pay64 = pay64;
+            const int64_t n_warps = pl.nt * pl.tile * pl.tile;
             vgs_prof_begin(h, VGS_PROF_ESTIMATE_PAIRS, s);
             k_est_pairs<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, s>>>(p);
             vgs_prof_end(h, VGS_PROF_ESTIMATE_PAIRS, s);

@@ -226,10 +226,21 @@ __global__ void __launch_bounds__(NLL_MAX_THREADS, 1) k_nll_scores(const NllPara
                 const int64_t n_chunks = (L + 63) >> 6;
                 const uint4 *w4 = (const uint4 *)w;
                 double acc = 0.0;
-                for (int64_t c = lane; c < n_chunks; c += 32) {
-                    const uint4 q = __ldg(w4 + c);
-                    const uint32_t prev = c ? __ldg(w + 4 * c - 1) : 0u;
-                    scan_chunk<decltype(T), false>(T, q, prev, c << 6, skip, L, acc);
+                if (n_chunks >= 32) {
+                    for (int64_t c = lane; c < n_chunks; c += 32) {
+                        const uint4 q = __ldg(w4 + c);
+                        const uint32_t prev = c ? __ldg(w + 4 * c - 1) : 0u;
+                        scan_chunk<decltype(T), false>(T, q, prev, c << 6, skip, L, acc);
+                    }
+                } else {
+                    // short sequence (< 2048 symbols): one 16-symbol word per lane and step, so that all lanes work
+                    const int64_t n_words = (L + 15) >> 4;
+                    for (int64_t wi = lane; wi < n_words; wi += 32) {
+                        const uint32_t cur = __ldg(w + wi);
+                        const uint32_t prev = wi ? __ldg(w + wi - 1) : 0u;
+                        const int64_t t0 = wi << 4;
+                        scan_chunk<decltype(T), false>(T, make_uint4(cur, 0u, 0u, 0u), prev, t0, skip, min(L, t0 + 16), acc);
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
