@@ -216,7 +216,8 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
 int vgs_ensure_ph(vgs_context *h, cudaStream_t s);  // builds the perfect hashes on first use
 bool vgs_kmer_applicable(vgs_context *h);
 // returns VGS_OK, an error, or -1 when the set needs the scan kernel (a model without a root context)
-int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, double *M, int64_t ld, cudaStream_t s);
+int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately, double *M,
+                    int64_t ld, cudaStream_t s);
 int vgs_assemble_impl(vgs_context *h, const TilePlan &p, const float *gathered32, const double *gathered64,
                       float *D32, double *D64, cudaStream_t s);
 

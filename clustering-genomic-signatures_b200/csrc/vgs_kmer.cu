@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(KG_THREADS, 1) k_kmer_dmma(const KgParams p) {
 struct KgEpi {
     const double *partial;
     const int32_t *pairs;   // [n_pairs][2] (sb, mb)
-    int n_pairs, split, depth;
+    int n_pairs, split, depth, skip_diag;
     const ModelMeta *meta;
     const uint8_t *arena;   // per-model tier-1 tables (their own order)
     const uint32_t *seq;
@@ -290,6 +290,44 @@ struct KgEpi {
     int64_t n_seq, n_models, ld;
     double *M;
 };
+
+// terms t in [order_m, D) of a model shallower than D (positions the (D+1)-mer histogram does not cover)
+__device__ __forceinline__ double kmer_head(const KgEpi &p, const ModelMeta &mm, int64_t s) {
+    if (mm.order >= p.depth) return 0.0;
+    const double *tab = (const double *)(p.arena + mm.nll_off);
+    const uint32_t fmask = vgs_lowmask(mm.order + 1);
+    const uint32_t *w = p.seq + p.seq_off[s];
+    const int64_t L = p.seq_len[s];
+    const int64_t top = L < p.depth ? L : p.depth;
+    uint32_t code = 0;
+    double head = 0.0;
+    for (int64_t t = 0; t < top; ++t) {
+        const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
+        code = (code << 2) | x;
+        if (t >= mm.order) head += tab[code & fmask];
+    }
+    return head;
+}
+
+// diagonal scores M[m][m] as plain dot products (one warp each, fixed summation order).  The distance tiles need
+// M[i][i] of every row and column they touch; computing those few entries here instead of whole diagonal blocks
+// keeps a rank's work equal to its share, and makes M[i][i] the same number whatever the sharding.
+__global__ void k_kmer_diag(const KgEpi p, const double *__restrict__ C, const double *__restrict__ Tu, int64_t K) {
+    const int lane = threadIdx.x & 31;
+    const int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (m >= p.n_models || m >= p.n_seq) return;
+    const double *c = C + m * K, *t = Tu + m * K;
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t k = 2 * lane; k < K; k += 64) {
+        const double2 cv = *(const double2 *)(c + k), tv = *(const double2 *)(t + k);
+        a0 = __fma_rn(cv.x, tv.x, a0);
+        a1 = __fma_rn(cv.y, tv.y, a1);
+    }
+    double v = a0 + a1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) p.M[m * p.ld + m] = kmer_head(p, p.meta[m], m) + v;
+}
 
 __global__ void k_kmer_epilogue(const KgEpi p) {
     const int pair = blockIdx.x;
@@ -299,25 +337,10 @@ __global__ void k_kmer_epilogue(const KgEpi p) {
         const int r = e / KG_BLOCK, c = e % KG_BLOCK;
         const int64_t s = (int64_t)sb * KG_BLOCK + r, m = (int64_t)mb * KG_BLOCK + c;
         if (s >= p.n_seq || m >= p.n_models) continue;
+        if (p.skip_diag && s == m) continue;  // written by k_kmer_diag
         double v = 0.0;
         for (int q = 0; q < p.split; ++q) v += p.partial[((int64_t)pair * p.split + q) * KG_BLOCK * KG_BLOCK + e];
-        const ModelMeta mm = p.meta[m];
-        if (mm.order < p.depth) {
-            const double *tab = (const double *)(p.arena + mm.nll_off);
-            const uint32_t fmask = vgs_lowmask(mm.order + 1);
-            const uint32_t *w = p.seq + p.seq_off[s];
-            const int64_t L = p.seq_len[s];
-            const int64_t top = L < p.depth ? L : p.depth;
-            uint32_t code = 0;
-            double head = 0.0;
-            for (int64_t t = 0; t < top; ++t) {
-                const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
-                code = (code << 2) | x;
-                if (t >= mm.order) head += tab[code & fmask];
-            }
-            v = head + v;
-        }
-        p.M[s * p.ld + m] = v;
+        p.M[s * p.ld + m] = kmer_head(p, p.meta[m], s) + v;
     }
 }
 
@@ -353,7 +376,8 @@ static int ensure_kmer_tables(vgs_context *h, cudaStream_t s) {
 }
 
 // scores for the needed (sequence-block, model-block) pairs at 128-granularity; need[sb * nb_m + mb] != 0
-int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, double *M, int64_t ld, cudaStream_t s) {
+int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately, double *M,
+                    int64_t ld, cudaStream_t s) {
     int rc = ensure_kmer_tables(h, s);
     if (rc) return rc;
     if (h->kmer_has_nan) return -1;  // caller falls back to the scan kernel
@@ -374,54 +398,65 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
         for (int64_t mb = 0; mb < nb_m; ++mb)
             if (need[(size_t)(sb * nb_m + mb)]) { pairs.push_back((int32_t)sb); pairs.push_back((int32_t)mb); }
     const int n_pairs = (int)(pairs.size() / 2);
-    if (n_pairs == 0) return VGS_OK;
-    const int64_t ksteps = K / KD_BK;   // unit boundaries are multiples of 16 k-mers (one MMA stage; two FMA stages)
-    // split K so that the FULL problem (every block pair) gives >= ~8 units per SM.  The split depends only on the
-    // problem shape, never on which block pairs this call computes, so every entry is summed in the same order
-    // however the tile space is sharded (1/2/4/8-rank matrices stay bit-identical).
-    const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, ksteps),
-                                                                  (8 * 148 + nb_s * nb_m - 1) / (nb_s * nb_m)));
-    std::vector<KgUnit> units;
-    for (int pi = 0; pi < n_pairs; ++pi)
-        for (int q = 0; q < split; ++q) {
-            KgUnit un;
-            un.sb = pairs[2 * pi]; un.mb = pairs[2 * pi + 1];
-            un.k0 = (int32_t)(ksteps * q / split * KD_BK);
-            un.k1 = (int32_t)(ksteps * (q + 1) / split * KD_BK);
-            un.slot = pi * split + q;
-            units.push_back(un);
+    if (n_pairs == 0 && !diag_separately) return VGS_OK;
+    int split = 1;
+    int32_t *d_pairs = nullptr;
+    if (n_pairs > 0) {
+        const int64_t ksteps = K / KD_BK;   // unit boundaries are multiples of 16 k-mers (one MMA stage; two FMA stages)
+        // split K so that the FULL problem (every block pair) gives >= ~8 units per SM.  The split depends only on the
+        // problem shape, never on which block pairs this call computes, so every entry is summed in the same order
+        // however the tile space is sharded (1/2/4/8-rank matrices stay bit-identical).
+        split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, ksteps),
+                                                                      (8 * 148 + nb_s * nb_m - 1) / (nb_s * nb_m)));
+        std::vector<KgUnit> units;
+        for (int pi = 0; pi < n_pairs; ++pi)
+            for (int q = 0; q < split; ++q) {
+                KgUnit un;
+                un.sb = pairs[2 * pi]; un.mb = pairs[2 * pi + 1];
+                un.k0 = (int32_t)(ksteps * q / split * KD_BK);
+                un.k1 = (int32_t)(ksteps * (q + 1) / split * KD_BK);
+                un.slot = pi * split + q;
+                units.push_back(un);
+            }
+        const int64_t part_elems = (int64_t)n_pairs * split * KG_BLOCK * KG_BLOCK;
+        if ((rc = vgs_reserve(h, &h->d_kmer_partial, part_elems))) return rc;
+        const int64_t meta_bytes = (int64_t)units.size() * sizeof(KgUnit) + pairs.size() * 4 + 256;
+        if ((rc = vgs_ensure_scratch2(h, meta_bytes))) return rc;
+        KgUnit *d_units = (KgUnit *)h->d_scratch2;
+        d_pairs = (int32_t *)((char *)h->d_scratch2 + (units.size() * sizeof(KgUnit) + 127) / 128 * 128);
+        VGS_CUDA(cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(KgUnit), cudaMemcpyHostToDevice, s));
+        VGS_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, s));
+        if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
+        VGS_CUDA(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(int), s));
+        KgParams p;
+        p.C = h->d_kmer_C; p.Tu = h->d_kmer_T; p.units = d_units; p.n_units = (int)units.size();
+        p.K = K; p.n_seq = h->n_seq; p.n_models = h->n_models; p.partial = h->d_kmer_partial; p.counter = h->d_counters + 2;
+        const int grid = std::min<int>((int)units.size(), h->sm_count);
+        static int use_fma = -1;
+        if (use_fma < 0) { const char *e = getenv("VGS_KMER_GEMM"); use_fma = (e && e[0] == 'f') ? 1 : 0; }
+        vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
+        if (use_fma) {
+            k_kmer_gemm<<<grid, KG_THREADS, 0, s>>>(p);
+        } else {
+            const int smem = KD_STAGES * KD_STAGE_DOUBLES * 8;
+            VGS_CUDA(cudaFuncSetAttribute(k_kmer_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k_kmer_dmma<<<grid, KG_THREADS, smem, s>>>(p);
         }
-    const int64_t part_elems = (int64_t)n_pairs * split * KG_BLOCK * KG_BLOCK;
-    if ((rc = vgs_reserve(h, &h->d_kmer_partial, part_elems))) return rc;
-    const int64_t meta_bytes = (int64_t)units.size() * sizeof(KgUnit) + pairs.size() * 4 + 256;
-    if ((rc = vgs_ensure_scratch2(h, meta_bytes))) return rc;
-    KgUnit *d_units = (KgUnit *)h->d_scratch2;
-    int32_t *d_pairs = (int32_t *)((char *)h->d_scratch2 + (units.size() * sizeof(KgUnit) + 127) / 128 * 128);
-    VGS_CUDA(cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(KgUnit), cudaMemcpyHostToDevice, s));
-    VGS_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, s));
-    if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
-    VGS_CUDA(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(int), s));
-    KgParams p;
-    p.C = h->d_kmer_C; p.Tu = h->d_kmer_T; p.units = d_units; p.n_units = (int)units.size();
-    p.K = K; p.n_seq = h->n_seq; p.n_models = h->n_models; p.partial = h->d_kmer_partial; p.counter = h->d_counters + 2;
-    const int grid = std::min<int>((int)units.size(), h->sm_count);
-    static int use_fma = -1;
-    if (use_fma < 0) { const char *e = getenv("VGS_KMER_GEMM"); use_fma = (e && e[0] == 'f') ? 1 : 0; }
-    vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
-    if (use_fma) {
-        k_kmer_gemm<<<grid, KG_THREADS, 0, s>>>(p);
-    } else {
-        const int smem = KD_STAGES * KD_STAGE_DOUBLES * 8;
-        VGS_CUDA(cudaFuncSetAttribute(k_kmer_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_kmer_dmma<<<grid, KG_THREADS, smem, s>>>(p);
+        vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
+        VGS_LAUNCH_CHECK(h);
     }
-    vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
-    VGS_LAUNCH_CHECK(h);
     KgEpi e;
     e.partial = h->d_kmer_partial; e.pairs = d_pairs; e.n_pairs = n_pairs; e.split = split; e.depth = D;
     e.meta = h->d_meta; e.arena = h->d_nll; e.seq = h->d_seq; e.seq_off = h->d_seq_off; e.seq_len = h->d_seq_len;
-    e.n_seq = h->n_seq; e.n_models = h->n_models; e.ld = ld; e.M = M;
-    k_kmer_epilogue<<<dim3((unsigned)n_pairs, 8), 256, 0, s>>>(e);
-    VGS_LAUNCH_CHECK(h);
+    e.n_seq = h->n_seq; e.n_models = h->n_models; e.ld = ld; e.M = M; e.skip_diag = diag_separately ? 1 : 0;
+    if (n_pairs > 0) {
+        k_kmer_epilogue<<<dim3((unsigned)n_pairs, 8), 256, 0, s>>>(e);
+        VGS_LAUNCH_CHECK(h);
+    }
+    if (diag_separately) {
+        const int64_t nd = std::min(h->n_seq, h->n_models);
+        k_kmer_diag<<<(unsigned)((nd * 32 + 255) / 256), 256, 0, s>>>(e, h->d_kmer_C, h->d_kmer_T, K);
+        VGS_LAUNCH_CHECK(h);
+    }
     return VGS_OK;
 }

@@ -419,7 +419,7 @@ extern "C" int vgs_nll_scores(vgs_handle h, int64_t s_begin, int64_t s_end, int6
         std::vector<char> need((size_t)(nb_s * nb_m), 0);
         for (int64_t sb = s_begin / 128; sb <= (s_end - 1) / 128; ++sb)
             for (int64_t mb = m_begin / 128; mb <= (m_end - 1) / 128; ++mb) need[(size_t)(sb * nb_m + mb)] = 1;
-        rc = vgs_kmer_scores(h, need, nb_s, nb_m, M_d, ld, (cudaStream_t)stream);
+        rc = vgs_kmer_scores(h, need, nb_s, nb_m, false, M_d, ld, (cudaStream_t)stream);
         if (rc != -1) return rc;
     }
     std::vector<int32_t> seqs((size_t)(s_end - s_begin));
@@ -443,7 +443,7 @@ extern "C" int vgs_nll_scores_h(vgs_handle h, int skip_mode, int mode, double *M
     if (mode == VGS_NLL_KMER && skip_mode == VGS_SKIP_ORDER && vgs_kmer_applicable(h)) {
         const int64_t nb_s = (h->n_seq + 127) / 128, nb_m = (h->n_models + 127) / 128;
         std::vector<char> need((size_t)(nb_s * nb_m), 1);
-        rc = vgs_kmer_scores(h, need, nb_s, nb_m, h->d_M, h->n_models, s);
+        rc = vgs_kmer_scores(h, need, nb_s, nb_m, false, h->d_M, h->n_models, s);
         if (rc > 0) return rc;
     }
     if (rc == -1 && (rc = vgs_nll_score_lists(h, lists, h->n_models, 0, h->n_models, false, skip_mode, mode, h->d_M, h->n_models, s))) return rc;
@@ -498,7 +498,7 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
     if (rc) return rc;
     if (mode == VGS_NLL_KMER && vgs_kmer_applicable(h) && pl.tile % 128 == 0) {
         // needed (sequence-block, model-block) pairs at the contraction's 128 x 128 granularity; the diagonal
-        // scores M[i][i] of every touched row/column block ride along as diagonal blocks
+        // scores M[i][i] come from k_kmer_diag (all of them, on every rank: N dot products)
         const int64_t nb = (pl.n + 127) / 128, per = pl.tile / 128;
         std::vector<char> need((size_t)(nb * nb), 0);
         for (int64_t k = rank; k < pl.n_tiles; k += pl.world) {
@@ -508,11 +508,9 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
                 for (int64_t b = J * per; b < std::min(nb, (J + 1) * per); ++b) {
                     need[(size_t)(a * nb + b)] = 1;
                     need[(size_t)(b * nb + a)] = 1;
-                    need[(size_t)(a * nb + a)] = 1;
-                    need[(size_t)(b * nb + b)] = 1;
                 }
         }
-        rc = vgs_kmer_scores(h, need, nb, nb, h->d_M, h->n_models, s);
+        rc = vgs_kmer_scores(h, need, nb, nb, true, h->d_M, h->n_models, s);
         if (rc > 0) return rc;
         if (rc == VGS_OK) {
             if (pl.slots > 0) {
