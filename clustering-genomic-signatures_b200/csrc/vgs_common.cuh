@@ -53,6 +53,17 @@ struct ModelMeta {
     int32_t l1_depth;     // tier 2: low byte = depth D1 of the first-level map, bit 8 = 32-bit entries
 };
 
+// device-resident work lists (scan units, contraction units) of a (plan, rank) are cached across calls so that a
+// steady-state step issues no host->device list upload and no host-side list building
+struct WorkCache {
+    uint64_t key = 0;
+    void *dev = nullptr;
+    int64_t bytes = 0;
+    int n[4] = {0, 0, 0, 0};   // entry counts (per tier / units, pairs)
+    int split = 1, threads = 0;
+    int64_t off2 = 0;          // byte offset of the second array inside dev
+};
+
 struct vgs_context {
     int device = 0;
     int sm_count = 0;
@@ -68,6 +79,8 @@ struct vgs_context {
     int64_t h_logp_cap = 0;
     bool nll_ready = false;     // false when loaded with VGS_LOAD_SKIP_NLL
     void *pool = nullptr;       // host thread pool (VgsPool, vgs_core.cu)
+    std::vector<WorkCache> wcache;
+    uint64_t model_gen = 0;     // bumped by every vgs_load_models
     int max_order = 0;
     int64_t max_nll_bytes_t1 = 0, max_nll_bytes_t2 = 0, max_nll_bytes_t3 = 0;
     int64_t max_pair_bytes = 0;  // hash + fp32 rows of the largest model
@@ -212,12 +225,20 @@ void vgs_tile_coords(const TilePlan &p, int64_t k, int64_t *I, int64_t *J);
 // launchers implemented in the kernel translation units
 int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &seq_lists_per_block, int64_t block,
                         int64_t m_begin, int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld,
-                        cudaStream_t s);
+                        cudaStream_t s, uint64_t cache_key = 0);
+WorkCache *vgs_wcache_find(vgs_context *h, uint64_t key);
+WorkCache *vgs_wcache_add(vgs_context *h, uint64_t key, int64_t bytes);   // nullptr on allocation failure
+void vgs_wcache_invalidate(vgs_context *h);   // keys dropped, allocations kept
+void vgs_wcache_clear(vgs_context *h);
+inline uint64_t vgs_mix(uint64_t a, uint64_t b) {
+    a ^= b + 0x9E3779B97F4A7C15ull + (a << 6) + (a >> 2);
+    return a;
+}
 int vgs_ensure_ph(vgs_context *h, cudaStream_t s);  // builds the perfect hashes on first use
 bool vgs_kmer_applicable(vgs_context *h);
 // returns VGS_OK, an error, or -1 when the set needs the scan kernel (a model without a root context)
 int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately, double *M,
-                    int64_t ld, cudaStream_t s);
+                    int64_t ld, cudaStream_t s, uint64_t cache_key = 0);
 int vgs_assemble_impl(vgs_context *h, const TilePlan &p, const float *gathered32, const double *gathered64,
                       float *D32, double *D64, cudaStream_t s);
 

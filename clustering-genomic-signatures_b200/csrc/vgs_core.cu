@@ -120,6 +120,46 @@ int vgs_ensure_M(vgs_context *h) {
     return VGS_OK;
 }
 
+WorkCache *vgs_wcache_find(vgs_context *h, uint64_t key) {
+    if (!key) return nullptr;
+    for (auto &w : h->wcache)
+        if (w.key == key) return &w;
+    return nullptr;
+}
+WorkCache *vgs_wcache_add(vgs_context *h, uint64_t key, int64_t bytes) {
+    // an invalidated entry (key 0) keeps its allocation: reuse it when it is large enough
+    for (auto &w : h->wcache)
+        if (w.key == 0 && w.bytes >= bytes) {
+            void *dev = w.dev;
+            const int64_t cap = w.bytes;
+            w = WorkCache();
+            w.key = key; w.dev = dev; w.bytes = cap;
+            return &w;
+        }
+    if (h->wcache.size() >= 32) {  // oldest out (cudaFree waits for the device)
+        cudaFree(h->wcache.front().dev);
+        h->wcache.erase(h->wcache.begin());
+    }
+    WorkCache w;
+    w.key = key;
+    w.bytes = std::max<int64_t>(bytes, 16);
+    if (cudaMalloc(&w.dev, (size_t)w.bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    h->wcache.push_back(w);
+    return &h->wcache.back();
+}
+// a new model set invalidates the lists; the allocations stay for the next set (stream order keeps in-flight readers
+// safe: the next writer is a copy enqueued behind them on the caller's stream)
+void vgs_wcache_invalidate(vgs_context *h) {
+    for (auto &w : h->wcache) w.key = 0;
+}
+void vgs_wcache_clear(vgs_context *h) {
+    for (auto &w : h->wcache) cudaFree(w.dev);
+    h->wcache.clear();
+}
+
 int vgs_read_error_flag(vgs_context *h, cudaStream_t s) {
     int flag = 0;
     VGS_CUDA(cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -173,7 +213,11 @@ extern "C" int vgs_create(int device, vgs_handle *out) {
 }
 
 // the device buffers stay allocated (grow-only, vgs_reserve); only the logical contents are dropped
-static void free_models(vgs_context *h) { h->n_models = 0; h->total_ctx = 0; h->kmer_tables_ready = false; }
+static void free_models(vgs_context *h) {
+    h->n_models = 0; h->total_ctx = 0; h->kmer_tables_ready = false;
+    h->model_gen++;
+    vgs_wcache_invalidate(h);
+}
 static void free_sequences(vgs_context *h) { h->n_seq = 0; h->total_symbols = 0; h->total_words = 0; h->kmer_counts_ready = false; }
 static void free_all_buffers(vgs_context *h) {
     for (auto &kv : h->caps) {
@@ -189,6 +233,7 @@ extern "C" int vgs_destroy(vgs_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     free_all_buffers(h);
+    vgs_wcache_clear(h);
     cudaFree(h->d_scratch);
     cudaFree(h->d_scratch2);
     cudaFree(h->d_err);

@@ -313,12 +313,12 @@ __device__ __forceinline__ double kmer_head(const KgEpi &p, const ModelMeta &mm,
 // M[i][i] of every row and column they touch; computing those few entries here instead of whole diagonal blocks
 // keeps a rank's work equal to its share, and makes M[i][i] the same number whatever the sharding.
 __global__ void k_kmer_diag(const KgEpi p, const double *__restrict__ C, const double *__restrict__ Tu, int64_t K) {
-    const int lane = threadIdx.x & 31;
-    const int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (m >= p.n_models || m >= p.n_seq) return;
+    __shared__ double part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t m = blockIdx.x;   // one 256-thread block per model: 2 K doubles streamed with 16-byte loads
     const double *c = C + m * K, *t = Tu + m * K;
     double a0 = 0.0, a1 = 0.0;
-    for (int64_t k = 2 * lane; k < K; k += 64) {
+    for (int64_t k = 2 * threadIdx.x; k < K; k += 2 * blockDim.x) {
         const double2 cv = *(const double2 *)(c + k), tv = *(const double2 *)(t + k);
         a0 = __fma_rn(cv.x, tv.x, a0);
         a1 = __fma_rn(cv.y, tv.y, a1);
@@ -326,7 +326,13 @@ __global__ void k_kmer_diag(const KgEpi p, const double *__restrict__ C, const d
     double v = a0 + a1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) p.M[m * p.ld + m] = kmer_head(p, p.meta[m], m) + v;
+    if (lane == 0) part[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+        p.M[m * p.ld + m] = kmer_head(p, p.meta[m], m) + s;
+    }
 }
 
 __global__ void k_kmer_epilogue(const KgEpi p) {
@@ -377,14 +383,17 @@ static int ensure_kmer_tables(vgs_context *h, cudaStream_t s) {
 
 // scores for the needed (sequence-block, model-block) pairs at 128-granularity; need[sb * nb_m + mb] != 0
 int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately, double *M,
-                    int64_t ld, cudaStream_t s) {
+                    int64_t ld, cudaStream_t s, uint64_t cache_key) {
     int rc = ensure_kmer_tables(h, s);
     if (rc) return rc;
     if (h->kmer_has_nan) return -1;  // caller falls back to the scan kernel
     const int D = h->max_order;
     const int64_t K = std::max<int64_t>(16, (int64_t)1 << (2 * (D + 1)));
-    // 1. histograms (cached per sequence set)
-    if (!h->kmer_counts_ready) {
+    // 1. histograms of the resident sequences (a pass over the packed sequences; part of every call unless the
+    //    caller pinned them with VGS_KMER_KEEP_COUNTS=1)
+    static int keep_counts = -1;
+    if (keep_counts < 0) { const char *e = getenv("VGS_KMER_KEEP_COUNTS"); keep_counts = (e && e[0] == '1') ? 1 : 0; }
+    if (!h->kmer_counts_ready || !keep_counts) {
         if ((rc = vgs_reserve(h, &h->d_kmer_C, h->n_seq * K))) return rc;
         const int smem = (int)(((int64_t)1 << (2 * (D + 1))) * 4);
         VGS_CUDA(cudaFuncSetAttribute(k_kmer_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -392,46 +401,68 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
         VGS_LAUNCH_CHECK(h);
         h->kmer_counts_ready = true;
     }
-    // 2. unit list
-    std::vector<int32_t> pairs;
-    for (int64_t sb = 0; sb < nb_s; ++sb)
-        for (int64_t mb = 0; mb < nb_m; ++mb)
-            if (need[(size_t)(sb * nb_m + mb)]) { pairs.push_back((int32_t)sb); pairs.push_back((int32_t)mb); }
-    const int n_pairs = (int)(pairs.size() / 2);
-    if (n_pairs == 0 && !diag_separately) return VGS_OK;
-    int split = 1;
+    // 2. unit list (cached on the device per (plan, rank) when the caller gives a key)
+    int n_pairs = 0, split = 1, n_units = 0;
+    KgUnit *d_units = nullptr;
     int32_t *d_pairs = nullptr;
-    if (n_pairs > 0) {
-        const int64_t ksteps = K / KD_BK;   // unit boundaries are multiples of 16 k-mers (one MMA stage; two FMA stages)
-        // split K so that the FULL problem (every block pair) gives >= ~8 units per SM.  The split depends only on the
-        // problem shape, never on which block pairs this call computes, so every entry is summed in the same order
-        // however the tile space is sharded (1/2/4/8-rank matrices stay bit-identical).
-        split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, ksteps),
-                                                                      (8 * 148 + nb_s * nb_m - 1) / (nb_s * nb_m)));
-        std::vector<KgUnit> units;
-        for (int pi = 0; pi < n_pairs; ++pi)
-            for (int q = 0; q < split; ++q) {
-                KgUnit un;
-                un.sb = pairs[2 * pi]; un.mb = pairs[2 * pi + 1];
-                un.k0 = (int32_t)(ksteps * q / split * KD_BK);
-                un.k1 = (int32_t)(ksteps * (q + 1) / split * KD_BK);
-                un.slot = pi * split + q;
-                units.push_back(un);
+    if (WorkCache *wc = vgs_wcache_find(h, cache_key)) {
+        n_pairs = wc->n[0]; n_units = wc->n[1]; split = wc->split;
+        d_units = (KgUnit *)wc->dev;
+        d_pairs = (int32_t *)((char *)wc->dev + wc->off2);
+    } else {
+        std::vector<int32_t> pairs;
+        for (int64_t sb = 0; sb < nb_s; ++sb)
+            for (int64_t mb = 0; mb < nb_m; ++mb)
+                if (need[(size_t)(sb * nb_m + mb)]) { pairs.push_back((int32_t)sb); pairs.push_back((int32_t)mb); }
+        n_pairs = (int)(pairs.size() / 2);
+        if (n_pairs > 0) {
+            const int64_t ksteps = K / KD_BK;   // unit boundaries are multiples of 16 k-mers (one MMA stage; two FMA stages)
+            // split K so that the FULL problem (every block pair) gives >= ~8 units per SM.  The split depends only on the
+            // problem shape, never on which block pairs this call computes, so every entry is summed in the same order
+            // however the tile space is sharded (1/2/4/8-rank matrices stay bit-identical).
+            split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, ksteps),
+                                                                          (8 * 148 + nb_s * nb_m - 1) / (nb_s * nb_m)));
+            std::vector<KgUnit> units;
+            for (int pi = 0; pi < n_pairs; ++pi)
+                for (int q = 0; q < split; ++q) {
+                    KgUnit un;
+                    un.sb = pairs[2 * pi]; un.mb = pairs[2 * pi + 1];
+                    un.k0 = (int32_t)(ksteps * q / split * KD_BK);
+                    un.k1 = (int32_t)(ksteps * (q + 1) / split * KD_BK);
+                    un.slot = pi * split + q;
+                    units.push_back(un);
+                }
+            n_units = (int)units.size();
+            const int64_t off2 = ((int64_t)units.size() * (int64_t)sizeof(KgUnit) + 127) / 128 * 128;
+            const int64_t meta_bytes = off2 + (int64_t)pairs.size() * 4 + 256;
+            char *base = nullptr;
+            if (cache_key) {
+                WorkCache *wc = vgs_wcache_add(h, cache_key, meta_bytes);
+                if (wc) {
+                    wc->n[0] = n_pairs; wc->n[1] = n_units; wc->split = split; wc->off2 = off2;
+                    base = (char *)wc->dev;
+                }
             }
+            if (!base) {
+                if ((rc = vgs_ensure_scratch2(h, meta_bytes))) return rc;
+                base = (char *)h->d_scratch2;
+            }
+            d_units = (KgUnit *)base;
+            d_pairs = (int32_t *)(base + off2);
+            VGS_CUDA(cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(KgUnit), cudaMemcpyHostToDevice, s));
+            VGS_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, s));
+        }
+    }
+    if (n_pairs == 0 && !diag_separately) return VGS_OK;
+    if (n_pairs > 0) {
         const int64_t part_elems = (int64_t)n_pairs * split * KG_BLOCK * KG_BLOCK;
         if ((rc = vgs_reserve(h, &h->d_kmer_partial, part_elems))) return rc;
-        const int64_t meta_bytes = (int64_t)units.size() * sizeof(KgUnit) + pairs.size() * 4 + 256;
-        if ((rc = vgs_ensure_scratch2(h, meta_bytes))) return rc;
-        KgUnit *d_units = (KgUnit *)h->d_scratch2;
-        d_pairs = (int32_t *)((char *)h->d_scratch2 + (units.size() * sizeof(KgUnit) + 127) / 128 * 128);
-        VGS_CUDA(cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(KgUnit), cudaMemcpyHostToDevice, s));
-        VGS_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, s));
         if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
         VGS_CUDA(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(int), s));
         KgParams p;
-        p.C = h->d_kmer_C; p.Tu = h->d_kmer_T; p.units = d_units; p.n_units = (int)units.size();
+        p.C = h->d_kmer_C; p.Tu = h->d_kmer_T; p.units = d_units; p.n_units = n_units;
         p.K = K; p.n_seq = h->n_seq; p.n_models = h->n_models; p.partial = h->d_kmer_partial; p.counter = h->d_counters + 2;
-        const int grid = std::min<int>((int)units.size(), h->sm_count);
+        const int grid = std::min<int>(n_units, h->sm_count);
         static int use_fma = -1;
         if (use_fma < 0) { const char *e = getenv("VGS_KMER_GEMM"); use_fma = (e && e[0] == 'f') ? 1 : 0; }
         vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
@@ -455,7 +486,7 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
     }
     if (diag_separately) {
         const int64_t nd = std::min(h->n_seq, h->n_models);
-        k_kmer_diag<<<(unsigned)((nd * 32 + 255) / 256), 256, 0, s>>>(e, h->d_kmer_C, h->d_kmer_T, K);
+        k_kmer_diag<<<(unsigned)nd, 256, 0, s>>>(e, h->d_kmer_C, h->d_kmer_T, K);
         VGS_LAUNCH_CHECK(h);
     }
     return VGS_OK;

@@ -315,60 +315,86 @@ static int launch_nll_tier(vgs_context *h, const NllParams &p, int mode, int64_t
 // seq_lists_per_block[B] = sequences to score against every model of model-block B (models
 // B*block .. min(n, (B+1)*block)-1); an empty outer vector means "all sequences, contiguous".
 int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &lists, int64_t block, int64_t m_begin,
-                        int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld, cudaStream_t s) {
+                        int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld, cudaStream_t s,
+                        uint64_t cache_key) {
     if (mode == VGS_NLL_KMER) mode = VGS_NLL_WARP;  // the scan kernels have two modes
-    std::vector<NllUnit> units[3];
-    std::vector<int32_t> flat;
-    std::vector<int64_t> list_off(lists.size() + 1, 0);
-    for (size_t b = 0; b < lists.size(); ++b) {
-        list_off[b + 1] = list_off[b] + (int64_t)lists[b].size();
-        flat.insert(flat.end(), lists[b].begin(), lists[b].end());
-    }
-    {
-        std::vector<int64_t> sizes;
+    int rc;
+    size_t n_u[3] = {0, 0, 0};
+    NllUnit *d_units = nullptr;
+    int32_t *d_list = nullptr;
+    if (WorkCache *wc = vgs_wcache_find(h, cache_key)) {
+        // steady state: the unit list of this (plan, rank) is already on the device
+        for (int t = 0; t < 3; ++t) n_u[t] = (size_t)wc->n[t];
+        g_nll_threads = wc->threads;
+        d_units = (NllUnit *)wc->dev;
+        d_list = (int32_t *)((char *)wc->dev + wc->off2);
+    } else {
+        std::vector<NllUnit> units[3];
+        std::vector<int32_t> flat;
+        std::vector<int64_t> list_off(lists.size() + 1, 0);
+        for (size_t b = 0; b < lists.size(); ++b) {
+            list_off[b + 1] = list_off[b] + (int64_t)lists[b].size();
+            flat.insert(flat.end(), lists[b].begin(), lists[b].end());
+        }
+        {
+            std::vector<int64_t> sizes;
+            for (int64_t m = m_begin; m < m_end; ++m) {
+                const size_t b = (size_t)(m / block);
+                if (b >= lists.size()) break;
+                sizes.push_back((int64_t)lists[b].size() + (add_diagonal ? 1 : 0));
+            }
+            vgs_choose_nll_threads(sizes);
+        }
         for (int64_t m = m_begin; m < m_end; ++m) {
             const size_t b = (size_t)(m / block);
             if (b >= lists.size()) break;
-            sizes.push_back((int64_t)lists[b].size() + (add_diagonal ? 1 : 0));
+            const std::vector<int32_t> &L = lists[b];
+            const int t = h->h_meta[(size_t)m].tier - 1;
+            bool diag_needed = add_diagonal && m < h->n_seq && !std::binary_search(L.begin(), L.end(), (int32_t)m);
+            int64_t cnt = (int64_t)L.size();
+            if (cnt == 0 && !diag_needed) continue;
+            // even split into ceil(cnt / threads) units
+            const int64_t per_unit = vgs_nll_threads();
+            int64_t nu = std::max<int64_t>(1, (cnt + (diag_needed ? 1 : 0) + per_unit - 1) / per_unit);
+            for (int64_t k = 0; k < nu; ++k) {
+                int64_t a = cnt * k / nu, e = cnt * (k + 1) / nu;
+                NllUnit un;
+                un.model = (int32_t)m;
+                un.list_off = (int32_t)(list_off[b] + a);
+                un.count = (int32_t)(e - a);
+                un.extra = (k == nu - 1 && diag_needed) ? (int32_t)m : -1;
+                units[t].push_back(un);
+            }
         }
-        vgs_choose_nll_threads(sizes);
-    }
-    for (int64_t m = m_begin; m < m_end; ++m) {
-        const size_t b = (size_t)(m / block);
-        if (b >= lists.size()) break;
-        const std::vector<int32_t> &L = lists[b];
-        const int t = h->h_meta[(size_t)m].tier - 1;
-        bool diag_needed = add_diagonal && m < h->n_seq && !std::binary_search(L.begin(), L.end(), (int32_t)m);
-        int64_t cnt = (int64_t)L.size();
-        if (cnt == 0 && !diag_needed) continue;
-        // even split into ceil(cnt / threads) units
-        const int64_t per_unit = vgs_nll_threads();
-        int64_t n_u = std::max<int64_t>(1, (cnt + (diag_needed ? 1 : 0) + per_unit - 1) / per_unit);
-        for (int64_t k = 0; k < n_u; ++k) {
-            int64_t a = cnt * k / n_u, e = cnt * (k + 1) / n_u;
-            NllUnit un;
-            un.model = (int32_t)m;
-            un.list_off = (int32_t)(list_off[b] + a);
-            un.count = (int32_t)(e - a);
-            un.extra = (k == n_u - 1 && diag_needed) ? (int32_t)m : -1;
-            units[t].push_back(un);
+        for (int t = 0; t < 3; ++t) n_u[t] = units[t].size();
+        const int64_t n_units_total = (int64_t)(n_u[0] + n_u[1] + n_u[2]);
+        if (n_units_total == 0) return VGS_OK;
+        const int64_t off2 = (n_units_total * (int64_t)sizeof(NllUnit) + 127) / 128 * 128;
+        const int64_t bytes = off2 + (int64_t)flat.size() * 4 + 256;
+        char *base = nullptr;
+        if (cache_key) {
+            WorkCache *wc = vgs_wcache_add(h, cache_key, bytes);
+            if (wc) {
+                for (int t = 0; t < 3; ++t) wc->n[t] = (int)n_u[t];
+                wc->threads = g_nll_threads;
+                wc->off2 = off2;
+                base = (char *)wc->dev;
+            }
         }
+        if (!base) {
+            if ((rc = vgs_ensure_scratch2(h, bytes))) return rc;
+            base = (char *)h->d_scratch2;
+        }
+        d_units = (NllUnit *)base;
+        d_list = (int32_t *)(base + off2);
+        size_t at = 0;
+        for (int t = 0; t < 3; ++t) {
+            if (n_u[t]) VGS_CUDA(cudaMemcpyAsync(d_units + at, units[t].data(), n_u[t] * sizeof(NllUnit), cudaMemcpyHostToDevice, s));
+            at += n_u[t];
+        }
+        if (!flat.empty()) VGS_CUDA(cudaMemcpyAsync(d_list, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, s));
     }
-    if (units[0].empty() && units[1].empty() && units[2].empty()) return VGS_OK;
-    const int64_t n_units_total = (int64_t)(units[0].size() + units[1].size() + units[2].size());
-    int64_t bytes = n_units_total * (int64_t)sizeof(NllUnit) + (int64_t)flat.size() * 4 + 256;
-    int rc = vgs_ensure_scratch2(h, bytes);
-    if (rc) return rc;
-    NllUnit *d_units = (NllUnit *)h->d_scratch2;
-    int32_t *d_list = (int32_t *)((char *)h->d_scratch2 + (n_units_total * sizeof(NllUnit) + 127) / 128 * 128);
-    if (!units[0].empty())
-        VGS_CUDA(cudaMemcpyAsync(d_units, units[0].data(), units[0].size() * sizeof(NllUnit), cudaMemcpyHostToDevice, s));
-    if (!units[1].empty())
-        VGS_CUDA(cudaMemcpyAsync(d_units + units[0].size(), units[1].data(), units[1].size() * sizeof(NllUnit), cudaMemcpyHostToDevice, s));
-    if (!units[2].empty())
-        VGS_CUDA(cudaMemcpyAsync(d_units + units[0].size() + units[1].size(), units[2].data(), units[2].size() * sizeof(NllUnit),
-                                 cudaMemcpyHostToDevice, s));
-    if (!flat.empty()) VGS_CUDA(cudaMemcpyAsync(d_list, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, s));
+    if (n_u[0] + n_u[1] + n_u[2] == 0) return VGS_OK;
     // pageable sources: the copies above have consumed the host vectors when they return
     NllParams p;
     p.meta = h->d_meta; p.arena = h->d_nll; p.hash = h->d_hash; p.logp = h->d_logp;
@@ -377,19 +403,19 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
     p.skip_none = skip_mode == VGS_SKIP_NONE;
     p.M = M; p.ld = ld;
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
-    if (!units[0].empty()) {
+    if (n_u[0]) {
         p.counter = h->d_counters;
-        p.units = d_units; p.n_units = (int)units[0].size();
+        p.units = d_units; p.n_units = (int)n_u[0];
         if ((rc = launch_nll_tier<1>(h, p, mode, h->max_nll_bytes_t1, s))) return rc;
     }
-    if (!units[1].empty()) {
+    if (n_u[1]) {
         p.counter = h->d_counters + 1;
-        p.units = d_units + units[0].size(); p.n_units = (int)units[1].size();
+        p.units = d_units + n_u[0]; p.n_units = (int)n_u[1];
         if ((rc = launch_nll_tier<2>(h, p, mode, h->max_nll_bytes_t2, s))) return rc;
     }
-    if (!units[2].empty()) {
+    if (n_u[2]) {
         p.counter = h->d_counters + 3;
-        p.units = d_units + units[0].size() + units[1].size(); p.n_units = (int)units[2].size();
+        p.units = d_units + n_u[0] + n_u[1]; p.n_units = (int)n_u[2];
         if ((rc = launch_nll_tier<3>(h, p, mode, h->max_nll_bytes_t3, s))) return rc;
     }
     return VGS_OK;
@@ -492,55 +518,67 @@ __global__ void k_nll_combine(TilePlan pl, int rank, const double *__restrict__ 
     }
 }
 
+static int launch_nll_combine(vgs_context *h, const TilePlan &pl, int rank, int64_t length, float *pay32, double *pay64,
+                              cudaStream_t s) {
+    if (pl.slots <= 0) return VGS_OK;
+    const dim3 grid((unsigned)pl.slots, (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, pl.tile * pl.tile / 2048)));
+    k_nll_combine<<<grid, 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
+    VGS_LAUNCH_CHECK(h);
+    return VGS_OK;
+}
+
 static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePlan &pl, int rank, float *pay32, double *pay64,
                           cudaStream_t s) {
     int rc = vgs_ensure_M(h);
     if (rc) return rc;
+    // the work lists depend only on (model set, plan, rank): built once, then reused from the device
+    uint64_t key = vgs_mix(0x5647534eull, h->model_gen);
+    key = vgs_mix(key, (uint64_t)pl.n);
+    key = vgs_mix(key, (uint64_t)pl.tile);
+    key = vgs_mix(key, (uint64_t)pl.world * 1024u + (uint64_t)rank);
     if (mode == VGS_NLL_KMER && vgs_kmer_applicable(h) && pl.tile % 128 == 0) {
         // needed (sequence-block, model-block) pairs at the contraction's 128 x 128 granularity; the diagonal
         // scores M[i][i] come from k_kmer_diag (all of them, on every rank: N dot products)
+        const uint64_t kkey = vgs_mix(key, 2);
         const int64_t nb = (pl.n + 127) / 128, per = pl.tile / 128;
-        std::vector<char> need((size_t)(nb * nb), 0);
+        std::vector<char> need;
+        if (!vgs_wcache_find(h, kkey)) {
+            need.assign((size_t)(nb * nb), 0);
+            for (int64_t k = rank; k < pl.n_tiles; k += pl.world) {
+                int64_t I, J;
+                vgs_tile_coords(pl, k, &I, &J);
+                for (int64_t a = I * per; a < std::min(nb, (I + 1) * per); ++a)
+                    for (int64_t b = J * per; b < std::min(nb, (J + 1) * per); ++b) {
+                        need[(size_t)(a * nb + b)] = 1;
+                        need[(size_t)(b * nb + a)] = 1;
+                    }
+            }
+        }
+        rc = vgs_kmer_scores(h, need, nb, nb, true, h->d_M, h->n_models, s, kkey);
+        if (rc > 0) return rc;
+        if (rc == VGS_OK) return launch_nll_combine(h, pl, rank, length, pay32, pay64, s);
+    }
+    const uint64_t skey = vgs_mix(key, 1);
+    std::vector<std::vector<int32_t>> lists;
+    if (!vgs_wcache_find(h, skey)) {
+        // which sequence blocks does this rank need against each model block?
+        lists.resize((size_t)pl.nt);
+        std::vector<std::vector<char>> need((size_t)pl.nt, std::vector<char>((size_t)pl.nt, 0));
         for (int64_t k = rank; k < pl.n_tiles; k += pl.world) {
             int64_t I, J;
             vgs_tile_coords(pl, k, &I, &J);
-            for (int64_t a = I * per; a < std::min(nb, (I + 1) * per); ++a)
-                for (int64_t b = J * per; b < std::min(nb, (J + 1) * per); ++b) {
-                    need[(size_t)(a * nb + b)] = 1;
-                    need[(size_t)(b * nb + a)] = 1;
-                }
+            need[(size_t)J][(size_t)I] = 1;  // model block J scores sequence block I ...
+            need[(size_t)I][(size_t)J] = 1;  // ... and model block I scores sequence block J
         }
-        rc = vgs_kmer_scores(h, need, nb, nb, true, h->d_M, h->n_models, s);
-        if (rc > 0) return rc;
-        if (rc == VGS_OK) {
-            if (pl.slots > 0) {
-                k_nll_combine<<<dim3((unsigned)pl.slots, (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, pl.tile * pl.tile / 2048))), 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
-                VGS_LAUNCH_CHECK(h);
-            }
-            return VGS_OK;
-        }
+        for (int64_t B = 0; B < pl.nt; ++B)
+            for (int64_t S = 0; S < pl.nt; ++S)
+                if (need[(size_t)B][(size_t)S])
+                    for (int64_t x = S * pl.tile; x < std::min(pl.n, (S + 1) * pl.tile); ++x) lists[(size_t)B].push_back((int32_t)x);
     }
-    // which sequence blocks does this rank need against each model block?
-    std::vector<std::vector<int32_t>> lists((size_t)pl.nt);
-    std::vector<std::vector<char>> need((size_t)pl.nt, std::vector<char>((size_t)pl.nt, 0));
-    for (int64_t k = rank; k < pl.n_tiles; k += pl.world) {
-        int64_t I, J;
-        vgs_tile_coords(pl, k, &I, &J);
-        need[(size_t)J][(size_t)I] = 1;  // model block J scores sequence block I ...
-        need[(size_t)I][(size_t)J] = 1;  // ... and model block I scores sequence block J
-    }
-    for (int64_t B = 0; B < pl.nt; ++B)
-        for (int64_t S = 0; S < pl.nt; ++S)
-            if (need[(size_t)B][(size_t)S])
-                for (int64_t x = S * pl.tile; x < std::min(pl.n, (S + 1) * pl.tile); ++x) lists[(size_t)B].push_back((int32_t)x);
     // models whose block touches no owned tile need nothing; the diagonal score M[m][m] rides along
-    rc = vgs_nll_score_lists(h, lists, pl.tile, 0, h->n_models, true, VGS_SKIP_ORDER, mode, h->d_M, h->n_models, s);
+    rc = vgs_nll_score_lists(h, lists, pl.tile, 0, h->n_models, true, VGS_SKIP_ORDER, mode, h->d_M, h->n_models, s, skey);
     if (rc) return rc;
-    if (pl.slots > 0) {
-        k_nll_combine<<<dim3((unsigned)pl.slots, (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, pl.tile * pl.tile / 2048))), 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
-        VGS_LAUNCH_CHECK(h);
-    }
-    return VGS_OK;
+    return launch_nll_combine(h, pl, rank, length, pay32, pay64, s);
 }
 
 extern "C" int vgs_nll_tiles(vgs_handle h, int64_t length, int mode, int64_t tile, int rank, int world, float *payload_d,
