@@ -57,6 +57,9 @@ SIGNATURES = [
     ("vgs_assemble", c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     ("vgs_matrix_to_triples", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     ("vgs_average_link", c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, _P(c_i64)]),
+    ("vgs_retrieval_metrics", c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    ("vgs_silhouette", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    ("vgs_cluster_distance_std", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, _P(c_i64)]),
 ]
 
 
@@ -287,6 +290,40 @@ class Handle:
         m = c_i64()
         _check(lib().vgs_average_link(self._h, n, _dev_ptr(D32), k, _np_ptr(labels), _np_ptr(merges), ctypes.byref(m)))
         return labels, merges[: m.value]
+
+    def retrieval_metrics(self, D, labels):
+        """D: torch CUDA [n, n] float32 or float64; labels int32 [n_tax, n].
+        Returns (in_top [n_tax, n], dist_to [n_tax, n], avg [n]) float64."""
+        import torch
+        n = int(D.shape[0])
+        labels = np.ascontiguousarray(labels, dtype=np.int32).reshape(-1, n)
+        t = labels.shape[0]
+        in_top = np.zeros((t, n)); dist_to = np.zeros((t, n)); avg = np.zeros(n)
+        d32 = _dev_ptr(D) if D.dtype == torch.float32 else None
+        d64 = _dev_ptr(D) if D.dtype == torch.float64 else None
+        assert d32 is not None or d64 is not None, "matrix must be float32 or float64"
+        _check(lib().vgs_retrieval_metrics(self._h, n, d32, d64, t, _np_ptr(labels), _np_ptr(in_top), _np_ptr(dist_to), _np_ptr(avg)))
+        return in_top, dist_to, avg
+
+    def silhouette(self, D32, clusters):
+        """D32: torch CUDA float32 [n, n]; clusters int labels [n].  Returns (a, b, s) float64 [n]."""
+        n = int(D32.shape[0])
+        clusters = np.ascontiguousarray(clusters, dtype=np.int32)
+        a = np.zeros(n); b = np.zeros(n); s = np.zeros(n)
+        _check(lib().vgs_silhouette(self._h, n, _dev_ptr(D32), _np_ptr(clusters), _np_ptr(a), _np_ptr(b), _np_ptr(s)))
+        return a, b, s
+
+    def cluster_distance_std(self, D, clusters):
+        """Per-cluster numpy.std of the distances between distinct members (ascending label order)."""
+        import torch
+        n = int(D.shape[0])
+        clusters = np.ascontiguousarray(clusters, dtype=np.int32)
+        out = np.zeros(n)
+        k = c_i64()
+        d32 = _dev_ptr(D) if D.dtype == torch.float32 else None
+        d64 = _dev_ptr(D) if D.dtype == torch.float64 else None
+        _check(lib().vgs_cluster_distance_std(self._h, n, d32, d64, _np_ptr(clusters), n, _np_ptr(out), ctypes.byref(k)))
+        return out[: k.value]
 
     def matrix_to_triples(self, n, D32, triples, stream):
         _check(lib().vgs_matrix_to_triples(self._h, n, _dev_ptr(D32), _dev_ptr(triples), c_vp(stream)))

@@ -172,6 +172,27 @@ int vgs_matrix_to_triples(vgs_handle h, int64_t n, const float *D32_d, float *tr
 int vgs_average_link(vgs_handle h, int64_t n, const float *D32_d, int64_t k, int32_t *labels_out_h,
                      double *merge_dist_out_h, int64_t *n_merges_out);
 
+/* ---- passes over the finished matrix.
+ *      vgs_retrieval_metrics: src/test_distance_function.py:75-79, :96-104 + src/util/distance_metrics.py:1-60.
+ *      For every model i its distances to all n models (itself included) are ranked ascending, ties in list order
+ *      (Python's stable sorted()); labels_h is [n_tax][n] (e.g. genus, family).  With k = number of models sharing
+ *      i's label: in_top[t][i] = (# of the k nearest that share the label) / k (procent_of_taxonomy_in_top),
+ *      dist_to[t][i] = mean |d| over the models sharing the label (average_distance_to_taxonomy),
+ *      avg[i] = mean of row i (average_distance).  Exactly one of D32_d / D64_d is non-null. ---------------- */
+int vgs_retrieval_metrics(vgs_handle h, int64_t n, const float *D32_d, const double *D64_d, int n_tax,
+                          const int32_t *labels_h, double *in_top_out_h, double *dist_to_out_h, double *avg_out_h);
+/* ClusteringMetrics.silhouette_metric (src/clustering/clustering_metrics.pyx:29-84) on the float32 [N][N] matrix:
+ * a[i] = mean distance to the other members of i's cluster (0 for a singleton), b[i] = smallest mean distance to
+ * another cluster (both rounded to float32 as the reference's C-float returns), s[i] = (b - a) / max(b, a).
+ * cluster_h[n]: any integer labels.  a_out_h / b_out_h nullable. */
+int vgs_silhouette(vgs_handle h, int64_t n, const float *D32_d, const int32_t *cluster_h, double *a_out_h, double *b_out_h,
+                   double *s_out_h);
+/* ClusteringMetrics.average_distance_std (src/clustering/clustering_metrics.pyx:168-185): population standard
+ * deviation (numpy.std, fp64) of the distances between distinct members, per cluster in ascending label order;
+ * 0 for singletons.  std_out_h has room for `capacity` clusters. */
+int vgs_cluster_distance_std(vgs_handle h, int64_t n, const float *D32_d, const double *D64_d, const int32_t *cluster_h,
+                             int64_t capacity, double *std_out_h, int64_t *n_clusters_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -365,3 +365,80 @@ def average_link(D32, k):
         for i in members[a]:
             labels[i] = ci
     return labels, merges
+
+
+# ----------------------------------------------------------------------------- metrics (f4)
+def retrieval_metrics(D, labels):
+    """Per-model retrieval metrics restating src/test_distance_function.py:96-104 (``calculate_distances``:
+    distances to every model, ``sorted`` on the distance alone, stable) and src/util/distance_metrics.py:43-60
+    (``procent_of_taxonomy_in_top``, ``average_distance_to_taxonomy``) plus the row mean of :11.
+    D: [N, N] array of the values ``d.distance`` returns (Python floats); labels: one taxon label per model.
+    Returns (in_top[N], dist_to[N], avg[N]) as Python-float lists, summed in the reference's (sorted) order."""
+    n = len(labels)
+    in_top, dist_to, avg = [], [], []
+    for i in range(n):
+        sorted_results = sorted(zip([float(x) for x in D[i]], range(n)), key=lambda t: t[0])
+        same = [j for j in range(n) if labels[j] == labels[i]]
+        k = len(same)
+        hits = 0
+        for r in range(k):
+            _, j = sorted_results[r]
+            if labels[j] == labels[i]:
+                hits += 1
+        in_top.append(hits / k)
+        st = [abs(dist) for dist, j in sorted_results if labels[j] == labels[i]]
+        dist_to.append(sum(st) / len(st))
+        avg.append(sum([dist for dist, _ in sorted_results]) / len(sorted_results))
+    return in_top, dist_to, avg
+
+
+def silhouette(D32, clusters):
+    """src/clustering/clustering_metrics.pyx:35-84 on the float32 [N, N] matrix.  Sums accumulate in numpy
+    float32 like the reference (here in ascending member order; the reference uses set order) and the two
+    averages pass through a C float.  Returns (a[N], b[N], s[N]); s is NaN where the reference would fail
+    (single cluster: inf/inf; a == b == 0: 0/0)."""
+    D32 = np.asarray(D32, dtype=np.float32)
+    n = D32.shape[0]
+    comps = {}
+    for i, c in enumerate(clusters):
+        comps.setdefault(c, []).append(i)
+    comps = list(comps.values())
+    a = np.zeros(n)
+    b = np.zeros(n)
+    for comp in comps:
+        for v1 in comp:
+            total = 0
+            for v2 in comp:
+                if v1 == v2:
+                    continue
+                total += D32[v1, v2]
+            others = len(comp) - 1
+            a[v1] = float(np.float32(0 if others == 0 else total / others))
+            best = np.inf
+            for other in comps:
+                if other is comp:
+                    continue
+                total = 0
+                for v2 in other:
+                    total += D32[v1, v2]
+                average = float(np.float32(total / len(other)))
+                if average < best:
+                    best = average
+            b[v1] = best
+    with np.errstate(invalid="ignore", divide="ignore"):
+        s = (b - a) / np.where(a > b, a, b)
+    return a, b, s
+
+
+def cluster_distance_std(D, clusters):
+    """src/clustering/clustering_metrics.pyx:168-185: numpy.std of the distances between distinct members of each
+    cluster (0 for a singleton), clusters in ascending label order."""
+    comps = {}
+    for i, c in enumerate(clusters):
+        comps.setdefault(c, []).append(i)
+    out = []
+    for c in sorted(comps):
+        comp = comps[c]
+        vals = [float(D[x, y]) for x in comp for y in comp if x != y]
+        out.append(0.0 if len(vals) < 1 else float(np.std(vals)))
+    return out
