@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="models in the CPU-baseline sample")
+    ap.add_argument("--breakdown", action="store_true",
+                    help="N > 1: also time the phases of a step (tiles / all-gather / assemble) with CUDA events; stderr")
     return ap.parse_args()
 
 
@@ -432,6 +434,29 @@ def main():
 
     # ---- end to end through the host-buffer C-ABI
     e2e_ms, _, _ = timed(e2e_step, max(3, args.steps // 4), 1, False)
+
+    if args.breakdown and world > 1:
+        def ev():
+            return torch.cuda.Event(enable_timing=True)
+        acc = np.zeros(3)
+        reps = 10
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+            barrier()
+            e0.record()
+            h.nll_tiles(L, args.mode, tile, rank, world, payload, stream) if kind == "nll" else (
+                h.estimate_tiles(tile, rank, world, payload, stream) if kind == "estimate" else
+                h.pair_tiles(kind, tile, rank, world, payload, stream))
+            e1.record()
+            dist.all_gather_into_tensor(gathered, payload)
+            e2.record()
+            h.assemble(n, tile, world, symmetric, gathered, D32, stream)
+            e3.record()
+            torch.cuda.synchronize()
+            acc += np.array([e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)])
+        sys.stderr.write("breakdown rank %d: tiles %.3f ms, all-gather (incl. wait for the slowest rank) %.3f ms, assemble %.3f ms\n"
+                         % (rank, acc[0] / reps, acc[1] / reps, acc[2] / reps))
 
     sweep = None
     if kind == "nll" and not args.no_mode_sweep:

@@ -16,6 +16,7 @@
 //   - other rows are updated from their own distances to left/right (_merge_weights :101-117), the merged row from
 //     left's and right's rows (_merge_heaps :124-146).
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -160,6 +161,209 @@ __global__ void k_al_refresh(AlState s) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// persistent variant: the whole merge loop in ONE cooperative kernel, one grid barrier per merge.
+//
+// Rows are dealt to the CTAs (row x belongs to CTA x % gridDim.x).  Every CTA keeps its own copy of the small per-cluster
+// state (size, smallest member, alive / never-merged flags: 5 bytes per cluster) in shared memory and applies every
+// merge to it, so the only cross-CTA traffic per merge is one candidate record per CTA:
+//   A(t)  CTA b posts (a) the best (distance, dict key) among the nearest-neighbour caches of its rows and (b) its
+//         best candidate for the nearest neighbour of the row merged in step t-1 (whose new entries D[l][x] it wrote
+//         itself for its own x) -- grid barrier --
+//   B(t)  every CTA reduces all records identically: first (b) -> the merged row's neighbour, then the global argmin
+//         -> (left, right); it updates D[x][left], D[left][x] for its rows x, refreshes their caches (one comparison,
+//         or a block-wide rescan of the row when the cache pointed at left / right), applies the merge to its state.
+// Every D entry a CTA reads in step t was written by itself or before the barrier of step t (D and the candidate
+// records are read with ld.global.cg: no stale L1 lines).  Same arithmetic, same
+// tie-breaking and therefore the same merges as the multi-kernel path above (kept for n too large for the shared state).
+// ---------------------------------------------------------------------------------------------------------
+#define ALP_THREADS 1024
+
+struct AlCand {
+    double d;
+    int key, i, j, pad;
+};
+
+__device__ __forceinline__ bool al_better(const AlCand &a, const AlCand &b) {  // is a strictly preferable to b?
+    if (a.i < 0) return false;
+    if (b.i < 0) return true;
+    return a.d < b.d || (a.d == b.d && a.key < b.key);
+}
+__device__ __forceinline__ AlCand al_shfl_xor(const AlCand &c, int o) {
+    AlCand r;
+    r.d = __shfl_xor_sync(0xffffffffu, c.d, o);
+    r.key = __shfl_xor_sync(0xffffffffu, c.key, o);
+    r.i = __shfl_xor_sync(0xffffffffu, c.i, o);
+    r.j = __shfl_xor_sync(0xffffffffu, c.j, o);
+    r.pad = 0;
+    return r;
+}
+// block-wide argmin; every thread returns the winner.  Ties on (d, key) cannot occur between distinct candidates
+// (keys are unique), so the reduction order does not matter.
+__device__ AlCand al_block_best(AlCand c, AlCand *scratch /* [33] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const AlCand other = al_shfl_xor(c, o);
+        if (al_better(other, c)) c = other;
+    }
+    __syncthreads();
+    if (lane == 0) scratch[warp] = c;
+    __syncthreads();
+    if (warp == 0) {
+        AlCand v;
+        v.d = 0.0; v.key = 0; v.i = -1; v.j = -1; v.pad = 0;
+        if (lane < (int)(blockDim.x >> 5)) v = scratch[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const AlCand other = al_shfl_xor(v, o);
+            if (al_better(other, v)) v = other;
+        }
+        if (lane == 0) scratch[32] = v;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+__device__ __forceinline__ void al_grid_barrier(unsigned int *counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(ALP_THREADS, 1)
+k_al_persistent(AlState s, int steps, AlCand *cand /* [2][gridDim.x][2] */, unsigned int *barrier_ctr) {
+    extern __shared__ __align__(16) unsigned char al_smem[];
+    const int n = (int)s.n, nb = (int)gridDim.x, b = (int)blockIdx.x, tid = (int)threadIdx.x;
+    unsigned short *size = (unsigned short *)al_smem;
+    unsigned short *minmem = size + n;
+    unsigned char *flags = (unsigned char *)(minmem + n);            // bit 0 alive, bit 1 never merged
+    int *rescan = (int *)(al_smem + (((size_t)5 * n + 15) & ~(size_t)15));
+    __shared__ AlCand scratch[33];
+    __shared__ int n_rescan;
+    for (int i = tid; i < n; i += ALP_THREADS) { size[i] = 1; minmem[i] = (unsigned short)i; flags[i] = 3; }
+    __syncthreads();
+    int pend = -1;
+    unsigned int bar_target = 0;
+    int done_steps = 0;
+    for (int t = 0; t < steps; ++t) {
+        // ---- A: this CTA's candidates
+        AlCand ca, cb;
+        ca.d = 0.0; ca.key = 0; ca.i = -1; ca.j = -1; ca.pad = 0;
+        cb = ca;
+        for (int x = b + tid * nb; x < n; x += ALP_THREADS * nb) {
+            if (!(flags[x] & 1) || x == pend) continue;
+            const int j = s.nn_j[x];
+            if (j >= 0) {
+                AlCand c;
+                c.d = s.nn_d[x]; c.key = s.okey[x]; c.i = x; c.j = j; c.pad = 0;
+                if (al_better(c, ca)) ca = c;
+            }
+            if (pend >= 0) {
+                AlCand c;
+                c.d = __ldcg(&s.D[(int64_t)pend * n + x]); c.key = minmem[x]; c.i = x; c.j = x; c.pad = 0;
+                if (al_better(c, cb)) cb = c;
+            }
+        }
+        ca = al_block_best(ca, scratch);
+        cb = al_block_best(cb, scratch);
+        AlCand *post = cand + ((size_t)(t & 1) * nb + b) * 2;
+        if (tid == 0) { post[0] = ca; post[1] = cb; }
+        bar_target += (unsigned int)nb;
+        al_grid_barrier(barrier_ctr, bar_target);
+        // ---- B: identical reduction in every CTA
+        const AlCand *all = cand + (size_t)(t & 1) * nb * 2;
+        AlCand ga, gb;
+        ga.d = 0.0; ga.key = 0; ga.i = -1; ga.j = -1; ga.pad = 0;
+        gb = ga;
+        for (int q = tid; q < nb; q += ALP_THREADS) {
+            AlCand a2, b2;
+            a2.d = __ldcg(&all[2 * q].d); a2.key = __ldcg(&all[2 * q].key); a2.i = __ldcg(&all[2 * q].i); a2.j = __ldcg(&all[2 * q].j); a2.pad = 0;
+            b2.d = __ldcg(&all[2 * q + 1].d); b2.key = __ldcg(&all[2 * q + 1].key); b2.i = __ldcg(&all[2 * q + 1].i); b2.j = __ldcg(&all[2 * q + 1].j); b2.pad = 0;
+            if (al_better(a2, ga)) ga = a2;
+            if (al_better(b2, gb)) gb = b2;
+        }
+        gb = al_block_best(gb, scratch);
+        ga = al_block_best(ga, scratch);
+        if (pend >= 0) {
+            // the row merged in the previous step: its neighbour, and its own candidacy (dict key n + t - 1)
+            if (pend % nb == b && tid == 0) { s.nn_d[pend] = gb.i >= 0 ? gb.d : INFINITY; s.nn_j[pend] = gb.i >= 0 ? gb.i : -1; }
+            if (gb.i >= 0) {
+                AlCand c;
+                c.d = gb.d; c.key = n + t - 1; c.i = pend; c.j = gb.i; c.pad = 0;
+                if (al_better(c, ga)) ga = c;
+            }
+        }
+        if (ga.i < 0 || !(ga.d < INFINITY)) break;  // no edge left (the reference's loop breaks)
+        const int l = ga.i, r = ga.j;
+        if (b == 0 && tid == 0) s.merges[t] = ga.d;
+        done_steps = t + 1;
+        if (tid == 0) n_rescan = 0;
+        __syncthreads();
+        const int nl = size[l], nr = size[r];
+        const bool l_single = (flags[l] & 2) != 0, r_single = (flags[r] & 2) != 0;
+        const int new_min = minmem[l] < minmem[r] ? minmem[l] : minmem[r];
+        for (int x = b + tid * nb; x < n; x += ALP_THREADS * nb) {
+            if (!(flags[x] & 1) || x == l || x == r) continue;
+            const bool x_single = (flags[x] & 2) != 0;
+            const bool xl32 = x_single && l_single, xr32 = x_single && r_single;
+            const double col = al_new_dist(nl, __ldcg(&s.D[(int64_t)x * n + l]), xl32, nr, __ldcg(&s.D[(int64_t)x * n + r]), xr32);
+            const double row = al_new_dist(nl, __ldcg(&s.D[(int64_t)l * n + x]), xl32, nr, __ldcg(&s.D[(int64_t)r * n + x]), xr32);
+            s.D[(int64_t)x * n + l] = col;
+            s.D[(int64_t)l * n + x] = row;
+            const int cur = s.nn_j[x];
+            if (cur < 0 || cur == l || cur == r) {
+                rescan[atomicAdd(&n_rescan, 1)] = x;
+            } else {
+                const double nd = s.nn_d[x];
+                if (col < nd || (col == nd && new_min < (int)minmem[cur])) { s.nn_d[x] = col; s.nn_j[x] = l; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            flags[r] &= (unsigned char)~1;
+            flags[l] &= (unsigned char)~2;
+            size[l] = (unsigned short)(nl + nr);
+            minmem[l] = (unsigned short)new_min;
+            if (l % nb == b) s.okey[l] = n + t;
+            if (r % nb == b) s.parent[r] = l;
+        }
+        __syncthreads();
+        // block-wide rescans of the rows whose cache pointed at the merged clusters
+        const int nres = n_rescan;
+        for (int q = 0; q < nres; ++q) {
+            const int x = rescan[q];
+            const double *row = s.D + (int64_t)x * n;
+            AlCand c;
+            c.d = 0.0; c.key = 0; c.i = -1; c.j = -1; c.pad = 0;
+            for (int j = tid; j < n; j += ALP_THREADS) {
+                if (!(flags[j] & 1) || j == x) continue;
+                AlCand v;
+                v.d = __ldcg(row + j); v.key = minmem[j]; v.i = j; v.j = j; v.pad = 0;
+                if (al_better(v, c)) c = v;
+            }
+            c = al_block_best(c, scratch);
+            if (tid == 0) { s.nn_d[x] = c.i >= 0 ? c.d : INFINITY; s.nn_j[x] = c.i; }
+        }
+        __syncthreads();
+        pend = l;
+    }
+    if (b == 0) {
+        __syncthreads();
+        for (int i = tid; i < n; i += ALP_THREADS) s.minmem[i] = minmem[i];
+        if (tid == 0) s.sel[3] = done_steps;
+    }
+}
+
 extern "C" int vgs_average_link(vgs_handle h, int64_t n, const float *D32_d, int64_t k, int32_t *labels_out_h,
                                 double *merge_dist_out_h, int64_t *n_merges_out) {
     VGS_CHECK_ARG(h && n > 0 && D32_d && labels_out_h, "vgs_average_link: bad arguments");
@@ -189,7 +393,37 @@ extern "C" int vgs_average_link(vgs_handle h, int64_t n, const float *D32_d, int
     k_al_rescan_all<<<(unsigned)n, 128, 0, st>>>(s);
     VGS_LAUNCH_CHECK(h);
     const int64_t steps = n - k;
-    for (int64_t step = 0; step < steps; ++step) {
+    // persistent path: needs the per-cluster state (5 bytes each) + a rescan list in shared memory and a co-resident grid
+    bool persistent = false;
+    {
+        static int force_multi = -1;
+        if (force_multi < 0) { const char *e = getenv("VGS_UPGMA_MULTI_KERNEL"); force_multi = (e && e[0] == '1') ? 1 : 0; }
+        const int nb = h->sm_count;
+        const int64_t rows_per_cta = (n + nb - 1) / nb;
+        const int64_t smem = ((5 * n + 15) & ~(int64_t)15) + rows_per_cta * 4 + 16;
+        if (!force_multi && steps > 0 && smem + 2048 <= (int64_t)h->max_smem_optin) {
+            int coop = 0, per_sm = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+            if (cudaFuncSetAttribute(k_al_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_al_persistent, ALP_THREADS, (size_t)smem) == cudaSuccess &&
+                coop && per_sm >= 1) {
+                AlCand *d_cand = nullptr;
+                unsigned int *d_bar = nullptr;
+                if ((rc = vgs_ensure_scratch(h, (int64_t)nb * 4 * sizeof(AlCand) + 256))) return rc;
+                d_bar = (unsigned int *)h->d_scratch;
+                d_cand = (AlCand *)((char *)h->d_scratch + 256);
+                VGS_CUDA(cudaMemsetAsync(d_bar, 0, 256, st));
+                int steps_i = (int)steps;
+                void *args[] = {(void *)&s, (void *)&steps_i, (void *)&d_cand, (void *)&d_bar};
+                VGS_CUDA(cudaLaunchCooperativeKernel((const void *)k_al_persistent, dim3((unsigned)nb), dim3(ALP_THREADS), args, (size_t)smem, st));
+                h->launches++;
+                persistent = true;
+            } else {
+                cudaGetLastError();
+            }
+        }
+    }
+    for (int64_t step = 0; step < steps && !persistent; ++step) {
         k_al_argmin<<<1, 1024, 0, st>>>(s);
         k_al_update<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s);
         k_al_meta<<<1, 1, 0, st>>>(s, (int)step);
