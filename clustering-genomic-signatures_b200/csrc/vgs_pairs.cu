@@ -35,8 +35,9 @@ struct PairParams {
     const uint8_t *ph;      // perfect-hash arena (deep sets)
     TilePlan pl;
     int rank, kind, jg, n_groups, n_dir;
-    double *S, *U;
+    double *S, *U, *V;      // V: Projection only (squares of the staged model's rows at the shared contexts)
     int32_t *C;
+    const double *norm2;    // Projection only: sum of squares of every fp32 row entry, per model
     int *err;
 };
 
@@ -57,11 +58,38 @@ __device__ __forceinline__ double sq4(const float4 a, const float4 b) {
     return r;
 }
 
+__device__ __forceinline__ double norm4(const float4 a) {
+    double r = __dmul_rn((double)a.x, (double)a.x);
+    r = __fma_rn((double)a.y, (double)a.y, r);
+    r = __fma_rn((double)a.z, (double)a.z, r);
+    r = __fma_rn((double)a.w, (double)a.w, r);
+    return r;
+}
+
+// per-model sum of squares in exactly the order k_pair_partials accumulates a streamed model (lane-strided partial
+// sums, xor-shuffle tree): when every context of a model is shared with its partner, the two sums are equal bit for bit
+__global__ void k_pair_norms(int64_t n_models, const ModelMeta *__restrict__ meta, const float4 *__restrict__ prob32,
+                             double *__restrict__ norm2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (m >= n_models) return;
+    const ModelMeta mm = meta[m];
+    double a = 0.0;
+    for (int ci = lane; ci < mm.n_ctx; ci += 32) a += norm4(__ldg(prob32 + mm.ctx_off + ci));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) norm2[m] = a;
+}
+
 // UMAP = true : shallow sets; each staged model carries a dense map over every string of length <= max order
 //               (one u16 gather gives presence AND the longest-suffix fallback row: no probing loop, no divergence)
 // UMAP = false: deep sets; exact-context hash probes, and for the union a probe per shorter suffix
-template <bool STAGED, bool UMAP, int MAXJ>
-__global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams p) {
+// KIND: Projection needs one direction only: ||v_x - v_y||^2 = S + (|v_x|^2 - A_x) + (|v_y|^2 - A_y) with S the squared
+// differences and A_x, A_y the squares of x's and y's rows over the SHARED contexts (an absent context is a zero row)
+// THREADS: one CTA per SM (the staged tables fill shared memory), so the warps that hide the gather latency must all
+// come from that CTA: 1024 threads where the accumulators leave 64 registers per thread, 512 otherwise.
+template <bool STAGED, bool UMAP, int MAXJ, int KIND, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_pair_partials(const PairParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ int64_t sI, sJ;
@@ -130,13 +158,13 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
     }
 
     const int64_t part_base = ((q * 2 + dir) * T) * T;
-    const int kind = p.kind;
-    for (int xx = warp; xx < nx; xx += PAIR_THREADS / 32) {
+    constexpr int kind = KIND;
+    for (int xx = warp; xx < nx; xx += THREADS / 32) {
         const ModelMeta xm = p.meta[x0 + xx];
-        double s[MAXJ], u[MAXJ];
+        double s[MAXJ], u[MAXJ], v[MAXJ];   // v is dead (and removed by the compiler) unless KIND is Projection
         int c[MAXJ];
 #pragma unroll
-        for (int yy = 0; yy < MAXJ; ++yy) { s[yy] = 0.0; u[yy] = 0.0; c[yy] = 0; }
+        for (int yy = 0; yy < MAXJ; ++yy) { s[yy] = 0.0; u[yy] = 0.0; v[yy] = 0.0; c[yy] = 0; }
         for (int ci = lane; ci < xm.n_ctx; ci += 32) {
             const uint32_t key = __ldg(p.key + xm.ctx_off + ci);
             const float4 px = __ldg(p.prob32 + xm.ctx_off + ci);
@@ -157,8 +185,10 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
                         const double v = sq4(px, yr[yy][id]);
                         if (exact) { s[yy] += v; c[yy] += 1; } else { u[yy] += v; }
                     } else {
-                        if (exact) { s[yy] += sq4(px, yr[yy][id]); c[yy] += 1; }
-                        else u[yy] += sq4(px, make_float4(0.f, 0.f, 0.f, 0.f));
+                        if (exact) {
+                            const float4 py = yr[yy][id];
+                            s[yy] += sq4(px, py); u[yy] += norm4(px); v[yy] += norm4(py); c[yy] += 1;
+                        }
                     }
                 }
             } else {
@@ -174,8 +204,10 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
                     const int shift = ymeta[yy].hash_shift;
                     int id = seed >= 0 ? vgs_ph_find(blob, lgr, lgcap, seed, key) : vgs_hash_find(gslots, mask, shift, key);
                     if (id >= 0) {
-                        s[yy] += sq4(px, yr[yy][id]);
+                        const float4 py = yr[yy][id];
+                        s[yy] += sq4(px, py);
                         c[yy] += 1;
+                        if (kind == VGS_PAIR_PROJECTION) { u[yy] += norm4(px); v[yy] += norm4(py); }
                     } else if (kind == VGS_PAIR_FROBENIUS_UNION) {
                         int top = len - 1 < ymeta[yy].order ? len - 1 : ymeta[yy].order;
                         for (int ln = top; ln >= 0 && id < 0; --ln) {
@@ -184,8 +216,6 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
                         }
                         if (id < 0) atomicOr(p.err, 1);
                         else u[yy] += sq4(px, yr[yy][id]);
-                    } else if (kind == VGS_PAIR_PROJECTION) {
-                        u[yy] += sq4(px, make_float4(0.f, 0.f, 0.f, 0.f));
                     }
                 }
             }
@@ -193,17 +223,19 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_partials(const PairParams
 #pragma unroll
         for (int yy = 0; yy < MAXJ; ++yy) {
             if (yy >= ny) break;
-            double sv = s[yy], uv = u[yy];
+            double sv = s[yy], uv = u[yy], vv = v[yy];
             int cv = c[yy];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 sv += __shfl_xor_sync(0xffffffffu, sv, o);
                 uv += __shfl_xor_sync(0xffffffffu, uv, o);
+                if (kind == VGS_PAIR_PROJECTION) vv += __shfl_xor_sync(0xffffffffu, vv, o);
                 cv += __shfl_xor_sync(0xffffffffu, cv, o);
             }
             if (lane == 0) {
                 const int64_t e = part_base + (int64_t)xx * T + (g * p.jg + yy);
                 p.S[e] = sv; p.U[e] = uv; p.C[e] = cv;
+                if (kind == VGS_PAIR_PROJECTION) p.V[e] = vv;
             }
         }
     }
@@ -236,16 +268,20 @@ __global__ void k_pair_combine(PairParams p, float *__restrict__ pay32, double *
             const int cnt = C0[ab];
             if (p.kind == VGS_PAIR_FROBENIUS_INTERSECTION) {
                 d = cnt > 0 ? sqrt(s) / sqrt((double)cnt) : vgs_nan();  // empty intersection: 0/0 in the reference
+            } else if (p.kind == VGS_PAIR_PROJECTION) {
+                // x = the streamed model of the canonical orientation (tile row a), y = the staged one (column b).
+                // The unshared squares come from the norms; exactly zero when every context is shared, otherwise at
+                // least one whole probability row (>= 0.25), far above the cancellation error of the subtraction.
+                const int64_t mx = I * T + a, my = J * T + b;
+                const double ux = cnt == p.meta[mx].n_ctx ? 0.0 : fmax(0.0, p.norm2[mx] - U0[ab]);
+                const double uy = cnt == p.meta[my].n_ctx ? 0.0 : fmax(0.0, p.norm2[my] - p.V[(q * 2) * T * T + ab]);
+                d = sqrt(s + ux + uy);
             } else {
                 const double u_ij = U0[ab];
                 const double u_ji = (I == J) ? U0[ba] : U1[ba];
                 const double ssq = s + u_ij + u_ji;
-                if (p.kind == VGS_PAIR_FROBENIUS_UNION) {
-                    const int n_union = p.meta[i].n_ctx + p.meta[j].n_ctx - cnt;
-                    d = sqrt(ssq) / sqrt((double)n_union);
-                } else {
-                    d = sqrt(ssq);
-                }
+                const int n_union = p.meta[i].n_ctx + p.meta[j].n_ctx - cnt;
+                d = sqrt(ssq) / sqrt((double)n_union);
             }
         }
         pay32[q * T * T + e] = (float)d;
@@ -253,12 +289,32 @@ __global__ void k_pair_combine(PairParams p, float *__restrict__ pay32, double *
     }
 }
 
+template <int KIND>
+constexpr int pair_threads() { return KIND == VGS_PAIR_FROBENIUS_INTERSECTION ? 1024 : 512; }
+
+template <int KIND>
+static int launch_pair(const PairParams &p, bool staged, bool umap, int64_t n_cta, int smem, cudaStream_t s) {
+    constexpr int TH = pair_threads<KIND>();
+    if (staged && umap) {
+        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, true, PAIR_MAX_JG, KIND, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_pair_partials<true, true, PAIR_MAX_JG, KIND, TH><<<(unsigned)n_cta, TH, smem, s>>>(p);
+    } else if (staged) {
+        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, false, PAIR_DEEP_JG, KIND, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_pair_partials<true, false, PAIR_DEEP_JG, KIND, TH><<<(unsigned)n_cta, TH, smem, s>>>(p);
+    } else if (umap) {
+        k_pair_partials<false, true, PAIR_MAX_JG, KIND, 256><<<(unsigned)n_cta, 256, 0, s>>>(p);
+    } else {
+        k_pair_partials<false, false, PAIR_DEEP_JG, KIND, 256><<<(unsigned)n_cta, 256, 0, s>>>(p);
+    }
+    return VGS_OK;
+}
+
 static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int rank, float *pay32, double *pay64, cudaStream_t s) {
     PairParams p;
     p.meta = h->d_meta; p.key = h->d_key; p.prob32 = h->d_prob32; p.hash = h->d_hash;
     p.pl = pl; p.rank = rank; p.kind = kind; p.err = h->d_err;
-    p.n_dir = kind == VGS_PAIR_FROBENIUS_INTERSECTION ? 1 : 2;
-    // how many staged models fit?  prefer >= 2 CTAs per SM
+    p.n_dir = kind == VGS_PAIR_FROBENIUS_UNION ? 2 : 1;
+    // how many staged models fit?
     const bool umap = h->umap_stride > 0;
     p.umap = h->d_umap; p.umap_stride = h->umap_stride;
     if (!umap) {
@@ -272,10 +328,10 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
     bool staged = per_model <= cap;
     int jg = 4;
     if (staged) {
-        int64_t budget = cap / 2;
+        // one CTA per SM with up to 1024 threads: as many staged models as fit (each streamed context is then probed
+        // against all of them from the same registers)
         const int64_t max_jg = umap ? PAIR_MAX_JG : PAIR_DEEP_JG;
-        jg = (int)std::min<int64_t>(max_jg, budget / per_model);
-        if (jg < 2) jg = (int)std::min<int64_t>(max_jg, cap / per_model);
+        jg = (int)std::min<int64_t>(max_jg, cap / per_model);
         if (jg < 1) jg = 1;
     }
     jg = (int)std::min<int64_t>(jg, pl.tile);
@@ -283,28 +339,28 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
     p.jg = jg;
     p.n_groups = (int)((pl.tile + jg - 1) / jg);
     const int64_t part = pl.slots * 2 * pl.tile * pl.tile;
-    int rc = vgs_ensure_scratch2(h, part * 20 + 1024);
+    int rc = vgs_ensure_scratch2(h, part * 28 + h->n_models * 8 + 1024);
     if (rc) return rc;
     p.S = (double *)h->d_scratch2;
     p.U = p.S + part;
-    p.C = (int32_t *)(p.U + part);
+    p.V = p.U + part;
+    double *norm2 = p.V + part;
+    p.norm2 = norm2;
+    p.C = (int32_t *)(norm2 + h->n_models);
     if (pl.slots == 0) return VGS_OK;
-    VGS_CUDA(cudaMemsetAsync(h->d_scratch2, 0, (size_t)(part * 20), s));
+    VGS_CUDA(cudaMemsetAsync(h->d_scratch2, 0, (size_t)(part * 28 + h->n_models * 8), s));
+    if (kind == VGS_PAIR_PROJECTION) {
+        k_pair_norms<<<(unsigned)((h->n_models * 32 + 255) / 256), 256, 0, s>>>(h->n_models, h->d_meta, h->d_prob32, norm2);
+        VGS_LAUNCH_CHECK(h);
+    }
     const int64_t n_cta = pl.slots * p.n_dir * p.n_groups;
     VGS_CHECK_ARG(n_cta < ((int64_t)1 << 31), "pair kernel grid too large");
     const int smem = staged ? (int)(per_model * jg) : 0;
     vgs_prof_begin(h, VGS_PROF_PAIR_PARTIALS, s);
-    if (staged && umap) {
-        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, true, PAIR_MAX_JG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_pair_partials<true, true, PAIR_MAX_JG><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
-    } else if (staged) {
-        VGS_CUDA(cudaFuncSetAttribute(k_pair_partials<true, false, PAIR_DEEP_JG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_pair_partials<true, false, PAIR_DEEP_JG><<<(unsigned)n_cta, PAIR_THREADS, smem, s>>>(p);
-    } else if (umap) {
-        k_pair_partials<false, true, PAIR_MAX_JG><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
-    } else {
-        k_pair_partials<false, false, PAIR_DEEP_JG><<<(unsigned)n_cta, PAIR_THREADS, 0, s>>>(p);
-    }
+    if (kind == VGS_PAIR_FROBENIUS_INTERSECTION) rc = launch_pair<VGS_PAIR_FROBENIUS_INTERSECTION>(p, staged, umap, n_cta, smem, s);
+    else if (kind == VGS_PAIR_FROBENIUS_UNION) rc = launch_pair<VGS_PAIR_FROBENIUS_UNION>(p, staged, umap, n_cta, smem, s);
+    else rc = launch_pair<VGS_PAIR_PROJECTION>(p, staged, umap, n_cta, smem, s);
+    if (rc) return rc;
     vgs_prof_end(h, VGS_PROF_PAIR_PARTIALS, s);
     VGS_LAUNCH_CHECK(h);
     k_pair_combine<<<(unsigned)pl.slots, 256, 0, s>>>(p, pay32, pay64);

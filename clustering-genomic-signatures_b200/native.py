@@ -131,6 +131,9 @@ class Handle:
         self.device = int(device)
         _check(lib().vgs_create(self.device, ctypes.byref(self._h)))
         self._keep = []
+        self.n_models = 0
+        self.total_contexts = 0
+        self.n_seq = 0
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

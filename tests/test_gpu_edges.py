@@ -161,7 +161,7 @@ def test_empty_intersection_is_nan_like_the_reference():
     assert np.isnan(D[0, 1]) and np.isnan(D[1, 2]) and np.isnan(D[0, 2]) and D[0, 0] == 0.0
     P = h.pair_matrix_h("projection")[1]
     assert np.all(np.isfinite(P))
-    assert rel_err(P, O.projection_matrix([a, b, c])) < 1e-9
+    assert rel_err(P, O.projection_matrix([a, b, c])[0]) < 1e-9
 
 
 def test_argument_errors():
