@@ -273,13 +273,19 @@ __device__ __forceinline__ int vgs_longest_suffix(const uint2 *__restrict__ slot
 }
 
 // ---- hash-and-displace perfect hash -------------------------------------------------------------------------
+// multiplier pairs by seed (a switch, not an indexed local array: an array would be materialised in local memory and
+// re-written on every call)
 __host__ __device__ __forceinline__ uint32_t vgs_ph_a2(int seed) {
-    const uint32_t t[8] = {0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u, 0x2545F491u};
-    return t[seed & 7];
+    switch (seed & 7) {
+        case 0: return 0x85EBCA6Bu; case 1: return 0xC2B2AE35u; case 2: return 0x27D4EB2Fu; case 3: return 0x165667B1u;
+        case 4: return 0xD3A2646Du; case 5: return 0xFD7046C5u; case 6: return 0xB55A4F09u; default: return 0x2545F491u;
+    }
 }
 __host__ __device__ __forceinline__ uint32_t vgs_ph_a3(int seed) {
-    const uint32_t t[8] = {0x9E3779B9u, 0x7F4A7C15u, 0x94D049BBu, 0xBF58476Du, 0x1B873593u, 0xCC9E2D51u, 0x38495AB5u, 0x6C8E9CF5u};
-    return t[seed & 7];
+    switch (seed & 7) {
+        case 0: return 0x9E3779B9u; case 1: return 0x7F4A7C15u; case 2: return 0x94D049BBu; case 3: return 0xBF58476Du;
+        case 4: return 0x1B873593u; case 5: return 0xCC9E2D51u; case 6: return 0x38495AB5u; default: return 0x6C8E9CF5u;
+    }
 }
 __device__ __forceinline__ uint32_t vgs_ph_slot(uint32_t key, uint32_t disp, int lgcap, int seed) {
     const uint32_t h2 = (key * vgs_ph_a2(seed)) >> (32 - lgcap);

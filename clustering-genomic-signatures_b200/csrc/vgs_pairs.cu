@@ -157,6 +157,21 @@ __global__ void __launch_bounds__(THREADS) k_pair_partials(const PairParams p) {
         }
     }
 
+    // per staged model, in registers for the whole CTA lifetime: perfect-hash multipliers and shifts
+    uint32_t ya2[MAXJ], ya3[MAXJ], ysh[MAXJ];   // ysh = (32 - lgr) | (32 - lgcap) << 8 | (lgr << 16)
+    bool all_ph = true;
+    if (!UMAP) {
+#pragma unroll
+        for (int yy = 0; yy < MAXJ; ++yy) {
+            ya2[yy] = 0u; ya3[yy] = 0u; ysh[yy] = 0u;
+            if (yy < ny) {
+                const int seed = ymeta[yy].ph_seed;
+                all_ph = all_ph && seed >= 0;
+                ya2[yy] = vgs_ph_a2(seed); ya3[yy] = vgs_ph_a3(seed);
+                ysh[yy] = (uint32_t)(32 - ymeta[yy].ph_lgr) | ((uint32_t)ymeta[yy].hash_shift << 8) | ((uint32_t)ymeta[yy].ph_lgr << 16);
+            }
+        }
+    }
     const int64_t part_base = ((q * 2 + dir) * T) * T;
     constexpr int kind = KIND;
     for (int xx = warp; xx < nx; xx += THREADS / 32) {
@@ -195,14 +210,22 @@ __global__ void __launch_bounds__(THREADS) k_pair_partials(const PairParams p) {
 #pragma unroll
                 for (int yy = 0; yy < MAXJ; ++yy) {
                     if (yy >= ny) break;
-                    // exact-context probe: perfect hash (two loads, no loop); a model whose build failed falls
-                    // back to the probing hash in global memory
+                    // exact-context probe: perfect hash (two dependent loads, no loop); a model whose build failed
+                    // (never seen so far) falls back to the probing hash in global memory
                     const uint8_t *blob = (const uint8_t *)yh[yy];
-                    const int lgr = ymeta[yy].ph_lgr, lgcap = 32 - ymeta[yy].hash_shift, seed = ymeta[yy].ph_seed;
-                    const uint2 *gslots = p.hash + ymeta[yy].hash_off;
-                    const uint32_t mask = ymeta[yy].hash_mask;
-                    const int shift = ymeta[yy].hash_shift;
-                    int id = seed >= 0 ? vgs_ph_find(blob, lgr, lgcap, seed, key) : vgs_hash_find(gslots, mask, shift, key);
+                    int id;
+                    if (all_ph) {
+                        const uint32_t sh = ysh[yy];
+                        const uint32_t dsp = ((const uint16_t *)blob)[(key * 0x9E3779B1u) >> (sh & 31u)];
+                        const uint32_t csh = (sh >> 8) & 63u;
+                        const uint32_t h2 = (key * ya2[yy]) >> csh, h3 = ((key * ya3[yy]) >> csh) | 1u;
+                        const uint2 e = ((const uint2 *)(blob + (((2u << (sh >> 16)) + 15u) & ~15u)))[(h2 + dsp * h3) & (0xFFFFFFFFu >> csh)];
+                        id = e.x == key ? (int)e.y : -1;
+                    } else {
+                        const int seed = ymeta[yy].ph_seed;
+                        id = seed >= 0 ? vgs_ph_find(blob, ymeta[yy].ph_lgr, 32 - ymeta[yy].hash_shift, seed, key)
+                                       : vgs_hash_find(p.hash + ymeta[yy].hash_off, ymeta[yy].hash_mask, ymeta[yy].hash_shift, key);
+                    }
                     if (id >= 0) {
                         const float4 py = yr[yy][id];
                         s[yy] += sq4(px, py);
@@ -212,7 +235,9 @@ __global__ void __launch_bounds__(THREADS) k_pair_partials(const PairParams p) {
                         int top = len - 1 < ymeta[yy].order ? len - 1 : ymeta[yy].order;
                         for (int ln = top; ln >= 0 && id < 0; --ln) {
                             const uint32_t k2 = vgs_key(ln, code & vgs_lowmask(ln));
-                            id = seed >= 0 ? vgs_ph_find(blob, lgr, lgcap, seed, k2) : vgs_hash_find(gslots, mask, shift, k2);
+                            const int seed = ymeta[yy].ph_seed;
+                            id = seed >= 0 ? vgs_ph_find(blob, ymeta[yy].ph_lgr, 32 - ymeta[yy].hash_shift, seed, k2)
+                                           : vgs_hash_find(p.hash + ymeta[yy].hash_off, ymeta[yy].hash_mask, ymeta[yy].hash_shift, k2);
                         }
                         if (id < 0) atomicOr(p.err, 1);
                         else u[yy] += sq4(px, yr[yy][id]);
