@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -347,27 +348,112 @@ __global__ void k_build_dense(const ModelMeta *__restrict__ meta, const uint2 *_
     }
 }
 
-// tier 2: L1 map over 6-mers (bit 31 = some longer context ends in this 6-mer), deep hash, logp rows
+// tier 2 / 3: first-level map over D1-mers + extension trie + logp rows (layout: vgs_load_models_ex)
+//   map entry   : ctx_id of the longest context that is a suffix of the D1-mer (n_ctx = the NaN row if none), or
+//                 FLAG | block when some longer context ends in this D1-mer
+//   trie entry  : {value = ctx_id of the longest real context that is a suffix of the node string, child block or NONE};
+//                 entry x of block b belongs to the string "x + string(b)"; entries without a node of their own keep
+//                 the value of the block's own string, so a scan needs no "missing child" test beyond child == NONE
+template <bool WIDE>
+__device__ void build_extension_trie(const ModelMeta &mm, void *l1v, void *extv, const uint8_t *__restrict__ len,
+                                     const uint32_t *__restrict__ code, int *counter) {
+    typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type Entry;
+    typedef typename std::conditional<WIDE, uint32_t, uint16_t>::type MapT;
+    const int HALF = WIDE ? 32 : 16;
+    const Entry NONE = WIDE ? 0xFFFFFFFFull : 0xFFFFull;
+    const uint32_t FLAG = WIDE ? 0x80000000u : 0x8000u;
+    MapT *l1 = (MapT *)l1v;
+    Entry *ext = (Entry *)extv;
+    const int d1 = mm.l1_depth & 0xFF;
+    const uint32_t n1 = 1u << (2 * d1);
+    const Entry CLAIM = (Entry)FLAG;   // child field = CLAIM | context id while a node's block is being allocated
+    auto mk = [&](Entry child, Entry value) { return (child << HALF) | value; };
+    auto child_of = [&](Entry e) { return (uint32_t)(e >> HALF); };
+    // (a) flag the D1-mers in which a longer context ends
+    for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
+        if (len[mm.ctx_off + c] <= d1) continue;
+        const uint32_t li = code[mm.ctx_off + c] & (n1 - 1);
+        if (WIDE) atomicOr((unsigned int *)l1 + li, FLAG);
+        else atomicOr((unsigned int *)l1 + (li >> 1), (li & 1u) ? 0x80000000u : 0x00008000u);  // the u16 flag inside its word
+    }
+    __syncthreads();
+    // (b) one block per flagged D1-mer, pre-filled with the map's own answer
+    for (uint32_t li = threadIdx.x; li < n1; li += blockDim.x) {
+        const uint32_t e = l1[li];
+        if (!(e & FLAG)) continue;
+        const uint32_t blk = (uint32_t)atomicAdd(counter, 1);
+        const Entry fill = mk(NONE, (Entry)(e & (FLAG - 1u)));
+        for (int x = 0; x < 4; ++x) ext[4 * (size_t)blk + x] = fill;
+        l1[li] = (MapT)(FLAG | blk);
+    }
+    __syncthreads();
+    // (c) level by level: the node of length l2 of every context at least that long
+    for (int l2 = d1 + 1; l2 <= mm.order; ++l2) {
+        // every thread revisits its contexts in the three sub-steps; `slot` is recomputed (cheap walk from the map)
+        auto slot_of = [&](uint32_t cd) -> size_t {
+            uint32_t blk = (uint32_t)l1[cd & (n1 - 1)] & (FLAG - 1u);
+            for (int l = d1; l < l2 - 1; ++l) blk = child_of(ext[4 * (size_t)blk + ((cd >> (2 * l)) & 3u)]);
+            return 4 * (size_t)blk + ((cd >> (2 * (l2 - 1))) & 3u);
+        };
+        // (i) a context that IS this node stamps its id
+        for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
+            if (len[mm.ctx_off + c] != l2) continue;
+            const size_t sl = slot_of(code[mm.ctx_off + c]);
+            if (WIDE) ((uint32_t *)ext)[2 * sl] = (uint32_t)c;       // low half = value (little endian)
+            else ((uint16_t *)ext)[2 * sl] = (uint16_t)c;
+        }
+        __syncthreads();
+        // (ii) contexts that continue below this node elect one of them (smallest id) ...
+        for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
+            if (len[mm.ctx_off + c] <= l2) continue;
+            const size_t sl = slot_of(code[mm.ctx_off + c]);
+            const Entry cur = ext[sl];
+            const Entry value = cur & ((((Entry)1) << HALF) - 1);
+            if (WIDE) atomicMin((unsigned long long *)ext + sl, (unsigned long long)mk(CLAIM | (Entry)c, value));
+            else atomicMin((unsigned int *)ext + sl, (unsigned int)mk(CLAIM | (Entry)c, value));
+        }
+        __syncthreads();
+        // (iii) ... which allocates the node's child block, pre-filled with the node's value
+        for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
+            if (len[mm.ctx_off + c] <= l2) continue;
+            const size_t sl = slot_of(code[mm.ctx_off + c]);
+            const Entry cur = ext[sl];
+            if (child_of(cur) != (FLAG | (uint32_t)c)) continue;   // block numbers have the FLAG bit clear: no confusion
+            const Entry value = cur & ((((Entry)1) << HALF) - 1);
+            const uint32_t blk = (uint32_t)atomicAdd(counter, 1);
+            const Entry fill = mk(NONE, value);
+            for (int x = 0; x < 4; ++x) ext[4 * (size_t)blk + x] = fill;
+            ext[sl] = mk((Entry)blk, value);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint2 *__restrict__ hash,
                                   const uint32_t *__restrict__ key, const uint8_t *__restrict__ len,
                                   const uint32_t *__restrict__ code, const double *__restrict__ logp,
                                   uint8_t *__restrict__ arena) {
     const ModelMeta mm = meta[blockIdx.x];
     if (mm.tier < 2) return;
+    __shared__ int n_blocks_used;
+    if (threadIdx.x == 0) n_blocks_used = 0;
     uint32_t *l1 = (uint32_t *)(arena + mm.nll_off);
-    unsigned long long *deep = (unsigned long long *)(arena + mm.nll_off + mm.deep_off);
+    void *ext = (void *)(arena + mm.nll_off + mm.deep_off);
     double *rows = (double *)(arena + mm.nll_off + mm.logp_off);
     const uint2 *slots = hash + mm.hash_off;
     const int d1 = mm.l1_depth & 0xFF;
     const bool wide = (mm.l1_depth & 0x100) != 0;
-    uint16_t *l1n = (uint16_t *)l1;
     const uint32_t n1 = 1u << (2 * d1);
+    for (int i = threadIdx.x; i < 4 * mm.n_ctx; i += blockDim.x) rows[i] = logp[4 * mm.ctx_off + i];
+    if (threadIdx.x < 4) rows[4 * mm.n_ctx + threadIdx.x] = vgs_nan();
     // "no context" points at the extra all-NaN row behind the model's rows: no special case in the scan
     if (wide) {
         for (uint32_t hc = threadIdx.x; hc < n1; hc += blockDim.x) {
             int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, d1 < mm.order ? d1 : mm.order, hc, d1);
             l1[hc] = id >= 0 ? (uint32_t)id : (uint32_t)mm.n_ctx;
         }
+        __syncthreads();
+        build_extension_trie<true>(mm, l1, ext, len, code, &n_blocks_used);
     } else {
         // u16 map, built in shared memory level by level without any hash probe: every context of length l <= D1
         // stamps its id on the 4^(D1-l) histories it is a suffix of; longer contexts overwrite shorter ones
@@ -392,34 +478,9 @@ __global__ void k_build_two_level(const ModelMeta *__restrict__ meta, const uint
             }
             __syncthreads();
         }
+        build_extension_trie<false>(mm, smap, ext, len, code, &n_blocks_used);
+        uint16_t *l1n = (uint16_t *)l1;
         for (uint32_t hc = threadIdx.x; hc < n1; hc += blockDim.x) l1n[hc] = smap[hc];
-    }
-    for (int i = threadIdx.x; i < 4 * mm.n_ctx; i += blockDim.x) rows[i] = logp[4 * mm.ctx_off + i];
-    if (threadIdx.x < 4) rows[4 * mm.n_ctx + threadIdx.x] = vgs_nan();
-    __syncthreads();
-    // deep node table: EVERY suffix of length 7..len of every deep context is a node (real or virtual) whose value is
-    // the ctx_id of the longest real context that is a suffix of the node string.  A scan can then walk upwards from
-    // length 7 and stop at the first missing node, whether or not the context set is suffix-closed.
-    for (int c = threadIdx.x; c < mm.n_ctx; c += blockDim.x) {
-        const int ln = len[mm.ctx_off + c];
-        if (ln <= d1) continue;
-        const uint32_t cd = code[mm.ctx_off + c];
-        const uint32_t li = cd & (n1 - 1);
-        if (wide) atomicOr(&l1[li], 0x80000000u);
-        else atomicOr(&l1[li >> 1], (li & 1u) ? 0x80000000u : 0x00008000u);  // the u16 flag bit inside its 32-bit word
-        for (int l2 = d1 + 1; l2 <= ln; ++l2) {
-            const uint32_t sc = cd & vgs_lowmask(l2);
-            const uint32_t k = vgs_key(l2, sc);
-            int val = l2 == ln ? c : vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, sc, l2);
-            if (val < 0) val = mm.n_ctx;  // no real context below this virtual node: the NaN row
-            uint32_t s = vgs_hash_slot(k, mm.deep_shift);
-            const unsigned long long want = ((unsigned long long)(uint32_t)val << 32) | k;
-            while (true) {
-                const unsigned long long old = atomicCAS(&deep[s], 0ull, want);
-                if (old == 0ull || (uint32_t)old == k) break;  // same node from another context: same value
-                s = (s + 1) & mm.deep_mask;
-            }
-        }
     }
 }
 
@@ -611,28 +672,36 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
             mm.deep_mask = 0; mm.deep_shift = 0; mm.deep_off = 0; mm.logp_off = 0;
             h->max_nll_bytes_t1 = std::max<int64_t>(h->max_nll_bytes_t1, mm.nll_bytes);
         } else {
-            mm.tier = n >= 0x7FFF ? 3 : 2;
             // first-level map over the last D1 symbols: as deep as shared memory allows (D1 = order means the map
-            // alone answers every history: two gathers per base, no deep walk).  u16 entries (bit 15 = "a longer
-            // context ends here") unless the model has >= 32767 contexts.
-            const bool wide = n >= 0x7FFF;
-            int d1 = wide ? VGS_L1_DEPTH : std::min(order, VGS_L1_MAX_DEPTH);
-            int64_t dcap = 8, l1_bytes = 0, n_nodes = 0;
-            int dlg = 3;
-            for (;; --d1) {
-                n_nodes = 0;  // deep nodes: every suffix of length d1+1..len of every context longer than d1
-                for (int ln = d1 + 1; ln <= order; ++ln) n_nodes += len_hist[ln] * (ln - d1);
-                dlg = log2_ceil_pow2(2 * std::max<int64_t>(n_nodes, 1), &dcap);
-                l1_bytes = (((int64_t)1 << (2 * d1)) * (wide ? 4 : 2) + 15) / 16 * 16;
-                if (d1 <= VGS_L1_DEPTH || l1_bytes + dcap * 8 + (n + 1) * 32 <= VGS_T2_SMEM_BUDGET) break;
+            // alone answers every history: two gathers per base).  Histories whose D1-mer is the suffix of a longer
+            // context continue in an extension trie: blocks of four entries {value, child block}, one per further
+            // history symbol; a missing child carries its parent's value, so the walk is one load per level and ends
+            // at "no child".  u16 map entries / u32 trie entries (tier 2) unless the model has >= 32767 contexts or
+            // may need >= 32767 blocks (tier 3: u32 / u64).
+            int64_t l1_bytes = 0, n_blocks = 0;
+            bool wide = n >= 0x7FFF;
+            int d1 = 0;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                d1 = wide ? VGS_L1_DEPTH : std::min(order, VGS_L1_MAX_DEPTH);
+                for (;; --d1) {
+                    // upper bound on the blocks: one per context longer than D1 (its D1-mer) plus one per proper
+                    // suffix of length > D1 of such a context
+                    n_blocks = 0;
+                    for (int ln = d1 + 1; ln <= order; ++ln) n_blocks += len_hist[ln] * (ln - d1);
+                    l1_bytes = (((int64_t)1 << (2 * d1)) * (wide ? 4 : 2) + 15) / 16 * 16;
+                    if (d1 <= VGS_L1_DEPTH || l1_bytes + n_blocks * (wide ? 32 : 16) + (n + 1) * 32 <= VGS_T2_SMEM_BUDGET) break;
+                }
+                if (wide || n_blocks < 0x7FFF) break;
+                wide = true;  // too many blocks for 15-bit block numbers
             }
+            mm.tier = wide ? 3 : 2;
             mm.l1_depth = d1 | (wide ? 0x100 : 0);
             mm.deep_off = (int32_t)l1_bytes;
-            mm.deep_mask = (uint32_t)(dcap - 1);
-            mm.deep_shift = 32 - dlg;
-            mm.logp_off = (int32_t)(l1_bytes + dcap * 8);
+            mm.deep_mask = (uint32_t)n_blocks;   // capacity of the trie in blocks
+            mm.deep_shift = 0;
+            mm.logp_off = (int32_t)(l1_bytes + std::max<int64_t>(n_blocks, 1) * (wide ? 32 : 16));
             int64_t bytes = mm.logp_off + (n + 1) * 32;  // + one all-NaN row for histories without any context
-            if (bytes >= ((int64_t)1 << 31)) {
+            if (bytes >= ((int64_t)1 << 31) || n_blocks >= ((int64_t)1 << 31)) {
                 vgs_set_error("model %lld is too large for the two-level NLL table", (long long)m);
                 return VGS_ERR_UNSUPPORTED;
             }
@@ -756,7 +825,6 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     }
 
     // 3. build the NLL tables
-    if (h->max_nll_bytes_t2 > 0 || h->max_nll_bytes_t3 > 0) VGS_CUDA(cudaMemsetAsync(h->d_nll, 0, (size_t)nll_bytes, s));  // deep hashes start empty
     if (h->max_nll_bytes_t1 > 0) {
         // grid.x covers up to 4^6 histories with 256-thread blocks
         dim3 grid(16, (unsigned)std::min<int64_t>(n_models, 65535));

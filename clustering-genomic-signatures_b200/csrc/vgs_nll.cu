@@ -64,42 +64,43 @@ struct DenseTable {  // tier 1
     }
 };
 
-// rare path of the two-level table, out of line so that the unrolled per-base code stays small: walk up the deep
-// node table from length D1 + 1; the first missing node ends the walk (every suffix of a deep context is a node, and a
-// node's value is already the longest real context below it)
-__device__ __noinline__ uint32_t nll_deep_walk(const uint2 *deep, uint32_t deep_mask, int deep_shift, int d1, int order,
-                                               uint32_t hist, uint32_t id) {
-#pragma unroll 1
-    for (int ln = d1 + 1; ln <= order; ++ln) {
-        const int r = vgs_hash_find(deep, deep_mask, deep_shift, vgs_key(ln, hist & vgs_lowmask(ln)));
-        if (r < 0) break;
-        id = (uint32_t)r;
-    }
-    return id;
-}
-
 template <bool WIDE>
-struct TwoLevelTable {  // tier 2 (u16 first-level entries) and tier 3 (u32 entries, models with >= 32767 contexts)
+struct TwoLevelTable {  // tier 2 (u16 map, u32 trie entries) and tier 3 (u32 / u64: >= 32767 contexts or blocks)
     const void *l1;
-    const uint2 *deep;
-    const double *rows;   // [n_ctx + 1][4]: the last row is NaN ("no context"), first-level entries point at it
-    uint32_t deep_mask, d1mask;
-    int deep_shift, order, d1;
+    const void *ext;      // extension trie: blocks of four {value, child} entries (vgs_core.cu, k_build_two_level)
+    const double *rows;   // [n_ctx + 1][4]: the last row is NaN ("no context"), map entries point at it
+    uint32_t d1mask;
+    int d1x2;
     __device__ __forceinline__ void bind(const uint8_t *blob, const ModelMeta &mm) {
         l1 = (const void *)blob;
-        d1 = mm.l1_depth & 0xFF;
+        const int d1 = mm.l1_depth & 0xFF;
+        d1x2 = 2 * d1;
         d1mask = vgs_lowmask(d1);
-        deep = (const uint2 *)(blob + mm.deep_off);
+        ext = (const void *)(blob + mm.deep_off);
         rows = (const double *)(blob + mm.logp_off);
-        deep_mask = mm.deep_mask;
-        deep_shift = mm.deep_shift;
-        order = mm.order;
     }
-    // first-level entry of a history -> ctx_id, taking the deep walk when the entry asks for it
+    // map entry of a history -> ctx_id.  A flagged entry (a longer context ends in this D1-mer) continues in the trie:
+    // one load per further history symbol, until the node has no child for it.
     __device__ __forceinline__ uint32_t resolve(uint32_t e, uint32_t hist) const {
         const uint32_t flag = WIDE ? 0x80000000u : 0x8000u;
         uint32_t id = e & (flag - 1u);
-        if (e & flag) id = nll_deep_walk(deep, deep_mask, deep_shift, d1, order, hist, id);
+        if (e & flag) {
+            uint32_t blk = id;
+            uint32_t h = hist >> d1x2;
+#pragma unroll 1
+            do {
+                if (WIDE) {
+                    const uint2 w = ((const uint2 *)ext)[4 * (size_t)blk + (h & 3u)];
+                    id = w.x; blk = w.y;
+                    if (blk == 0xFFFFFFFFu) break;
+                } else {
+                    const uint32_t w = ((const uint32_t *)ext)[4 * blk + (h & 3u)];
+                    id = w & 0xFFFFu; blk = w >> 16;
+                    if (blk == 0xFFFFu) break;
+                }
+                h >>= 2;
+            } while (true);
+        }
         return id;
     }
     __device__ __forceinline__ uint32_t entry(uint32_t hist) const {
@@ -109,9 +110,9 @@ struct TwoLevelTable {  // tier 2 (u16 first-level entries) and tier 3 (u32 entr
         const uint32_t hist = f >> 2;
         return rows[4 * resolve(entry(hist), hist) + (f & 3u)];
     }
-    // One fully scored word in three phases, so that the unrolled code is branch-free except for the rare deep walk:
-    // (1) the 16 first-level gathers, (2) entries that ask for the deep table (~0.1 % of the bases at D1 = 8) are
-    // resolved by the out-of-line walk, (3) the 16 row gathers and adds, in order.
+    // One fully scored word in three phases, so that the unrolled code is branch-free except for the rare trie walk:
+    // (1) the 16 first-level gathers, (2) flagged entries (~0.5 % of the bases at D1 = 8, depth 9) take the trie,
+    // (3) the 16 row gathers and adds, in order.
     template <bool SEQ>
     __device__ __forceinline__ void word16(uint32_t cur, uint32_t prev, double &acc) const {
         uint32_t e[16];
