@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(KG_THREADS, 1) k_kmer_gemm(const KgParams p) {
 // per k4-step (32 MMAs, 8192 FMAs): ~8x fewer shared-memory wavefronts per FMA.  Operand tiles keep the global
 // layout (row-major, k contiguous) in k4-slices [slice][row][4], so a half-warp fragment load is 128 contiguous
 // bytes (conflict free) and the global->shared copies are plain 16-byte cp.async (LDGSTS), 3 stages deep.
-#define KD_BK 16
+#ifndef KD_BK
+#define KD_BK 16      // k-mers per pipeline stage (32 measured 2 % slower: 253 registers, same pipe utilisation)
+#endif
 #define KD_STAGES 3
 #define KD_STAGE_DOUBLES (2 * KD_BK * KG_BLOCK)   // A tile + B tile of one stage
 
@@ -223,10 +225,11 @@ __global__ void __launch_bounds__(KG_THREADS, 1) k_kmer_dmma(const KgParams p) {
         auto issue = [&](int step) {
             double *st = dsm + (size_t)(step % KD_STAGES) * KD_STAGE_DOUBLES;
             const int64_t k = (int64_t)un.k0 + (int64_t)step * KD_BK;
+            constexpr int CPR = KD_BK / 2;                // 16-byte chunks per operand row and stage
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = tid + KG_THREADS * j;       // 1024 16-byte chunks per operand tile
-                const int row = c >> 3, ck = c & 7;       // chunk ck covers k = 2 ck, 2 ck + 1
+            for (int j = 0; j < KG_BLOCK * CPR / KG_THREADS; ++j) {
+                const int c = tid + KG_THREADS * j;
+                const int row = c / CPR, ck = c % CPR;    // chunk ck covers k = 2 ck, 2 ck + 1
                 const int dst = ((ck >> 1) * KG_BLOCK + row) * 4 + (ck & 1) * 2;
                 const int64_t srow = (int64_t)un.sb * KG_BLOCK + row, mrow = (int64_t)un.mb * KG_BLOCK + row;
                 const bool s_ok = srow < p.n_seq, m_ok = mrow < p.n_models;
@@ -360,7 +363,7 @@ bool vgs_kmer_applicable(vgs_context *h) {
 
 static int ensure_kmer_tables(vgs_context *h, cudaStream_t s) {
     const int D = h->max_order;
-    const int64_t K = std::max<int64_t>(16, (int64_t)1 << (2 * (D + 1)));  // row stride, padded to one MMA k-stage
+    const int64_t K = std::max<int64_t>(KD_BK, (int64_t)1 << (2 * (D + 1)));  // row stride, padded to one MMA k-stage
     if (h->kmer_tables_ready) return VGS_OK;
     int rc;
     if ((rc = vgs_reserve(h, &h->d_kmer_T, h->n_models * K))) return rc;
@@ -388,7 +391,7 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
     if (rc) return rc;
     if (h->kmer_has_nan) return -1;  // caller falls back to the scan kernel
     const int D = h->max_order;
-    const int64_t K = std::max<int64_t>(16, (int64_t)1 << (2 * (D + 1)));
+    const int64_t K = std::max<int64_t>(KD_BK, (int64_t)1 << (2 * (D + 1)));
     // 1. histograms of the resident sequences (a pass over the packed sequences; part of every call unless the
     //    caller pinned them with VGS_KMER_KEEP_COUNTS=1)
     static int keep_counts = -1;
@@ -416,7 +419,7 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
                 if (need[(size_t)(sb * nb_m + mb)]) { pairs.push_back((int32_t)sb); pairs.push_back((int32_t)mb); }
         n_pairs = (int)(pairs.size() / 2);
         if (n_pairs > 0) {
-            const int64_t ksteps = K / KD_BK;   // unit boundaries are multiples of 16 k-mers (one MMA stage; two FMA stages)
+            const int64_t ksteps = K / KD_BK;   // unit boundaries are multiples of one MMA stage
             // split K so that the FULL problem (every block pair) gives >= ~8 units per SM.  The split depends only on the
             // problem shape, never on which block pairs this call computes, so every entry is summed in the same order
             // however the tile space is sharded (1/2/4/8-rank matrices stay bit-identical).

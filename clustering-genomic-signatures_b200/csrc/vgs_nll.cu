@@ -56,11 +56,17 @@ struct DenseTable {  // tier 1
         fmask = vgs_lowmask(mm.order + 1);
     }
     __device__ __forceinline__ double term(uint32_t f) const { return tab[f & fmask]; }
-    // the 16 symbols of one fully scored word, in order
-    template <bool SEQ>
-    __device__ __forceinline__ void word16(uint32_t cur, uint32_t prev, double &acc) const {
+    // the 16 symbols of one word, in order.  MASKED: only the positions whose bit is set in `valid` (bit j = symbol
+    // j of the word) are scored; the others still gather (any index is inside the table) but add +0.0, which leaves
+    // the sum bit-identical -- a partial word at the start / end of a sequence costs the same as a full one and
+    // does not diverge from its neighbours in the warp
+    template <bool MASKED>
+    __device__ __forceinline__ void word16(uint32_t cur, uint32_t prev, uint32_t valid, double &acc) const {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc += tab[__funnelshift_r(cur, prev, 30 - 2 * j) & fmask];
+        for (int j = 0; j < 16; ++j) {
+            const double v = tab[__funnelshift_r(cur, prev, 30 - 2 * j) & fmask];
+            acc += (!MASKED || ((valid >> j) & 1u)) ? v : 0.0;
+        }
     }
 };
 
@@ -113,15 +119,18 @@ struct TwoLevelTable {  // tier 2 (u16 map, u32 trie entries) and tier 3 (u32 / 
     // One fully scored word in three phases, so that the unrolled code is branch-free except for the rare trie walk:
     // (1) the 16 first-level gathers, (2) flagged entries (~0.5 % of the bases at D1 = 8, depth 9) take the trie,
     // (3) the 16 row gathers and adds, in order.
-    template <bool SEQ>
-    __device__ __forceinline__ void word16(uint32_t cur, uint32_t prev, double &acc) const {
+    template <bool MASKED>
+    __device__ __forceinline__ void word16(uint32_t cur, uint32_t prev, uint32_t valid, double &acc) const {
         uint32_t e[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) e[j] = entry(__funnelshift_r(cur, prev, 30 - 2 * j) >> 2);
 #pragma unroll
         for (int j = 0; j < 16; ++j) e[j] = resolve(e[j], __funnelshift_r(cur, prev, 30 - 2 * j) >> 2);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc += rows[4 * e[j] + ((cur >> (30 - 2 * j)) & 3u)];
+        for (int j = 0; j < 16; ++j) {
+            const double v = rows[4 * e[j] + ((cur >> (30 - 2 * j)) & 3u)];
+            acc += (!MASKED || ((valid >> j) & 1u)) ? v : 0.0;   // see DenseTable::word16
+        }
     }
 };
 
@@ -135,18 +144,12 @@ __device__ __forceinline__ void scan_chunk(const TAB &T, const uint4 q, uint32_t
     for (int k = 0; k < 4; ++k) {
         const uint32_t cur = ws[k];
         const int64_t tw = t0 + 16 * k;
-        if (tw >= skip && tw + 16 <= L) {
-            if (SEQ) T.template word16<true>(cur, prev, acc);
-            else T.template word16<false>(cur, prev, part[k]);
-        } else if (tw < L && tw + 16 > skip) {
-#pragma unroll 1
-            for (int j = 0; j < 16; ++j) {
-                const int64_t t = tw + j;
-                if (t >= skip && t < L) {
-                    const double v = T.term(__funnelshift_r(cur, prev, 30 - 2 * j));
-                    if (SEQ) acc += v; else part[k] += v;
-                }
-            }
+        // positions [max(skip, tw), min(L, tw + 16)) of this word are scored; one code path for full and partial words
+        const int64_t lo64 = skip - tw, hi64 = L - tw;
+        const int lo = lo64 < 0 ? 0 : (lo64 > 16 ? 16 : (int)lo64), hi = hi64 < 0 ? 0 : (hi64 > 16 ? 16 : (int)hi64);
+        if (hi > lo) {
+            const uint32_t valid = (0xFFFFu >> (16 - hi)) & (0xFFFFu << lo);
+            T.template word16<true>(cur, prev, valid, SEQ ? acc : part[k]);
         }
         prev = cur;
     }
@@ -291,7 +294,9 @@ static int launch_nll(vgs_context *h, const NllParams &p, int smem_bytes, cudaSt
     auto kern = k_nll_scores<TIER, MODE, STAGED>;
     if (STAGED) VGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 1;
-    const int threads = vgs_nll_threads();
+    // warp mode: a unit's sequences are dealt to the warps one at a time, so the CTA can always be full (one CTA per
+    // SM when the table is staged: all the latency hiding comes from its own warps)
+    const int threads = (MODE == VGS_NLL_WARP && !getenv("VGS_NLL_THREADS")) ? NLL_MAX_THREADS : vgs_nll_threads();
     VGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, STAGED ? smem_bytes : 0));
     if (per_sm < 1) per_sm = 1;
     int grid = std::min(p.n_units, h->sm_count * per_sm);
