@@ -91,6 +91,8 @@ struct vgs_context {
     float4 *d_prob32 = nullptr;
     double *d_prob64 = nullptr;
     double *d_logp = nullptr;
+    double *d_invp = nullptr;   // Estimate: 1 / p, built on first use per model set
+    uint64_t invp_gen = ~0ull;
     uint2 *d_hash = nullptr;
     int64_t hash_slots = 0;
     uint8_t *d_nll = nullptr;

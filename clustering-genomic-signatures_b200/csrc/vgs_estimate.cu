@@ -66,14 +66,70 @@ __global__ void k_est_count_down(int k, int64_t first_seq, const uint32_t *__res
     }
 }
 
+// all levels of one sequence in one CTA (K <= 7: the top level fits in shared memory): histogram of the K-mers with
+// shared-memory atomics, then the shorter levels by the same left-extension sums, ping-ponging between two shared
+// arrays; every level is written to the global table as it is finished.  One launch instead of memset + K launches,
+// and no atomics in L2.
+__global__ void __launch_bounds__(512) k_est_count_fused(int K, int64_t first_seq, const uint32_t *__restrict__ seq,
+                                                         const int64_t *__restrict__ seq_off, const int64_t *__restrict__ seq_len,
+                                                         uint32_t *__restrict__ tables, int64_t per_seq) {
+    extern __shared__ uint32_t est_sm[];
+    const int64_t s = first_seq + blockIdx.x;
+    const int64_t L = seq_len[s];
+    const uint32_t *w = seq + seq_off[s];
+    uint32_t *out = tables + (int64_t)blockIdx.x * per_seq;
+    const int64_t nK = (int64_t)1 << (2 * K);
+    uint32_t *up = est_sm, *cur = est_sm + nK;
+    for (int64_t c = threadIdx.x; c < nK; c += blockDim.x) up[c] = 0u;
+    __syncthreads();
+    {
+        const uint32_t kmask = vgs_lowmask(K);
+        const int64_t span = (L + blockDim.x - 1) / blockDim.x;
+        const int64_t a = (int64_t)threadIdx.x * span, e = min(L, a + span);
+        if (a < e) {
+            int64_t t = max((int64_t)0, a - (K - 1));
+            uint32_t code = 0;
+            for (; t < e; ++t) {
+                const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
+                code = ((code << 2) | x) & kmask;
+                if (t >= a && t >= K - 1) atomicAdd(&up[code], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int64_t c = threadIdx.x; c < nK; c += blockDim.x) out[level_off(K) + c] = up[c];
+    for (int k = K - 1; k >= 1; --k) {
+        const int64_t n = (int64_t)1 << (2 * k);
+        uint32_t prefix = 0xFFFFFFFFu;
+        if (L >= k) {
+            prefix = 0;
+            for (int t = 0; t < k; ++t) prefix = (prefix << 2) | ((w[t >> 4] >> (30 - 2 * (t & 15))) & 3u);
+        }
+        for (int64_t c = threadIdx.x; c < n; c += blockDim.x) {
+            uint32_t v = up[c] + up[n + c] + up[2 * n + c] + up[3 * n + c];
+            if ((uint32_t)c == prefix) v += 1u;
+            cur[c] = v;
+            out[level_off(k) + c] = v;
+        }
+        __syncthreads();
+        uint32_t *tmp = up; up = cur; cur = tmp;
+    }
+}
+
+__global__ void k_est_invp(int64_t n, const double *__restrict__ prob64, double *__restrict__ invp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const double v = prob64[i]; invp[i] = v > 0 ? __ddiv_rn(1.0, v) : 0.0; }
+}
+
 struct EstParams {
     const ModelMeta *meta;
     const uint32_t *key;
     const double *prob64;
+    const double *invp;      // 1 / p per (context, symbol), 0 where p == 0 (built once per model set)
     const uint32_t *tables;  // count tables of the J-block's sequences
     int64_t per_seq;
     TilePlan pl;
-    int64_t J;               // tile column; every owned tile (I, J) of the column is done by one launch
+    int64_t J0, J1;          // tile columns [J0, J1); every owned tile (I, J) of these columns is done by one launch
     int rank;
     float *pay32;
     double *pay64;
@@ -83,17 +139,19 @@ __global__ void k_est_pairs(const EstParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t T = p.pl.tile;
-    if (warp >= p.pl.nt * T * T) return;
-    const int64_t I = warp / (T * T), within = warp % (T * T);
-    const int64_t k = I * p.pl.nt + p.J;
+    const int64_t nJ = p.J1 - p.J0;
+    if (warp >= p.pl.nt * nJ * T * T) return;
+    const int64_t tile_idx = warp / (T * T), within = warp % (T * T);
+    const int64_t I = tile_idx / nJ, J = p.J0 + tile_idx % nJ;
+    const int64_t k = I * p.pl.nt + J;
     if (k % p.pl.world != p.rank) return;   // tile (I, J) belongs to another rank
     const int64_t q = k / p.pl.world;
     const int64_t ii = within / T, jj = within % T;
-    const int64_t i = I * T + ii, j = p.J * T + jj;
+    const int64_t i = I * T + ii, j = J * T + jj;
     double acc = 0.0;
     if (i < p.pl.n && j < p.pl.n) {
         const ModelMeta mm = p.meta[i];
-        const uint32_t *tab = p.tables + jj * p.per_seq;
+        const uint32_t *tab = p.tables + (j - p.J0 * T) * p.per_seq;
         for (int ci = lane; ci < mm.n_ctx; ci += 32) {
             const uint32_t key = __ldg(p.key + mm.ctx_off + ci);
             const int len = (31 - __clz(key)) >> 1;
@@ -103,18 +161,24 @@ __global__ void k_est_pairs(const EstParams p) {
             int64_t tot = c0 + c1 + c2 + c3;
             if (tot != 0 && (c0 == 0 || c1 == 0 || c2 == 0 || c3 == 0)) { c0++; c1++; c2++; c3++; tot += 4; }
             if (tot > 0) {
-                const double *pr = p.prob64 + 4 * (mm.ctx_off + ci);
-                const double pv[4] = {pr[0], pr[1], pr[2], pr[3]};
+                // (obs - exp)^2 / exp with obs = count / total: ONE division per context (1 / total) and the
+                // precomputed 1 / p instead of six; every factor is within an ulp of the exact quotient, far inside
+                // the 1e-9 bound on the statistic (the counts fluctuate by >= 1e-3 relative)
+                const double2 *pr = (const double2 *)(p.prob64 + 4 * (mm.ctx_off + ci));
+                const double2 *ir = (const double2 *)(p.invp + 4 * (mm.ctx_off + ci));
+                const double2 p01 = __ldg(pr), p23 = __ldg(pr + 1), i01 = __ldg(ir), i23 = __ldg(ir + 1);
+                const double pv[4] = {p01.x, p01.y, p23.x, p23.y};
+                const double iv[4] = {i01.x, i01.y, i23.x, i23.y};
                 const int64_t cv[4] = {c0, c1, c2, c3};
+                const double rtot = __ddiv_rn(1.0, (double)tot);
                 int last = -1;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) if (pv[x] > 0) last = x;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     if (pv[x] > 0 && x != last) {
-                        const double obs = __ddiv_rn((double)cv[x], (double)tot);
-                        const double d = __dsub_rn(obs, pv[x]);
-                        acc = __dadd_rn(acc, __ddiv_rn(__dmul_rn(d, d), pv[x]));
+                        const double d = __dsub_rn(__dmul_rn((double)cv[x], rtot), pv[x]);
+                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(d, d), iv[x]));
                     }
                 }
             }
@@ -134,10 +198,13 @@ static int est_tiles_impl(vgs_context *h, const TilePlan &pl, int rank, float *p
     const int64_t per_seq = level_off(K + 1);  // u32 entries for levels 1..K
     size_t free_b = 0, total_b = 0;
     VGS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const int64_t need = per_seq * 4 * pl.tile;
-    if (need > (int64_t)(free_b / 2) + h->scratch_bytes) {
+    // count tables for as many tile columns at a time as fit in the budget (all of them for the usual shapes)
+    const int64_t budget = std::max<int64_t>(per_seq * 4 * pl.tile, std::min<int64_t>((int64_t)4 << 30, (int64_t)(free_b / 2) + h->scratch2_bytes));
+    const int64_t cols_per_batch = std::max<int64_t>(1, std::min<int64_t>(pl.nt, budget / (per_seq * 4 * pl.tile)));
+    const int64_t need = per_seq * 4 * pl.tile * cols_per_batch;
+    if (per_seq * 4 * pl.tile > (int64_t)(free_b / 2) + h->scratch2_bytes) {
         vgs_set_error("EstimateVLMC count tables for order %d need %lld bytes per tile column; reduce the tile size", h->max_order,
-                      (long long)need);
+                      (long long)(per_seq * 4 * pl.tile));
         return VGS_ERR_UNSUPPORTED;
     }
     int rc = vgs_ensure_scratch2(h, need + 256);
@@ -145,31 +212,52 @@ static int est_tiles_impl(vgs_context *h, const TilePlan &pl, int rank, float *p
     uint32_t *tables = (uint32_t *)h->d_scratch2;
     if (pl.slots > 0) VGS_CUDA(cudaMemsetAsync(pay32, 0, (size_t)(pl.slots * pl.tile * pl.tile * 4), s));
     if (pay64 && pl.slots > 0) VGS_CUDA(cudaMemsetAsync(pay64, 0, (size_t)(pl.slots * pl.tile * pl.tile * 8), s));
-    for (int64_t J = 0; J < pl.nt; ++J) {
-        // owned tiles in this column
-        bool any = false;
-        for (int64_t I = 0; I < pl.nt && !any; ++I) any = ((I * pl.nt + J) % pl.world) == rank;
-        if (!any) continue;
-        const int64_t j0 = J * pl.tile, nj = std::min(pl.n, (J + 1) * pl.tile) - j0;
-        VGS_CUDA(cudaMemsetAsync(tables, 0, (size_t)(per_seq * 4 * nj), s));
-        int64_t max_len = 1;
-        for (int64_t j = j0; j < j0 + nj; ++j) max_len = std::max(max_len, h->h_seq_len[(size_t)j]);
-        dim3 gtop((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_len + 256 * 128 - 1) / (256 * 128), 64)), (unsigned)nj);
-        vgs_prof_begin(h, VGS_PROF_ESTIMATE_COUNTS, s);
-        k_est_count_top<<<gtop, 128, 0, s>>>(K, j0, h->d_seq, h->d_seq_off, h->d_seq_len, tables, per_seq);
+    if ((rc = vgs_reserve(h, &h->d_invp, h->total_ctx * 4))) return rc;
+    if (h->invp_gen != h->model_gen) {
+        k_est_invp<<<(unsigned)((h->total_ctx * 4 + 255) / 256), 256, 0, s>>>(h->total_ctx * 4, h->d_prob64, h->d_invp);
         VGS_LAUNCH_CHECK(h);
-        for (int k = K - 1; k >= 1; --k) {
-            const int64_t n = (int64_t)1 << (2 * k);
-            dim3 g((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 4096)), (unsigned)nj);
-            k_est_count_down<<<g, 256, 0, s>>>(k, j0, h->d_seq, h->d_seq_off, h->d_seq_len, tables, per_seq);
+        h->invp_gen = h->model_gen;
+    }
+    const bool fused = K <= 7;
+    const int fused_smem = fused ? (int)(((((int64_t)1) << (2 * K)) + (((int64_t)1) << (2 * (K - 1)))) * 4) : 0;
+    if (fused) VGS_CUDA(cudaFuncSetAttribute(k_est_count_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
+    for (int64_t J0 = 0; J0 < pl.nt; J0 += cols_per_batch) {
+        const int64_t J1 = std::min(pl.nt, J0 + cols_per_batch);
+        // owned tiles in these columns?
+        bool any = false;
+        for (int64_t J = J0; J < J1 && !any; ++J)
+            for (int64_t I = 0; I < pl.nt && !any; ++I) any = ((I * pl.nt + J) % pl.world) == rank;
+        if (!any) continue;
+        const int64_t j0 = J0 * pl.tile, nj = std::min(pl.n, J1 * pl.tile) - j0;
+        vgs_prof_begin(h, VGS_PROF_ESTIMATE_COUNTS, s);
+        if (fused) {
+            k_est_count_fused<<<(unsigned)nj, 512, fused_smem, s>>>(K, j0, h->d_seq, h->d_seq_off, h->d_seq_len, tables, per_seq);
             VGS_LAUNCH_CHECK(h);
+        } else {
+            for (int64_t b0 = 0; b0 < nj; b0 += 32768) {   // grid.y limit
+                const int64_t nb = std::min<int64_t>(32768, nj - b0);
+                uint32_t *tb = tables + b0 * per_seq;
+                VGS_CUDA(cudaMemsetAsync(tb, 0, (size_t)(per_seq * 4 * nb), s));
+                int64_t max_len = 1;
+                for (int64_t j = j0 + b0; j < j0 + b0 + nb; ++j) max_len = std::max(max_len, h->h_seq_len[(size_t)j]);
+                dim3 gtop((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_len + 256 * 128 - 1) / (256 * 128), 64)), (unsigned)nb);
+                k_est_count_top<<<gtop, 128, 0, s>>>(K, j0 + b0, h->d_seq, h->d_seq_off, h->d_seq_len, tb, per_seq);
+                VGS_LAUNCH_CHECK(h);
+                for (int k = K - 1; k >= 1; --k) {
+                    const int64_t n = (int64_t)1 << (2 * k);
+                    dim3 g((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 4096)), (unsigned)nb);
+                    k_est_count_down<<<g, 256, 0, s>>>(k, j0 + b0, h->d_seq, h->d_seq_off, h->d_seq_len, tb, per_seq);
+                    VGS_LAUNCH_CHECK(h);
+                }
+            }
         }
         vgs_prof_end(h, VGS_PROF_ESTIMATE_COUNTS, s);
         {
             EstParams p;
-            p.meta = h->d_meta; p.key = h->d_key; p.prob64 = h->d_prob64; p.tables = tables; p.per_seq = per_seq;
-            p.pl = pl; p.J = J; p.rank = rank; p.pay32 = pay32; p.pay64 = pay64;
-            const int64_t n_warps = pl.nt * pl.tile * pl.tile;
+            p.meta = h->d_meta; p.key = h->d_key; p.prob64 = h->d_prob64; p.invp = h->d_invp; p.tables = tables; p.per_seq = per_seq;
+            p.pl = pl; p.J0 = J0; p.J1 = J1; p.rank = rank; p.pay32 = pay32; p.pay64 = pay64;
+            const int64_t n_warps = pl.nt * (J1 - J0) * pl.tile * pl.tile;
+            VGS_CHECK_ARG((n_warps * 32 + 255) / 256 < ((int64_t)1 << 31), "estimate kernel grid too large");
             vgs_prof_begin(h, VGS_PROF_ESTIMATE_PAIRS, s);
             k_est_pairs<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, s>>>(p);
             vgs_prof_end(h, VGS_PROF_ESTIMATE_PAIRS, s);
