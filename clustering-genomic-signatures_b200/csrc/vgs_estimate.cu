@@ -196,8 +196,10 @@ __global__ void k_est_pairs(const EstParams p) {
 static int est_tiles_impl(vgs_context *h, const TilePlan &pl, int rank, float *pay32, double *pay64, cudaStream_t s) {
     const int K = h->max_order + 1;
     const int64_t per_seq = level_off(K + 1);  // u32 entries for levels 1..K
+    // memory budget for the count tables: queried only when the existing scratch is too small for everything at once
+    // (cudaMemGetInfo is a blocking driver call; a steady-state step must not make it)
     size_t free_b = 0, total_b = 0;
-    VGS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (per_seq * 4 * pl.tile * pl.nt + 256 > h->scratch2_bytes) VGS_CUDA(cudaMemGetInfo(&free_b, &total_b));
     // count tables for as many tile columns at a time as fit in the budget (all of them for the usual shapes)
     const int64_t budget = std::max<int64_t>(per_seq * 4 * pl.tile, std::min<int64_t>((int64_t)4 << 30, (int64_t)(free_b / 2) + h->scratch2_bytes));
     const int64_t cols_per_batch = std::max<int64_t>(1, std::min<int64_t>(pl.nt, budget / (per_seq * 4 * pl.tile)));

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--k", type=int, default=200)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--skip-nll", action="store_true")
+    ap.add_argument("--host-sequences", action="store_true",
+                    help="sample the sequences with the numpy sampler on the host (slow at N = 20000) instead of vgs_sample_sequences")
     args = ap.parse_args()
 
     import torch
@@ -52,7 +54,7 @@ def main():
     out["gen_models_s"] = time.time() - t0
     out["config"]["total_contexts"] = fm.total_contexts
     seqs = None
-    if not args.skip_nll:
+    if not args.skip_nll and args.host_sequences:
         t0 = time.time()
         seqs = synthetic.sample_sequences(fm, L, 5)
         out["gen_sequences_s"] = time.time() - t0
@@ -64,6 +66,15 @@ def main():
     out["load_models_s"] = time.time() - t0
     if seqs is not None:
         h.load_sequences_packed(*pack_sequences(seqs))
+    elif not args.skip_nll:
+        # the device sampler (row f2): every rank draws the same MT19937 stream, so the sequence sets are identical
+        import random
+        t0 = time.time()
+        st = np.array(random.Random(5).getstate()[1], dtype=np.uint32)
+        h.sample_sequences(L, 500, st)
+        torch.cuda.synchronize()
+        out["sample_sequences_on_device_s"] = time.time() - t0
+        seqs = True
     free_after = h.device_info()["free_bytes"]
     out["hbm_free_after_load_gb"] = free_after / 1e9
 
@@ -109,12 +120,14 @@ def main():
     D32 = job.D32
     # ---- NLL
     if seqs is not None:
-        jobn, msn = run("nll", "sequential")
         T_m = 32.0 * n_ctx + 2.0 * 4.0 ** orders
         algn = n * (np.ceil(L / 4.0) + np.minimum(T_m, L * 10.0) + 8.0).sum()
-        out["nll"] = {"ms": msn, "pair_distances_per_s": pairs / (msn / 1e3), "tile": jobn.tile, "mode": "sequential",
-                      "algorithmic_GBps_per_gpu": algn / world / (msn / 1e3) / 1e9,
-                      "roofline_frac_of_measured_hbm": algn / world / (msn / 1e3) / 1e9 / peak}
+        for mode in ("sequential", "warp"):
+            jobn, msn = run("nll", mode)
+            out["nll" if mode == "sequential" else "nll_warp"] = {
+                "ms": msn, "pair_distances_per_s": pairs / (msn / 1e3), "tile": jobn.tile, "mode": mode,
+                "algorithmic_GBps_per_gpu": algn / world / (msn / 1e3) / 1e9,
+                "roofline_frac_of_measured_hbm": algn / world / (msn / 1e3) / 1e9 / peak}
     # ---- average link on the Frobenius matrix (rank 0; the matrix is resident on every rank)
     if rank == 0:
         torch.cuda.synchronize()
