@@ -131,6 +131,13 @@ struct vgs_context {
     // k-mer contraction mode (vgs_kmer.cu)
     double *d_kmer_T = nullptr, *d_kmer_C = nullptr, *d_kmer_partial = nullptr;
     bool kmer_tables_ready = false, kmer_counts_ready = false, kmer_has_nan = false;
+    // exact int8 tensor-core contraction (vgs_kmer_i8.cu)
+    int8_t *d_i8_digits = nullptr;   // [n_models * 8][K8] balanced base-256 digits of round(ln p * 2^51)
+    uint8_t *d_i8_C = nullptr;       // [n_seq][K8] k-mer counts (low bytes)
+    int32_t *d_i8_over = nullptr;    // [n_seq] counts of frequent k-mers | [n_seq][64] {k, count >> 8}
+    uint64_t i8_tables_gen = ~0ull;
+    bool i8_tables_ok = false;
+    int i8_counts_state = 0;         // 0 = not checked for this sequence set, 1 = usable, 2 = too many frequent k-mers
     float *d_out32 = nullptr;   // staging for the *_h entry points
     double *d_out64 = nullptr;
 
@@ -241,6 +248,9 @@ bool vgs_kmer_applicable(vgs_context *h);
 // returns VGS_OK, an error, or -1 when the set needs the scan kernel (a model without a root context)
 int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately, double *M,
                     int64_t ld, cudaStream_t s, uint64_t cache_key = 0);
+int vgs_kmer_i8_prepare_tables(vgs_context *h, const double *T, int64_t K, cudaStream_t s);
+int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool diag_separately, const double *T, int64_t K,
+                       double *M, int64_t ld, cudaStream_t s);
 int vgs_assemble_impl(vgs_context *h, const TilePlan &p, const float *gathered32, const double *gathered64,
                       float *D32, double *D64, cudaStream_t s);
 

@@ -219,7 +219,7 @@ static void free_models(vgs_context *h) {
     h->model_gen++;
     vgs_wcache_invalidate(h);
 }
-static void free_sequences(vgs_context *h) { h->n_seq = 0; h->total_symbols = 0; h->total_words = 0; h->kmer_counts_ready = false; }
+static void free_sequences(vgs_context *h) { h->n_seq = 0; h->total_symbols = 0; h->total_words = 0; h->kmer_counts_ready = false; h->i8_counts_state = 0; }
 static void free_all_buffers(vgs_context *h) {
     for (auto &kv : h->caps) {
         void **p = (void **)kv.first;

@@ -392,18 +392,6 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
     if (h->kmer_has_nan) return -1;  // caller falls back to the scan kernel
     const int D = h->max_order;
     const int64_t K = std::max<int64_t>(KD_BK, (int64_t)1 << (2 * (D + 1)));
-    // 1. histograms of the resident sequences (a pass over the packed sequences; part of every call unless the
-    //    caller pinned them with VGS_KMER_KEEP_COUNTS=1)
-    static int keep_counts = -1;
-    if (keep_counts < 0) { const char *e = getenv("VGS_KMER_KEEP_COUNTS"); keep_counts = (e && e[0] == '1') ? 1 : 0; }
-    if (!h->kmer_counts_ready || !keep_counts) {
-        if ((rc = vgs_reserve(h, &h->d_kmer_C, h->n_seq * K))) return rc;
-        const int smem = (int)(((int64_t)1 << (2 * (D + 1))) * 4);
-        VGS_CUDA(cudaFuncSetAttribute(k_kmer_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_kmer_hist<<<(unsigned)h->n_seq, 256, smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K, h->d_kmer_C);
-        VGS_LAUNCH_CHECK(h);
-        h->kmer_counts_ready = true;
-    }
     // 2. unit list (cached on the device per (plan, rank) when the caller gives a key)
     int n_pairs = 0, split = 1, n_units = 0;
     KgUnit *d_units = nullptr;
@@ -457,6 +445,31 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
         }
     }
     if (n_pairs == 0 && !diag_separately) return VGS_OK;
+    // 3. the exact int8 tensor-core path (vgs_kmer_i8.cu) when the set qualifies; VGS_KMER_GEMM=dmma|fma keeps fp64
+    {
+        static int want_i8 = -1;
+        if (want_i8 < 0) { const char *e = getenv("VGS_KMER_GEMM"); want_i8 = (e && (e[0] == 'd' || e[0] == 'f')) ? 0 : 1; }
+        if (want_i8) {
+            rc = vgs_kmer_i8_prepare_tables(h, h->d_kmer_T, K, s);
+            if (rc > 0) return rc;
+            if (rc == VGS_OK) {
+                rc = vgs_kmer_i8_scores(h, d_pairs, n_pairs, diag_separately, h->d_kmer_T, K, M, ld, s);
+                if (rc != -1) return rc;
+            }
+        }
+    }
+    // 4. fp64 path: histograms of the resident sequences as doubles (a pass over the packed sequences; part of every
+    //    call unless the caller pinned them with VGS_KMER_KEEP_COUNTS=1)
+    static int keep_counts = -1;
+    if (keep_counts < 0) { const char *e = getenv("VGS_KMER_KEEP_COUNTS"); keep_counts = (e && e[0] == '1') ? 1 : 0; }
+    if (!h->kmer_counts_ready || !keep_counts) {
+        if ((rc = vgs_reserve(h, &h->d_kmer_C, h->n_seq * K))) return rc;
+        const int smem = (int)(((int64_t)1 << (2 * (D + 1))) * 4);
+        VGS_CUDA(cudaFuncSetAttribute(k_kmer_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_kmer_hist<<<(unsigned)h->n_seq, 256, smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K, h->d_kmer_C);
+        VGS_LAUNCH_CHECK(h);
+        h->kmer_counts_ready = true;
+    }
     if (n_pairs > 0) {
         const int64_t part_elems = (int64_t)n_pairs * split * KG_BLOCK * KG_BLOCK;
         if ((rc = vgs_reserve(h, &h->d_kmer_partial, part_elems))) return rc;

@@ -1,0 +1,490 @@
+// vgs_kmer_i8.cu -- the NLL k-mer contraction as an EXACT integer GEMM on the 5th-generation tensor cores
+// (tcgen05.mma kind::i8, accumulators in tensor memory).
+//
+// Same quantity as vgs_kmer.cu:  M[s][m] = sum_k C[s][k] * T[m][k] + head(s, m)   (src/vlmc/vlmc.pyx:79-101 restated
+// as a contraction).  ln p needs 53 bits, so no floating-point tensor-core format can carry T --
+// but the contraction is a sum of (small integer) x (fixed-point number), and that is exact in integer arithmetic:
+//
+//   T[m][k]  ->  q = round(T * 2^51)  (|T| <= 1000 < 2^10, so |q| < 2^61), written as eight balanced base-256 digits
+//                q = sum_p d_p * 256^p,  d_p in [-128, 127]                      -- int8 "B" operand, 8 rows per model
+//   C[s][k]  ->  the low byte of the k-mer count                                   -- uint8 "A" operand
+//   S_p[s][m] = sum_k (C[s][k] & 255) * d_p[m][k]   int32, exact: |S_p| <= 16384 * 255 * 128 < 2^31
+//   M[s][m]  = 2^-51 * sum_p S_p * 256^p   (two int64 halves, one fp64 rounding each)
+//               + the same fold of 256 * (C[s][k] >> 8) * d_p[m][k] over the few k-mers of a sequence that occur more
+//                 than 255 times (listed by the histogram kernel, added by k_i8_frequent: exact integers again)
+//
+// The only error is the 2^-52 quantisation of each ln p: |dM| <= L * 2^-52 ~ 2e-12 absolute on |M| ~ 1e4, tighter than
+// any fp64 summation order -- and every (s, m) entry is the same bits whatever the tiling, so 1/2/4/8-rank matrices
+// stay identical and duplicates score exactly alike.  Sets with more than 64 such frequent k-mers in one sequence (or
+// without a root context) take the fp64 MMA path of vgs_kmer.cu.
+//
+// Kernel.  CTA tile = 128 sequences x 128 operand rows (16 models x 8 digits), K in stages of 128 k-mers.  All four
+// warps fill a 3-stage shared-memory ring with 16-byte cp.async in the canonical no-swizzle K-major UMMA layout
+// ([16-byte k-chunk][row], chunk stride padded by 16 bytes against bank conflicts); one thread issues four
+// tcgen05.mma (M128 N128 K32) per stage and commits them to the stage's mbarrier, which frees the slot; after the
+// last stage the warps read their 32 TMEM lanes with tcgen05.ld, fold the eight digit sums of each model and write M.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "vgs_common.cuh"
+
+#define I8_TM 128
+#define I8_TN 128
+#define I8_MODELS_PER_TILE (I8_TN / 8)
+#define I8_BK 128            // k-mers (= bytes per operand row) per stage
+#define I8_CHUNKS (I8_BK / 16)
+#define I8_STAGES 3
+#define I8_THREADS 128
+#define I8_LBO (I8_TM * 16 + 16)                      // bytes between consecutive 16-byte k-chunks (padded)
+#define I8_SBO 128                                    // bytes between consecutive 8-row groups
+#define I8_OPERAND_BYTES (I8_CHUNKS * I8_LBO)
+#define I8_STAGE_BYTES (2 * I8_OPERAND_BYTES)
+#define I8_TMEM_COLS 128
+#define I8_SCALE_BITS 51
+#define I8_MAX_OVER 64       // per sequence: k-mers whose count exceeds one byte (their high part is added in the epilogue)
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void i8_cp_async16(uint32_t smem_dst, const void *gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void i8_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void i8_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void i8_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void i8_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void i8_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start address, leading byte
+// offset (between the two 16-byte k-chunks of one MMA) and stride byte offset (between 8-row groups), all >> 4;
+// version 1 = Blackwell
+__device__ __forceinline__ uint64_t i8_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((I8_LBO >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((I8_SBO >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = unsigned 8 bit, B = signed 8 bit, both K-major,
+// N = 128, M = 128, dense, no saturation
+__device__ __forceinline__ uint32_t i8_instr_desc() {
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(I8_TN >> 3) << 17) | ((uint32_t)(I8_TM >> 4) << 24);
+}
+__device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void i8_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(vgs_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void i8_tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// plain spin on an mbarrier phase (unique labels: this is inlined at several call sites)
+__device__ __forceinline__ void i8_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(vgs_smem_addr(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// the eight exact digit sums of one (sequence, model) -> fp64
+__device__ __forceinline__ double i8_fold(const long long *S) {
+    const long long lo = S[0] + S[1] * 256 + S[2] * 65536 + S[3] * 16777216;
+    const long long hi = S[4] + S[5] * 256 + S[6] * 65536 + S[7] * 16777216;
+    const double v = __fma_rn((double)hi, 4294967296.0, (double)lo);
+    return v * (1.0 / 2251799813685248.0);   // 2^-51, exact
+}
+
+// fixed-point form of one table entry and its digits (the same rounding everywhere)
+__device__ __forceinline__ long long i8_quantise(double t) { return __double2ll_rn(t * 2251799813685248.0); }
+
+// adds 256 * hi * digits(T[m][k]) for the frequent k-mers of sequence s
+__device__ __forceinline__ void i8_add_frequent(long long *S, const uint2 *__restrict__ list, int n_over, const double *__restrict__ Trow) {
+    for (int o = 0; o < n_over; ++o) {
+        const uint2 e = list[o];
+        long long q = i8_quantise(Trow[e.x]);
+        const long long w = 256ll * (long long)e.y;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const long long d = ((q + 128) & 255) - 128;
+            S[p] += w * d;
+            q = (q - d) >> 8;
+        }
+    }
+}
+
+// ---- operand builders ----------------------------------------------------------------------------------------
+// digits[(m * 8 + p) * K8 + k] = p-th balanced base-256 digit of round(T[m][k] * 2^51)
+__global__ void k_i8_digits(int64_t n_models, int64_t K, int64_t K8, const double *__restrict__ T, int8_t *__restrict__ digits,
+                            int *__restrict__ flag) {
+    const int64_t m = blockIdx.y;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K8; k += (int64_t)gridDim.x * blockDim.x) {
+        long long q = 0;
+        if (k < K) {
+            const double t = T[m * K + k];
+            if (!(fabs(t) <= 1000.0)) atomicOr(flag, 1);   // not a log-probability (or NaN): no fixed-point form
+            else q = i8_quantise(t);
+        }
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const long long d = ((q + 128) & 255) - 128;
+            digits[(m * 8 + p) * K8 + k] = (int8_t)d;
+            q = (q - d) >> 8;
+        }
+    }
+}
+
+// per-sequence (D+1)-mer histogram, low bytes as the uint8 operand (one CTA per sequence); k-mers counted more than 255
+// times go to the sequence's list {k, count >> 8}; more than I8_MAX_OVER of them raise the flag
+__global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
+                          const int64_t *__restrict__ seq_len, int64_t K8, uint8_t *__restrict__ C8, int32_t *__restrict__ over_cnt,
+                          uint2 *__restrict__ over_list, int *__restrict__ flag) {
+    extern __shared__ uint32_t hist[];
+    __shared__ int n_over;
+    if (threadIdx.x == 0) n_over = 0;
+    const int64_t s = blockIdx.x;
+    const int64_t K = (int64_t)1 << (2 * (depth + 1));
+    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0u;
+    __syncthreads();
+    const int64_t L = seq_len[s];
+    const uint32_t *w = seq + seq_off[s];
+    const uint32_t kmask = vgs_lowmask(depth + 1);
+    const int64_t span = (L + blockDim.x - 1) / blockDim.x;
+    const int64_t a = (int64_t)threadIdx.x * span, e = min(L, a + span);
+    if (a < e) {
+        int64_t t = max((int64_t)0, a - depth);
+        uint32_t code = 0;
+        for (; t < e; ++t) {
+            const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
+            code = ((code << 2) | x) & kmask;
+            if (t >= a && t >= depth) atomicAdd(&hist[code], 1u);
+        }
+    }
+    __syncthreads();
+    uint8_t *out = C8 + s * K8;
+    // four counts per thread and store (K8 is a multiple of 128)
+    for (int64_t k4 = threadIdx.x; k4 < K8 / 4; k4 += blockDim.x) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t k = 4 * k4 + j;
+            const uint32_t c = k < K ? hist[k] : 0u;
+            if (c > 255u) {
+                const int idx = atomicAdd(&n_over, 1);
+                if (idx < I8_MAX_OVER) over_list[s * I8_MAX_OVER + idx] = make_uint2((uint32_t)k, c >> 8);
+            }
+            packed |= (c & 255u) << (8 * j);
+        }
+        ((uint32_t *)out)[k4] = packed;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        over_cnt[s] = n_over < I8_MAX_OVER ? n_over : I8_MAX_OVER;
+        if (n_over > I8_MAX_OVER) atomicOr(flag, 2);
+    }
+}
+
+struct I8Params {
+    const uint8_t *C8;      // [n_seq][K8]
+    const int8_t *digits;   // [n_models * 8][K8]
+    const int32_t *over_cnt;  // [n_seq] frequent k-mers per sequence
+    const uint2 *over_list;   // [n_seq][I8_MAX_OVER] {k, count >> 8}
+    const double *T;          // [n_models][K] fp64 tables (source of the digits; read for the frequent k-mers)
+    int64_t K;
+    const int32_t *pairs;   // [n_pairs][2] (sequence 128-block, model 128-block)
+    int n_pairs;
+    int64_t K8, n_seq, n_models, ld;
+    double *M;
+    int skip_diag, depth;
+    const ModelMeta *meta;
+    const uint8_t *arena;
+    const uint32_t *seq;
+    const int64_t *seq_off, *seq_len;
+};
+
+// terms t in [order_m, D) of a model shallower than D (positions the (D+1)-mer histogram does not cover)
+__device__ __forceinline__ double i8_head(const I8Params &p, const ModelMeta &mm, int64_t s) {
+    if (mm.order >= p.depth) return 0.0;
+    const double *tab = (const double *)(p.arena + mm.nll_off);
+    const uint32_t fmask = vgs_lowmask(mm.order + 1);
+    const uint32_t *w = p.seq + p.seq_off[s];
+    const int64_t L = p.seq_len[s];
+    const int64_t top = L < p.depth ? L : p.depth;
+    uint32_t code = 0;
+    double head = 0.0;
+    for (int64_t t = 0; t < top; ++t) {
+        const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
+        code = (code << 2) | x;
+        if (t >= mm.order) head += tab[code & fmask];
+    }
+    return head;
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 2) k_kmer_i8mma(const I8Params p) {
+    extern __shared__ __align__(128) uint8_t i8_smem[];
+    __shared__ __align__(8) uint64_t bar[I8_STAGES];
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem0 = vgs_smem_addr(i8_smem);
+
+    if (tid == 0) {
+        for (int i = 0; i < I8_STAGES; ++i) vgs_mbar_init(&bar[i], 1);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(vgs_smem_addr(&tmem_base_slot)),
+                     "r"((uint32_t)I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    i8_tc_fence_before();
+    __syncthreads();
+    i8_tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t idesc = i8_instr_desc();
+    const int n_steps = (int)(p.K8 / I8_BK);
+    const int n_tiles = p.n_pairs * 8;        // a 128 x 128-model block pair = 8 tiles of 16 models
+    int64_t g0 = 0;                           // global stage counter (continues across tiles: mbarrier parities)
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int pair = tile >> 3;
+        const int64_t s0 = (int64_t)p.pairs[2 * pair] * 128;
+        const int64_t m0 = (int64_t)p.pairs[2 * pair + 1] * 128 + (int64_t)(tile & 7) * I8_MODELS_PER_TILE;
+        const int64_t b_row0 = m0 * 8, b_rows = p.n_models * 8;
+
+        auto fill = [&](int64_t g, int step) {
+            const int stage = (int)(g % I8_STAGES);
+            if (g >= I8_STAGES) i8_mbar_wait(&bar[stage], (uint32_t)((g / I8_STAGES - 1) & 1));   // MMAs of the slot's last use
+            const uint32_t sa = smem0 + (uint32_t)stage * I8_STAGE_BYTES, sb = sa + I8_OPERAND_BYTES;
+            const int64_t k0 = (int64_t)step * I8_BK;
+            const int c = tid & 7;
+#pragma unroll
+            for (int i = 0; i < I8_TM / 16; ++i) {
+                const int r = (tid >> 3) + 16 * i;
+                const uint32_t off = (uint32_t)(c * I8_LBO + r * 16);
+                const int64_t ra = s0 + r, rb = b_row0 + r;
+                const bool a_ok = ra < p.n_seq, b_ok = rb < b_rows;
+                i8_cp_async16(sa + off, p.C8 + (a_ok ? ra : 0) * p.K8 + k0 + c * 16, a_ok ? 16 : 0);
+                i8_cp_async16(sb + off, p.digits + (b_ok ? rb : 0) * p.K8 + k0 + c * 16, b_ok ? 16 : 0);
+            }
+        };
+
+#pragma unroll
+        for (int i = 0; i < I8_STAGES - 1; ++i) {
+            if (i < n_steps) fill(g0 + i, i);
+            i8_cp_async_commit();
+        }
+        for (int step = 0; step < n_steps; ++step) {
+            i8_cp_async_wait<I8_STAGES - 2>();
+            i8_fence_proxy_async();            // this thread's cp.async writes -> visible to the tensor-core (async) proxy
+            __syncthreads();
+            if (tid == 0) {
+                i8_tc_fence_after();
+                const int stage = (int)((g0 + step) % I8_STAGES);
+                const uint32_t sa = smem0 + (uint32_t)stage * I8_STAGE_BYTES, sb = sa + I8_OPERAND_BYTES;
+#pragma unroll
+                for (int j = 0; j < I8_BK / 32; ++j) {
+                    const uint64_t da = i8_smem_desc(sa + (uint32_t)(2 * j) * I8_LBO), db = i8_smem_desc(sb + (uint32_t)(2 * j) * I8_LBO);
+                    i8_mma(tmem_base, da, db, idesc, (step > 0 || j > 0) ? 1u : 0u);
+                }
+                i8_commit(&bar[stage]);
+            }
+            const int nxt = step + I8_STAGES - 1;
+            if (nxt < n_steps) fill(g0 + nxt, nxt);
+            i8_cp_async_commit();
+        }
+        // all MMAs of this tile done?
+        {
+            const int64_t g_last = g0 + n_steps - 1;
+            i8_mbar_wait(&bar[(int)(g_last % I8_STAGES)], (uint32_t)((g_last / I8_STAGES) & 1));
+        }
+        i8_tc_fence_after();
+        // epilogue: thread = one sequence row (TMEM lane), 16 columns (two models) at a time
+        const int64_t s = s0 + 32 * warp + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+#pragma unroll 1
+        for (int j = 0; j < I8_TN / 16; ++j) {
+            int32_t v[16];
+            i8_tmem_ld16(taddr + (uint32_t)(16 * j), v);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int64_t m = m0 + 2 * j + q;
+                if (s < p.n_seq && m < p.n_models && !(p.skip_diag && s == m)) {
+                    long long S[8];
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) S[d] = (long long)v[8 * q + d];
+                    p.M[s * p.ld + m] = i8_head(p, p.meta[m], s) + i8_fold(S);   // + k_i8_frequent for rows that need it
+                }
+            }
+        }
+        i8_tc_fence_before();
+        __syncthreads();                       // TMEM is free for the next tile's first (overwriting) MMA
+        g0 += n_steps;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)I8_TMEM_COLS) : "memory");
+    }
+}
+
+// second term of the sequences that have frequent k-mers: M[s][m] += fold(256 * sum_o hi_o * digits(T[m][k_o])).
+// One CTA per (block pair, sequence row); rows without frequent k-mers leave at once.  The term is an exact integer
+// sum folded once, so M[s][m] = fold(low bytes) + fold(high parts) is the same bits wherever it is computed.
+__global__ void __launch_bounds__(128) k_i8_frequent(const I8Params p) {
+    const int pair = blockIdx.x >> 7, r = blockIdx.x & 127;
+    const int64_t s = (int64_t)p.pairs[2 * pair] * 128 + r;
+    if (s >= p.n_seq) return;
+    const int n_over = p.over_cnt[s];
+    if (n_over == 0) return;
+    const int64_t m = (int64_t)p.pairs[2 * pair + 1] * 128 + threadIdx.x;
+    if (m >= p.n_models || (p.skip_diag && s == m)) return;
+    long long S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    i8_add_frequent(S, p.over_list + s * I8_MAX_OVER, n_over, p.T + m * p.K);
+    p.M[s * p.ld + m] += i8_fold(S);
+}
+
+// diagonal scores M[m][m] with the same arithmetic (one CTA per model): identical bits to the GEMM's entry
+__global__ void __launch_bounds__(256) k_i8_diag(const I8Params p) {
+    __shared__ int part[8][8];
+    __shared__ unsigned long long corr[8];
+    const int64_t m = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 8) corr[threadIdx.x] = 0ull;
+    int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t *c = (const uint32_t *)(p.C8 + m * p.K8);
+    for (int64_t k4 = threadIdx.x; k4 < p.K8 / 4; k4 += blockDim.x) {
+        const uint32_t cv = c[k4];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t dv = ((const uint32_t *)(p.digits + (m * 8 + q) * p.K8))[k4];
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv), "r"(dv));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0) part[warp][q] = acc[q];
+    }
+    __syncthreads();
+    // frequent k-mers of this sequence: exact integer sums, any order
+    const int n_over = p.over_cnt[m];
+    if ((int)threadIdx.x < n_over) {
+        long long S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        i8_add_frequent(S, p.over_list + m * I8_MAX_OVER + threadIdx.x, 1, p.T + m * p.K);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) atomicAdd(&corr[q], (unsigned long long)S[q]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long S[8], Sc[8];
+        for (int q = 0; q < 8; ++q) {
+            int t = 0;
+            for (int w2 = 0; w2 < 8; ++w2) t += part[w2][q];
+            S[q] = (long long)t;
+            Sc[q] = (long long)corr[q];
+        }
+        double v = i8_head(p, p.meta[m], m) + i8_fold(S);
+        if (n_over) v += i8_fold(Sc);
+        p.M[m * p.ld + m] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------------
+static int64_t i8_k8(vgs_context *h) { return std::max<int64_t>(I8_BK, (int64_t)1 << (2 * (h->max_order + 1))); }
+
+// builds (once per model set) the digit operand from the fp64 tables; returns VGS_OK, an error, or -1 = not applicable
+int vgs_kmer_i8_prepare_tables(vgs_context *h, const double *T, int64_t K, cudaStream_t s) {
+    if (h->i8_tables_gen == h->model_gen) return h->i8_tables_ok ? VGS_OK : -1;
+    const int64_t K8 = i8_k8(h);
+    int rc;
+    if ((rc = vgs_reserve(h, &h->d_i8_digits, h->n_models * 8 * K8))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
+    VGS_CUDA(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(int), s));
+    for (int64_t m0 = 0; m0 < h->n_models; m0 += 65535) {
+        dim3 grid((unsigned)std::min<int64_t>((K8 + 255) / 256, 64), (unsigned)std::min<int64_t>(h->n_models - m0, 65535));
+        k_i8_digits<<<grid, 256, 0, s>>>(h->n_models - m0, K, K8, T + m0 * K, h->d_i8_digits + m0 * 8 * K8, h->d_counters + 9);
+        VGS_LAUNCH_CHECK(h);
+    }
+    int flag = 0;
+    VGS_CUDA(cudaMemcpyAsync(&flag, h->d_counters + 9, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGS_CUDA(cudaStreamSynchronize(s));
+    h->i8_tables_ok = flag == 0;
+    h->i8_tables_gen = h->model_gen;
+    return h->i8_tables_ok ? VGS_OK : -1;
+}
+
+// scores for the given (sequence-block, model-block) pairs at 128 granularity (d_pairs on the device).
+// Returns VGS_OK, an error, or -1 when a sequence has too many frequent k-mers (caller uses the fp64 path).
+int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool diag_separately, const double *T, int64_t K,
+                       double *M, int64_t ld, cudaStream_t s) {
+    const int D = h->max_order;
+    const int64_t K8 = i8_k8(h);
+    int rc;
+    if ((rc = vgs_reserve(h, &h->d_i8_C, h->n_seq * K8))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_i8_over, h->n_seq * (I8_MAX_OVER * 2 + 1) + 2))) return rc;
+    int32_t *over_cnt = (int32_t *)h->d_i8_over;
+    uint2 *over_list = (uint2 *)(h->d_i8_over + ((h->n_seq + 1) / 2) * 2);
+    if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
+    // histograms of the resident sequences: part of every call (a pass over the packed sequences)
+    const int hist_smem = (int)(((int64_t)1 << (2 * (D + 1))) * 4);
+    VGS_CUDA(cudaFuncSetAttribute(k_i8_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    if (h->i8_counts_state == 0) VGS_CUDA(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(int), s));
+    k_i8_hist<<<(unsigned)h->n_seq, 256, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, h->d_i8_C, over_cnt, over_list,
+                                                         h->d_counters + 10);
+    VGS_LAUNCH_CHECK(h);
+    if (h->i8_counts_state == 0) {
+        // first call on this sequence set: few enough frequent k-mers per sequence?  (one synchronisation per loaded set)
+        int flag = 0;
+        VGS_CUDA(cudaMemcpyAsync(&flag, h->d_counters + 10, sizeof(int), cudaMemcpyDeviceToHost, s));
+        VGS_CUDA(cudaStreamSynchronize(s));
+        h->i8_counts_state = flag ? 2 : 1;
+    }
+    if (h->i8_counts_state == 2) return -1;
+    I8Params p;
+    p.C8 = h->d_i8_C; p.digits = h->d_i8_digits; p.pairs = d_pairs; p.n_pairs = n_pairs;
+    p.over_cnt = over_cnt; p.over_list = over_list; p.T = T; p.K = K;
+    p.K8 = K8; p.n_seq = h->n_seq; p.n_models = h->n_models; p.ld = ld; p.M = M;
+    p.skip_diag = diag_separately ? 1 : 0; p.depth = D;
+    p.meta = h->d_meta; p.arena = h->d_nll; p.seq = h->d_seq; p.seq_off = h->d_seq_off; p.seq_len = h->d_seq_len;
+    if (n_pairs > 0) {
+        const int smem = I8_STAGES * I8_STAGE_BYTES;
+        VGS_CUDA(cudaFuncSetAttribute(k_kmer_i8mma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int grid = std::min(n_pairs * 8, 2 * h->sm_count);
+        vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
+        k_kmer_i8mma<<<grid, I8_THREADS, smem, s>>>(p);
+        vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
+        VGS_LAUNCH_CHECK(h);
+        k_i8_frequent<<<(unsigned)(n_pairs * 128), 128, 0, s>>>(p);
+        VGS_LAUNCH_CHECK(h);
+    }
+    if (diag_separately) {
+        const int64_t nd = std::min(h->n_seq, h->n_models);
+        k_i8_diag<<<(unsigned)nd, 256, 0, s>>>(p);
+        VGS_LAUNCH_CHECK(h);
+    }
+    return VGS_OK;
+}
