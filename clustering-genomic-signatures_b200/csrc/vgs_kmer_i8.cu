@@ -18,11 +18,15 @@
 // stay identical and duplicates score exactly alike.  Sets with more than 64 such frequent k-mers in one sequence (or
 // without a root context) take the fp64 MMA path of vgs_kmer.cu.
 //
-// Kernel.  CTA tile = 128 sequences x 128 operand rows (16 models x 8 digits), K in stages of 128 k-mers.  All four
-// warps fill a 3-stage shared-memory ring with 16-byte cp.async in the canonical no-swizzle K-major UMMA layout
-// ([16-byte k-chunk][row], chunk stride padded by 16 bytes against bank conflicts); one thread issues four
-// tcgen05.mma (M128 N128 K32) per stage and commits them to the stage's mbarrier, which frees the slot; after the
-// last stage the warps read their 32 TMEM lanes with tcgen05.ld, fold the eight digit sums of each model and write M.
+// Layout.  Both operands live in HBM already in the canonical no-swizzle K-major UMMA layout, tiled as
+// [128-row block][16-byte k-chunk][128 rows][16 bytes]: a pipeline stage (128 rows x 128 k-mers) of either operand is
+// ONE contiguous 16 KB block, moved by a single 1-D bulk async copy (TMA) that completes on the stage's mbarrier.
+// Kernel.  CTA tile = 128 sequences x 128 operand rows (16 models x 8 digits).  One thread drives the whole main
+// loop asynchronously: it re-arms a free stage (expect_tx + two bulk copies), waits for the next full stage, issues
+// four tcgen05.mma (M128 N128 K32) on it and commits them to the stage's "empty" mbarrier.  The other threads sleep
+// at a CTA barrier until the last commit has landed; then the four warps read their 32 TMEM lanes with tcgen05.ld,
+// fold the eight digit sums of each model and write M.  Two CTAs per SM overlap one tile's epilogue with the
+// other's main loop.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -36,7 +40,7 @@
 #define I8_CHUNKS (I8_BK / 16)
 #define I8_STAGES 3
 #define I8_THREADS 128
-#define I8_LBO (I8_TM * 16 + 16)                      // bytes between consecutive 16-byte k-chunks (padded)
+#define I8_LBO (I8_TM * 16)                           // bytes between consecutive 16-byte k-chunks
 #define I8_SBO 128                                    // bytes between consecutive 8-row groups
 #define I8_OPERAND_BYTES (I8_CHUNKS * I8_LBO)
 #define I8_STAGE_BYTES (2 * I8_OPERAND_BYTES)
@@ -44,14 +48,12 @@
 #define I8_SCALE_BITS 51
 #define I8_MAX_OVER 64       // per sequence: k-mers whose count exceeds one byte (their high part is added in the epilogue)
 
-// ---- PTX wrappers --------------------------------------------------------------------------------------------
-__device__ __forceinline__ void i8_cp_async16(uint32_t smem_dst, const void *gmem_src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+// byte offset of element (row, k) in the tiled operand layout [row >> 7][k >> 4][row & 127][k & 15]
+__host__ __device__ __forceinline__ int64_t i8_tiled(int64_t row, int64_t k, int64_t K8) {
+    return (((row >> 7) * (K8 >> 4) + (k >> 4)) << 11) + ((row & 127) << 4) + (k & 15);
 }
-__device__ __forceinline__ void i8_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void i8_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void i8_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void i8_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void i8_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -136,10 +138,10 @@ __device__ __forceinline__ void i8_add_frequent(long long *S, const uint2 *__res
 }
 
 // ---- operand builders ----------------------------------------------------------------------------------------
-// digits[(m * 8 + p) * K8 + k] = p-th balanced base-256 digit of round(T[m][k] * 2^51)
-__global__ void k_i8_digits(int64_t n_models, int64_t K, int64_t K8, const double *__restrict__ T, int8_t *__restrict__ digits,
+// digits[tiled(m * 8 + p, k)] = p-th balanced base-256 digit of round(T[m][k] * 2^51)
+__global__ void k_i8_digits(int64_t m_base, int64_t K, int64_t K8, const double *__restrict__ T, int8_t *__restrict__ digits,
                             int *__restrict__ flag) {
-    const int64_t m = blockIdx.y;
+    const int64_t m = m_base + blockIdx.y;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K8; k += (int64_t)gridDim.x * blockDim.x) {
         long long q = 0;
         if (k < K) {
@@ -150,7 +152,7 @@ __global__ void k_i8_digits(int64_t n_models, int64_t K, int64_t K8, const doubl
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
             const long long d = ((q + 128) & 255) - 128;
-            digits[(m * 8 + p) * K8 + k] = (int8_t)d;
+            digits[i8_tiled(m * 8 + p, k, K8)] = (int8_t)d;
             q = (q - d) >> 8;
         }
     }
@@ -183,8 +185,7 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
         }
     }
     __syncthreads();
-    uint8_t *out = C8 + s * K8;
-    // four counts per thread and store (K8 is a multiple of 128)
+    // four counts per thread and store (K8 is a multiple of 128), tiled layout
     for (int64_t k4 = threadIdx.x; k4 < K8 / 4; k4 += blockDim.x) {
         uint32_t packed = 0;
 #pragma unroll
@@ -197,7 +198,7 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
             }
             packed |= (c & 255u) << (8 * j);
         }
-        ((uint32_t *)out)[k4] = packed;
+        *(uint32_t *)(C8 + i8_tiled(s, 4 * k4, K8)) = packed;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -244,13 +245,13 @@ __device__ __forceinline__ double i8_head(const I8Params &p, const ModelMeta &mm
 
 __global__ void __launch_bounds__(I8_THREADS, 2) k_kmer_i8mma(const I8Params p) {
     extern __shared__ __align__(128) uint8_t i8_smem[];
-    __shared__ __align__(8) uint64_t bar[I8_STAGES];
+    __shared__ __align__(8) uint64_t full[I8_STAGES], empty[I8_STAGES];
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = vgs_smem_addr(i8_smem);
 
     if (tid == 0) {
-        for (int i = 0; i < I8_STAGES; ++i) vgs_mbar_init(&bar[i], 1);
+        for (int i = 0; i < I8_STAGES; ++i) { vgs_mbar_init(&full[i], 1); vgs_mbar_init(&empty[i], 1); }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(vgs_smem_addr(&tmem_base_slot)),
@@ -264,61 +265,50 @@ __global__ void __launch_bounds__(I8_THREADS, 2) k_kmer_i8mma(const I8Params p) 
     const uint32_t tmem_base = tmem_base_slot;
     const uint32_t idesc = i8_instr_desc();
     const int n_steps = (int)(p.K8 / I8_BK);
+    const int64_t chunks_per_row_block = p.K8 >> 4;      // 2 KB blocks per 128-row block
     const int n_tiles = p.n_pairs * 8;        // a 128 x 128-model block pair = 8 tiles of 16 models
     int64_t g0 = 0;                           // global stage counter (continues across tiles: mbarrier parities)
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int pair = tile >> 3;
-        const int64_t s0 = (int64_t)p.pairs[2 * pair] * 128;
+        const int64_t sb = p.pairs[2 * pair];
+        const int64_t s0 = sb * 128;
         const int64_t m0 = (int64_t)p.pairs[2 * pair + 1] * 128 + (int64_t)(tile & 7) * I8_MODELS_PER_TILE;
-        const int64_t b_row0 = m0 * 8, b_rows = p.n_models * 8;
+        if (m0 >= p.n_models) continue;                  // the last 128-model block of the set may be partly empty
+        const int64_t nb = m0 / I8_MODELS_PER_TILE;      // 128-row block of the digit operand (16 models x 8 digits)
 
-        auto fill = [&](int64_t g, int step) {
-            const int stage = (int)(g % I8_STAGES);
-            if (g >= I8_STAGES) i8_mbar_wait(&bar[stage], (uint32_t)((g / I8_STAGES - 1) & 1));   // MMAs of the slot's last use
-            const uint32_t sa = smem0 + (uint32_t)stage * I8_STAGE_BYTES, sb = sa + I8_OPERAND_BYTES;
-            const int64_t k0 = (int64_t)step * I8_BK;
-            const int c = tid & 7;
-#pragma unroll
-            for (int i = 0; i < I8_TM / 16; ++i) {
-                const int r = (tid >> 3) + 16 * i;
-                const uint32_t off = (uint32_t)(c * I8_LBO + r * 16);
-                const int64_t ra = s0 + r, rb = b_row0 + r;
-                const bool a_ok = ra < p.n_seq, b_ok = rb < b_rows;
-                i8_cp_async16(sa + off, p.C8 + (a_ok ? ra : 0) * p.K8 + k0 + c * 16, a_ok ? 16 : 0);
-                i8_cp_async16(sb + off, p.digits + (b_ok ? rb : 0) * p.K8 + k0 + c * 16, b_ok ? 16 : 0);
-            }
-        };
-
-#pragma unroll
-        for (int i = 0; i < I8_STAGES - 1; ++i) {
-            if (i < n_steps) fill(g0 + i, i);
-            i8_cp_async_commit();
-        }
-        for (int step = 0; step < n_steps; ++step) {
-            i8_cp_async_wait<I8_STAGES - 2>();
-            i8_fence_proxy_async();            // this thread's cp.async writes -> visible to the tensor-core (async) proxy
-            __syncthreads();
-            if (tid == 0) {
+        if (tid == 0) {
+            const uint8_t *a_src = p.C8 + ((sb * chunks_per_row_block) << 11);
+            const uint8_t *b_src = (const uint8_t *)p.digits + ((nb * chunks_per_row_block) << 11);
+            auto load = [&](int64_t g, int step) {
+                const int stage = (int)(g % I8_STAGES);
+                if (g >= I8_STAGES) i8_mbar_wait(&empty[stage], (uint32_t)((g / I8_STAGES - 1) & 1));   // MMAs of the slot's last use
+                uint8_t *sa = i8_smem + (size_t)stage * I8_STAGE_BYTES;
+                vgs_mbar_expect_tx(&full[stage], (uint32_t)I8_STAGE_BYTES);
+                vgs_bulk_g2s(sa, a_src + (size_t)step * I8_OPERAND_BYTES, I8_OPERAND_BYTES, &full[stage]);
+                vgs_bulk_g2s(sa + I8_OPERAND_BYTES, b_src + (size_t)step * I8_OPERAND_BYTES, I8_OPERAND_BYTES, &full[stage]);
+            };
+            for (int i = 0; i < I8_STAGES - 1 && i < n_steps; ++i) load(g0 + i, i);
+            for (int step = 0; step < n_steps; ++step) {
+                const int nxt = step + I8_STAGES - 1;
+                if (nxt < n_steps) load(g0 + nxt, nxt);
+                const int64_t g = g0 + step;
+                const int stage = (int)(g % I8_STAGES);
+                i8_mbar_wait(&full[stage], (uint32_t)((g / I8_STAGES) & 1));
                 i8_tc_fence_after();
-                const int stage = (int)((g0 + step) % I8_STAGES);
-                const uint32_t sa = smem0 + (uint32_t)stage * I8_STAGE_BYTES, sb = sa + I8_OPERAND_BYTES;
+                const uint32_t sa = smem0 + (uint32_t)stage * I8_STAGE_BYTES, sbm = sa + I8_OPERAND_BYTES;
 #pragma unroll
                 for (int j = 0; j < I8_BK / 32; ++j) {
-                    const uint64_t da = i8_smem_desc(sa + (uint32_t)(2 * j) * I8_LBO), db = i8_smem_desc(sb + (uint32_t)(2 * j) * I8_LBO);
+                    const uint64_t da = i8_smem_desc(sa + (uint32_t)(2 * j) * I8_LBO), db = i8_smem_desc(sbm + (uint32_t)(2 * j) * I8_LBO);
                     i8_mma(tmem_base, da, db, idesc, (step > 0 || j > 0) ? 1u : 0u);
                 }
-                i8_commit(&bar[stage]);
+                i8_commit(&empty[stage]);
             }
-            const int nxt = step + I8_STAGES - 1;
-            if (nxt < n_steps) fill(g0 + nxt, nxt);
-            i8_cp_async_commit();
-        }
-        // all MMAs of this tile done?
-        {
+            // all MMAs of this tile done?
             const int64_t g_last = g0 + n_steps - 1;
-            i8_mbar_wait(&bar[(int)(g_last % I8_STAGES)], (uint32_t)((g_last / I8_STAGES) & 1));
+            i8_mbar_wait(&empty[(int)(g_last % I8_STAGES)], (uint32_t)((g_last / I8_STAGES) & 1));
         }
+        __syncthreads();                       // the other threads sleep here during the main loop
         i8_tc_fence_after();
         // epilogue: thread = one sequence row (TMEM lane), 16 columns (two models) at a time
         const int64_t s = s0 + 32 * warp + lane;
@@ -372,12 +362,11 @@ __global__ void __launch_bounds__(256) k_i8_diag(const I8Params p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 8) corr[threadIdx.x] = 0ull;
     int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const uint32_t *c = (const uint32_t *)(p.C8 + m * p.K8);
     for (int64_t k4 = threadIdx.x; k4 < p.K8 / 4; k4 += blockDim.x) {
-        const uint32_t cv = c[k4];
+        const uint32_t cv = *(const uint32_t *)(p.C8 + i8_tiled(m, 4 * k4, p.K8));
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const uint32_t dv = ((const uint32_t *)(p.digits + (m * 8 + q) * p.K8))[k4];
+            const uint32_t dv = *(const uint32_t *)(p.digits + i8_tiled(m * 8 + q, 4 * k4, p.K8));
             asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv), "r"(dv));
         }
     }
@@ -421,12 +410,14 @@ int vgs_kmer_i8_prepare_tables(vgs_context *h, const double *T, int64_t K, cudaS
     if (h->i8_tables_gen == h->model_gen) return h->i8_tables_ok ? VGS_OK : -1;
     const int64_t K8 = i8_k8(h);
     int rc;
-    if ((rc = vgs_reserve(h, &h->d_i8_digits, h->n_models * 8 * K8))) return rc;
+    const int64_t digit_rows = (h->n_models * 8 + 127) / 128 * 128;
+    if ((rc = vgs_reserve(h, &h->d_i8_digits, digit_rows * K8))) return rc;
+    VGS_CUDA(cudaMemsetAsync(h->d_i8_digits, 0, (size_t)(digit_rows * K8), s));   // rows of the last block beyond the set
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
     VGS_CUDA(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(int), s));
     for (int64_t m0 = 0; m0 < h->n_models; m0 += 65535) {
         dim3 grid((unsigned)std::min<int64_t>((K8 + 255) / 256, 64), (unsigned)std::min<int64_t>(h->n_models - m0, 65535));
-        k_i8_digits<<<grid, 256, 0, s>>>(h->n_models - m0, K, K8, T + m0 * K, h->d_i8_digits + m0 * 8 * K8, h->d_counters + 9);
+        k_i8_digits<<<grid, 256, 0, s>>>(m0, K, K8, T, h->d_i8_digits, h->d_counters + 9);
         VGS_LAUNCH_CHECK(h);
     }
     int flag = 0;
@@ -444,7 +435,8 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
     const int D = h->max_order;
     const int64_t K8 = i8_k8(h);
     int rc;
-    if ((rc = vgs_reserve(h, &h->d_i8_C, h->n_seq * K8))) return rc;
+    const int64_t count_rows = (h->n_seq + 127) / 128 * 128;
+    if ((rc = vgs_reserve(h, &h->d_i8_C, count_rows * K8))) return rc;
     if ((rc = vgs_reserve(h, &h->d_i8_over, h->n_seq * (I8_MAX_OVER * 2 + 1) + 2))) return rc;
     int32_t *over_cnt = (int32_t *)h->d_i8_over;
     uint2 *over_list = (uint2 *)(h->d_i8_over + ((h->n_seq + 1) / 2) * 2);
@@ -452,7 +444,10 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
     // histograms of the resident sequences: part of every call (a pass over the packed sequences)
     const int hist_smem = (int)(((int64_t)1 << (2 * (D + 1))) * 4);
     VGS_CUDA(cudaFuncSetAttribute(k_i8_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
-    if (h->i8_counts_state == 0) VGS_CUDA(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(int), s));
+    if (h->i8_counts_state == 0) {
+        VGS_CUDA(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(int), s));
+        VGS_CUDA(cudaMemsetAsync(h->d_i8_C, 0, (size_t)(count_rows * K8), s));   // rows of the last block beyond the set
+    }
     k_i8_hist<<<(unsigned)h->n_seq, 256, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, h->d_i8_C, over_cnt, over_list,
                                                          h->d_counters + 10);
     VGS_LAUNCH_CHECK(h);
