@@ -427,6 +427,7 @@ def main():
     l0 = h.launch_count()
     ms_step, tb, te = timed(device_step, args.steps, 0, True)
     launches = h.launch_count() - l0
+    nll_kernel = h.last_nll_kernel() if kind == "nll" else -1   # which score kernel the timed steps used
     k_ms, k_n = h.profile_read(prof_id)
     h.profile_enable(False)
     clocks = sampler.stop(tb, te) if rank == 0 else None
@@ -495,24 +496,43 @@ def main():
     k_avg_ms = k_ms / max(k_n, 1)
     launches_per_step = max(1, k_n // args.steps)
     achieved = alg_bytes_rank / launches_per_step / (k_avg_ms / 1000.0) / 1e9 if k_avg_ms > 0 else None
+    kernel_name = {0: {3: "k_kmer_i8mma", 1: "k_kmer_dmma", 2: "k_kmer_gemm"}.get(nll_kernel, "k_nll_scores") if kind == "nll" else "",
+                   1: "k_pair_partials", 2: "k_est_pairs"}[prof_id]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": (achieved / peak_gbs) if achieved else None, "traffic": None,
-                "kernel": {0: "k_kmer_dmma" if (kind == "nll" and args.mode == "kmer") else "k_nll_scores",
-                           1: "k_pair_partials", 2: "k_est_pairs"}[prof_id],
+                "kernel": kernel_name,
                 "kernel_ms_per_launch": k_avg_ms, "kernel_launches_per_step": launches_per_step,
                 "kernel_share_of_step": (k_ms / args.steps) / ms_step if ms_step > 0 else None,
                 "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_formula": alg_desc, "peak_source": peak_src}
     # ncu dram bytes per launch of the dominant kernel, when a committed profile summary provides it
     traffic_key = args.workload + ("_" + args.mode if kind == "nll" else "")
+    if nll_kernel == 3:
+        traffic_key = args.workload + "_i8mma"
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             roofline["traffic"] = json.load(fh).get(traffic_key)
     except Exception:
         pass
-    if kind == "nll" and args.mode == "kmer" and k_avg_ms > 0:
+    Kdim = max(16.0, 4.0 ** (orders.max() + 1)) if kind == "nll" else 0.0
+    if nll_kernel == 3 and k_avg_ms > 0:
+        # the dominant kernel is an int8 tensor-core GEMM (tcgen05.mma kind::i8): [N seq] x [8 digit rows per model] x
+        # [4^(D+1) k-mers], 2 integer ops per MAC.  Its roof is the tensor pipe: int8 runs at twice the bf16 rate on
+        # B200, so peak = 2 x the measured cuBLAS bf16 burst figure (the kernel is timed alone).
+        K8 = max(128.0, 4.0 ** (orders.max() + 1))
+        ops = 2.0 * n * (8.0 * n) * K8 / world
+        peak_bf16 = float(peaks.get("bf16_tflops", 1590.0))
+        a_tops = ops / (k_avg_ms / 1e3) / 1e12
+        roofline.update({"bound": "tensor", "achieved": a_tops, "peak": 2.0 * peak_bf16, "unit": "TFLOP/s",
+                         "frac": a_tops / (2.0 * peak_bf16),
+                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (int8 tensor rate = 2 x bf16; of measured)"
+                         if "bf16_tflops" in peaks else "2 x fallback 1590 TF/s bf16 (of fallback)",
+                         "ops_per_step": ops * world, "ops_formula": "2 x N_seq x (8 x N_models) x max(128, 4^(D+1)) int8 ops",
+                         "hbm_view": {"achieved_GBps": achieved, "frac_of_hbm_peak": (achieved / peak_gbs) if achieved else None,
+                                      "note": "SURVEY 8d algorithmic bytes of the scan formulation / kernel time"}})
+    elif kind == "nll" and nll_kernel in (1, 2) and k_avg_ms > 0:
         # the contraction is an fp64 MMA kernel: report it against the fp64 pipe as well
         # (64 fp64 FMA lanes per SM: 2 * 64 * SMs * max SM clock)
-        flops = 2.0 * n * n * max(16.0, 4.0 ** (orders.max() + 1)) / world
+        flops = 2.0 * n * n * Kdim / world
         peak64 = 2.0 * 64 * sm_count * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
         roofline["fp64"] = {"achieved_tflops": flops / (k_avg_ms / 1e3) / 1e12, "peak_tflops": peak64,
                             "frac": flops / (k_avg_ms / 1e3) / 1e12 / peak64,
@@ -522,9 +542,10 @@ def main():
         "metric": "pair-distances/sec", "value": pairs / (ms_step / 1000.0), "unit": unit, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64" if kind in ("nll", "estimate") else "f32 rows, f64 accumulate", "data": "synthetic",
+        "dtype": ("int8 x int8 -> int32 exact fixed point (ln p quantised to 2^-51), f64 result" if nll_kernel == 3 else
+                  "f64" if kind in ("nll", "estimate") else "f32 rows, f64 accumulate"), "data": "synthetic",
         "config": {"workload": desc, "n_models": n, "seq_len": L, "pairs_per_step": pairs, "total_contexts": fm.total_contexts,
-                   "nll_mode": args.mode if kind == "nll" else None, "tile": tile if world > 1 else None,
+                   "nll_mode": args.mode if kind == "nll" else None, "nll_kernel": kernel_name if kind == "nll" else None, "tile": tile if world > 1 else None,
                    "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "parallelism": "tile-sharded upper triangle + NCCL all-gather" if world > 1 else "single GPU",
                    "sm_count": sm_count},

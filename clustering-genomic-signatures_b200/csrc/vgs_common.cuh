@@ -137,6 +137,7 @@ struct vgs_context {
     int32_t *d_i8_over = nullptr;    // [n_seq] counts of frequent k-mers | [n_seq][64] {k, count >> 8}
     uint64_t i8_tables_gen = ~0ull;
     bool i8_tables_ok = false;
+    int last_nll_kernel = 0;         // VGS_NLL_KERNEL_* of the most recent score launch
     int i8_counts_state = 0;         // 0 = not checked for this sequence set, 1 = usable, 2 = too many frequent k-mers
     float *d_out32 = nullptr;   // staging for the *_h entry points
     double *d_out64 = nullptr;

@@ -394,10 +394,11 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
     const int64_t K = std::max<int64_t>(KD_BK, (int64_t)1 << (2 * (D + 1)));
     // 2. unit list (cached on the device per (plan, rank) when the caller gives a key)
     int n_pairs = 0, split = 1, n_units = 0;
+    bool diag_covered = false;   // every diagonal 128-block is among the pairs: the contraction itself produces M[i][i]
     KgUnit *d_units = nullptr;
     int32_t *d_pairs = nullptr;
     if (WorkCache *wc = vgs_wcache_find(h, cache_key)) {
-        n_pairs = wc->n[0]; n_units = wc->n[1]; split = wc->split;
+        n_pairs = wc->n[0]; n_units = wc->n[1]; split = wc->split; diag_covered = wc->n[2] != 0;
         d_units = (KgUnit *)wc->dev;
         d_pairs = (int32_t *)((char *)wc->dev + wc->off2);
     } else {
@@ -406,6 +407,8 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
             for (int64_t mb = 0; mb < nb_m; ++mb)
                 if (need[(size_t)(sb * nb_m + mb)]) { pairs.push_back((int32_t)sb); pairs.push_back((int32_t)mb); }
         n_pairs = (int)(pairs.size() / 2);
+        diag_covered = true;
+        for (int64_t a = 0; a < std::min(nb_s, nb_m); ++a) diag_covered = diag_covered && need[(size_t)(a * nb_m + a)];
         if (n_pairs > 0) {
             const int64_t ksteps = K / KD_BK;   // unit boundaries are multiples of one MMA stage
             // split K so that the FULL problem (every block pair) gives >= ~8 units per SM.  The split depends only on the
@@ -430,7 +433,7 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
             if (cache_key) {
                 WorkCache *wc = vgs_wcache_add(h, cache_key, meta_bytes);
                 if (wc) {
-                    wc->n[0] = n_pairs; wc->n[1] = n_units; wc->split = split; wc->off2 = off2;
+                    wc->n[0] = n_pairs; wc->n[1] = n_units; wc->n[2] = diag_covered ? 1 : 0; wc->split = split; wc->off2 = off2;
                     base = (char *)wc->dev;
                 }
             }
@@ -453,7 +456,9 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
             rc = vgs_kmer_i8_prepare_tables(h, h->d_kmer_T, K, s);
             if (rc > 0) return rc;
             if (rc == VGS_OK) {
-                rc = vgs_kmer_i8_scores(h, d_pairs, n_pairs, diag_separately, h->d_kmer_T, K, M, ld, s);
+                // exact integers: the GEMM's own M[i][i] has the same bits as the dot-product kernel's, so skip that kernel
+                // whenever the pairs already cover the diagonal blocks (always on one GPU)
+                rc = vgs_kmer_i8_scores(h, d_pairs, n_pairs, diag_separately && !diag_covered, h->d_kmer_T, K, M, ld, s);
                 if (rc != -1) return rc;
             }
         }
@@ -482,6 +487,7 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
         static int use_fma = -1;
         if (use_fma < 0) { const char *e = getenv("VGS_KMER_GEMM"); use_fma = (e && e[0] == 'f') ? 1 : 0; }
         vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
+        h->last_nll_kernel = use_fma ? VGS_NLL_KERNEL_FMA : VGS_NLL_KERNEL_DMMA;
         if (use_fma) {
             k_kmer_gemm<<<grid, KG_THREADS, 0, s>>>(p);
         } else {

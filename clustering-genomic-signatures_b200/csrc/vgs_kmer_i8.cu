@@ -362,12 +362,22 @@ __global__ void __launch_bounds__(256) k_i8_diag(const I8Params p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 8) corr[threadIdx.x] = 0ull;
     int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int64_t k4 = threadIdx.x; k4 < p.K8 / 4; k4 += blockDim.x) {
-        const uint32_t cv = *(const uint32_t *)(p.C8 + i8_tiled(m, 4 * k4, p.K8));
+    // one 16-byte k-chunk per thread and step: the chunk of the count row and of the eight digit rows (consecutive rows
+    // of one 128-row block: 8 x 16 contiguous bytes)
+    const int64_t n_chunks = p.K8 >> 4;
+    const uint8_t *c_base = p.C8 + (((m >> 7) * n_chunks) << 11) + ((m & 127) << 4);
+    const int64_t dr = m * 8;
+    const uint8_t *d_base = (const uint8_t *)p.digits + (((dr >> 7) * n_chunks) << 11) + ((dr & 127) << 4);
+    for (int64_t ch = threadIdx.x; ch < n_chunks; ch += blockDim.x) {
+        const uint4 cv = *(const uint4 *)(c_base + (ch << 11));
+        const uint4 *dp = (const uint4 *)(d_base + (ch << 11));
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const uint32_t dv = *(const uint32_t *)(p.digits + i8_tiled(m * 8 + q, 4 * k4, p.K8));
-            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv), "r"(dv));
+            const uint4 dv = dp[q];
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv.x), "r"(dv.x));
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv.y), "r"(dv.y));
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv.z), "r"(dv.z));
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv.w), "r"(dv.w));
         }
     }
 #pragma unroll
@@ -469,6 +479,7 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
         const int smem = I8_STAGES * I8_STAGE_BYTES;
         VGS_CUDA(cudaFuncSetAttribute(k_kmer_i8mma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const int grid = std::min(n_pairs * 8, 2 * h->sm_count);
+        h->last_nll_kernel = VGS_NLL_KERNEL_I8MMA;
         vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
         k_kmer_i8mma<<<grid, I8_THREADS, smem, s>>>(p);
         vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);

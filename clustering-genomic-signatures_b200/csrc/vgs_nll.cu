@@ -324,6 +324,7 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
                         int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld, cudaStream_t s,
                         uint64_t cache_key) {
     if (mode == VGS_NLL_KMER) mode = VGS_NLL_WARP;  // the scan kernels have two modes
+    h->last_nll_kernel = VGS_NLL_KERNEL_SCAN;
     int rc;
     size_t n_u[3] = {0, 0, 0};
     NllUnit *d_units = nullptr;
@@ -426,6 +427,8 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
     }
     return VGS_OK;
 }
+
+extern "C" int vgs_last_nll_kernel(vgs_handle h) { return h ? h->last_nll_kernel : 0; }
 
 static int check_nll_ready(vgs_context *h) {
     VGS_CHECK_ARG(h, "null handle");

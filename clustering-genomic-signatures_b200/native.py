@@ -56,6 +56,7 @@ SIGNATURES = [
     ("vgs_estimate_tiles", c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     ("vgs_assemble", c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     ("vgs_matrix_to_triples", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    ("vgs_last_nll_kernel", c_int, [c_vp]),
     ("vgs_average_link", c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, _P(c_i64)]),
     ("vgs_retrieval_metrics", c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     ("vgs_silhouette", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -163,6 +164,10 @@ class Handle:
         ms, n = ctypes.c_double(), c_i64()
         _check(lib().vgs_profile_read(self._h, kernel_id, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def last_nll_kernel(self):
+        """0 scan, 1 fp64 MMA contraction, 2 fp64 FMA contraction, 3 exact int8 tensor-core contraction."""
+        return int(lib().vgs_last_nll_kernel(self._h))
 
     def poll_error(self, stream):
         """Synchronise `stream` and raise what the kernels flagged (RuntimeError / KeyError)."""

@@ -129,6 +129,13 @@ int vgs_sample_sequences(vgs_handle h, int64_t length, int64_t pre_sample, uint3
 /* ---- log-likelihood scores: VLMC.log_likelihood / log_likelihood_ignore_initial_bias
  *      (src/vlmc/vlmc.pyx:79-101).  M[s * ld + m] for s in [s_begin, s_end), m in [m_begin, m_end);
  *      NaN marks a failed lookup.  M_d is a device pointer to the full [n_seq][ld] matrix. ----------- */
+/* which kernel the most recent vgs_nll_* call used for the scores (bench.py picks the roofline from it) */
+#define VGS_NLL_KERNEL_SCAN 0   /* k_nll_scores (sequential / warp)                                         */
+#define VGS_NLL_KERNEL_DMMA 1   /* k_kmer_dmma: fp64 mma.sync contraction                                   */
+#define VGS_NLL_KERNEL_FMA 2    /* k_kmer_gemm: fp64 FMA contraction (VGS_KMER_GEMM=fma)                    */
+#define VGS_NLL_KERNEL_I8MMA 3  /* k_kmer_i8mma: exact int8 contraction on tcgen05 tensor cores (default)   */
+int vgs_last_nll_kernel(vgs_handle h);
+
 int vgs_nll_scores(vgs_handle h, int64_t s_begin, int64_t s_end, int64_t m_begin, int64_t m_end, int skip_mode,
                    int mode, double *M_d, int64_t ld, void *stream);
 int vgs_nll_scores_h(vgs_handle h, int skip_mode, int mode, double *M_out_h /* [n_seq][n_models] */);
