@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <type_traits>
 #include <atomic>
 #include <condition_variable>
@@ -590,6 +591,13 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     VGS_CHECK_ARG(h, "null handle");
     VGS_CHECK_ARG(n_models > 0 && ctx_offsets_h && ctx_len_h && ctx_code_h && prob_h, "vgs_load_models: null/empty input");
     VGS_CUDA(cudaSetDevice(h->device));
+    static int load_timing = -1;
+    if (load_timing < 0) { const char *e = getenv("VGS_LOAD_TIMING"); load_timing = (e && e[0] == '1') ? 1 : 0; }
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (load_timing) fprintf(stderr, "[vgs_load_models] %-28s %8.3f ms\n", what,
+                                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     free_models(h);
     const int64_t total = ctx_offsets_h[n_models];
     VGS_CHECK_ARG(ctx_offsets_h[0] == 0 && total > 0, "vgs_load_models: ctx_offsets must start at 0");
@@ -712,6 +720,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         nll_bytes += ((int64_t)mm.nll_bytes + 255) / 256 * 256;
     }
 
+    lap("host: validate + plan");
     int rc;
     if ((rc = vgs_reserve(h, &h->d_meta, n_models))) return rc;
     if ((rc = vgs_reserve(h, &h->d_key, total))) return rc;
@@ -753,6 +762,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
             h->umap_stride = stride;
         }
     }
+    lap("enqueued: uploads + keys/hash/umap");
     if (!want_nll) {
         // negative probabilities are still rejected (the reference fails on them at scoring time)
         for (int64_t i = 0; i < total * 4; ++i)
@@ -824,6 +834,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         }
     }
 
+    lap("host: ln p computed + streamed");
     // 3. build the NLL tables
     if (h->max_nll_bytes_t1 > 0) {
         // grid.x covers up to 4^6 histories with 256-thread blocks
@@ -841,7 +852,9 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         VGS_LAUNCH_CHECK(h);
     }
     h->nll_ready = true;
+    lap("enqueued: NLL table builds");
     VGS_CUDA(cudaStreamSynchronize(s));
+    lap("stream drained");
     return VGS_OK;
 }
 

@@ -28,3 +28,10 @@ print("load_models            %.2f ms" % T(lambda: h.load_models_raw(1000, arrs[
 print("load_sequences_packed  %.2f ms" % T(lambda: h.load_sequences_packed(arrs["words"], arrs["woff"], arrs["lens"])))
 print("nll_matrix_h (no f64)  %.2f ms" % T(lambda: h.nll_matrix_h(10000, "sequential", want_f64=False, out32=out)))
 print("pair_matrix_h          %.2f ms" % T(lambda: h.pair_matrix_h("frobenius_intersection", want_f64=False, out32=out)))
+print("nll_matrix_h kmer (no f64) %.2f ms" % T(lambda: h.nll_matrix_h(10000, "kmer", want_f64=False, out32=out)))
+import os as _os
+print("host cores:", _os.cpu_count())
+print("load_models skip_nll   %.2f ms" % T(lambda: h.load_models_raw(1000, arrs["off"], arrs["len"], arrs["code"], arrs["prob"], skip_nll=True)))
+import ctypes
+a = torch.empty(16 << 20, dtype=torch.uint8).pin_memory(); d = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
+print("H2D 16 MiB pinned      %.2f ms" % T(lambda: d.copy_(a, non_blocking=True)))
