@@ -31,13 +31,18 @@ def main():
     h.load_sequences_packed(*pack_sequences(seqs))
     stream = torch.cuda.current_stream().cuda_stream
     ok = True
-    for kind in ("nll", "frobenius_intersection", "frobenius_union", "projection", "estimate"):
-        job = MatrixJob(h, kind, n, length=L)
+    for kind in ("nll", "nll_kmer", "frobenius_intersection", "frobenius_union", "projection", "estimate"):
+        if kind == "nll_kmer":   # the int8 tensor-core contraction: 128-granular tiles
+            job = MatrixJob(h, "nll", n, length=L, mode="kmer", tile=128)
+        else:
+            job = MatrixJob(h, kind, n, length=L)
         D = job.run().clone()
         job.check()
         ref = torch.empty_like(D)
         if kind == "nll":
             h.nll_matrix(L, "sequential", ref, None, stream)
+        elif kind == "nll_kmer":
+            h.nll_matrix(L, "kmer", ref, None, stream)
         elif kind == "estimate":
             h.estimate_matrix(ref, None, stream)
         else:
