@@ -168,7 +168,7 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
     if (threadIdx.x == 0) n_over = 0;
     const int64_t s = blockIdx.x;
     const int64_t K = (int64_t)1 << (2 * (depth + 1));
-    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0u;
+    for (int64_t k = threadIdx.x; k < (K < 16 ? 16 : K); k += blockDim.x) hist[k] = 0u;   // at least one 16-count chunk
     __syncthreads();
     const int64_t L = seq_len[s];
     const uint32_t *w = seq + seq_off[s];
@@ -185,20 +185,27 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
         }
     }
     __syncthreads();
-    // four counts per thread and store (K8 is a multiple of 128), tiled layout
-    for (int64_t k4 = threadIdx.x; k4 < K8 / 4; k4 += blockDim.x) {
-        uint32_t packed = 0;
+    // one 16-byte k-chunk (16 counts) per thread and store, tiled layout (K8 is a multiple of 128)
+    const int64_t n_chunks = K8 >> 4;
+    uint8_t *out = C8 + (((s >> 7) * n_chunks) << 11) + ((s & 127) << 4);
+    for (int64_t ch = threadIdx.x; ch < n_chunks; ch += blockDim.x) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (16 * ch < K) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t k = 4 * k4 + j;
-            const uint32_t c = k < K ? hist[k] : 0u;
-            if (c > 255u) {
-                const int idx = atomicAdd(&n_over, 1);
-                if (idx < I8_MAX_OVER) over_list[s * I8_MAX_OVER + idx] = make_uint2((uint32_t)k, c >> 8);
+            for (int q = 0; q < 4; ++q) {
+                const uint4 c4 = *(const uint4 *)&hist[16 * ch + 4 * q];
+                const uint32_t cs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (cs[j] > 255u) {
+                        const int idx = atomicAdd(&n_over, 1);
+                        if (idx < I8_MAX_OVER) over_list[s * I8_MAX_OVER + idx] = make_uint2((uint32_t)(16 * ch + 4 * q + j), cs[j] >> 8);
+                    }
+                    w[q] |= (cs[j] & 255u) << (8 * j);
+                }
             }
-            packed |= (c & 255u) << (8 * j);
         }
-        *(uint32_t *)(C8 + i8_tiled(s, 4 * k4, K8)) = packed;
+        *(uint4 *)(out + (ch << 11)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -452,7 +459,7 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
     uint2 *over_list = (uint2 *)(h->d_i8_over + ((h->n_seq + 1) / 2) * 2);
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
     // histograms of the resident sequences: part of every call (a pass over the packed sequences)
-    const int hist_smem = (int)(((int64_t)1 << (2 * (D + 1))) * 4);
+    const int hist_smem = (int)(std::max<int64_t>(16, (int64_t)1 << (2 * (D + 1))) * 4);
     VGS_CUDA(cudaFuncSetAttribute(k_i8_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     if (h->i8_counts_state == 0) {
         VGS_CUDA(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(int), s));

@@ -527,8 +527,48 @@ __global__ void k_nll_combine(TilePlan pl, int rank, const double *__restrict__ 
     }
 }
 
+// single-GPU form: every entry of the [n][n] matrix straight from M, no payload / assemble pass.  Entry (j, i) adds
+// the same two quotients as (i, j) in the other order, so both triangles carry the same bits as the tiled path.
+__global__ void __launch_bounds__(256) k_nll_combine_full(int64_t n, const double *__restrict__ M, int64_t ld, double length,
+                                                          float *__restrict__ D32, double *__restrict__ D64, int *__restrict__ err) {
+    __shared__ double t_ji[32][33];   // M[j][i] for the tile, read row-wise (coalesced), used column-wise
+    __shared__ double d_i[32], d_j[32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t j = j0 + r, i = i0 + tx;
+        t_ji[r][tx] = (j < n && i < n) ? M[j * ld + i] : 0.0;
+    }
+    if (threadIdx.x < 32) {
+        const int64_t i = i0 + threadIdx.x;
+        d_i[threadIdx.x] = i < n ? M[i * ld + i] : 0.0;
+    } else if (threadIdx.x < 64) {
+        const int64_t j = j0 + threadIdx.x - 32;
+        d_j[threadIdx.x - 32] = j < n ? M[j * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t i = i0 + r, j = j0 + tx;
+        if (i >= n || j >= n) continue;
+        const double mij = M[i * ld + j], mji = t_ji[tx][r];
+        const double lr = __ddiv_rn(__dsub_rn(d_i[r], mij), length);
+        const double rl = __ddiv_rn(__dsub_rn(d_j[tx], mji), length);
+        // the tiled path computes (min, max) and mirrors it: add in that orientation so the bits agree
+        const double d = i <= j ? __ddiv_rn(__dadd_rn(lr, rl), 2.0) : __ddiv_rn(__dadd_rn(rl, lr), 2.0);
+        if (d != d) atomicOr(err, 1);
+        D32[i * n + j] = (float)d;
+        if (D64) D64[i * n + j] = d;
+    }
+}
+
 static int launch_nll_combine(vgs_context *h, const TilePlan &pl, int rank, int64_t length, float *pay32, double *pay64,
-                              cudaStream_t s) {
+                              cudaStream_t s, float *D32_direct = nullptr, double *D64_direct = nullptr) {
+    if (D32_direct) {
+        const unsigned g = (unsigned)((pl.n + 31) / 32);
+        k_nll_combine_full<<<dim3(g, g), 256, 0, s>>>(pl.n, h->d_M, h->n_models, (double)length, D32_direct, D64_direct, h->d_err);
+        VGS_LAUNCH_CHECK(h);
+        return VGS_OK;
+    }
     if (pl.slots <= 0) return VGS_OK;
     const dim3 grid((unsigned)pl.slots, (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, pl.tile * pl.tile / 2048)));
     k_nll_combine<<<grid, 256, 0, s>>>(pl, rank, h->d_M, h->n_models, (double)length, pay32, pay64, h->d_err);
@@ -536,8 +576,9 @@ static int launch_nll_combine(vgs_context *h, const TilePlan &pl, int rank, int6
     return VGS_OK;
 }
 
+// D32_direct (single GPU, whole matrix): the distances go straight into the [n][n] matrix instead of a tile payload
 static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePlan &pl, int rank, float *pay32, double *pay64,
-                          cudaStream_t s) {
+                          cudaStream_t s, float *D32_direct = nullptr, double *D64_direct = nullptr) {
     int rc = vgs_ensure_M(h);
     if (rc) return rc;
     // the work lists depend only on (model set, plan, rank): built once, then reused from the device
@@ -565,7 +606,7 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
         }
         rc = vgs_kmer_scores(h, need, nb, nb, true, h->d_M, h->n_models, s, kkey);
         if (rc > 0) return rc;
-        if (rc == VGS_OK) return launch_nll_combine(h, pl, rank, length, pay32, pay64, s);
+        if (rc == VGS_OK) return launch_nll_combine(h, pl, rank, length, pay32, pay64, s, D32_direct, D64_direct);
     }
     const uint64_t skey = vgs_mix(key, 1);
     std::vector<std::vector<int32_t>> lists;
@@ -587,7 +628,7 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
     // models whose block touches no owned tile need nothing; the diagonal score M[m][m] rides along
     rc = vgs_nll_score_lists(h, lists, pl.tile, 0, h->n_models, true, VGS_SKIP_ORDER, mode, h->d_M, h->n_models, s, skey);
     if (rc) return rc;
-    return launch_nll_combine(h, pl, rank, length, pay32, pay64, s);
+    return launch_nll_combine(h, pl, rank, length, pay32, pay64, s, D32_direct, D64_direct);
 }
 
 extern "C" int vgs_nll_tiles(vgs_handle h, int64_t length, int mode, int64_t tile, int rank, int world, float *payload_d,
@@ -616,12 +657,8 @@ extern "C" int vgs_nll_matrix(vgs_handle h, int64_t length, int mode, float *D32
     cudaStream_t s = (cudaStream_t)stream;
     TilePlan pl;
     vgs_make_plan(&pl, h->n_models, mode == VGS_NLL_KMER ? 128 : default_tile(h->n_models), 1, 1);
-    const int64_t pay_elems = pl.slots * pl.tile * pl.tile;
-    if ((rc = vgs_ensure_scratch(h, pay_elems * (D64_d ? 12 : 4) + 256))) return rc;
-    float *pay32 = (float *)h->d_scratch;
-    double *pay64 = D64_d ? (double *)((char *)h->d_scratch + (pay_elems * 4 + 255) / 256 * 256) : nullptr;
-    if ((rc = nll_tiles_impl(h, length, mode, pl, 0, pay32, pay64, s))) return rc;
-    return vgs_assemble_impl(h, pl, pay32, pay64, D32_d, D64_d, s);
+    // one GPU: scores for every block, then the distances straight into the matrix (no payload, no assemble)
+    return nll_tiles_impl(h, length, mode, pl, 0, nullptr, nullptr, s, D32_d, D64_d);
 }
 
 extern "C" int vgs_nll_matrix_h(vgs_handle h, int64_t length, int mode, float *D32_out_h, double *D64_out_h) {
