@@ -160,6 +160,9 @@ __global__ void k_i8_digits(int64_t m_base, int64_t K, int64_t K8, const double 
 
 // per-sequence (D+1)-mer histogram, low bytes as the uint8 operand (one CTA per sequence); k-mers counted more than 255
 // times go to the sequence's list {k, count >> 8}; more than I8_MAX_OVER of them raise the flag
+// PACK16: two 16-bit counters per shared-memory word (every sequence shorter than 65536): half the shared memory,
+// twice the resident CTAs
+template <bool PACK16>
 __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
                           const int64_t *__restrict__ seq_len, int64_t K8, uint8_t *__restrict__ C8, int32_t *__restrict__ over_cnt,
                           uint2 *__restrict__ over_list, int *__restrict__ flag) {
@@ -168,7 +171,8 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
     if (threadIdx.x == 0) n_over = 0;
     const int64_t s = blockIdx.x;
     const int64_t K = (int64_t)1 << (2 * (depth + 1));
-    for (int64_t k = threadIdx.x; k < (K < 16 ? 16 : K); k += blockDim.x) hist[k] = 0u;   // at least one 16-count chunk
+    const int64_t n_words = (K < 16 ? 16 : K) / (PACK16 ? 2 : 1);   // at least one 16-count chunk
+    for (int64_t k = threadIdx.x; k < n_words; k += blockDim.x) hist[k] = 0u;
     __syncthreads();
     const int64_t L = seq_len[s];
     const uint32_t *w = seq + seq_off[s];
@@ -181,7 +185,10 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
         for (; t < e; ++t) {
             const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
             code = ((code << 2) | x) & kmask;
-            if (t >= a && t >= depth) atomicAdd(&hist[code], 1u);
+            if (t >= a && t >= depth) {
+                if (PACK16) atomicAdd(&hist[code >> 1], (code & 1u) ? 0x10000u : 1u);
+                else atomicAdd(&hist[code], 1u);
+            }
         }
     }
     __syncthreads();
@@ -193,8 +200,14 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
         if (16 * ch < K) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint4 c4 = *(const uint4 *)&hist[16 * ch + 4 * q];
-                const uint32_t cs[4] = {c4.x, c4.y, c4.z, c4.w};
+                uint32_t cs[4];
+                if (PACK16) {
+                    const uint2 c2 = *(const uint2 *)&hist[8 * ch + 2 * q];
+                    cs[0] = c2.x & 0xFFFFu; cs[1] = c2.x >> 16; cs[2] = c2.y & 0xFFFFu; cs[3] = c2.y >> 16;
+                } else {
+                    const uint4 c4 = *(const uint4 *)&hist[16 * ch + 4 * q];
+                    cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (cs[j] > 255u) {
@@ -459,14 +472,22 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
     uint2 *over_list = (uint2 *)(h->d_i8_over + ((h->n_seq + 1) / 2) * 2);
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
     // histograms of the resident sequences: part of every call (a pass over the packed sequences)
-    const int hist_smem = (int)(std::max<int64_t>(16, (int64_t)1 << (2 * (D + 1))) * 4);
-    VGS_CUDA(cudaFuncSetAttribute(k_i8_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    int64_t max_len = 0;
+    for (int64_t i = 0; i < h->n_seq; ++i) max_len = std::max(max_len, h->h_seq_len[(size_t)i]);
+    const bool pack16 = max_len < 65536;
+    const int hist_smem = (int)(std::max<int64_t>(16, (int64_t)1 << (2 * (D + 1))) * (pack16 ? 2 : 4));
+    VGS_CUDA(cudaFuncSetAttribute(k_i8_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    VGS_CUDA(cudaFuncSetAttribute(k_i8_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     if (h->i8_counts_state == 0) {
         VGS_CUDA(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(int), s));
         VGS_CUDA(cudaMemsetAsync(h->d_i8_C, 0, (size_t)(count_rows * K8), s));   // rows of the last block beyond the set
     }
-    k_i8_hist<<<(unsigned)h->n_seq, 256, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, h->d_i8_C, over_cnt, over_list,
-                                                         h->d_counters + 10);
+    if (pack16)
+        k_i8_hist<true><<<(unsigned)h->n_seq, 256, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, h->d_i8_C, over_cnt,
+                                                                   over_list, h->d_counters + 10);
+    else
+        k_i8_hist<false><<<(unsigned)h->n_seq, 256, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, h->d_i8_C, over_cnt,
+                                                                    over_list, h->d_counters + 10);
     VGS_LAUNCH_CHECK(h);
     if (h->i8_counts_state == 0) {
         // first call on this sequence set: few enough frequent k-mers per sequence?  (one synchronisation per loaded set)

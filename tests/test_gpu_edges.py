@@ -183,12 +183,14 @@ def test_argument_errors():
         h.nll_matrix_h(4, "sequential")                        # one sequence per model is required
 
 
-def test_int8_contraction_with_frequent_kmers():
+@pytest.mark.parametrize("L", [30000, 70000])
+def test_int8_contraction_with_frequent_kmers(L):
     """Shallow models and long sequences: every k-mer count is far above one byte, so the int8 tensor-core path
-    runs entirely on its 'frequent k-mer' term (count >> 8) plus the low bytes; still exact to fixed-point rounding."""
+    runs entirely on its 'frequent k-mer' term (count >> 8) plus the low bytes; still exact to fixed-point rounding.
+    L = 70000 also takes the histogram kernel with 32-bit counters."""
     fm, _ = synthetic.make_family_models(37, 9, 2, 12, 4)
     assert int(fm.orders().max()) == 2
-    seqs = synthetic.sample_sequences(fm, 30000, 5)
+    seqs = synthetic.sample_sequences(fm, L, 5)
     h = native.Handle(0)
     h.load_models(fm)
     h.load_sequences_packed(*pack_sequences(seqs))
@@ -197,8 +199,8 @@ def test_int8_contraction_with_frequent_kmers():
     Mk = h.nll_scores_h(native.SKIP_ORDER, "kmer")
     assert h.last_nll_kernel() == 3, "expected the int8 tensor-core contraction"
     assert rel_err(Mk, M_or) < 1e-12
-    D = h.nll_matrix_h(30000, "kmer")[1]
-    assert rel_err(D, co.nll_from_scores(M_or, 30000)) < 1e-9 and np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+    D = h.nll_matrix_h(L, "kmer")[1]
+    assert rel_err(D, co.nll_from_scores(M_or, L)) < 1e-9 and np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
     # the fp64 MMA path gives the same scores to rounding
     import os
     import subprocess
@@ -206,12 +208,12 @@ def test_int8_contraction_with_frequent_kmers():
     code = ("import numpy as np, sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "from clustering_genomic_signatures_b200 import native, synthetic\n"
             "from clustering_genomic_signatures_b200.flat import pack_sequences\n"
-            "fm, _ = synthetic.make_family_models(37, 9, 2, 12, 4); seqs = synthetic.sample_sequences(fm, 30000, 5)\n"
+            "fm, _ = synthetic.make_family_models(37, 9, 2, 12, 4); seqs = synthetic.sample_sequences(fm, int(sys.argv[2]), 5)\n"
             "h = native.Handle(0); h.load_models(fm); h.load_sequences_packed(*pack_sequences(seqs))\n"
             "M = h.nll_scores_h(native.SKIP_ORDER, 'kmer'); assert h.last_nll_kernel() == 1\n"
             "np.save(sys.argv[1], M)\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                             os.path.dirname(os.path.abspath(__file__)))
     out = "/tmp/_vgs_dmma_scores.npy"
     env = dict(os.environ, VGS_KMER_GEMM="dmma")
-    subprocess.check_call([sys.executable, "-c", code, out], env=env)
+    subprocess.check_call([sys.executable, "-c", code, out, str(L)], env=env)
     assert rel_err(np.load(out), Mk) < 1e-12
