@@ -18,15 +18,18 @@
 // stay identical and duplicates score exactly alike.  Sets with more than 64 such frequent k-mers in one sequence (or
 // without a root context) take the fp64 MMA path of vgs_kmer.cu.
 //
-// Layout.  Both operands live in HBM already in the canonical no-swizzle K-major UMMA layout, tiled as
-// [128-row block][16-byte k-chunk][128 rows][16 bytes]: a pipeline stage (128 rows x 128 k-mers) of either operand is
+// Layout.  Both operands live in HBM already as the shared-memory image of the canonical K-major SWIZZLE_128B UMMA layout, tiled as
+// [128-row block][128-k-mer block][128 rows x 128 bytes, 128-byte swizzled]: a pipeline stage (128 rows x 128 k-mers) of either operand is
 // ONE contiguous 16 KB block, moved by a single 1-D bulk async copy (TMA) that completes on the stage's mbarrier.
-// Kernel.  CTA tile = 128 sequences x 128 operand rows (16 models x 8 digits).  One thread drives the whole main
-// loop asynchronously: it re-arms a free stage (expect_tx + two bulk copies), waits for the next full stage, issues
-// four tcgen05.mma (M128 N128 K32) on it and commits them to the stage's "empty" mbarrier.  The other threads sleep
-// at a CTA barrier until the last commit has landed; then the four warps read their 32 TMEM lanes with tcgen05.ld,
-// fold the eight digit sums of each model and write M.  Two CTAs per SM overlap one tile's epilogue with the
-// other's main loop.
+// Kernel.  CTA tile = 128 sequences x 4 accumulators of 128 operand rows (4 x 16 models x 8 digits): the whole tensor
+// memory of the SM (512 columns), one CTA per SM.  One thread drives the main loop asynchronously: it re-arms a free
+// stage (expect_tx + one bulk copy per operand tile), waits for the next full stage, issues the tcgen05.mma
+// (M128 N128 K32) of that stage round-robin over the four accumulators -- four independent accumulation chains,
+// where a single chain is bound by the latency of its own previous MMA (measured: one chain per CTA and two CTAs
+// per SM reached 43 % tensor-pipe activity) -- and commits them to the stage's "empty" mbarrier.  The other
+// threads sleep at a CTA barrier until the last commit has landed; then the four warps read their 32 TMEM lanes with
+// tcgen05.ld, fold the eight digit sums of each model and write M.  The count tile is shared by the four
+// accumulators, so operand traffic per MAC drops by 37 % against 128 x 128 tiles.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -36,36 +39,47 @@
 #define I8_TM 128
 #define I8_TN 128
 #define I8_MODELS_PER_TILE (I8_TN / 8)
-#define I8_BK 128            // k-mers (= bytes per operand row) per stage
+#define I8_BK 128            // k-mers (= bytes per operand row) per stage = one 128-byte swizzle atom
+#ifndef I8_NACC
+#define I8_NACC 2            // accumulators (128 x 128 each) per CTA, all fed by the same count tile
+#endif
 #define I8_CHUNKS (I8_BK / 16)
-#define I8_STAGES 3
+#ifndef I8_STAGES
+#define I8_STAGES 2
+#endif
+#ifndef I8_CTAS_PER_SM
+#define I8_CTAS_PER_SM 2     // measured (cfg 3, GEMM ms): NACC x STAGES x CTAs = 2x2x2 0.134, 1x3x2 0.151, 4x2x1 0.168, 2x4x1 0.214
+#endif
 #define I8_THREADS 128
-#define I8_LBO (I8_TM * 16)                           // bytes between consecutive 16-byte k-chunks
-#define I8_SBO 128                                    // bytes between consecutive 8-row groups
-#define I8_OPERAND_BYTES (I8_CHUNKS * I8_LBO)
-#define I8_STAGE_BYTES (2 * I8_OPERAND_BYTES)
-#define I8_TMEM_COLS 128
+#define I8_SBO 1024                                   // bytes between consecutive 8-row groups (8 rows x 128 bytes)
+#define I8_OPERAND_BYTES (I8_TM * I8_BK)              // one operand tile of one stage: 128 rows x 128 bytes = 16 KB
+#define I8_STAGE_BYTES ((1 + I8_NACC) * I8_OPERAND_BYTES)   // the count tile + one digit tile per accumulator
+#define I8_TMEM_COLS (I8_NACC * I8_TN)
 #define I8_SCALE_BITS 51
 #define I8_MAX_OVER 64       // per sequence: k-mers whose count exceeds one byte (their high part is added in the epilogue)
 
-// byte offset of element (row, k) in the tiled operand layout [row >> 7][k >> 4][row & 127][k & 15]
+// byte offset of element (row, k) in the tiled operand layout: [row >> 7][k >> 7] tiles of 128 rows x 128 bytes, each
+// the shared-memory image of the K-major SWIZZLE_128B canonical layout (row r at r * 128, its 16-byte chunk c stored
+// at chunk position c ^ (r & 7)): the tensor core reads eight rows of one k-chunk from eight different bank groups
 __host__ __device__ __forceinline__ int64_t i8_tiled(int64_t row, int64_t k, int64_t K8) {
-    return (((row >> 7) * (K8 >> 4) + (k >> 4)) << 11) + ((row & 127) << 4) + (k & 15);
+    return (((row >> 7) * (K8 >> 7) + (k >> 7)) << 14) + ((row & 127) << 7) + ((((k >> 4) & 7) ^ (row & 7)) << 4) + (k & 15);
 }
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void i8_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void i8_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start address, leading byte
-// offset (between the two 16-byte k-chunks of one MMA) and stride byte offset (between 8-row groups), all >> 4;
-// version 1 = Blackwell
+// shared-memory matrix descriptor, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor): start address >> 4, leading
+// byte offset (unused by swizzled K-major layouts: 1), stride byte offset (between 8-row groups) >> 4, version 1 =
+// Blackwell, layout type 2 = SWIZZLE_128B.  The four K = 32 slices of a 128-byte row are reached by advancing the
+// start address by 32 bytes (the tile is 1024-byte aligned, so the swizzle phase is that of the address bits).
 __device__ __forceinline__ uint64_t i8_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((I8_LBO >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)1 << 16;
     d |= (uint64_t)((I8_SBO >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = unsigned 8 bit, B = signed 8 bit, both K-major,
@@ -194,7 +208,6 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
     __syncthreads();
     // one 16-byte k-chunk (16 counts) per thread and store, tiled layout (K8 is a multiple of 128)
     const int64_t n_chunks = K8 >> 4;
-    uint8_t *out = C8 + (((s >> 7) * n_chunks) << 11) + ((s & 127) << 4);
     for (int64_t ch = threadIdx.x; ch < n_chunks; ch += blockDim.x) {
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (16 * ch < K) {
@@ -218,7 +231,7 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
                 }
             }
         }
-        *(uint4 *)(out + (ch << 11)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *(uint4 *)(C8 + i8_tiled(s, 16 * ch, K8)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -263,8 +276,8 @@ __device__ __forceinline__ double i8_head(const I8Params &p, const ModelMeta &mm
     return head;
 }
 
-__global__ void __launch_bounds__(I8_THREADS, 2) k_kmer_i8mma(const I8Params p) {
-    extern __shared__ __align__(128) uint8_t i8_smem[];
+__global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const I8Params p) {
+    extern __shared__ __align__(1024) uint8_t i8_smem[];
     __shared__ __align__(8) uint64_t full[I8_STAGES], empty[I8_STAGES];
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -285,42 +298,58 @@ __global__ void __launch_bounds__(I8_THREADS, 2) k_kmer_i8mma(const I8Params p) 
     const uint32_t tmem_base = tmem_base_slot;
     const uint32_t idesc = i8_instr_desc();
     const int n_steps = (int)(p.K8 / I8_BK);
-    const int64_t chunks_per_row_block = p.K8 >> 4;      // 2 KB blocks per 128-row block
-    const int n_tiles = p.n_pairs * 8;        // a 128 x 128-model block pair = 8 tiles of 16 models
+    const int64_t tiles_per_row_block = p.K8 >> 7;       // 16 KB tiles per 128-row block
+    // a 128 x 128-model block pair = 8 sub-tiles of 16 models; a CTA tile takes I8_NACC of them (one accumulator each,
+    // all fed by the same count tile).  Consecutive MMAs go to different accumulators: four independent accumulation
+    // chains keep the tensor pipe busy where a single chain waits for its own previous MMA.
+    const int tiles_per_pair = 8 / I8_NACC;
+    const int n_tiles = p.n_pairs * tiles_per_pair;
     int64_t g0 = 0;                           // global stage counter (continues across tiles: mbarrier parities)
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int pair = tile >> 3;
+        const int pair = tile / tiles_per_pair;
         const int64_t sb = p.pairs[2 * pair];
         const int64_t s0 = sb * 128;
-        const int64_t m0 = (int64_t)p.pairs[2 * pair + 1] * 128 + (int64_t)(tile & 7) * I8_MODELS_PER_TILE;
+        const int64_t m0 = (int64_t)p.pairs[2 * pair + 1] * 128 + (int64_t)(tile % tiles_per_pair) * (I8_NACC * I8_MODELS_PER_TILE);
         if (m0 >= p.n_models) continue;                  // the last 128-model block of the set may be partly empty
-        const int64_t nb = m0 / I8_MODELS_PER_TILE;      // 128-row block of the digit operand (16 models x 8 digits)
+        // sub-tiles that hold models (the rest of the last block is skipped: no copies, no MMAs, no output)
+        int n_acc = (int)((p.n_models - m0 + I8_MODELS_PER_TILE - 1) / I8_MODELS_PER_TILE);
+        if (n_acc > I8_NACC) n_acc = I8_NACC;
+        const int64_t nb = m0 / I8_MODELS_PER_TILE;      // first 128-row block of the digit operand (16 models x 8 digits)
 
         if (tid == 0) {
-            const uint8_t *a_src = p.C8 + ((sb * chunks_per_row_block) << 11);
-            const uint8_t *b_src = (const uint8_t *)p.digits + ((nb * chunks_per_row_block) << 11);
+            const uint8_t *a_src = p.C8 + ((sb * tiles_per_row_block) << 14);
+            const uint8_t *b_src = (const uint8_t *)p.digits + ((nb * tiles_per_row_block) << 14);
+            const size_t b_block_stride = (size_t)tiles_per_row_block << 14;
             auto load = [&](int64_t g, int step) {
                 const int stage = (int)(g % I8_STAGES);
                 if (g >= I8_STAGES) i8_mbar_wait(&empty[stage], (uint32_t)((g / I8_STAGES - 1) & 1));   // MMAs of the slot's last use
                 uint8_t *sa = i8_smem + (size_t)stage * I8_STAGE_BYTES;
-                vgs_mbar_expect_tx(&full[stage], (uint32_t)I8_STAGE_BYTES);
+                vgs_mbar_expect_tx(&full[stage], (uint32_t)((1 + n_acc) * I8_OPERAND_BYTES));
                 vgs_bulk_g2s(sa, a_src + (size_t)step * I8_OPERAND_BYTES, I8_OPERAND_BYTES, &full[stage]);
-                vgs_bulk_g2s(sa + I8_OPERAND_BYTES, b_src + (size_t)step * I8_OPERAND_BYTES, I8_OPERAND_BYTES, &full[stage]);
+                for (int b = 0; b < n_acc; ++b)
+                    vgs_bulk_g2s(sa + (size_t)(1 + b) * I8_OPERAND_BYTES, b_src + b * b_block_stride + (size_t)step * I8_OPERAND_BYTES,
+                                 I8_OPERAND_BYTES, &full[stage]);
             };
             for (int i = 0; i < I8_STAGES - 1 && i < n_steps; ++i) load(g0 + i, i);
             for (int step = 0; step < n_steps; ++step) {
                 const int nxt = step + I8_STAGES - 1;
-                if (nxt < n_steps) load(g0 + nxt, nxt);
+                if (nxt < n_steps) load(g0 + nxt, nxt);   // refill first: the copies get the longest head start
                 const int64_t g = g0 + step;
                 const int stage = (int)(g % I8_STAGES);
                 i8_mbar_wait(&full[stage], (uint32_t)((g / I8_STAGES) & 1));
                 i8_tc_fence_after();
-                const uint32_t sa = smem0 + (uint32_t)stage * I8_STAGE_BYTES, sbm = sa + I8_OPERAND_BYTES;
+                const uint32_t sa = smem0 + (uint32_t)stage * I8_STAGE_BYTES;
 #pragma unroll
                 for (int j = 0; j < I8_BK / 32; ++j) {
-                    const uint64_t da = i8_smem_desc(sa + (uint32_t)(2 * j) * I8_LBO), db = i8_smem_desc(sbm + (uint32_t)(2 * j) * I8_LBO);
-                    i8_mma(tmem_base, da, db, idesc, (step > 0 || j > 0) ? 1u : 0u);
+                    const uint64_t da = i8_smem_desc(sa + (uint32_t)(32 * j));
+#pragma unroll
+                    for (int b = 0; b < I8_NACC; ++b) {
+                        if (b < n_acc) {
+                            const uint64_t db = i8_smem_desc(sa + (uint32_t)(1 + b) * I8_OPERAND_BYTES + (uint32_t)(32 * j));
+                            i8_mma(tmem_base + (uint32_t)(b * I8_TN), da, db, idesc, (step > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
                 }
                 i8_commit(&empty[stage]);
             }
@@ -334,7 +363,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) k_kmer_i8mma(const I8Params p) 
         const int64_t s = s0 + 32 * warp + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
 #pragma unroll 1
-        for (int j = 0; j < I8_TN / 16; ++j) {
+        for (int j = 0; j < n_acc * (I8_TN / 16); ++j) {
             int32_t v[16];
             i8_tmem_ld16(taddr + (uint32_t)(16 * j), v);
 #pragma unroll
@@ -349,7 +378,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) k_kmer_i8mma(const I8Params p) 
             }
         }
         i8_tc_fence_before();
-        __syncthreads();                       // TMEM is free for the next tile's first (overwriting) MMA
+        __syncthreads();                       // TMEM is free for the next tile's first (overwriting) MMAs
         g0 += n_steps;
     }
     __syncthreads();
@@ -385,15 +414,12 @@ __global__ void __launch_bounds__(256) k_i8_diag(const I8Params p) {
     // one 16-byte k-chunk per thread and step: the chunk of the count row and of the eight digit rows (consecutive rows
     // of one 128-row block: 8 x 16 contiguous bytes)
     const int64_t n_chunks = p.K8 >> 4;
-    const uint8_t *c_base = p.C8 + (((m >> 7) * n_chunks) << 11) + ((m & 127) << 4);
     const int64_t dr = m * 8;
-    const uint8_t *d_base = (const uint8_t *)p.digits + (((dr >> 7) * n_chunks) << 11) + ((dr & 127) << 4);
     for (int64_t ch = threadIdx.x; ch < n_chunks; ch += blockDim.x) {
-        const uint4 cv = *(const uint4 *)(c_base + (ch << 11));
-        const uint4 *dp = (const uint4 *)(d_base + (ch << 11));
+        const uint4 cv = *(const uint4 *)(p.C8 + i8_tiled(m, 16 * ch, p.K8));
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const uint4 dv = dp[q];
+            const uint4 dv = *(const uint4 *)((const uint8_t *)p.digits + i8_tiled(dr + q, 16 * ch, p.K8));
             asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv.x), "r"(dv.x));
             asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv.y), "r"(dv.y));
             asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(cv.z), "r"(dv.z));
@@ -506,7 +532,7 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
     if (n_pairs > 0) {
         const int smem = I8_STAGES * I8_STAGE_BYTES;
         VGS_CUDA(cudaFuncSetAttribute(k_kmer_i8mma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        const int grid = std::min(n_pairs * 8, 2 * h->sm_count);
+        const int grid = std::min(n_pairs * (8 / I8_NACC), I8_CTAS_PER_SM * h->sm_count);
         h->last_nll_kernel = VGS_NLL_KERNEL_I8MMA;
         vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
         k_kmer_i8mma<<<grid, I8_THREADS, smem, s>>>(p);
