@@ -21,15 +21,18 @@
 // Layout.  Both operands live in HBM already as the shared-memory image of the canonical K-major SWIZZLE_128B UMMA layout, tiled as
 // [128-row block][128-k-mer block][128 rows x 128 bytes, 128-byte swizzled]: a pipeline stage (128 rows x 128 k-mers) of either operand is
 // ONE contiguous 16 KB block, moved by a single 1-D bulk async copy (TMA) that completes on the stage's mbarrier.
-// Kernel.  CTA tile = 128 sequences x 4 accumulators of 128 operand rows (4 x 16 models x 8 digits): the whole tensor
-// memory of the SM (512 columns), one CTA per SM.  One thread drives the main loop asynchronously: it re-arms a free
-// stage (expect_tx + one bulk copy per operand tile), waits for the next full stage, issues the tcgen05.mma
-// (M128 N128 K32) of that stage round-robin over the four accumulators -- four independent accumulation chains,
-// where a single chain is bound by the latency of its own previous MMA (measured: one chain per CTA and two CTAs
-// per SM reached 43 % tensor-pipe activity) -- and commits them to the stage's "empty" mbarrier.  The other
-// threads sleep at a CTA barrier until the last commit has landed; then the four warps read their 32 TMEM lanes with
-// tcgen05.ld, fold the eight digit sums of each model and write M.  The count tile is shared by the four
-// accumulators, so operand traffic per MAC drops by 37 % against 128 x 128 tiles.
+// Kernel.  CTA tile = 128 sequences x I8_NACC accumulators of 128 operand rows (16 models x 8 digits each), all fed by
+// the same count tile; 2 accumulators x 2 stages (48 KB each) x 2 CTAs per SM.  One thread drives the main loop
+// asynchronously: it re-arms a free stage (expect_tx + one bulk copy per operand tile), waits for the next full
+// stage, issues the tcgen05.mma (M128 N128 K32) of that stage and commits them to the stage's "empty" mbarrier.  The
+// other threads sleep at a CTA barrier until the last commit has landed; then the four warps read their 32 TMEM
+// lanes with tcgen05.ld, fold the eight digit sums of each model and write M; the second CTA of the SM keeps the
+// tensor pipe busy meanwhile.
+// Measured on cfg 3 (GEMM ms; accumulators x stages x CTAs/SM): 2x2x2 0.134, 1x3x2 0.151, 4x2x1 0.168, 2x4x1 0.214, and
+// a 2 x 2 tile (two count tiles x two digit tiles, half the operand traffic) 0.154: every variant issues one
+// M128 N128 K32 MMA per ~148 cycles per SM, i.e. the kernel sits at the single-CTA (cta_group::1) MMA rate, about half
+// of the int8 peak; operand traffic, shared-memory swizzle (none vs 128 B: same time) and pipeline depth are not the
+// limit.  The next step is cta_group::2 (CTA pairs, M = 256).
 #include <stdlib.h>
 
 #include <algorithm>
