@@ -504,6 +504,7 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
     int64_t max_len = 0;
     for (int64_t i = 0; i < h->n_seq; ++i) max_len = std::max(max_len, h->h_seq_len[(size_t)i]);
     const bool pack16 = max_len < 65536;
+    const int hist_threads = max_len >= 8192 ? 512 : 256;   // shorter per-thread symbol chains on long sequences
     const int hist_smem = (int)(std::max<int64_t>(16, (int64_t)1 << (2 * (D + 1))) * (pack16 ? 2 : 4));
     VGS_CUDA(cudaFuncSetAttribute(k_i8_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     VGS_CUDA(cudaFuncSetAttribute(k_i8_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
@@ -512,10 +513,10 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
         VGS_CUDA(cudaMemsetAsync(h->d_i8_C, 0, (size_t)(count_rows * K8), s));   // rows of the last block beyond the set
     }
     if (pack16)
-        k_i8_hist<true><<<(unsigned)h->n_seq, 256, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, h->d_i8_C, over_cnt,
+        k_i8_hist<true><<<(unsigned)h->n_seq, hist_threads, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, h->d_i8_C, over_cnt,
                                                                    over_list, h->d_counters + 10);
     else
-        k_i8_hist<false><<<(unsigned)h->n_seq, 256, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, h->d_i8_C, over_cnt,
+        k_i8_hist<false><<<(unsigned)h->n_seq, hist_threads, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, h->d_i8_C, over_cnt,
                                                                     over_list, h->d_counters + 10);
     VGS_LAUNCH_CHECK(h);
     if (h->i8_counts_state == 0) {
