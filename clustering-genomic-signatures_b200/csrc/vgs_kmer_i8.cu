@@ -21,8 +21,9 @@
 // Layout.  Both operands live in HBM already as the shared-memory image of the canonical K-major SWIZZLE_128B UMMA layout, tiled as
 // [128-row block][128-k-mer block][128 rows x 128 bytes, 128-byte swizzled]: a pipeline stage (128 rows x 128 k-mers) of either operand is
 // ONE contiguous 16 KB block, moved by a single 1-D bulk async copy (TMA) that completes on the stage's mbarrier.
-// Kernel.  CTA tile = 128 sequences x I8_NACC accumulators of 128 operand rows (16 models x 8 digits each), all fed by
-// the same count tile; 2 accumulators x 2 stages (48 KB each) x 2 CTAs per SM.  One thread drives the main loop
+// Kernel (template <NACC, STAGES>).  CTA tile = 128 sequences x NACC accumulators of 128 operand rows (16 models x 8
+// digits each), all fed by the same count tile; two CTAs per SM.  <2, 2> (128 x 256 tiles, 48 KB stages) when that
+// still fills the CTA slots, <1, 3> (twice as many tiles of half the latency) for multi-GPU shares and small sets.  One thread drives the main loop
 // asynchronously: it re-arms a free stage (expect_tx + one bulk copy per operand tile), waits for the next full
 // stage, issues the tcgen05.mma (M128 N128 K32) of that stage and commits them to the stage's "empty" mbarrier.  The
 // other threads sleep at a CTA barrier until the last commit has landed; then the four warps read their 32 TMEM
@@ -43,21 +44,13 @@
 #define I8_TN 128
 #define I8_MODELS_PER_TILE (I8_TN / 8)
 #define I8_BK 128            // k-mers (= bytes per operand row) per stage = one 128-byte swizzle atom
-#ifndef I8_NACC
-#define I8_NACC 2            // accumulators (128 x 128 each) per CTA, all fed by the same count tile
-#endif
 #define I8_CHUNKS (I8_BK / 16)
-#ifndef I8_STAGES
-#define I8_STAGES 2
-#endif
 #ifndef I8_CTAS_PER_SM
 #define I8_CTAS_PER_SM 2     // measured (cfg 3, GEMM ms): NACC x STAGES x CTAs = 2x2x2 0.134, 1x3x2 0.151, 4x2x1 0.168, 2x4x1 0.214
 #endif
 #define I8_THREADS 128
 #define I8_SBO 1024                                   // bytes between consecutive 8-row groups (8 rows x 128 bytes)
 #define I8_OPERAND_BYTES (I8_TM * I8_BK)              // one operand tile of one stage: 128 rows x 128 bytes = 16 KB
-#define I8_STAGE_BYTES ((1 + I8_NACC) * I8_OPERAND_BYTES)   // the count tile + one digit tile per accumulator
-#define I8_TMEM_COLS (I8_NACC * I8_TN)
 #define I8_SCALE_BITS 51
 #define I8_MAX_OVER 64       // per sequence: k-mers whose count exceeds one byte (their high part is added in the epilogue)
 
@@ -279,19 +272,22 @@ __device__ __forceinline__ double i8_head(const I8Params &p, const ModelMeta &mm
     return head;
 }
 
+template <int NACC, int STAGES>
 __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const I8Params p) {
+    constexpr int STAGE_BYTES = (1 + NACC) * I8_OPERAND_BYTES;   // the count tile + one digit tile per accumulator
+    constexpr int TMEM_COLS = NACC * I8_TN;
     extern __shared__ __align__(1024) uint8_t i8_smem[];
-    __shared__ __align__(8) uint64_t full[I8_STAGES], empty[I8_STAGES];
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = vgs_smem_addr(i8_smem);
 
     if (tid == 0) {
-        for (int i = 0; i < I8_STAGES; ++i) { vgs_mbar_init(&full[i], 1); vgs_mbar_init(&empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { vgs_mbar_init(&full[i], 1); vgs_mbar_init(&empty[i], 1); }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(vgs_smem_addr(&tmem_base_slot)),
-                     "r"((uint32_t)I8_TMEM_COLS)
+                     "r"((uint32_t)TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -302,10 +298,10 @@ __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const
     const uint32_t idesc = i8_instr_desc();
     const int n_steps = (int)(p.K8 / I8_BK);
     const int64_t tiles_per_row_block = p.K8 >> 7;       // 16 KB tiles per 128-row block
-    // a 128 x 128-model block pair = 8 sub-tiles of 16 models; a CTA tile takes I8_NACC of them (one accumulator each,
+    // a 128 x 128-model block pair = 8 sub-tiles of 16 models; a CTA tile takes NACC of them (one accumulator each,
     // all fed by the same count tile).  Consecutive MMAs go to different accumulators: four independent accumulation
     // chains keep the tensor pipe busy where a single chain waits for its own previous MMA.
-    const int tiles_per_pair = 8 / I8_NACC;
+    const int tiles_per_pair = 8 / NACC;
     const int n_tiles = p.n_pairs * tiles_per_pair;
     int64_t g0 = 0;                           // global stage counter (continues across tiles: mbarrier parities)
 
@@ -313,11 +309,11 @@ __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const
         const int pair = tile / tiles_per_pair;
         const int64_t sb = p.pairs[2 * pair];
         const int64_t s0 = sb * 128;
-        const int64_t m0 = (int64_t)p.pairs[2 * pair + 1] * 128 + (int64_t)(tile % tiles_per_pair) * (I8_NACC * I8_MODELS_PER_TILE);
+        const int64_t m0 = (int64_t)p.pairs[2 * pair + 1] * 128 + (int64_t)(tile % tiles_per_pair) * (NACC * I8_MODELS_PER_TILE);
         if (m0 >= p.n_models) continue;                  // the last 128-model block of the set may be partly empty
         // sub-tiles that hold models (the rest of the last block is skipped: no copies, no MMAs, no output)
         int n_acc = (int)((p.n_models - m0 + I8_MODELS_PER_TILE - 1) / I8_MODELS_PER_TILE);
-        if (n_acc > I8_NACC) n_acc = I8_NACC;
+        if (n_acc > NACC) n_acc = NACC;
         const int64_t nb = m0 / I8_MODELS_PER_TILE;      // first 128-row block of the digit operand (16 models x 8 digits)
 
         if (tid == 0) {
@@ -325,29 +321,29 @@ __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const
             const uint8_t *b_src = (const uint8_t *)p.digits + ((nb * tiles_per_row_block) << 14);
             const size_t b_block_stride = (size_t)tiles_per_row_block << 14;
             auto load = [&](int64_t g, int step) {
-                const int stage = (int)(g % I8_STAGES);
-                if (g >= I8_STAGES) i8_mbar_wait(&empty[stage], (uint32_t)((g / I8_STAGES - 1) & 1));   // MMAs of the slot's last use
-                uint8_t *sa = i8_smem + (size_t)stage * I8_STAGE_BYTES;
+                const int stage = (int)(g % STAGES);
+                if (g >= STAGES) i8_mbar_wait(&empty[stage], (uint32_t)((g / STAGES - 1) & 1));   // MMAs of the slot's last use
+                uint8_t *sa = i8_smem + (size_t)stage * STAGE_BYTES;
                 vgs_mbar_expect_tx(&full[stage], (uint32_t)((1 + n_acc) * I8_OPERAND_BYTES));
                 vgs_bulk_g2s(sa, a_src + (size_t)step * I8_OPERAND_BYTES, I8_OPERAND_BYTES, &full[stage]);
                 for (int b = 0; b < n_acc; ++b)
                     vgs_bulk_g2s(sa + (size_t)(1 + b) * I8_OPERAND_BYTES, b_src + b * b_block_stride + (size_t)step * I8_OPERAND_BYTES,
                                  I8_OPERAND_BYTES, &full[stage]);
             };
-            for (int i = 0; i < I8_STAGES - 1 && i < n_steps; ++i) load(g0 + i, i);
+            for (int i = 0; i < STAGES - 1 && i < n_steps; ++i) load(g0 + i, i);
             for (int step = 0; step < n_steps; ++step) {
-                const int nxt = step + I8_STAGES - 1;
+                const int nxt = step + STAGES - 1;
                 if (nxt < n_steps) load(g0 + nxt, nxt);   // refill first: the copies get the longest head start
                 const int64_t g = g0 + step;
-                const int stage = (int)(g % I8_STAGES);
-                i8_mbar_wait(&full[stage], (uint32_t)((g / I8_STAGES) & 1));
+                const int stage = (int)(g % STAGES);
+                i8_mbar_wait(&full[stage], (uint32_t)((g / STAGES) & 1));
                 i8_tc_fence_after();
-                const uint32_t sa = smem0 + (uint32_t)stage * I8_STAGE_BYTES;
+                const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
 #pragma unroll
                 for (int j = 0; j < I8_BK / 32; ++j) {
                     const uint64_t da = i8_smem_desc(sa + (uint32_t)(32 * j));
 #pragma unroll
-                    for (int b = 0; b < I8_NACC; ++b) {
+                    for (int b = 0; b < NACC; ++b) {
                         if (b < n_acc) {
                             const uint64_t db = i8_smem_desc(sa + (uint32_t)(1 + b) * I8_OPERAND_BYTES + (uint32_t)(32 * j));
                             i8_mma(tmem_base + (uint32_t)(b * I8_TN), da, db, idesc, (step > 0 || j > 0) ? 1u : 0u);
@@ -358,7 +354,7 @@ __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const
             }
             // all MMAs of this tile done?
             const int64_t g_last = g0 + n_steps - 1;
-            i8_mbar_wait(&empty[(int)(g_last % I8_STAGES)], (uint32_t)((g_last / I8_STAGES) & 1));
+            i8_mbar_wait(&empty[(int)(g_last % STAGES)], (uint32_t)((g_last / STAGES) & 1));
         }
         __syncthreads();                       // the other threads sleep here during the main loop
         i8_tc_fence_after();
@@ -386,7 +382,7 @@ __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const
     }
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)I8_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -534,12 +530,21 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
     p.skip_diag = diag_separately ? 1 : 0; p.depth = D;
     p.meta = h->d_meta; p.arena = h->d_nll; p.seq = h->d_seq; p.seq_off = h->d_seq_off; p.seq_len = h->d_seq_len;
     if (n_pairs > 0) {
-        const int smem = I8_STAGES * I8_STAGE_BYTES;
-        VGS_CUDA(cudaFuncSetAttribute(k_kmer_i8mma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        const int grid = std::min(n_pairs * (8 / I8_NACC), I8_CTAS_PER_SM * h->sm_count);
+        // two accumulators per CTA (128 x 256 tiles, less operand traffic) when that still fills the CTA slots, else
+        // one (twice as many tiles of half the latency: multi-GPU shares, small sets)
+        const int slots = I8_CTAS_PER_SM * h->sm_count;
+        const bool wide = (int64_t)n_pairs * 4 * 4 >= (int64_t)slots * 3;
         h->last_nll_kernel = VGS_NLL_KERNEL_I8MMA;
         vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
-        k_kmer_i8mma<<<grid, I8_THREADS, smem, s>>>(p);
+        if (wide) {
+            const int smem = 2 * (1 + 2) * I8_OPERAND_BYTES;
+            VGS_CUDA(cudaFuncSetAttribute(k_kmer_i8mma<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k_kmer_i8mma<2, 2><<<std::min(n_pairs * 4, slots), I8_THREADS, smem, s>>>(p);
+        } else {
+            const int smem = 3 * (1 + 1) * I8_OPERAND_BYTES;
+            VGS_CUDA(cudaFuncSetAttribute(k_kmer_i8mma<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k_kmer_i8mma<1, 3><<<std::min(n_pairs * 8, slots), I8_THREADS, smem, s>>>(p);
+        }
         vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
         VGS_LAUNCH_CHECK(h);
         k_i8_frequent<<<(unsigned)(n_pairs * 128), 128, 0, s>>>(p);
