@@ -8,7 +8,7 @@
 //   hash[...]      uint2 {key, ctx_id} open addressing, load <= 0.5  (every exact-context probe)
 //   nll blob arena: per model either
 //       tier 1 (order <= 6): dense table  f64[4^(order+1)]  indexed by (history << 2 | symbol)
-//       tier 2 (order  > 6): [u32 L1 map over 6-mers | uint2 deep hash (len > 6) | f64 logp rows]
+//       tier 2 / 3 (order > 6): [first-level map over D1-mers | extension trie blocks (len > D1) | f64 logp rows + NaN row]
 //   sequences: 2-bit packed, 16 symbols / u32, first symbol in the top bits, 16-byte aligned starts
 #pragma once
 #include <cuda_runtime.h>
@@ -40,9 +40,9 @@ struct ModelMeta {
     int32_t hash_shift;   // 32 - log2(capacity)
     int32_t tier;         // 1 dense, 2 two-level (u16 map), 3 two-level (u32 map, >= 32767 contexts)
     int32_t nll_bytes;    // blob size, multiple of 16
-    uint32_t deep_mask;   // tier 2: deep hash capacity - 1 (0 if no deep contexts)
+    uint32_t deep_mask;   // tier 2 / 3: capacity of the extension trie in blocks
     int32_t deep_shift;
-    int32_t deep_off;     // byte offset of the deep hash inside the blob
+    int32_t deep_off;     // byte offset of the extension trie inside the blob
     int32_t logp_off;     // byte offset of the logp rows inside the blob
     // perfect hash (hash-and-displace) over the same contexts: exactly two dependent loads per exact-context
     // probe, no probing loop -> no warp divergence (pair kernels on deep sets)

@@ -54,9 +54,10 @@ typedef enum {
 /* NLL accumulation modes for vgs_nll_* */
 #define VGS_NLL_SEQUENTIAL 0 /* one lane per (sequence, model), strictly left-to-right fp64: bit-exact */
 #define VGS_NLL_WARP 1       /* one warp per (sequence, model), 128-bit loads, shuffle reduction     */
-#define VGS_NLL_KMER 2       /* (order+1)-mer histogram per sequence x dense tables, fp64 contraction;
-                                sets with every order <= 6 and a root context, else falls back to WARP;
-                                the tile edge of vgs_nll_tiles must then be a multiple of 128          */
+#define VGS_NLL_KMER 2       /* (order+1)-mer histogram per sequence x dense tables as an exact int8 contraction
+                                on the tcgen05 tensor cores (ln p in 2^-51 fixed point; fp64 MMA fallback); sets
+                                with every order <= 6 and a root context, else falls back to WARP; the tile edge
+                                of vgs_nll_tiles must then be a multiple of 128                           */
 
 /* skip modes (src/vlmc/vlmc.pyx:79-85) */
 #define VGS_SKIP_ORDER 0 /* log_likelihood_ignore_initial_bias: first `order` symbols not scored */
