@@ -201,3 +201,23 @@ def test_gloo_world2_sharding_round_trip(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "rank %d ok" % r in o, o
+
+
+def test_bench_reference_arm_runs_on_cpu_and_keeps_the_contract():
+    """`bench.py --impl reference` times the compiled reference on the host cores: no GPU needed, one JSON line with
+    the contract's keys.  (Skipped where oracle/_ref was not built.)"""
+    import json
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "frobenius",
+                          "--cpu-sample", "24", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "pair-distances/sec" and line["unit"] == "pair-distances/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"] and line["gpu_launches"] == 0
