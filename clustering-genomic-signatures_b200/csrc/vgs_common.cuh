@@ -135,6 +135,8 @@ struct vgs_context {
     int8_t *d_i8_digits = nullptr;   // [n_models * 8][K8] balanced base-256 digits of round(ln p * 2^51)
     uint8_t *d_i8_C = nullptr;       // [n_seq][K8] k-mer counts (low bytes)
     int32_t *d_i8_over = nullptr;    // [n_seq] counts of frequent k-mers | [n_seq][64] {k, count >> 8}
+    int32_t *d_i8_P = nullptr;       // k-split launches: exact int32 digit sums [n_seq][n_models * 8], zero between calls
+    int64_t i8_P_elems = 0;
     uint64_t i8_tables_gen = ~0ull;
     bool i8_tables_ok = false;
     int last_nll_kernel = 0;         // VGS_NLL_KERNEL_* of the most recent score launch

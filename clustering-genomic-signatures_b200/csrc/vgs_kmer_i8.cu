@@ -245,6 +245,8 @@ struct I8Params {
     int64_t K;
     const int32_t *pairs;   // [n_pairs][2] (sequence 128-block, model 128-block)
     int n_pairs;
+    int split;              // k-split: each tile's K range is cut into `split` units (1 = none)
+    int32_t *P;             // split > 1: exact int32 digit sums [n_seq][n_models * 8], added atomically, zero between calls
     int64_t K8, n_seq, n_models, ld;
     double *M;
     int skip_diag, depth;
@@ -296,16 +298,22 @@ __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const
     i8_tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
     const uint32_t idesc = i8_instr_desc();
-    const int n_steps = (int)(p.K8 / I8_BK);
+    const int n_steps_total = (int)(p.K8 / I8_BK);
     const int64_t tiles_per_row_block = p.K8 >> 7;       // 16 KB tiles per 128-row block
     // a 128 x 128-model block pair = 8 sub-tiles of 16 models; a CTA tile takes NACC of them (one accumulator each,
     // all fed by the same count tile).  Consecutive MMAs go to different accumulators: four independent accumulation
     // chains keep the tensor pipe busy where a single chain waits for its own previous MMA.
     const int tiles_per_pair = 8 / NACC;
-    const int n_tiles = p.n_pairs * tiles_per_pair;
+    const int n_units = p.n_pairs * tiles_per_pair * p.split;
     int64_t g0 = 0;                           // global stage counter (continues across tiles: mbarrier parities)
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // k-split (launches with fewer tiles than CTA slots: multi-GPU shares, small sets): a unit is one part of a
+    // tile's K range; its digit sums are added to P with integer atomics -- exact and order-independent, so the
+    // result has the same bits as the unsplit tile -- and k_i8_fold turns P into M afterwards.
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int tile = unit / p.split, part = unit % p.split;
+        const int step_begin = (int)((int64_t)n_steps_total * part / p.split);
+        const int n_steps = (int)((int64_t)n_steps_total * (part + 1) / p.split) - step_begin;
         const int pair = tile / tiles_per_pair;
         const int64_t sb = p.pairs[2 * pair];
         const int64_t s0 = sb * 128;
@@ -325,9 +333,9 @@ __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const
                 if (g >= STAGES) i8_mbar_wait(&empty[stage], (uint32_t)((g / STAGES - 1) & 1));   // MMAs of the slot's last use
                 uint8_t *sa = i8_smem + (size_t)stage * STAGE_BYTES;
                 vgs_mbar_expect_tx(&full[stage], (uint32_t)((1 + n_acc) * I8_OPERAND_BYTES));
-                vgs_bulk_g2s(sa, a_src + (size_t)step * I8_OPERAND_BYTES, I8_OPERAND_BYTES, &full[stage]);
+                vgs_bulk_g2s(sa, a_src + (size_t)(step_begin + step) * I8_OPERAND_BYTES, I8_OPERAND_BYTES, &full[stage]);
                 for (int b = 0; b < n_acc; ++b)
-                    vgs_bulk_g2s(sa + (size_t)(1 + b) * I8_OPERAND_BYTES, b_src + b * b_block_stride + (size_t)step * I8_OPERAND_BYTES,
+                    vgs_bulk_g2s(sa + (size_t)(1 + b) * I8_OPERAND_BYTES, b_src + b * b_block_stride + (size_t)(step_begin + step) * I8_OPERAND_BYTES,
                                  I8_OPERAND_BYTES, &full[stage]);
             };
             for (int i = 0; i < STAGES - 1 && i < n_steps; ++i) load(g0 + i, i);
@@ -368,7 +376,12 @@ __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int64_t m = m0 + 2 * j + q;
-                if (s < p.n_seq && m < p.n_models && !(p.skip_diag && s == m)) {
+                if (s >= p.n_seq || m >= p.n_models) continue;
+                if (p.split > 1) {
+                    int32_t *dst = p.P + (s * p.n_models + m) * 8;
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) atomicAdd(dst + d, v[8 * q + d]);
+                } else if (!(p.skip_diag && s == m)) {
                     long long S[8];
 #pragma unroll
                     for (int d = 0; d < 8; ++d) S[d] = (long long)v[8 * q + d];
@@ -384,6 +397,21 @@ __global__ void __launch_bounds__(I8_THREADS, I8_CTAS_PER_SM) k_kmer_i8mma(const
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
+}
+
+// k-split launches: P -> M for every entry of the computed block pairs, and P back to zero for the next call
+__global__ void __launch_bounds__(128) k_i8_fold(const I8Params p) {
+    const int pair = blockIdx.x >> 7, r = blockIdx.x & 127;
+    const int64_t s = (int64_t)p.pairs[2 * pair] * 128 + r;
+    const int64_t m = (int64_t)p.pairs[2 * pair + 1] * 128 + threadIdx.x;
+    if (s >= p.n_seq || m >= p.n_models) return;
+    int4 *src = (int4 *)(p.P + (s * p.n_models + m) * 8);
+    const int4 lo = src[0], hi = src[1];
+    src[0] = make_int4(0, 0, 0, 0);
+    src[1] = make_int4(0, 0, 0, 0);
+    if (p.skip_diag && s == m) return;
+    const long long S[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    p.M[s * p.ld + m] = i8_head(p, p.meta[m], s) + i8_fold(S);
 }
 
 // second term of the sequences that have frequent k-mers: M[s][m] += fold(256 * sum_o hi_o * digits(T[m][k_o])).
@@ -534,6 +562,27 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
         // one (twice as many tiles of half the latency: multi-GPU shares, small sets)
         const int slots = I8_CTAS_PER_SM * h->sm_count;
         const bool wide = (int64_t)n_pairs * 4 * 4 >= (int64_t)slots * 3;
+        // fewer 128 x 128 tiles than CTA slots: cut every tile's K range so that the units fill the slots (at most 4
+        // parts, at least 8 pipeline steps each); needs the int32 sum buffer, kept below 1 GB
+        p.split = 1;
+        p.P = nullptr;
+        static int want_split = -1;
+        if (want_split < 0) { const char *e = getenv("VGS_I8_SPLITK"); want_split = (e && e[0] == '0') ? 0 : 1; }
+        const int64_t p_elems = h->n_seq * h->n_models * 8;
+        if (!wide && want_split && n_pairs * 8 * 2 <= slots && p_elems * 4 <= ((int64_t)1 << 30)) {
+            int split = std::min(4, slots / (n_pairs * 8));
+            split = (int)std::min<int64_t>(split, std::max<int64_t>(1, (K8 / I8_BK) / 8));
+            if (split > 1) {
+                int32_t *before = h->d_i8_P;
+                if ((rc = vgs_reserve(h, &h->d_i8_P, p_elems))) return rc;
+                if (h->d_i8_P != before || h->i8_P_elems != p_elems) {   // fresh or re-shaped buffer: all zero once
+                    VGS_CUDA(cudaMemsetAsync(h->d_i8_P, 0, (size_t)p_elems * 4, s));
+                    h->i8_P_elems = p_elems;
+                }
+                p.split = split;
+                p.P = h->d_i8_P;
+            }
+        }
         h->last_nll_kernel = VGS_NLL_KERNEL_I8MMA;
         vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
         if (wide) {
@@ -543,10 +592,14 @@ int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool
         } else {
             const int smem = 3 * (1 + 1) * I8_OPERAND_BYTES;
             VGS_CUDA(cudaFuncSetAttribute(k_kmer_i8mma<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            k_kmer_i8mma<1, 3><<<std::min(n_pairs * 8, slots), I8_THREADS, smem, s>>>(p);
+            k_kmer_i8mma<1, 3><<<std::min(n_pairs * 8 * p.split, slots), I8_THREADS, smem, s>>>(p);
         }
         vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
         VGS_LAUNCH_CHECK(h);
+        if (p.split > 1) {
+            k_i8_fold<<<(unsigned)(n_pairs * 128), 128, 0, s>>>(p);
+            VGS_LAUNCH_CHECK(h);
+        }
         k_i8_frequent<<<(unsigned)(n_pairs * 128), 128, 0, s>>>(p);
         VGS_LAUNCH_CHECK(h);
     }
