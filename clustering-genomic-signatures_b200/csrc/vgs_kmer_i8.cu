@@ -14,7 +14,7 @@
 //                 than 255 times (listed by the histogram kernel, added by k_i8_frequent: exact integers again)
 //
 // The only error is the 2^-52 quantisation of each ln p: |dM| <= L * 2^-52 ~ 2e-12 absolute on |M| ~ 1e4, tighter than
-// any fp64 summation order -- and every (s, m) entry is the same bits whatever the tiling, so 1/2/4/8-rank matrices
+// any fp64 summation order -- and every (s, m) entry is the same bits whatever the tiling or k-split, so 1/2/4/8-rank matrices
 // stay identical and duplicates score exactly alike.  Sets with more than 64 such frequent k-mers in one sequence (or
 // without a root context) take the fp64 MMA path of vgs_kmer.cu.
 //
