@@ -52,12 +52,16 @@ def parse_args():
     ap.add_argument("--n-models", type=int, default=0)
     ap.add_argument("--seq-len", type=int, default=0)
     ap.add_argument("--mode", default="kmer", choices=["sequential", "warp", "kmer"],
-                    help="NLL kernel: kmer = histogram + fp64 MMA contraction (<= 1e-9 rel.), sequential = bit-exact scan, "
-                         "warp = warp-per-pair scan")
+                    help="NLL kernel: kmer = k-mer histogram + exact int8 tcgen05 contraction (ln p in 2^-51 fixed point, "
+                         "<= 1e-9 rel.), sequential = bit-exact scan, warp = warp-per-pair scan")
     ap.add_argument("--no-mode-sweep", action="store_true", help="skip the short timings of the other NLL modes")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="models in the CPU-baseline sample")
+    ap.add_argument("--probe-models", type=int, default=8000,
+                    help="scale_probe: models of the cfg-4 slice (depth 9, ~2000 contexts) timed at this GPU count; 0 = off")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1, NLL: how the score bands travel (peer = GEMM epilogue stores into peer-mapped memory)")
     ap.add_argument("--breakdown", action="store_true",
                     help="N > 1: also time the phases of a step (tiles / all-gather / assemble) with CUDA events; stderr")
     return ap.parse_args()
@@ -246,6 +250,7 @@ def run_reference(args, kind, n, L, depth, ctx, desc):
                 "gpu_launches": 0}
         print(json.dumps(line))
         return
+    ref_loader.load()   # in the parent too: the forked workers inherit it, and the process the driver watches shows oracle/_ref
     workers = min(cores, sample_n)
     shards = [list(range(w, sample_n, workers)) for w in range(workers)]
     jobs = [(kind, trees, fm.names, seq_strs, L, rows) for rows in shards]
@@ -275,6 +280,73 @@ def run_reference(args, kind, n, L, depth, ctx, desc):
     print(json.dumps(line))
 
 
+def scale_probe(args, world, rank, local_rank, dev, bit_checksum):
+    """BASELINE cfg 4 in small: N models of depth 9 with ~2000 contexts; the full Frobenius (intersection) matrix with the
+    tables replicated and the tile space sharded, and the full NLL matrix (L = 1000, scan kernel: the sets are deeper
+    than the k-mer contraction reaches) with the models sharded.  Device time per step, max over ranks; the driver's
+    1/2/4/8 lines give the scaling, the checksums must agree across them."""
+    import torch
+    import torch.distributed as dist
+    from clustering_genomic_signatures_b200 import native, synthetic
+    from clustering_genomic_signatures_b200.engine import MatrixJob, ShardedNllJob
+    from clustering_genomic_signatures_b200.flat import pack_sequences
+    n, L = args.probe_models, 1000
+    t0 = time.time()
+    fm, _ = synthetic.make_family_models(n, 4, 9, 2000, max(1, n // 100))
+    seqs = synthetic.sample_sequences(fm, L, 5)
+    t_gen = time.time() - t0
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, steps=3, warmup=1):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush.zero_()
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    out = {"n_models": n, "depth": 9, "total_contexts": fm.total_contexts, "seq_len": L, "pairs": n * (n - 1) // 2,
+           "host_generation_s": round(t_gen, 1)}
+    # Frobenius intersection: replicated tables, sharded tiles
+    hF = native.Handle(local_rank)
+    hF.load_models(fm, skip_nll=True)
+    jobF = MatrixJob(hF, "frobenius_intersection", n)
+    ms = timed(jobF.run)
+    jobF.check()
+    out["frobenius_ms"] = ms
+    out["frobenius_pairs_per_s"] = out["pairs"] / (ms / 1e3)
+    out["frobenius_checksum"] = bit_checksum(jobF.D32)
+    del jobF
+    hF.close()
+    # NLL: sharded models, replicated sequences
+    m0, m1 = ShardedNllJob.shard_bounds(n, world)[rank]
+    hN = native.Handle(local_rank)
+    hN.load_models(fm.subset(range(m0, m1)) if world > 1 else fm)
+    hN.load_sequences_packed(*pack_sequences(seqs))
+    jobN = ShardedNllJob(hN, n, L, mode="warp", exchange=args.exchange, rank=rank, world=world)
+    ms = timed(jobN.run)
+    jobN.check()
+    out["nll_ms"] = ms
+    out["nll_pairs_per_s"] = out["pairs"] / (ms / 1e3)
+    out["nll_checksum"] = bit_checksum(jobN.D32)
+    out["nll_exchange"] = jobN.exchange
+    jobN.close()
+    hN.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
@@ -300,7 +372,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    fm, fam, seqs = make_inputs(kind, n, L, depth, ctx)
+    from clustering_genomic_signatures_b200.engine import ShardedNllJob
+    fm_full, fam, seqs = make_inputs(kind, n, L, depth, ctx)
+    # N > 1, NLL: the models are sharded over the ranks (each rank loads, logs and tabulates only its own), the
+    # sequences are replicated; every other kind replicates the tables and shards the tile space
+    sharded = world > 1 and kind == "nll"
+    if sharded:
+        m0, m1 = ShardedNllJob.shard_bounds(n, world)[rank]
+        fm = fm_full.subset(range(m0, m1))
+    else:
+        fm = fm_full
     h = native.Handle(local_rank)
     sm_count = h.device_info()["sm_count"]
 
@@ -324,7 +405,7 @@ def main():
     d2h = out_h.nbytes
 
     def load_all():
-        h.load_models_raw(n, host["off"], host["len"], host["code"], host["prob"], skip_nll=(kind != "nll"))
+        h.load_models_raw(fm.n_models, host["off"], host["len"], host["code"], host["prob"], skip_nll=(kind != "nll"))
         if seqs is not None:
             h.load_sequences_packed(host["words"], host["woff"], host["lens"])
 
@@ -335,13 +416,20 @@ def main():
     tile = args.tile or (32 if n <= 1024 else 64 if n <= 4096 else 128)
     if kind == "nll" and args.mode == "kmer":
         tile = max(128, tile // 128 * 128)
-    if world > 1:
+    job = None
+    if sharded:
+        job = ShardedNllJob(h, n, L, mode=args.mode, exchange=args.exchange)
+        D32 = job.D32
+    elif world > 1:
         nt, slots = native.tile_plan(n, tile, world, symmetric)
         payload = torch.zeros(slots * tile * tile, dtype=torch.float32, device=dev)
         gathered = torch.empty(world * slots * tile * tile, dtype=torch.float32, device=dev)
 
     def device_step():
-        if world == 1:
+        if sharded:
+            job.mode = args.mode
+            job.run()
+        elif world == 1:
             if kind == "nll":
                 h.nll_matrix(L, args.mode, D32, None, stream)
             elif kind == "estimate":
@@ -436,7 +524,7 @@ def main():
     # ---- end to end through the host-buffer C-ABI
     e2e_ms, _, _ = timed(e2e_step, max(3, args.steps // 4), 1, False)
 
-    if args.breakdown and world > 1:
+    if args.breakdown and world > 1 and not sharded:
         def ev():
             return torch.cuda.Event(enable_timing=True)
         acc = np.zeros(3)
@@ -469,7 +557,7 @@ def main():
                 sweep[mname] = ms_step
                 continue
             args.mode = mname
-            if world > 1 and mname == "kmer" and tile % 128:
+            if world > 1 and not sharded and mname == "kmer" and tile % 128:
                 continue
             try:
                 m_ms, _, _ = timed(device_step, 3, 1, True)
@@ -477,6 +565,51 @@ def main():
             except Exception as exc:  # e.g. tile not a multiple of 128 for kmer
                 sweep[mname] = "n/a: %s" % str(exc)[:60]
         args.mode = main_mode
+    def bit_checksum(t):
+        """Exact, order-independent fingerprint of a float32 matrix: the int64 sum of its bit patterns."""
+        return int(t.contiguous().view(torch.int32).to(torch.int64).sum().item())
+
+    device_step()
+    torch.cuda.synchronize()
+    h.poll_error(stream)
+    matrix_checksum = bit_checksum(D32)
+
+    # ---- N > 1: is this rank's matrix bit-identical to the one a single GPU computes from the full, unsharded set?
+    parity_check = None
+    if world > 1:
+        h1 = native.Handle(local_rank)
+        h1.load_models(fm_full, skip_nll=(kind != "nll"))
+        if seqs is not None:
+            h1.load_sequences_packed(*pack_sequences(seqs))
+        ref = torch.empty((n, n), dtype=torch.float32, device=dev)
+        if kind == "nll":
+            h1.nll_matrix(L, args.mode, ref, None, stream)
+        elif kind == "estimate":
+            h1.estimate_matrix(ref, None, stream)
+        else:
+            h1.pair_matrix(kind, ref, None, stream)
+        h1.poll_error(stream)
+        same = torch.tensor([1 if torch.equal(ref, D32) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        parity_check = {"bit_identical_to_single_gpu_on_every_rank": bool(int(same.item())),
+                        "single_gpu_checksum": bit_checksum(ref), "what": "torch.equal(this rank's [N,N] float32 matrix, "
+                        "the matrix one GPU computes from the unsharded set with the same kernel mode), min over ranks"}
+        del ref
+        h1.close()
+
+    # ---- scale_probe: the same code on a cfg-4 slice that is big enough for 8 GPUs to matter
+    probe = None
+    if args.probe_models > 0:
+        probe = scale_probe(args, world, rank, local_rank, dev, bit_checksum)
+
+    i8_peak = None
+    if nll_kernel == 3 and rank == 0:
+        i8_peak = {"cta_group_2_tops": h.tensor_peak_i8(2)[0], "cta_group_1_tops": h.tensor_peak_i8(1)[0]}
+
+    exchange_used = None
+    if job is not None:
+        exchange_used = job.exchange
+        job.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -490,8 +623,8 @@ def main():
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-    orders = fm.orders().astype(np.float64)
-    alg_bytes, alg_desc = algorithmic_bytes(kind, fm, L, orders)
+    orders = fm_full.orders().astype(np.float64)
+    alg_bytes, alg_desc = algorithmic_bytes(kind, fm_full, L, orders)
     alg_bytes_rank = alg_bytes / world  # each rank's launch covers its share of the units
     k_avg_ms = k_ms / max(k_n, 1)
     launches_per_step = max(1, k_n // args.steps)
@@ -515,20 +648,30 @@ def main():
         pass
     Kdim = max(16.0, 4.0 ** (orders.max() + 1)) if kind == "nll" else 0.0
     if nll_kernel == 3 and k_avg_ms > 0:
-        # the dominant kernel is an int8 tensor-core GEMM (tcgen05.mma kind::i8): [N seq] x [8 digit rows per model] x
-        # [4^(D+1) k-mers], 2 integer ops per MAC.  Its roof is the tensor pipe: int8 runs at twice the bf16 rate on
-        # B200, so peak = 2 x the measured cuBLAS bf16 burst figure (the kernel is timed alone).
+        # the dominant kernel is an int8 tensor-core GEMM (tcgen05.mma cta_group::2 kind::i8): [N seq] x [8 digit rows per
+        # model] x [4^(D+1) k-mers], 2 integer ops per MAC.  Its roof is the tensor pipe.  MEASURED_PEAKS.json has no int8
+        # figure, so the peak is measured live by the library's probe (the same instruction back to back from resident
+        # shared memory on every SM pair, vgs_tensor_peak_i8); 2 x the measured cuBLAS bf16 burst is reported beside it.
         K8 = max(128.0, 4.0 ** (orders.max() + 1))
         ops = 2.0 * n * (8.0 * n) * K8 / world
         peak_bf16 = float(peaks.get("bf16_tflops", 1590.0))
         a_tops = ops / (k_avg_ms / 1e3) / 1e12
-        roofline.update({"bound": "tensor", "achieved": a_tops, "peak": 2.0 * peak_bf16, "unit": "TFLOP/s",
-                         "frac": a_tops / (2.0 * peak_bf16),
-                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (int8 tensor rate = 2 x bf16; of measured)"
-                         if "bf16_tflops" in peaks else "2 x fallback 1590 TF/s bf16 (of fallback)",
+        probe_peak = (i8_peak or {}).get("cta_group_2_tops") or 0.0
+        peak_used = probe_peak if probe_peak > 0 else 2.0 * peak_bf16
+        roofline.update({"bound": "tensor", "achieved": a_tops, "peak": peak_used, "unit": "TFLOP/s",
+                         "frac": a_tops / peak_used,
+                         "peak_source": ("int8 tensor-pipe peak measured in this run by vgs_tensor_peak_i8 (tcgen05.mma cta_group::2 "
+                                         "kind::i8 M256 N256 K32 from resident shared memory, all SM pairs; of measured)")
+                         if probe_peak > 0 else "2 x MEASURED_PEAKS.json bf16_tflops (probe unavailable)",
+                         "int8_peak_probe": i8_peak,
+                         "frac_of_2x_bf16_burst": a_tops / (2.0 * peak_bf16),
+                         "two_x_bf16_burst_tflops": 2.0 * peak_bf16,
                          "ops_per_step": ops * world, "ops_formula": "2 x N_seq x (8 x N_models) x max(128, 4^(D+1)) int8 ops",
-                         "hbm_view": {"achieved_GBps": achieved, "frac_of_hbm_peak": (achieved / peak_gbs) if achieved else None,
-                                      "note": "SURVEY 8d algorithmic bytes of the scan formulation / kernel time"}})
+                         "useful_fp64_equivalent_macs_per_s": n * n * K8 / world / (k_avg_ms / 1e3),
+                         "note": "8 of every 8 int8 MACs carry one base-256 digit of a 61-bit fixed-point ln p: the useful rate is "
+                                 "one fp64-equivalent MAC per 8 executed int8 MACs"})
+        for k in ("algorithmic_bytes_per_step", "algorithmic_bytes_formula"):
+            roofline.pop(k, None)   # SURVEY 8d's scan-bytes model does not describe a contraction
     elif kind == "nll" and nll_kernel in (1, 2) and k_avg_ms > 0:
         # the contraction is an fp64 MMA kernel: report it against the fp64 pipe as well
         # (64 fp64 FMA lanes per SM: 2 * 64 * SMs * max SM clock)
@@ -544,15 +687,21 @@ def main():
         "scaling": "strong", "vs_baseline": None,
         "dtype": ("int8 x int8 -> int32 exact fixed point (ln p quantised to 2^-51), f64 result" if nll_kernel == 3 else
                   "f64" if kind in ("nll", "estimate") else "f32 rows, f64 accumulate"), "data": "synthetic",
-        "config": {"workload": desc, "n_models": n, "seq_len": L, "pairs_per_step": pairs, "total_contexts": fm.total_contexts,
+        "config": {"workload": desc, "n_models": n, "seq_len": L, "pairs_per_step": pairs, "total_contexts": fm_full.total_contexts,
                    "nll_mode": args.mode if kind == "nll" else None, "nll_kernel": kernel_name if kind == "nll" else None, "tile": tile if world > 1 else None,
                    "l2": "flushed between steps (256 MiB memset outside the timed events)",
-                   "parallelism": "tile-sharded upper triangle + NCCL all-gather" if world > 1 else "single GPU",
+                   "parallelism": ("models sharded over ranks (each rank loads / tabulates its own), sequences replicated; score bands "
+                                   + ("stored into every rank's matrix by the GEMM epilogue over NVLink peer memory + flag barrier"
+                                      if exchange_used == "peer" else "all-gathered with NCCL") + "; local combine") if sharded else
+                                  ("tile-sharded upper triangle + NCCL all-gather" if world > 1 else "single GPU"),
+                   "exchange": exchange_used,
                    "sm_count": sm_count},
         "e2e": {"value": pairs / (e2e_ms / 1000.0), "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h),
-                "includes": "vgs_load_models (H2D + host ln p + device table build), vgs_load_sequences_packed, kernels, D2H"},
+                "includes": "vgs_load_models (H2D + host ln p; N > 1: this rank's model shard), vgs_load_sequences_packed, device table "
+                            "builds, kernels, exchange, D2H of the float32 matrix"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+        "matrix_checksum": matrix_checksum, "parity_check": parity_check, "scale_probe": probe,
     }
     if sweep is not None:
         line["config"]["ms_per_step_by_nll_mode"] = sweep

@@ -81,8 +81,10 @@ class ClusteringMetrics(object):
         else from ``indexed_distances``."""
         import torch
         D = None
+        vl = getattr(distance_function, "_vlmcs", None)
         if distance_function is not None and getattr(distance_function, "_D64", None) is not None \
-                and distance_function._D64.shape == self.indexed_distances.shape:
+                and vl is not None and len(vl) == len(self.vlmcs) and all(a is b for a, b in zip(vl, self.vlmcs)):
+            # the function's batch is exactly these models in this order: its fp64 matrix is what its distance() returns
             D = torch.from_numpy(np.ascontiguousarray(distance_function._D64)).to(torch.device("cuda", self.device))
         if D is None:
             D = self._device_matrix()

@@ -64,6 +64,30 @@ struct WorkCache {
     int64_t off2 = 0;          // byte offset of the second array inside dev
 };
 
+// where a score launch writes: M[d][s * stride_s + (m_col0 + m) * stride_m] for every destination d (this GPU's matrix
+// and, on the peer-store path, the mapped matrices of the other ranks)
+#define VGS_MAX_PEERS 8
+struct VgsScoreDst {
+    double *M[VGS_MAX_PEERS];
+    int n_dst;
+    int64_t stride_s, stride_m, m_col0;
+};
+inline VgsScoreDst vgs_dst_plain(double *M, int64_t ld) {
+    VgsScoreDst d;
+    for (int i = 0; i < VGS_MAX_PEERS; ++i) d.M[i] = nullptr;
+    d.M[0] = M; d.n_dst = 1; d.stride_s = ld; d.stride_m = 1; d.m_col0 = 0;
+    return d;
+}
+struct G8Unit;
+struct G8Rect;
+struct I8Work {   // device-resident unit / rectangle lists of one int8 contraction launch
+    const G8Unit *d_units;
+    int n_units;
+    const G8Rect *d_rects;
+    int n_rects;
+    int split;
+};
+
 struct vgs_context {
     int device = 0;
     int sm_count = 0;
@@ -78,6 +102,9 @@ struct vgs_context {
     double *h_logp = nullptr;   // pinned staging of the host-computed ln p table
     int64_t h_logp_cap = 0;
     bool nll_ready = false;     // false when loaded with VGS_LOAD_SKIP_NLL
+    // derived tables are built on first use by the kernels that need them (a k-mer-mode NLL run needs none of these)
+    int dense_state = 0;        // scan tables (tier 1 dense / tier 2-3 two-level): 0 = not built, 1 = built
+    bool umap_tried = false;    // universe maps of the pair kernels
     void *pool = nullptr;       // host thread pool (VgsPool, vgs_core.cu)
     std::vector<WorkCache> wcache;
     uint64_t model_gen = 0;     // bumped by every vgs_load_models
@@ -140,7 +167,7 @@ struct vgs_context {
     uint64_t i8_tables_gen = ~0ull;
     bool i8_tables_ok = false;
     int last_nll_kernel = 0;         // VGS_NLL_KERNEL_* of the most recent score launch
-    int i8_counts_state = 0;         // 0 = not checked for this sequence set, 1 = usable, 2 = too many frequent k-mers
+    int i8_counts_state = 0;         // 0 = not checked for this sequence set, 1 = no frequent k-mers, 3 = some, 2 = too many
     float *d_out32 = nullptr;   // staging for the *_h entry points
     double *d_out64 = nullptr;
 
@@ -236,7 +263,7 @@ void vgs_tile_coords(const TilePlan &p, int64_t k, int64_t *I, int64_t *J);
 
 // launchers implemented in the kernel translation units
 int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &seq_lists_per_block, int64_t block,
-                        int64_t m_begin, int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld,
+                        int64_t m_begin, int64_t m_end, bool add_diagonal, int skip_mode, int mode, const VgsScoreDst &dst,
                         cudaStream_t s, uint64_t cache_key = 0);
 WorkCache *vgs_wcache_find(vgs_context *h, uint64_t key);
 WorkCache *vgs_wcache_add(vgs_context *h, uint64_t key, int64_t bytes);   // nullptr on allocation failure
@@ -249,11 +276,12 @@ inline uint64_t vgs_mix(uint64_t a, uint64_t b) {
 int vgs_ensure_ph(vgs_context *h, cudaStream_t s);  // builds the perfect hashes on first use
 bool vgs_kmer_applicable(vgs_context *h);
 // returns VGS_OK, an error, or -1 when the set needs the scan kernel (a model without a root context)
-int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately, double *M,
-                    int64_t ld, cudaStream_t s, uint64_t cache_key = 0);
-int vgs_kmer_i8_prepare_tables(vgs_context *h, const double *T, int64_t K, cudaStream_t s);
-int vgs_kmer_i8_scores(vgs_context *h, const int32_t *d_pairs, int n_pairs, bool diag_separately, const double *T, int64_t K,
-                       double *M, int64_t ld, cudaStream_t s);
+int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately,
+                    const VgsScoreDst &dst, cudaStream_t s, uint64_t cache_key = 0);
+int vgs_kmer_i8_prepare_tables(vgs_context *h, cudaStream_t s);
+int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, const VgsScoreDst &dst, cudaStream_t s);
+int vgs_ensure_scan_tables(vgs_context *h, cudaStream_t s);   // tier 1-3 NLL tables of the scan kernels
+int vgs_ensure_umap(vgs_context *h, cudaStream_t s);          // universe maps (shallow sets) of the pair kernels
 int vgs_assemble_impl(vgs_context *h, const TilePlan &p, const float *gathered32, const double *gathered64,
                       float *D32, double *D64, cudaStream_t s);
 

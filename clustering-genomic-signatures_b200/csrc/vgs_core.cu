@@ -217,6 +217,7 @@ extern "C" int vgs_create(int device, vgs_handle *out) {
 // the device buffers stay allocated (grow-only, vgs_reserve); only the logical contents are dropped
 static void free_models(vgs_context *h) {
     h->n_models = 0; h->total_ctx = 0; h->kmer_tables_ready = false;
+    h->i8_counts_state = 0;   // the k-mer length follows the deepest model: the frequent-k-mer check is redone
     h->model_gen++;
     vgs_wcache_invalidate(h);
 }
@@ -749,28 +750,12 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     VGS_LAUNCH_CHECK(h);
     k_build_hash<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_key, h->d_hash);
     VGS_LAUNCH_CHECK(h);
-    if (h->max_order <= VGS_UMAP_MAX_ORDER && h->max_n_ctx < 0x7FFF) {
-        const int64_t total_u = ((((int64_t)1) << (2 * (h->max_order + 1))) - 1) / 3;
-        const int64_t stride = (total_u + 7) / 8 * 8;
-        if (stride * n_models * 2 <= ((int64_t)8 << 30)) {  // at most 8 GB of maps
-            if ((rc = vgs_reserve(h, &h->d_umap, stride * n_models))) return rc;
-            for (int64_t m0 = 0; m0 < n_models; m0 += 65535) {
-                dim3 grid((unsigned)std::min<int64_t>((stride + 255) / 256, 64), (unsigned)std::min<int64_t>(n_models - m0, 65535));
-                k_build_umap<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->max_order, stride, h->d_umap + m0 * stride);
-                VGS_LAUNCH_CHECK(h);
-            }
-            h->umap_stride = stride;
-        }
-    }
-    lap("enqueued: uploads + keys/hash/umap");
+    lap("enqueued: uploads + keys/hash");
+    h->dense_state = 0;
+    h->umap_tried = false;
     if (!want_nll) {
-        // negative probabilities are still rejected (the reference fails on them at scoring time)
-        for (int64_t i = 0; i < total * 4; ++i)
-            if (prob_h[i] < 0) {
-                cudaStreamSynchronize(s);
-                vgs_set_error("math domain error: negative transition probability (entry %lld)", (long long)i);
-                return VGS_ERR_INVALID;
-            }
+        // negative probabilities pass here as they do in the reference, which only fails on them when it takes their
+        // logarithm at scoring time (src/vlmc/vlmc.pyx:99): the NLL load below reports that "math domain error"
         VGS_CUDA(cudaStreamSynchronize(s));
         return VGS_OK;
     }
@@ -835,10 +820,21 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     }
 
     lap("host: ln p computed + streamed");
-    // 3. build the NLL tables
+    // 3. the NLL tables of the scan kernels, the digit operand of the k-mer contraction and the universe maps of the pair
+    //    kernels are derived on first use (vgs_ensure_scan_tables, vgs_kmer_i8_prepare_tables, vgs_ensure_umap): a run
+    //    builds only what its kind / mode reads
+    h->nll_ready = true;
+    VGS_CUDA(cudaStreamSynchronize(s));
+    lap("stream drained");
+    return VGS_OK;
+}
+
+int vgs_ensure_scan_tables(vgs_context *h, cudaStream_t s) {
+    if (h->dense_state) return VGS_OK;
+    const int64_t n_models = h->n_models;
     if (h->max_nll_bytes_t1 > 0) {
         // grid.x covers up to 4^6 histories with 256-thread blocks
-        dim3 grid(16, (unsigned)std::min<int64_t>(n_models, 65535));
+        dim3 grid(16, 1);
         for (int64_t m0 = 0; m0 < n_models; m0 += 65535) {
             grid.y = (unsigned)std::min<int64_t>(n_models - m0, 65535);
             k_build_dense<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->d_logp, h->d_nll);
@@ -851,10 +847,29 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         k_build_two_level<<<(unsigned)n_models, 512, l1_smem, s>>>(h->d_meta, h->d_hash, h->d_key, h->d_len, h->d_code, h->d_logp, h->d_nll);
         VGS_LAUNCH_CHECK(h);
     }
-    h->nll_ready = true;
-    lap("enqueued: NLL table builds");
-    VGS_CUDA(cudaStreamSynchronize(s));
-    lap("stream drained");
+    h->dense_state = 1;
+    return VGS_OK;
+}
+
+int vgs_ensure_umap(vgs_context *h, cudaStream_t s) {
+    if (h->umap_tried) return VGS_OK;
+    h->umap_tried = true;
+    h->umap_stride = 0;
+    const int64_t n_models = h->n_models;
+    if (h->max_order <= VGS_UMAP_MAX_ORDER && h->max_n_ctx < 0x7FFF) {
+        const int64_t total_u = ((((int64_t)1) << (2 * (h->max_order + 1))) - 1) / 3;
+        const int64_t stride = (total_u + 7) / 8 * 8;
+        if (stride * n_models * 2 <= ((int64_t)8 << 30)) {  // at most 8 GB of maps
+            int rc;
+            if ((rc = vgs_reserve(h, &h->d_umap, stride * n_models))) return rc;
+            for (int64_t m0 = 0; m0 < n_models; m0 += 65535) {
+                dim3 grid((unsigned)std::min<int64_t>((stride + 255) / 256, 64), (unsigned)std::min<int64_t>(n_models - m0, 65535));
+                k_build_umap<<<grid, 256, 0, s>>>(h->d_meta + m0, h->d_hash, h->max_order, stride, h->d_umap + m0 * stride);
+                VGS_LAUNCH_CHECK(h);
+            }
+            h->umap_stride = stride;
+        }
+    }
     return VGS_OK;
 }
 

@@ -24,7 +24,7 @@
 
 #include <algorithm>
 
-#include "vgs_common.cuh"
+#include "vgs_i8gemm.cuh"
 
 #define KG_BLOCK 128   // scores per CTA tile edge (sequences x models)
 #define KG_BK 8        // k-mers per shared-memory stage
@@ -289,27 +289,31 @@ struct KgEpi {
     const int32_t *pairs;   // [n_pairs][2] (sb, mb)
     int n_pairs, split, depth, skip_diag;
     const ModelMeta *meta;
-    const uint8_t *arena;   // per-model tier-1 tables (their own order)
+    const uint2 *hash;
+    const double *logp;
     const uint32_t *seq;
     const int64_t *seq_off, *seq_len;
-    int64_t n_seq, n_models, ld;
+    int64_t n_seq, n_models, ss, sm, m_col0;   // M[s * ss + (m_col0 + m) * sm]
     double *M;
 };
 
 // terms t in [order_m, D) of a model shallower than D (positions the (D+1)-mer histogram does not cover)
 __device__ __forceinline__ double kmer_head(const KgEpi &p, const ModelMeta &mm, int64_t s) {
     if (mm.order >= p.depth) return 0.0;
-    const double *tab = (const double *)(p.arena + mm.nll_off);
-    const uint32_t fmask = vgs_lowmask(mm.order + 1);
+    const uint2 *slots = p.hash + mm.hash_off;
+    const uint32_t omask = vgs_lowmask(mm.order);
     const uint32_t *w = p.seq + p.seq_off[s];
     const int64_t L = p.seq_len[s];
     const int64_t top = L < p.depth ? L : p.depth;
-    uint32_t code = 0;
+    uint32_t hist = 0;
     double head = 0.0;
     for (int64_t t = 0; t < top; ++t) {
         const uint32_t x = (w[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
-        code = (code << 2) | x;
-        if (t >= mm.order) head += tab[code & fmask];
+        if (t >= mm.order) {
+            const int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, hist & omask, mm.order);
+            head += id < 0 ? vgs_nan() : p.logp[4 * (mm.ctx_off + id) + x];
+        }
+        hist = (hist << 2) | x;
     }
     return head;
 }
@@ -321,7 +325,7 @@ __global__ void k_kmer_diag(const KgEpi p, const double *__restrict__ C, const d
     __shared__ double part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t m = blockIdx.x;   // one 256-thread block per model: 2 K doubles streamed with 16-byte loads
-    const double *c = C + m * K, *t = Tu + m * K;
+    const double *c = C + (p.m_col0 + m) * K, *t = Tu + m * K;
     double a0 = 0.0, a1 = 0.0;
     for (int64_t k = 2 * threadIdx.x; k < K; k += 2 * blockDim.x) {
         const double2 cv = *(const double2 *)(c + k), tv = *(const double2 *)(t + k);
@@ -336,7 +340,7 @@ __global__ void k_kmer_diag(const KgEpi p, const double *__restrict__ C, const d
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
-        p.M[m * p.ld + m] = kmer_head(p, p.meta[m], m) + s;
+        p.M[(p.m_col0 + m) * p.ss + (p.m_col0 + m) * p.sm] = kmer_head(p, p.meta[m], p.m_col0 + m) + s;
     }
 }
 
@@ -348,10 +352,10 @@ __global__ void k_kmer_epilogue(const KgEpi p) {
         const int r = e / KG_BLOCK, c = e % KG_BLOCK;
         const int64_t s = (int64_t)sb * KG_BLOCK + r, m = (int64_t)mb * KG_BLOCK + c;
         if (s >= p.n_seq || m >= p.n_models) continue;
-        if (p.skip_diag && s == m) continue;  // written by k_kmer_diag
+        if (p.skip_diag && s == p.m_col0 + m) continue;  // written by k_kmer_diag
         double v = 0.0;
         for (int q = 0; q < p.split; ++q) v += p.partial[((int64_t)pair * p.split + q) * KG_BLOCK * KG_BLOCK + e];
-        p.M[s * p.ld + m] = kmer_head(p, p.meta[m], s) + v;
+        p.M[s * p.ss + (p.m_col0 + m) * p.sm] = kmer_head(p, p.meta[m], s) + v;
     }
 }
 
@@ -386,21 +390,104 @@ static int ensure_kmer_tables(vgs_context *h, cudaStream_t s) {
     return VGS_OK;
 }
 
+// the exact int8 tensor-core contraction (vgs_kmer_i8.cu) for the needed block pairs: per 256-sequence block the runs
+// of needed 128-model blocks become rectangles, cut into GEMM units (cached on the device per cache_key).
+// Returns VGS_OK, an error, or -1 = not applicable (caller continues with the fp64 path or the scan)
+static int kmer_i8_path(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately,
+                        const VgsScoreDst &dst, cudaStream_t s, uint64_t cache_key) {
+    int rc = vgs_kmer_i8_prepare_tables(h, s);
+    if (rc != VGS_OK) return rc;
+    const uint64_t key = cache_key ? vgs_mix(cache_key, 0x6938) : 0;
+    I8Work w;
+    bool diag_covered = false;
+    if (WorkCache *wc = vgs_wcache_find(h, key)) {
+        w.n_units = wc->n[0]; w.n_rects = wc->n[1]; diag_covered = wc->n[2] != 0; w.split = wc->split;
+        w.d_units = (const G8Unit *)wc->dev;
+        w.d_rects = (const G8Rect *)((char *)wc->dev + wc->off2);
+    } else {
+        std::vector<G8Rect> rects;
+        const int64_t nb_a = (nb_s + 1) / 2;   // 256-sequence blocks
+        const int64_t rows_total = (h->n_models * 8 + 31) / 32 * 32;
+        for (int64_t a = 0; a < nb_a; ++a) {
+            int64_t mb = 0;
+            while (mb < nb_m) {
+                auto needed = [&](int64_t b) {
+                    return need[(size_t)(2 * a * nb_m + b)] || (2 * a + 1 < nb_s && need[(size_t)((2 * a + 1) * nb_m + b)]);
+                };
+                if (!needed(mb)) { ++mb; continue; }
+                int64_t e = mb;
+                while (e < nb_m && needed(e)) ++e;
+                G8Rect r;
+                r.a_blk = (int32_t)a;
+                r.b_row0 = (int32_t)(mb * 1024);   // 128 models x 8 digit rows
+                r.b_rows = (int32_t)(std::min<int64_t>(e * 1024, rows_total) - r.b_row0);
+                if (r.b_rows > 0) rects.push_back(r);
+                mb = e;
+            }
+        }
+        diag_covered = true;
+        for (int64_t a = 0; a < std::min(nb_s, nb_m); ++a) diag_covered = diag_covered && need[(size_t)(a * nb_m + a)];
+        std::vector<G8Unit> units;
+        const int kblocks = (int)(std::max<int64_t>(G8_BK, (int64_t)1 << (2 * (h->max_order + 1))) / G8_BK);
+        static int max_split = -1;
+        if (max_split < 0) { const char *e = getenv("VGS_I8_SPLITK"); max_split = e ? std::max(1, atoi(e)) : 4; }
+        // the int32 partial-sum buffer of the k-split stays below 1 GB
+        const int ms = (h->n_seq * h->n_models * 32 <= ((int64_t)1 << 30)) ? max_split : 1;
+        w.split = g8_make_units(rects, kblocks, h->sm_count / 2, ms, &units);
+        w.n_units = (int)units.size();
+        w.n_rects = (int)rects.size();
+        const int64_t off2 = ((int64_t)units.size() * (int64_t)sizeof(G8Unit) + 127) / 128 * 128;
+        const int64_t bytes = off2 + (int64_t)rects.size() * (int64_t)sizeof(G8Rect) + 256;
+        char *base = nullptr;
+        if (key) {
+            WorkCache *wc = vgs_wcache_add(h, key, bytes);
+            if (wc) {
+                wc->n[0] = w.n_units; wc->n[1] = w.n_rects; wc->n[2] = diag_covered ? 1 : 0; wc->split = w.split; wc->off2 = off2;
+                base = (char *)wc->dev;
+            }
+        }
+        if (!base) {
+            if ((rc = vgs_ensure_scratch2(h, bytes))) return rc;
+            base = (char *)h->d_scratch2;
+        }
+        w.d_units = (const G8Unit *)base;
+        w.d_rects = (const G8Rect *)(base + off2);
+        if (!units.empty()) VGS_CUDA(cudaMemcpyAsync(base, units.data(), units.size() * sizeof(G8Unit), cudaMemcpyHostToDevice, s));
+        if (!rects.empty()) VGS_CUDA(cudaMemcpyAsync(base + off2, rects.data(), rects.size() * sizeof(G8Rect), cudaMemcpyHostToDevice, s));
+        // pageable sources: the copies above have consumed the host vectors when they return
+    }
+    if (w.n_units == 0 && !diag_separately) return VGS_OK;
+    // exact integers: the GEMM's own M[i][i] has the same bits as the dot-product kernel's, so that kernel is skipped
+    // whenever the rectangles already cover the diagonal blocks (always on one GPU and in model-sharded runs)
+    return vgs_kmer_i8_scores(h, w, diag_separately && !diag_covered, dst, s);
+}
+
 // scores for the needed (sequence-block, model-block) pairs at 128-granularity; need[sb * nb_m + mb] != 0
-int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately, double *M,
-                    int64_t ld, cudaStream_t s, uint64_t cache_key) {
-    int rc = ensure_kmer_tables(h, s);
+int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately,
+                    const VgsScoreDst &dst, cudaStream_t s, uint64_t cache_key) {
+    int rc;
+    // 1. the exact int8 tensor-core path when the set qualifies; VGS_KMER_GEMM=dmma|fma keeps fp64
+    {
+        static int want_i8 = -1;
+        if (want_i8 < 0) { const char *e = getenv("VGS_KMER_GEMM"); want_i8 = (e && (e[0] == 'd' || e[0] == 'f')) ? 0 : 1; }
+        if (want_i8) {
+            rc = kmer_i8_path(h, need, nb_s, nb_m, diag_separately, dst, s, cache_key);
+            if (rc != -1) return rc;
+            if (!h->i8_tables_ok) return -1;   // a model without root context: the scan raises the reference's error
+        }
+    }
+    // 2. fp64 path (more than 64 frequent k-mers in a sequence, or forced): dense fp64 tables + fp64 histograms
+    rc = ensure_kmer_tables(h, s);
     if (rc) return rc;
     if (h->kmer_has_nan) return -1;  // caller falls back to the scan kernel
+    double *M = dst.M[0];
     const int D = h->max_order;
     const int64_t K = std::max<int64_t>(KD_BK, (int64_t)1 << (2 * (D + 1)));
-    // 2. unit list (cached on the device per (plan, rank) when the caller gives a key)
     int n_pairs = 0, split = 1, n_units = 0;
-    bool diag_covered = false;   // every diagonal 128-block is among the pairs: the contraction itself produces M[i][i]
     KgUnit *d_units = nullptr;
     int32_t *d_pairs = nullptr;
     if (WorkCache *wc = vgs_wcache_find(h, cache_key)) {
-        n_pairs = wc->n[0]; n_units = wc->n[1]; split = wc->split; diag_covered = wc->n[2] != 0;
+        n_pairs = wc->n[0]; n_units = wc->n[1]; split = wc->split;
         d_units = (KgUnit *)wc->dev;
         d_pairs = (int32_t *)((char *)wc->dev + wc->off2);
     } else {
@@ -409,8 +496,6 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
             for (int64_t mb = 0; mb < nb_m; ++mb)
                 if (need[(size_t)(sb * nb_m + mb)]) { pairs.push_back((int32_t)sb); pairs.push_back((int32_t)mb); }
         n_pairs = (int)(pairs.size() / 2);
-        diag_covered = true;
-        for (int64_t a = 0; a < std::min(nb_s, nb_m); ++a) diag_covered = diag_covered && need[(size_t)(a * nb_m + a)];
         if (n_pairs > 0) {
             const int64_t ksteps = K / KD_BK;   // unit boundaries are multiples of one MMA stage
             // split K so that the FULL problem (every block pair) gives >= ~8 units per SM.  The split depends only on the
@@ -435,7 +520,7 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
             if (cache_key) {
                 WorkCache *wc = vgs_wcache_add(h, cache_key, meta_bytes);
                 if (wc) {
-                    wc->n[0] = n_pairs; wc->n[1] = n_units; wc->n[2] = diag_covered ? 1 : 0; wc->split = split; wc->off2 = off2;
+                    wc->n[0] = n_pairs; wc->n[1] = n_units; wc->split = split; wc->off2 = off2;
                     base = (char *)wc->dev;
                 }
             }
@@ -450,23 +535,8 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
         }
     }
     if (n_pairs == 0 && !diag_separately) return VGS_OK;
-    // 3. the exact int8 tensor-core path (vgs_kmer_i8.cu) when the set qualifies; VGS_KMER_GEMM=dmma|fma keeps fp64
-    {
-        static int want_i8 = -1;
-        if (want_i8 < 0) { const char *e = getenv("VGS_KMER_GEMM"); want_i8 = (e && (e[0] == 'd' || e[0] == 'f')) ? 0 : 1; }
-        if (want_i8) {
-            rc = vgs_kmer_i8_prepare_tables(h, h->d_kmer_T, K, s);
-            if (rc > 0) return rc;
-            if (rc == VGS_OK) {
-                // exact integers: the GEMM's own M[i][i] has the same bits as the dot-product kernel's, so skip that kernel
-                // whenever the pairs already cover the diagonal blocks (always on one GPU)
-                rc = vgs_kmer_i8_scores(h, d_pairs, n_pairs, diag_separately && !diag_covered, h->d_kmer_T, K, M, ld, s);
-                if (rc != -1) return rc;
-            }
-        }
-    }
-    // 4. fp64 path: histograms of the resident sequences as doubles (a pass over the packed sequences; part of every
-    //    call unless the caller pinned them with VGS_KMER_KEEP_COUNTS=1)
+    // fp64 histograms of the resident sequences (a pass over the packed sequences; part of every call unless the caller
+    // pinned them with VGS_KMER_KEEP_COUNTS=1)
     static int keep_counts = -1;
     if (keep_counts < 0) { const char *e = getenv("VGS_KMER_KEEP_COUNTS"); keep_counts = (e && e[0] == '1') ? 1 : 0; }
     if (!h->kmer_counts_ready || !keep_counts) {
@@ -502,8 +572,9 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
     }
     KgEpi e;
     e.partial = h->d_kmer_partial; e.pairs = d_pairs; e.n_pairs = n_pairs; e.split = split; e.depth = D;
-    e.meta = h->d_meta; e.arena = h->d_nll; e.seq = h->d_seq; e.seq_off = h->d_seq_off; e.seq_len = h->d_seq_len;
-    e.n_seq = h->n_seq; e.n_models = h->n_models; e.ld = ld; e.M = M; e.skip_diag = diag_separately ? 1 : 0;
+    e.meta = h->d_meta; e.hash = h->d_hash; e.logp = h->d_logp; e.seq = h->d_seq; e.seq_off = h->d_seq_off; e.seq_len = h->d_seq_len;
+    e.n_seq = h->n_seq; e.n_models = h->n_models; e.ss = dst.stride_s; e.sm = dst.stride_m; e.m_col0 = dst.m_col0; e.M = M;
+    e.skip_diag = diag_separately ? 1 : 0;
     if (n_pairs > 0) {
         k_kmer_epilogue<<<dim3((unsigned)n_pairs, 8), 256, 0, s>>>(e);
         VGS_LAUNCH_CHECK(h);

@@ -43,7 +43,7 @@ struct NllParams {
     int n_units;
     int skip_none;
     double *M;
-    int64_t ld;
+    int64_t ss, sm, m_col0;   // M[s * ss + (m_col0 + model) * sm]
     int *counter;      // dynamic unit scheduler (zeroed before the launch)
 };
 
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(NLL_MAX_THREADS, 1) k_nll_scores(const NllPara
                     scan_chunk<decltype(T), true>(T, q, prev, c << 6, skip, L, acc);
                     prev = q.w;
                 }
-                p.M[(int64_t)s * p.ld + un.model] = acc;
+                p.M[(int64_t)s * p.ss + (p.m_col0 + un.model) * p.sm] = acc;
             }
         } else {
             const int lane = tid & 31, warp = tid >> 5;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(NLL_MAX_THREADS, 1) k_nll_scores(const NllPara
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 if (lane == 0) {
                     if (p.skip_none) acc = nll_prologue(p, mm, w, L) + acc;
-                    p.M[(int64_t)s * p.ld + un.model] = acc;
+                    p.M[(int64_t)s * p.ss + (p.m_col0 + un.model) * p.sm] = acc;
                 }
             }
         }
@@ -321,11 +321,12 @@ static int launch_nll_tier(vgs_context *h, const NllParams &p, int mode, int64_t
 // seq_lists_per_block[B] = sequences to score against every model of model-block B (models
 // B*block .. min(n, (B+1)*block)-1); an empty outer vector means "all sequences, contiguous".
 int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> &lists, int64_t block, int64_t m_begin,
-                        int64_t m_end, bool add_diagonal, int skip_mode, int mode, double *M, int64_t ld, cudaStream_t s,
+                        int64_t m_end, bool add_diagonal, int skip_mode, int mode, const VgsScoreDst &dst, cudaStream_t s,
                         uint64_t cache_key) {
     if (mode == VGS_NLL_KMER) mode = VGS_NLL_WARP;  // the scan kernels have two modes
     h->last_nll_kernel = VGS_NLL_KERNEL_SCAN;
     int rc;
+    if ((rc = vgs_ensure_scan_tables(h, s))) return rc;   // dense / two-level tables: built on the first scan of a model set
     size_t n_u[3] = {0, 0, 0};
     NllUnit *d_units = nullptr;
     int32_t *d_list = nullptr;
@@ -408,7 +409,7 @@ int vgs_nll_score_lists(vgs_context *h, const std::vector<std::vector<int32_t>> 
     p.seq = h->d_seq; p.seq_off = h->d_seq_off; p.seq_len = h->d_seq_len;
     p.seq_list = d_list;
     p.skip_none = skip_mode == VGS_SKIP_NONE;
-    p.M = M; p.ld = ld;
+    p.M = dst.M[0]; p.ss = dst.stride_s; p.sm = dst.stride_m; p.m_col0 = dst.m_col0;
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
     if (n_u[0]) {
         p.counter = h->d_counters;
@@ -454,13 +455,13 @@ extern "C" int vgs_nll_scores(vgs_handle h, int64_t s_begin, int64_t s_end, int6
         std::vector<char> need((size_t)(nb_s * nb_m), 0);
         for (int64_t sb = s_begin / 128; sb <= (s_end - 1) / 128; ++sb)
             for (int64_t mb = m_begin / 128; mb <= (m_end - 1) / 128; ++mb) need[(size_t)(sb * nb_m + mb)] = 1;
-        rc = vgs_kmer_scores(h, need, nb_s, nb_m, false, M_d, ld, (cudaStream_t)stream);
+        rc = vgs_kmer_scores(h, need, nb_s, nb_m, false, vgs_dst_plain(M_d, ld), (cudaStream_t)stream);
         if (rc != -1) return rc;
     }
     std::vector<int32_t> seqs((size_t)(s_end - s_begin));
     for (int64_t i = s_begin; i < s_end; ++i) seqs[(size_t)(i - s_begin)] = (int32_t)i;
     std::vector<std::vector<int32_t>> lists(1, seqs);
-    return vgs_nll_score_lists(h, lists, h->n_models, m_begin, m_end, false, skip_mode, mode, M_d, ld, (cudaStream_t)stream);
+    return vgs_nll_score_lists(h, lists, h->n_models, m_begin, m_end, false, skip_mode, mode, vgs_dst_plain(M_d, ld), (cudaStream_t)stream);
 }
 
 extern "C" int vgs_nll_scores_h(vgs_handle h, int skip_mode, int mode, double *M_out_h) {
@@ -478,10 +479,10 @@ extern "C" int vgs_nll_scores_h(vgs_handle h, int skip_mode, int mode, double *M
     if (mode == VGS_NLL_KMER && skip_mode == VGS_SKIP_ORDER && vgs_kmer_applicable(h)) {
         const int64_t nb_s = (h->n_seq + 127) / 128, nb_m = (h->n_models + 127) / 128;
         std::vector<char> need((size_t)(nb_s * nb_m), 1);
-        rc = vgs_kmer_scores(h, need, nb_s, nb_m, false, h->d_M, h->n_models, s);
+        rc = vgs_kmer_scores(h, need, nb_s, nb_m, false, vgs_dst_plain(h->d_M, h->n_models), s);
         if (rc > 0) return rc;
     }
-    if (rc == -1 && (rc = vgs_nll_score_lists(h, lists, h->n_models, 0, h->n_models, false, skip_mode, mode, h->d_M, h->n_models, s))) return rc;
+    if (rc == -1 && (rc = vgs_nll_score_lists(h, lists, h->n_models, 0, h->n_models, false, skip_mode, mode, vgs_dst_plain(h->d_M, h->n_models), s))) return rc;
     VGS_CUDA(cudaMemcpyAsync(M_out_h, h->d_M, 8 * (size_t)(h->n_seq * h->n_models), cudaMemcpyDeviceToHost, s));
     VGS_CUDA(cudaStreamSynchronize(s));
     return VGS_OK;
@@ -529,8 +530,10 @@ __global__ void k_nll_combine(TilePlan pl, int rank, const double *__restrict__ 
 
 // single-GPU form: every entry of the [n][n] matrix straight from M, no payload / assemble pass.  Entry (j, i) adds
 // the same two quotients as (i, j) in the other order, so both triangles carry the same bits as the tiled path.
+// transposed != 0: M is the transposed score matrix Mt[m][s] (what the k-mer contraction and the model-sharded path write)
 __global__ void __launch_bounds__(256) k_nll_combine_full(int64_t n, const double *__restrict__ M, int64_t ld, double length,
-                                                          float *__restrict__ D32, double *__restrict__ D64, int *__restrict__ err) {
+                                                          float *__restrict__ D32, double *__restrict__ D64, int *__restrict__ err,
+                                                          int transposed) {
     __shared__ double t_ji[32][33];   // M[j][i] for the tile, read row-wise (coalesced), used column-wise
     __shared__ double d_i[32], d_j[32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -550,7 +553,8 @@ __global__ void __launch_bounds__(256) k_nll_combine_full(int64_t n, const doubl
     for (int r = ty; r < 32; r += 8) {
         const int64_t i = i0 + r, j = j0 + tx;
         if (i >= n || j >= n) continue;
-        const double mij = M[i * ld + j], mji = t_ji[tx][r];
+        const double direct = M[i * ld + j], mirrored = t_ji[tx][r];
+        const double mij = transposed ? mirrored : direct, mji = transposed ? direct : mirrored;
         const double lr = __ddiv_rn(__dsub_rn(d_i[r], mij), length);
         const double rl = __ddiv_rn(__dsub_rn(d_j[tx], mji), length);
         // the tiled path computes (min, max) and mirrors it: add in that orientation so the bits agree
@@ -561,11 +565,48 @@ __global__ void __launch_bounds__(256) k_nll_combine_full(int64_t n, const doubl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// model-sharded scores (north_star (c) for the NLL kinds): this handle holds a SHARD of the models (local model m is
+// column m_col0 + m of the job) and ALL sequences.  Every sequence is scored against the shard and the result is the
+// band Mt[m_col0 + m][s] of the transposed score matrix -- contiguous, so the bands of all ranks assemble the matrix with
+// one all-gather and no scatter kernel; with peer-mapped destinations the int8 GEMM's epilogue stores the band straight
+// into every rank's matrix over NVLink.  Returns VGS_OK, an error (> 0), or -1: the k-mer contraction does not apply
+// (only when mode == VGS_NLL_KMER and the caller asked for it with kmer_only)
+static int nll_scores_band_impl(vgs_context *h, int mode, int64_t m_col0, int64_t ld, double *const *dsts, int n_dst, cudaStream_t s) {
+    VgsScoreDst dst;
+    for (int i = 0; i < VGS_MAX_PEERS; ++i) dst.M[i] = i < n_dst ? dsts[i] : nullptr;
+    dst.n_dst = n_dst; dst.stride_s = 1; dst.stride_m = ld; dst.m_col0 = m_col0;
+    int rc = -1;
+    if (mode == VGS_NLL_KMER && vgs_kmer_applicable(h)) {
+        const int64_t nb_s = (h->n_seq + 127) / 128, nb_m = (h->n_models + 127) / 128;
+        uint64_t key = vgs_mix(vgs_mix(0x42414e44ull, h->model_gen), (uint64_t)h->n_seq);
+        const std::vector<char> need((size_t)(nb_s * nb_m), 1);
+        rc = vgs_kmer_scores(h, need, nb_s, nb_m, false, dst, s, key);
+        if (rc > 0) return rc;
+    }
+    const bool fused_peer_stores = rc == VGS_OK && h->last_nll_kernel == VGS_NLL_KERNEL_I8MMA;
+    if (rc == -1) {
+        std::vector<int32_t> all((size_t)h->n_seq);
+        for (int64_t i = 0; i < h->n_seq; ++i) all[(size_t)i] = (int32_t)i;
+        std::vector<std::vector<int32_t>> lists(1, all);
+        VgsScoreDst local = dst;
+        local.n_dst = 1;
+        if ((rc = vgs_nll_score_lists(h, lists, h->n_models, 0, h->n_models, false, VGS_SKIP_ORDER, mode, local, s))) return rc;
+    }
+    if (n_dst > 1 && !fused_peer_stores) {
+        // the scan (and the fp64 fallback) write the local band only: copy it to the peers (plain peer-to-peer copies)
+        const size_t off = (size_t)(m_col0 * ld), bytes = (size_t)(h->n_models * ld) * sizeof(double);
+        for (int d = 1; d < n_dst; ++d) VGS_CUDA(cudaMemcpyAsync(dsts[d] + off, dsts[0] + off, bytes, cudaMemcpyDefault, s));
+    }
+    return VGS_OK;
+}
+
 static int launch_nll_combine(vgs_context *h, const TilePlan &pl, int rank, int64_t length, float *pay32, double *pay64,
                               cudaStream_t s, float *D32_direct = nullptr, double *D64_direct = nullptr) {
     if (D32_direct) {
         const unsigned g = (unsigned)((pl.n + 31) / 32);
-        k_nll_combine_full<<<dim3(g, g), 256, 0, s>>>(pl.n, h->d_M, h->n_models, (double)length, D32_direct, D64_direct, h->d_err);
+        k_nll_combine_full<<<dim3(g, g), 256, 0, s>>>(pl.n, h->d_M, h->n_models, (double)length, D32_direct, D64_direct, h->d_err, 0);
         VGS_LAUNCH_CHECK(h);
         return VGS_OK;
     }
@@ -586,7 +627,19 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
     key = vgs_mix(key, (uint64_t)pl.n);
     key = vgs_mix(key, (uint64_t)pl.tile);
     key = vgs_mix(key, (uint64_t)pl.world * 1024u + (uint64_t)rank);
-    if (mode == VGS_NLL_KMER && vgs_kmer_applicable(h) && pl.tile % 128 == 0) {
+    if (mode == VGS_NLL_KMER && vgs_kmer_applicable(h) && D32_direct) {
+        // whole matrix on this GPU: all scores as one band of the transposed score matrix (coalesced epilogue stores),
+        // then the distances straight from it
+        double *dsts[1] = {h->d_M};
+        rc = nll_scores_band_impl(h, mode, 0, h->n_seq, dsts, 1, s);
+        if (rc > 0) return rc;
+        if (rc == VGS_OK) {
+            const unsigned g = (unsigned)((pl.n + 31) / 32);
+            k_nll_combine_full<<<dim3(g, g), 256, 0, s>>>(pl.n, h->d_M, h->n_seq, (double)length, D32_direct, D64_direct, h->d_err, 1);
+            VGS_LAUNCH_CHECK(h);
+            return VGS_OK;
+        }
+    } else if (mode == VGS_NLL_KMER && vgs_kmer_applicable(h) && pl.tile % 128 == 0) {
         // needed (sequence-block, model-block) pairs at the contraction's 128 x 128 granularity; the diagonal
         // scores M[i][i] come from k_kmer_diag (all of them, on every rank: N dot products)
         const uint64_t kkey = vgs_mix(key, 2);
@@ -604,7 +657,7 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
                     }
             }
         }
-        rc = vgs_kmer_scores(h, need, nb, nb, true, h->d_M, h->n_models, s, kkey);
+        rc = vgs_kmer_scores(h, need, nb, nb, true, vgs_dst_plain(h->d_M, h->n_models), s, kkey);
         if (rc > 0) return rc;
         if (rc == VGS_OK) return launch_nll_combine(h, pl, rank, length, pay32, pay64, s, D32_direct, D64_direct);
     }
@@ -626,7 +679,7 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
                     for (int64_t x = S * pl.tile; x < std::min(pl.n, (S + 1) * pl.tile); ++x) lists[(size_t)B].push_back((int32_t)x);
     }
     // models whose block touches no owned tile need nothing; the diagonal score M[m][m] rides along
-    rc = vgs_nll_score_lists(h, lists, pl.tile, 0, h->n_models, true, VGS_SKIP_ORDER, mode, h->d_M, h->n_models, s, skey);
+    rc = vgs_nll_score_lists(h, lists, pl.tile, 0, h->n_models, true, VGS_SKIP_ORDER, mode, vgs_dst_plain(h->d_M, h->n_models), s, skey);
     if (rc) return rc;
     return launch_nll_combine(h, pl, rank, length, pay32, pay64, s, D32_direct, D64_direct);
 }
@@ -643,6 +696,28 @@ extern "C" int vgs_nll_tiles(vgs_handle h, int64_t length, int mode, int64_t til
     TilePlan pl;
     vgs_make_plan(&pl, h->n_models, tile, world, 1);
     return nll_tiles_impl(h, length, mode, pl, rank, payload_d, nullptr, (cudaStream_t)stream);
+}
+
+
+extern "C" int vgs_nll_scores_band(vgs_handle h, int mode, int64_t m_col0, int64_t ld, double *const *Mt_dsts_h, int n_dst, void *stream) {
+    int rc = check_nll_ready(h);
+    if (rc) return rc;
+    VGS_CHECK_ARG(mode >= VGS_NLL_SEQUENTIAL && mode <= VGS_NLL_KMER, "vgs_nll_scores_band: bad mode");
+    VGS_CHECK_ARG(m_col0 >= 0 && ld >= h->n_seq && Mt_dsts_h && n_dst >= 1 && n_dst <= VGS_MAX_PEERS, "vgs_nll_scores_band: bad arguments");
+    for (int d = 0; d < n_dst; ++d) VGS_CHECK_ARG(Mt_dsts_h[d] != nullptr, "vgs_nll_scores_band: null destination");
+    VGS_CUDA(cudaSetDevice(h->device));
+    return nll_scores_band_impl(h, mode, m_col0, ld, Mt_dsts_h, n_dst, (cudaStream_t)stream);
+}
+
+extern "C" int vgs_nll_combine(vgs_handle h, int64_t n, const double *Mt_d, int64_t ld, int64_t length, float *D32_d, double *D64_d,
+                               void *stream) {
+    VGS_CHECK_ARG(h && n > 0 && Mt_d && ld >= n && length > 0 && D32_d, "vgs_nll_combine: bad arguments");
+    VGS_CUDA(cudaSetDevice(h->device));
+    const unsigned g = (unsigned)((n + 31) / 32);
+    VGS_CHECK_ARG(g <= 65535, "vgs_nll_combine: matrix too large");
+    k_nll_combine_full<<<dim3(g, g), 256, 0, (cudaStream_t)stream>>>(n, Mt_d, ld, (double)length, D32_d, D64_d, h->d_err, 1);
+    VGS_LAUNCH_CHECK(h);
+    return VGS_OK;
 }
 
 static int64_t default_tile(int64_t n) { return n <= 2048 ? 64 : (n <= 8192 ? 128 : 256); }

@@ -340,6 +340,10 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
     p.pl = pl; p.rank = rank; p.kind = kind; p.err = h->d_err;
     p.n_dir = kind == VGS_PAIR_FROBENIUS_UNION ? 2 : 1;
     // how many staged models fit?
+    {
+        int rcu = vgs_ensure_umap(h, s);   // shallow sets: dense universe maps, built on first use
+        if (rcu) return rcu;
+    }
     const bool umap = h->umap_stride > 0;
     p.umap = h->d_umap; p.umap_stride = h->umap_stride;
     if (!umap) {
@@ -422,6 +426,7 @@ extern "C" int vgs_pair_matrix(vgs_handle h, int kind, float *D32_d, double *D64
     // tile edge: 64/128 normally; a few huge models (tables larger than shared memory, read from L2/HBM) need many
     // more CTAs than pairs/4096, so the tile shrinks until the grid covers the SMs a few times
     int64_t tile = n <= 2048 ? 64 : 128;
+    if ((rc = vgs_ensure_umap(h, s))) return rc;
     {
         const int64_t per_model = h->umap_stride > 0 ? h->umap_stride * 2 + (int64_t)h->max_n_ctx * 16
                                                      : h->max_pair_bytes + (int64_t)h->max_n_ctx * 16;

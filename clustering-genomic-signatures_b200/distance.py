@@ -28,10 +28,26 @@ class _DeviceDistance(object):
 
     def __init__(self):
         self._index = None     # id(vlmc) -> row
-        self._names = None     # name -> row (the reference's equality is by name, vlmc.pyx:27-31)
+        self._vlmcs = None     # the batched objects themselves (strong references: an id() is only unique while its object lives)
         self._D64 = None
         self._D32 = None
         self.device = None
+        self._handle = None
+
+    def _get_handle(self):
+        """One device handle per distance object, created on first use (its device buffers are grow-only, so an
+        N^2 loop of un-batched distance() calls re-uses the same allocations)."""
+        dev = _default_device() if self.device is None else self.device
+        if self._handle is None or self._handle.device != dev:
+            if self._handle is not None:
+                self._handle.close()
+            self._handle = native.Handle(dev)
+        return self._handle
+
+    def close(self):
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
 
     # -- batch hook (same name as Projection.set_vlmcs in the reference)
     def set_vlmcs(self, vlmcs):
@@ -40,25 +56,27 @@ class _DeviceDistance(object):
     def distance_matrix(self, vlmcs):
         """float32 [N, N] matrix of ``distance(vlmcs[i], vlmcs[j])`` (src/clustering/util.pyx:23-33 layout)."""
         vlmcs = list(vlmcs)
-        h = native.Handle(_default_device() if self.device is None else self.device)
-        try:
-            h.load_models(vlmcs_to_flat(vlmcs), skip_nll=not self.needs_nll_tables)
-            D32, D64 = self._compute(h, vlmcs)
-        finally:
-            h.close()
+        h = self._get_handle()
+        h.load_models(vlmcs_to_flat(vlmcs), skip_nll=not self.needs_nll_tables)
+        D32, D64 = self._compute(h, vlmcs)
         self._D32, self._D64 = D32, D64
+        self._vlmcs = vlmcs
         self._index = {id(v): i for i, v in enumerate(vlmcs)}
-        self._names = {}
-        for i, v in enumerate(vlmcs):
-            self._names.setdefault(v.name, i)
+        self._batch_done(vlmcs)
         return D32
 
+    def _batch_done(self, vlmcs):
+        pass
+
     def _row(self, v):
+        """Row of ``v`` in the batched matrix, or None.  A hit needs the very same object: the reference reads the
+        two objects' trees on every call and never resolves a model by name (names are stripped of their training
+        parameters, so different models share one, src/vlmc/vlmc.pyx:62-70, src/test_increasing_parameter_distance.py)."""
         if self._index is None:
             return None
         r = self._index.get(id(v))
-        if r is None:
-            r = self._names.get(getattr(v, "name", None))
+        if r is None or self._vlmcs[r] is not v:
+            return None
         return r
 
     def _value(self, i, j):
@@ -70,12 +88,9 @@ class _DeviceDistance(object):
             return self._value(i, j)
         # not batched: this pair alone, still on the device
         pair = [left_vlmc, right_vlmc]
-        h = native.Handle(_default_device() if self.device is None else self.device)
-        try:
-            h.load_models(vlmcs_to_flat(pair), skip_nll=not self.needs_nll_tables)
-            D32, D64 = self._compute(h, pair, pair_only=True)
-        finally:
-            h.close()
+        h = self._get_handle()
+        h.load_models(vlmcs_to_flat(pair), skip_nll=not self.needs_nll_tables)
+        D32, D64 = self._compute(h, pair, pair_only=True)
         return self._scalar(D32, D64)
 
     def _scalar(self, D32, D64):
@@ -92,10 +107,13 @@ class NegativeLogLikelihood(_DeviceDistance):
     length_of_pregenerated_sequence = 500  # src/distance/negloglikelihood.pyx:12
     needs_nll_tables = True
 
-    def __init__(self, sequence_length, mode="sequential"):
+    def __init__(self, sequence_length, mode="kmer"):
         super().__init__()
         self.generated_sequence_length = sequence_length
-        self.mode = mode  # "sequential" is bit-identical to the reference's fp64 sum; "warp" is within 1e-12
+        # "kmer" (default): the exact int8 tensor-core contraction bench.py times -- within 1e-9 of the reference's
+        # fp64 sum (2e-14 measured), identical clusters downstream; sets deeper than 6 take the "warp" scan.
+        # "sequential": one lane per pair, the reference's own summation order, bit-identical fp64.
+        self.mode = mode
         self._seq_ids = None
 
     def _compute(self, h, vlmcs, pair_only=False):
@@ -103,8 +121,10 @@ class NegativeLogLikelihood(_DeviceDistance):
         sample_missing_sequences(vlmcs, L, self.length_of_pregenerated_sequence, h.device)
         buf, off = sequences_to_ascii([v.sequence for v in vlmcs])
         h.load_sequences_ascii(buf, off)
-        self._seq_ids = {id(v): v.sequence for v in vlmcs}
         return h.nll_matrix_h(L, self.mode)
+
+    def _batch_done(self, vlmcs):
+        self._seq_ids = {id(v): v.sequence for v in vlmcs}
 
     def _still_valid(self, left, right):
         # the reference re-samples when a model's cached sequence was reset or has another length
@@ -176,8 +196,10 @@ class EstimateVLMC(_DeviceDistance):
             seqs = [v.sequence for v in vlmcs]
         buf, off = sequences_to_ascii(seqs)
         h.load_sequences_ascii(buf, off)
-        self._seq_ids = {id(v): v.sequence for v in vlmcs}
         return h.estimate_matrix_h()
+
+    def _batch_done(self, vlmcs):
+        self._seq_ids = {id(v): v.sequence for v in vlmcs}
 
     def _still_valid(self, left, right):
         return self._seq_ids.get(id(right)) is right.sequence

@@ -67,9 +67,9 @@ class FlatModels:
             raise ValueError("context longer than %d symbols is not supported" % MAX_ORDER)
         if np.any(np.diff(self.ctx_offsets) <= 0):
             raise ValueError("every VLMC needs at least one context")
-        if np.any(self.prob < 0):
-            # the reference would raise ValueError from math.log at scoring time (vlmc.pyx:99)
-            raise ValueError("math domain error: negative transition probability")
+        # negative probabilities are not rejected here: the reference only fails on them when it takes their
+        # logarithm (ValueError from math.log, src/vlmc/vlmc.pyx:99) -- vgs_load_models does the same when it
+        # derives ln p for the NLL path, and Frobenius / Projection / Estimate accept them like the reference
         return self
 
     @classmethod

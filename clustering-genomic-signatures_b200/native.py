@@ -55,6 +55,15 @@ SIGNATURES = [
     ("vgs_pair_tiles", c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp]),
     ("vgs_estimate_tiles", c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     ("vgs_assemble", c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    ("vgs_nll_scores_band", c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp]),
+    ("vgs_nll_combine", c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    ("vgs_peer_alloc", c_int, [c_vp, c_i64, _P(c_vp), c_vp]),
+    ("vgs_peer_open", c_int, [c_vp, c_vp, _P(c_vp)]),
+    ("vgs_peer_close", c_int, [c_vp, c_vp]),
+    ("vgs_peer_free", c_int, [c_vp, c_vp]),
+    ("vgs_peer_barrier", c_int, [c_vp, c_vp, c_int, c_int, ctypes.c_uint32, c_vp]),
+    ("vgs_tensor_peak_i8", c_int, [c_vp, c_int, _P(ctypes.c_double), _P(ctypes.c_double)]),
+    ("vgs_g8_plan", c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, _P(c_int), _P(c_int)]),
     ("vgs_matrix_to_triples", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     ("vgs_last_nll_kernel", c_int, [c_vp]),
     ("vgs_average_link", c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, _P(c_i64)]),
@@ -122,6 +131,17 @@ def tile_plan(n, tile, world, symmetric=True):
     nt, slots = c_i64(), c_i64()
     _check(lib().vgs_tile_plan(n, tile, world, int(bool(symmetric)), ctypes.byref(nt), ctypes.byref(slots)))
     return nt.value, slots.value
+
+
+def g8_plan(rects, kblocks, n_cta_pairs, max_split=4):
+    """Unit list of the int8 GEMM for output rectangles [(a_blk, b_row0, b_rows), ...] (host only).
+    Returns (units int32 [n, 6] = a_blk, b_row0, n, kb0, kbn, partial; split)."""
+    rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 3)
+    cap = 64 + 16 * max_split * int(sum(-(-int(r[2]) // 32) for r in rects))
+    out = np.zeros((cap, 6), dtype=np.int32)
+    n, split = c_int(), c_int()
+    _check(lib().vgs_g8_plan(_np_ptr(rects), len(rects), kblocks, n_cta_pairs, max_split, _np_ptr(out), cap, ctypes.byref(n), ctypes.byref(split)))
+    return out[: n.value].copy(), split.value
 
 
 class Handle:
@@ -332,6 +352,43 @@ class Handle:
         d64 = _dev_ptr(D) if D.dtype == torch.float64 else None
         _check(lib().vgs_cluster_distance_std(self._h, n, d32, d64, _np_ptr(clusters), n, _np_ptr(out), ctypes.byref(k)))
         return out[: k.value]
+
+    # ---- model-sharded NLL / peer memory (multi-GPU)
+    def nll_scores_band(self, mode, m_col0, ld, dst_ptrs, stream):
+        """dst_ptrs: device addresses (ints) of the transposed score matrices to write, this GPU's first."""
+        arr = (c_vp * len(dst_ptrs))(*[c_vp(int(p)) for p in dst_ptrs])
+        _check(lib().vgs_nll_scores_band(self._h, NLL_MODES[mode], m_col0, ld, arr, len(dst_ptrs), c_vp(stream)))
+
+    def nll_combine(self, n, Mt, ld, length, D32, D64, stream):
+        _check(lib().vgs_nll_combine(self._h, n, _dev_ptr(Mt), ld, length, _dev_ptr(D32), _dev_ptr(D64), c_vp(stream)))
+
+    def peer_alloc(self, nbytes):
+        """(device address, 64-byte IPC handle) of a zeroed buffer other ranks can map."""
+        ptr = c_vp()
+        ipc = ctypes.create_string_buffer(64)
+        _check(lib().vgs_peer_alloc(self._h, nbytes, ctypes.byref(ptr), ipc))
+        return int(ptr.value), bytes(ipc.raw)
+
+    def peer_open(self, ipc):
+        ptr = c_vp()
+        _check(lib().vgs_peer_open(self._h, ctypes.create_string_buffer(ipc, 64), ctypes.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr):
+        _check(lib().vgs_peer_close(self._h, c_vp(ptr)))
+
+    def peer_free(self, ptr):
+        _check(lib().vgs_peer_free(self._h, c_vp(ptr)))
+
+    def peer_barrier(self, flag_ptrs, rank, epoch, stream):
+        arr = (c_vp * len(flag_ptrs))(*[c_vp(int(p)) for p in flag_ptrs])
+        _check(lib().vgs_peer_barrier(self._h, arr, rank, len(flag_ptrs), epoch & 0xFFFFFFFF, c_vp(stream)))
+
+    def tensor_peak_i8(self, cta_group=2):
+        """(TOPS, ms) of back-to-back tcgen05.mma kind::i8 from resident shared memory on every SM."""
+        tops, ms = ctypes.c_double(), ctypes.c_double()
+        _check(lib().vgs_tensor_peak_i8(self._h, cta_group, ctypes.byref(tops), ctypes.byref(ms)))
+        return tops.value, ms.value
 
     def matrix_to_triples(self, n, D32, triples, stream):
         _check(lib().vgs_matrix_to_triples(self._h, n, _dev_ptr(D32), _dev_ptr(triples), c_vp(stream)))

@@ -170,6 +170,38 @@ int vgs_estimate_tiles(vgs_handle h, int64_t tile, int rank, int world, float *p
 int vgs_assemble(vgs_handle h, int64_t n, int64_t tile, int world, int symmetric, const float *gathered_d,
                  float *D32_d, void *stream);
 
+/* ---- model-sharded NLL over several GPUs (north_star (c) for NegativeLogLikelihood, src/distance/negloglikelihood.pyx:17-26
+ *      evaluated for all pairs as src/clustering/util.pyx:12-14 does).  Rank r loads only ITS models with vgs_load_models
+ *      (local model m is model m_col0 + m of the job: host ln p, uploads and table builds shrink with the shard) and ALL
+ *      sequences.  vgs_nll_scores_band scores every sequence against the shard and writes the band
+ *      Mt[(m_col0 + m) * ld + s] of the TRANSPOSED fp64 score matrix into every destination in Mt_dsts_h (device
+ *      pointers, this GPU's first): with peer-mapped destinations (vgs_peer_*) the int8 GEMM's epilogue stores the band
+ *      straight into the other ranks' matrices over NVLink; with one destination the bands are contiguous and assemble
+ *      with a single NCCL all-gather, no scatter kernel.  vgs_nll_combine turns a complete Mt into the float32 (and
+ *      optionally fp64) [n][n] distance matrix; entry (i, j) needs Mt[j][i], Mt[i][j] and both diagonal scores. ------- */
+int vgs_nll_scores_band(vgs_handle h, int mode, int64_t m_col0, int64_t ld, double *const *Mt_dsts_h, int n_dst, void *stream);
+int vgs_nll_combine(vgs_handle h, int64_t n, const double *Mt_d, int64_t ld, int64_t length, float *D32_d, double *D64_d, void *stream);
+
+/* ---- peer memory over NVLink (one process per GPU): vgs_peer_alloc returns a zeroed device buffer and its 64-byte CUDA
+ *      IPC handle; the other ranks map it with vgs_peer_open (and unmap with vgs_peer_close); the owner frees it with
+ *      vgs_peer_free.  vgs_peer_barrier: flags_h[r] is rank r's array of `world` uint32 flags (peer-mapped here, own
+ *      array at index `rank`); every rank writes `epoch` to its slot in every rank's array behind the work already on
+ *      `stream` and waits for all slots of its own array -- the device-side barrier of the peer-store path. ------------ */
+int vgs_peer_alloc(vgs_handle h, int64_t bytes, void **dev_ptr_out, void *ipc_handle_out /* 64 bytes */);
+int vgs_peer_open(vgs_handle h, const void *ipc_handle /* 64 bytes */, void **dev_ptr_out);
+int vgs_peer_close(vgs_handle h, void *dev_ptr);
+int vgs_peer_free(vgs_handle h, void *dev_ptr);
+int vgs_peer_barrier(vgs_handle h, uint32_t *const *flags_h, int rank, int world, uint32_t epoch, void *stream);
+
+/* ---- measurement hooks for bench.py's roofline (no reference counterpart).  vgs_tensor_peak_i8: int8 ops/s (in TOPS)
+ *      of back-to-back tcgen05.mma kind::i8 M256 N256 K32 (cta_group 2) or M128 N256 K32 (cta_group 1) from resident
+ *      shared memory on every SM: the measured tensor-pipe ceiling of the contraction's own instruction.
+ *      vgs_g8_plan: the unit list the int8 GEMM would run for the given output rectangles {256-row A block, first B row,
+ *      B rows} (host only; rows in multiples of 32): units_out[i] = {a_blk, b_row0, n, kb0, kbn, partial}. -------------- */
+int vgs_tensor_peak_i8(vgs_handle h, int cta_group, double *tops_out, double *ms_out /* nullable */);
+int vgs_g8_plan(const int32_t *rects_h /* [n_rects][3] */, int n_rects, int kblocks, int n_cta_pairs, int max_split,
+                int32_t *units_out_h /* [capacity][6] */, int capacity, int *n_units_out, int *split_out);
+
 /* ---- matrix hand-off layouts of src/clustering/util.pyx:6-21: float32 [N*N][3] rows (i, j, d) ---- */
 int vgs_matrix_to_triples(vgs_handle h, int64_t n, const float *D32_d, float *triples_d, void *stream);
 

@@ -1,0 +1,154 @@
+"""Round-2 paths on a B200 (through the C ABI): the CTA-pair int8 contraction at awkward shapes, the model-sharded NLL
+path (every rank emulated on one GPU), the downstream parity of the headline (k-mer) mode at BASELINE cfg-3 size, the
+[N^2, 3] hand-off kernel, the tensor-peak probe."""
+import numpy as np
+import pytest
+
+import c_oracle
+import vlmc_oracle as O
+from clustering_genomic_signatures_b200 import native, synthetic
+from clustering_genomic_signatures_b200.engine import sharded_nll_emulated
+from clustering_genomic_signatures_b200.flat import pack_sequences
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    e = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    e[a == b] = 0
+    return float(e.max()) if e.size else 0.0
+
+
+@pytest.mark.parametrize("n,depth,ctx,L", [(5, 6, 60, 700), (37, 4, 40, 900), (130, 6, 150, 1200), (261, 5, 90, 500),
+                                           (300, 3, 20, 2500), (9, 0, 1, 300), (70, 1, 4, 400)])
+def test_int8_contraction_shapes(n, depth, ctx, L):
+    """Sets that are not multiples of the 256 x 32 tile quanta, k ranges shorter than one 128-byte stage (depth <= 2),
+    several units per CTA pair and k-split launches: scores against the C oracle, matrix symmetric with exact zeros."""
+    fm, _ = synthetic.make_family_models(n, 100 + n, depth, ctx, max(1, n // 10))
+    seqs = synthetic.sample_sequences(fm, L, 7)
+    h = native.Handle(0)
+    h.load_models(fm)
+    h.load_sequences_packed(*pack_sequences(seqs))
+    co = c_oracle.COracle(fm)
+    M_or = co.score_matrix(seqs)
+    Mk = h.nll_scores_h(native.SKIP_ORDER, "kmer")
+    assert h.last_nll_kernel() == 3, "expected the int8 tensor-core contraction"
+    assert rel_err(Mk, M_or) < 1e-12
+    D32, D64 = h.nll_matrix_h(L, "kmer")
+    assert rel_err(D64, co.nll_from_scores(M_or, L)) < 1e-9
+    assert np.array_equal(D64, D64.T) and np.all(np.diag(D64) == 0) and np.array_equal(D32, D64.astype(np.float32))
+    # a sub-range of sequences x models through the public scores call (row-major output, leading dimension > n)
+    import torch
+    ld = n + 3
+    M = torch.full((n, ld), -7.0, dtype=torch.float64, device="cuda")
+    s0, s1, m0, m1 = 0, n, 0, n
+    stream = torch.cuda.current_stream().cuda_stream
+    h.nll_scores(M, (s0, s1), (m0, m1), native.SKIP_ORDER, "kmer", stream)
+    h.poll_error(stream)
+    got = M.cpu().numpy()
+    assert np.array_equal(got[:, :n], Mk) and np.all(got[:, n:] == -7.0)
+
+
+def test_kmer_duplicates_score_exactly_alike():
+    """Integer sums: identical models give identical bits, so the reference's exact 0.0 between duplicates holds."""
+    fm, _ = synthetic.make_family_models(6, 5, 6, 100, 2)
+    idx = [0, 3, 0, 5, 3]
+    dup = fm.subset(idx)
+    seqs = synthetic.sample_sequences(fm, 900, 2)[idx]
+    h = native.Handle(0)
+    h.load_models(dup)
+    h.load_sequences_packed(*pack_sequences(seqs))
+    D = h.nll_matrix_h(900, "kmer")[1]
+    assert h.last_nll_kernel() == 3
+    assert D[0, 2] == 0.0 and D[1, 4] == 0.0 and D[2, 0] == 0.0 and D[4, 1] == 0.0 and D[0, 1] > 0.0
+
+
+@pytest.mark.parametrize("mode", ["kmer", "sequential", "warp"])
+def test_model_sharded_nll_is_bit_identical(mode):
+    """north_star (c) for the NLL kinds: 1/2/3/4/8 model shards (each rank emulated on this GPU) give the single-GPU
+    matrix bit for bit -- shallow set (int8 contraction in kmer mode) and deep set (scan)."""
+    import torch
+    for n, depth, ctx, L in ((300, 5, 100, 400), (45, 8, 150, 300)):
+        fm, _ = synthetic.make_family_models(n, 32, depth, ctx, 4)
+        seqs = synthetic.sample_sequences(fm, L, 6)
+        packed = pack_sequences(seqs)
+        h = native.Handle(0)
+        h.load_models(fm)
+        h.load_sequences_packed(*packed)
+        D32, D64 = h.nll_matrix_h(L, mode)
+        base = torch.from_numpy(D32).cuda()
+        for world in (1, 2, 3, 4, 8):
+            out = sharded_nll_emulated(fm, packed, L, mode, world)
+            assert torch.equal(out, base), (mode, n, world)
+        out = sharded_nll_emulated(fm, packed, L, mode, 2, mirror=True)   # two destinations per band
+        assert torch.equal(out, base), (mode, n, "mirror")
+        want = c_oracle.COracle(fm).nll_matrix(seqs)
+        if mode == "sequential":
+            assert np.array_equal(D64, want)
+        else:
+            assert rel_err(D64, want) < 1e-9
+
+
+def test_headline_mode_downstream_parity_cfg3():
+    """BASELINE cfg 3 (1000 models x 10 kbp).  The k-mer (int8 tensor-core) and warp matrices against the bit-exact
+    sequential one: fp64 entries within 1e-9, the float32 matrices differ in at most a handful of last-place roundings,
+    and average-link clustering (device kernel = the reference's algorithm, pinned on its goldens) gives the SAME labels
+    and merge order from all three -- and from the C oracle's average link on the sequential matrix."""
+    import torch
+    fm, fam = synthetic.config2(1000, 2)
+    seqs = synthetic.sample_sequences(fm, 10000, 3)
+    h = native.Handle(0)
+    h.load_models(fm)
+    h.load_sequences_packed(*pack_sequences(seqs))
+    k = int(fam.max()) + 1
+    D32s, D64s = h.nll_matrix_h(10000, "sequential")
+    off = ~np.eye(1000, dtype=bool)
+    labels_s, merges_s = h.average_link(torch.from_numpy(D32s).cuda(), k)
+    want_labels, want_merges = c_oracle.average_link(D32s, k)
+    assert np.array_equal(labels_s, want_labels) and np.array_equal(merges_s, want_merges)
+    for mode in ("kmer", "warp"):
+        D32, D64 = h.nll_matrix_h(10000, mode)
+        if mode == "kmer":
+            assert h.last_nll_kernel() == 3
+        assert np.max(np.abs(D64[off] - D64s[off]) / np.abs(D64s[off])) < 1e-9
+        assert np.array_equal(D32, D64.astype(np.float32)) and np.array_equal(D64, D64.T) and np.all(np.diag(D64) == 0)
+        differing = int((D32 != D32s).sum())
+        assert differing <= 200, "float32 entries that round differently from the bit-exact mode: %d of 10^6" % differing
+        # where they differ it is one unit in the last place
+        if differing:
+            a, b = D32[D32 != D32s], D32s[D32 != D32s]
+            assert np.all(np.abs(a.view(np.int32) - b.view(np.int32)) == 1)
+        labels, merges = h.average_link(torch.from_numpy(D32).cuda(), k)
+        assert np.array_equal(labels, labels_s), mode
+        assert np.allclose(merges, merges_s, rtol=1e-6, atol=0), mode
+        # family structure is recovered: every cluster is one family
+        for c in np.unique(labels):
+            assert len(set(fam[labels == c].tolist())) == 1
+
+
+def test_matrix_to_triples_kernel():
+    """vgs_matrix_to_triples = src/clustering/util.pyx:6-21's [N^2, 3] float32 rows (i, j, d), row-major in (i, j)."""
+    import torch
+    rng = np.random.default_rng(3)
+    for n in (1, 5, 300):
+        D = rng.random((n, n)).astype(np.float32)
+        h = native.Handle(0)
+        tri = torch.empty((n * n, 3), dtype=torch.float32, device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+        h.matrix_to_triples(n, torch.from_numpy(D).cuda(), tri, stream)
+        torch.cuda.synchronize()
+        got = tri.cpu().numpy()
+        ii, jj = np.divmod(np.arange(n * n), n)
+        assert np.array_equal(got[:, 0], ii.astype(np.float32)) and np.array_equal(got[:, 1], jj.astype(np.float32))
+        assert np.array_equal(got[:, 2], D.reshape(-1))
+        # and it is what the host mirror of calculate_distances_within_vlmcs / index_distances round-trips
+        assert np.array_equal(O.triples_to_matrix(got, n), D) if hasattr(O, "triples_to_matrix") else True
+
+
+def test_tensor_peak_probe():
+    h = native.Handle(0)
+    t2, ms2 = h.tensor_peak_i8(2)
+    t1, ms1 = h.tensor_peak_i8(1)
+    print("int8 tensor peak probe: cta_group::2 %.0f TOPS (%.3f ms), cta_group::1 %.0f TOPS (%.3f ms)" % (t2, ms2, t1, ms1))
+    assert 500.0 < t2 < 6000.0 and 250.0 < t1 < 6000.0

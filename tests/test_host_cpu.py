@@ -43,8 +43,10 @@ def test_flat_models_from_trees_and_back():
     assert sub.tree(0) == g["trees"][3] and sub.tree(1) == g["trees"][1]
     with pytest.raises(ValueError):
         flat.FlatModels.from_trees([{"A" * 16: {"A": 1.0, "C": 0.0, "G": 0.0, "T": 0.0}}])
-    with pytest.raises(ValueError):
-        flat.FlatModels.from_trees([{"": {"A": -0.1, "C": 0.5, "G": 0.3, "T": 0.3}}])
+    # negative probabilities load like in the reference, which only fails when it takes their logarithm (vlmc.pyx:99):
+    # the NLL load raises that "math domain error" (tests/test_gpu_edges.py::test_argument_errors)
+    neg = flat.FlatModels.from_trees([{"": {"A": -0.1, "C": 0.5, "G": 0.3, "T": 0.3}}])
+    assert neg.prob[0, 0] == -0.1
 
 
 def test_pack_sequences_layout():
@@ -201,6 +203,89 @@ def test_gloo_world2_sharding_round_trip(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "rank %d ok" % r in o, o
+
+
+GLOO_SHARD_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+root = sys.argv[1]
+for p in (root, os.path.join(root, "tests"), os.path.join(root, "oracle")):
+    sys.path.insert(0, p)
+import c_oracle
+from clustering_genomic_signatures_b200 import synthetic
+from clustering_genomic_signatures_b200.engine import ShardedNllJob
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), 2
+n, L = 23, 200
+fm, _ = synthetic.make_family_models(n, 3, 4, 30, 3)
+seqs = synthetic.sample_sequences(fm, L, 9)
+m0, m1 = ShardedNllJob.shard_bounds(n, world)[rank]
+per = -(-n // world)
+# this rank's band of the transposed score matrix: every sequence against ITS models only (the C oracle on the shard)
+band = np.zeros((per, n))
+band[: m1 - m0] = c_oracle.COracle(fm.subset(range(m0, m1))).score_matrix(seqs).T
+Mt = torch.zeros((per * world, n), dtype=torch.float64)
+Mt[rank * per:(rank + 1) * per] = torch.from_numpy(band)
+dist.all_gather_into_tensor(Mt, Mt[rank * per:(rank + 1) * per].clone())
+M = Mt.numpy()[:n].T.copy()                       # M[s][m]
+co = c_oracle.COracle(fm)
+assert np.array_equal(M, co.score_matrix(seqs)), "rank %d: gathered score matrix differs" % rank
+assert np.array_equal(co.nll_from_scores(M, L), co.nll_matrix(seqs))
+dist.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world2_model_sharded_nll(tmp_path):
+    """The N > 1 NLL plan on CPU: shard bounds, padded bands of the transposed score matrix, one all-gather that IS the
+    assembly, local combine -- against the C oracle on the unsharded set."""
+    script = tmp_path / "ws.py"
+    script.write_text(GLOO_SHARD_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "rank %d ok" % r in o, o
+
+
+def test_shard_bounds_cover_the_models():
+    from clustering_genomic_signatures_b200.engine import ShardedNllJob
+    for n in (1, 5, 23, 1000, 20000):
+        for world in (1, 2, 3, 4, 8):
+            b = ShardedNllJob.shard_bounds(n, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1)) and all(e >= a for a, e in b)
+            per = -(-n // world)
+            assert all(a == min(n, r * per) for r, (a, e) in enumerate(b))
+
+
+@pytest.mark.parametrize("rects,kblocks,pairs", [([(a, 0, 8000) for a in range(4)], 128, 74), ([(a, 0, 1024) for a in range(4)], 128, 74),
+                                                 ([(0, 0, 64)], 1, 74), ([(0, 0, 32)], 128, 74), ([(a, 0, 16000) for a in range(8)], 128, 74),
+                                                 ([(0, 0, 2400), (1, 1024, 1024)], 16, 74), ([(0, 32, 160032 - 32)], 4, 3)])
+def test_int8_gemm_unit_plan(rects, kblocks, pairs):
+    """The unit list of the CTA-pair int8 GEMM (host planner behind vgs_g8_plan): every (256-row block, 32-row quantum,
+    k block) of the requested rectangles is covered exactly once, widths are multiples of 32 up to 256, k-splits only
+    where the tiles do not fill the CTA pairs, and the dealt load per CTA pair stays close to the mean."""
+    units, split = native.g8_plan(rects, kblocks, pairs)
+    live = units[units[:, 2] > 0]
+    seen = set()
+    for a, b0, n, k0, kn, part in live:
+        assert n % 32 == 0 and 0 < n <= 256 and kn > 0 and b0 % 32 == 0
+        assert (part != 0) == (split > 1)
+        for r in range(b0, b0 + n, 32):
+            for k in range(k0, k0 + kn):
+                assert (a, r, k) not in seen
+                seen.add((a, r, k))
+    assert len(seen) == sum((r[2] // 32) * kblocks for r in rects)
+    assert all((a, r, k) in seen for a, b0, rows in rects for r in range(b0, b0 + rows, 32) for k in range(kblocks))
+    load = np.zeros(pairs)
+    for i, (a, b0, n, k0, kn, part) in enumerate(units):
+        load[i % pairs] += n * kn
+    if len(live) >= 2 * pairs:
+        assert load.max() <= 1.12 * load.mean()
+    if split > 1:
+        assert len(live) <= pairs + 4 * len(rects)
 
 
 def test_bench_reference_arm_runs_on_cpu_and_keeps_the_contract():
