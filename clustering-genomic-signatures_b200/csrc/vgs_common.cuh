@@ -108,7 +108,7 @@ struct vgs_context {
     void *pool = nullptr;       // host thread pool (VgsPool, vgs_core.cu)
     std::vector<WorkCache> wcache;
     uint64_t model_gen = 0;     // bumped by every vgs_load_models
-    int max_order = 0;
+    int max_order = 0, min_order = 0;
     int64_t max_nll_bytes_t1 = 0, max_nll_bytes_t2 = 0, max_nll_bytes_t3 = 0;
     int64_t max_pair_bytes = 0;  // hash + fp32 rows of the largest model
     ModelMeta *d_meta = nullptr;

@@ -607,6 +607,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     h->h_ctx_off.assign(ctx_offsets_h, ctx_offsets_h + n_models + 1);
     h->h_meta.assign((size_t)n_models, ModelMeta());
     h->max_order = 0;
+    h->min_order = VGS_MAX_ORDER + 1;
     h->max_nll_bytes_t1 = h->max_nll_bytes_t2 = h->max_nll_bytes_t3 = h->max_pair_bytes = 0;
     h->max_n_ctx = 0;
     h->umap_stride = 0;
@@ -673,6 +674,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         h->max_pair_bytes = std::max(h->max_pair_bytes, cap * 8 + n * 16);
         h->max_n_ctx = std::max<int>(h->max_n_ctx, (int)n);
         h->max_order = std::max(h->max_order, order);
+        h->min_order = std::min(h->min_order, order);
         mm.nll_off = nll_bytes;
         if (order <= VGS_DENSE_MAX_ORDER) {
             mm.tier = 1;

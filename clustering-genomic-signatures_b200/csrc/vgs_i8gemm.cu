@@ -17,7 +17,11 @@ int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters,
     if (n_clusters < 1) n_clusters = 1;
     int N = G8_MAX_N, split = 1;
     const int64_t wide = g8_count(rects, G8_MAX_N);
-    if (wide >= n_clusters) {
+    static int force_n = -1;   // tuning knob: VGS_G8_FORCE_N = tile width
+    if (force_n < 0) { const char *e = getenv("VGS_G8_FORCE_N"); force_n = e ? atoi(e) / 32 * 32 : 0; }
+    if (force_n >= 32 && force_n <= G8_MAX_N) {
+        N = force_n;
+    } else if (wide >= n_clusters) {
         // enough tiles: the smallest width that still fits the same number of waves -> (almost) every CTA pair gets the
         // same number of tiles, each a little narrower than 256
         const int64_t waves = (wide + n_clusters - 1) / n_clusters;
@@ -48,7 +52,16 @@ int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters,
     }
     // largest first, dealt to the CTA pairs in snake order (pair c runs units c, c + n_clusters, ...): the pairs that got
     // the largest units of one wave get the smallest of the next
-    std::stable_sort(out->begin(), out->end(), [](const G8Unit &a, const G8Unit &b) { return (int64_t)a.n * a.kbn > (int64_t)b.n * b.kbn; });
+    // ... and, among equals, units that read the same B rows next to each other: they run at the same time on neighbouring
+    // CTA pairs and walk k in step, so a B line is fetched from HBM once and served to the others from L2 (rectangle-major
+    // order re-read the digit operand once per 256-row A block: 4 x 131 MB at cfg 3)
+    std::stable_sort(out->begin(), out->end(), [](const G8Unit &a, const G8Unit &b) {
+        const int64_t wa = (int64_t)a.n * a.kbn, wb = (int64_t)b.n * b.kbn;
+        if (wa != wb) return wa > wb;
+        if (a.kb0 != b.kb0) return a.kb0 < b.kb0;
+        if (a.b_row0 != b.b_row0) return a.b_row0 < b.b_row0;
+        return a.a_blk < b.a_blk;
+    });
     const size_t nu = out->size();
     const size_t waves = (nu + (size_t)n_clusters - 1) / (size_t)n_clusters;
     G8Unit none;
@@ -94,6 +107,9 @@ extern "C" int vgs_g8_plan(const int32_t *rects_h, int n_rects, int kblocks, int
 // there is no library int8 GEMM to measure it with.  The probe issues the kernel's own instruction (tcgen05.mma
 // cta_group::2 kind::i8, M 256, N 256, K 32) back to back from resident shared memory -- no global loads, no epilogue --
 // on every SM pair, and reports executed int8 ops per second: the tensor pipe's ceiling for this instruction shape.
+// stage = 128 A rows + up to 256 B rows (a single CTA holds all 256 rows of B, a CTA of a pair its half) of 128 bytes
+#define PK_STAGE_BYTES (G8_A_BYTES + G8_MAX_N * G8_BK)
+#define PK_SMEM_BYTES (4 * PK_STAGE_BYTES)   // 192 KB (two stages used): one CTA per SM, like the GEMM
 template <int CG>
 __global__ void __launch_bounds__(128, 1) k_g8_peak(int iters, int *err) {
     extern __shared__ __align__(1024) uint8_t pk_smem[];
@@ -102,7 +118,7 @@ __global__ void __launch_bounds__(128, 1) k_g8_peak(int iters, int *err) {
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { vgs_mbar_init(&bar[0], 1); vgs_mbar_init(&bar[1], 1); }
     // operands: zeros (the tensor pipe does not look at the values)
-    for (int i = threadIdx.x; i < 2 * G8_STAGE_BYTES / 16; i += blockDim.x) ((uint4 *)pk_smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 2 * PK_STAGE_BYTES / 16; i += blockDim.x) ((uint4 *)pk_smem)[i] = make_uint4(0, 0, 0, 0);
     if (warp == 0) {
         if (CG == 2) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(vgs_smem_addr(&tmem_slot)), "r"(512u) : "memory");
@@ -123,7 +139,7 @@ __global__ void __launch_bounds__(128, 1) k_g8_peak(int iters, int *err) {
         const uint32_t sa = vgs_smem_addr(pk_smem);
         const uint32_t idesc = g8_idesc(CG == 2 ? 256 : 128, 256, 0);
         for (int it = 0; it < iters; ++it) {
-            const uint32_t st = sa + (uint32_t)(it & 1) * G8_STAGE_BYTES;
+            const uint32_t st = sa + (uint32_t)(it & 1) * PK_STAGE_BYTES;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint64_t da = g8_smem_desc(st + 32u * j), db = g8_smem_desc(st + G8_A_BYTES + 32u * j);
@@ -149,7 +165,7 @@ extern "C" int vgs_tensor_peak_i8(vgs_handle h, int cta_group, double *tops_out,
     VGS_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->own_stream;
     const int iters = 2048;   // x 4 MMAs of 256 x 256 x 32 (pair) / 128 x 256 x 32 (single CTA)
-    const int smem = 2 * G8_STAGE_BYTES;
+    const int smem = PK_SMEM_BYTES;
     const int n_cta = cta_group == 2 ? (h->sm_count / 2) * 2 : h->sm_count;
     cudaEvent_t e0, e1;
     VGS_CUDA(cudaEventCreate(&e0));

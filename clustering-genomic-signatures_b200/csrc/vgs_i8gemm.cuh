@@ -19,16 +19,20 @@
 // Kernel: one CTA pair (cluster of 2) per SM pair, persistent over a static list of units (tile x k range); 192 threads:
 //   warp 0   producer: per stage one expect_tx + two bulk copies (its 128 A rows, its half of the B rows)
 //   warp 1   leader CTA: the one thread that issues every tcgen05.mma of the pair and commits them to the stage's
-//            "empty" barriers of BOTH CTAs (multicast commit); peer CTA: forwards "my half of the stage has landed" to
-//            the leader (remote mbarrier arrive)
+//            "empty" barriers of BOTH CTAs (multicast commit); peer CTA: relays "my half of the stage has landed" to
+//            the leader's "full" barrier (relaxed remote mbarrier arrive: the 1-D bulk copy can only signal a barrier
+//            of the CTA it writes to)
 //   warps 2-5 epilogue: tcgen05.ld of their 32 TMEM lanes, 32 columns at a time, handed to the caller's functor.  The
 //            accumulator is double buffered (2 x 256 of the 512 TMEM columns), so the MMAs of unit t+1 run while unit t
 //            is folded and stored.
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "vgs_common.cuh"
 
 #define G8_BK 128                 // k per pipeline stage = bytes per operand row per stage = one swizzle atom
-#define G8_STAGES 6
+#define G8_STAGES 7                // 7 x 32 KB = 224 KB of the 227 KB a CTA can have
 #define G8_THREADS 192
 #define G8_A_ROWS 128             // A rows per CTA (256 per pair)
 #define G8_MAX_N 256              // B rows per unit (128 per CTA)
@@ -53,6 +57,9 @@ struct G8Args {
     int n_units;
     int a_signed;                     // A operand: 0 = unsigned 8 bit, 1 = signed
     int *err;                         // device error word (bit 2: watchdog)
+    int debug;                        // developer knob VGS_G8_DEBUG: bit 0 = skip the epilogue functor (timing experiments only)
+    int stages;                       // pipeline stages in use (<= G8_STAGES; tuning knob VGS_G8_STAGES)
+    long long *prof;                  // optional [n_clusters][8] cycle counters of the leader CTA (VGS_G8_PROF=1), else nullptr
 };
 
 __host__ __device__ __forceinline__ int64_t g8_off(int64_t row, int64_t k, int64_t rows_pad) {
@@ -131,25 +138,52 @@ __device__ __forceinline__ void g8_remote_arrive(uint64_t *bar, uint32_t rank) {
         "r"(rank)
         : "memory");
 }
+// relay arrival: "the bulk copies into my shared memory have completed" -- the data itself was made visible by the copy's
+// own complete_tx, so the arrival needs no release fence (a release.cluster here costs ~1000 cycles per stage and made
+// the relay the bottleneck of the whole pipeline)
+__device__ __forceinline__ void g8_remote_arrive_relaxed(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(vgs_smem_addr(bar)),
+        "r"(rank)
+        : "memory");
+}
 __device__ __forceinline__ void g8_local_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(vgs_smem_addr(bar)) : "memory");
 }
-// wait for a phase of an mbarrier (cluster-scope acquire: the signal may come from the other CTA); a signal that never
-// comes sets the error word and traps -- a failed launch, not a hung GPU
-__device__ __forceinline__ void g8_wait(uint64_t *bar, uint32_t parity, int *err) {
+// wait for a phase of an mbarrier.  CLUSTER: acquire at cluster scope (the arrival is a release from the other CTA's
+// threads); otherwise the default CTA-scope acquire (arrivals from this CTA's threads, from TMA completions and from
+// tcgen05.commit, and relaxed relay arrivals that carry no data of their own).  A signal that never comes sets the
+// error word and traps -- a failed launch, not a hung GPU.
+template <bool CLUSTER>
+__device__ __forceinline__ void g8_wait_t(uint64_t *bar, uint32_t parity, int *err) {
     uint32_t done = 0;
     long long t0 = 0;
     int spins = 0;
     while (true) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(vgs_smem_addr(bar)), "r"(parity)
-            : "memory");
+        if (CLUSTER)
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t"
+                "}\n"
+                : "=r"(done)
+                : "r"(vgs_smem_addr(bar)), "r"(parity)
+                : "memory");
+        else
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t"
+                "}\n"
+                : "=r"(done)
+                : "r"(vgs_smem_addr(bar)), "r"(parity)
+                : "memory");
         if (done) break;
         if (++spins == 1024) t0 = clock64();
         if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > G8_WATCHDOG_CYCLES) {
@@ -159,6 +193,8 @@ __device__ __forceinline__ void g8_wait(uint64_t *bar, uint32_t parity, int *err
         }
     }
 }
+__device__ __forceinline__ void g8_wait(uint64_t *bar, uint32_t parity, int *err) { g8_wait_t<false>(bar, parity, err); }
+__device__ __forceinline__ void g8_wait_cluster(uint64_t *bar, uint32_t parity, int *err) { g8_wait_t<true>(bar, parity, err); }
 __device__ __forceinline__ void g8_tmem_ld32(uint32_t taddr, int32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
@@ -178,20 +214,26 @@ __device__ __forceinline__ void g8_tmem_ld32(uint32_t taddr, int32_t (&v)[32]) {
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_gemm(const G8Args g, const Epi epi) {
     extern __shared__ __align__(1024) uint8_t g8_smem[];
-    __shared__ __align__(8) uint64_t full[G8_STAGES], empty[G8_STAGES], peer_full[G8_STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ __align__(8) uint64_t full[G8_STAGES], empty[G8_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = g8_cta_rank();
     const bool leader = rank == 0;
     const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const uint32_t smem0 = vgs_smem_addr(g8_smem);
+    const int NS = g.stages;
+    if (g.prof && tid == 0 && leader) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        g.prof[(gridDim.x >> 1) * 8 + (blockIdx.x >> 1) * 4 + 0] = (long long)ns;
+    }
     if (smem0 & 1023u) __trap();   // SWIZZLE_128B operand tiles need 1024-byte aligned stage buffers
 
     if (tid == 0) {
         for (int i = 0; i < G8_STAGES; ++i) {
-            vgs_mbar_init(&full[i], 1);
+            // leader: its own copies (one expect_tx arrival + the bytes) and the peer's relay arrival; peer: its own copies
+            vgs_mbar_init(&full[i], leader ? 2 : 1);
             vgs_mbar_init(&empty[i], 1);
-            vgs_mbar_init(&peer_full[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             vgs_mbar_init(&tmem_full[i], 1);
@@ -214,6 +256,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
         // ===== producer =====
         if (lane == 0) {
             int64_t gs = 0;   // stage use counter
+            long long t_wait = 0;
+            const long long t_begin = clock64();
             for (int ui = cluster; ui < g.n_units; ui += n_clusters) {
                 const G8Unit u = g.units[ui];
                 const uint32_t b_bytes = (uint32_t)(u.n >> 1) * G8_BK;
@@ -221,13 +265,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
                 const uint8_t *b_src = g.B + (((int64_t)u.kb0 * g.b_rows_pad + u.b_row0 + rank * (u.n >> 1)) << 7);
                 const int64_t a_step = g.a_rows_pad << 7, b_step = g.b_rows_pad << 7;
                 for (int kb = 0; kb < u.kbn; ++kb, ++gs) {
-                    const int st = (int)(gs % G8_STAGES);
-                    g8_wait(&empty[st], (uint32_t)(((gs / G8_STAGES) & 1) ^ 1), g.err);
+                    const int st = (int)(gs % NS);
+                    const long long t0 = g.prof ? clock64() : 0;
+                    g8_wait(&empty[st], (uint32_t)(((gs / NS) & 1) ^ 1), g.err);
+                    if (g.prof) t_wait += clock64() - t0;
                     uint8_t *dst = g8_smem + (size_t)st * G8_STAGE_BYTES;
                     vgs_mbar_expect_tx(&full[st], G8_A_BYTES + b_bytes);
                     vgs_bulk_g2s(dst, a_src + kb * a_step, G8_A_BYTES, &full[st]);
                     vgs_bulk_g2s(dst + G8_A_BYTES, b_src + kb * b_step, b_bytes, &full[st]);
                 }
+            }
+            if (g.prof && leader) {
+                g.prof[cluster * 8 + 5] = t_wait;                 // producer: waiting for a free stage
+                g.prof[cluster * 8 + 6] = clock64() - t_begin;    // producer: first to last copy issued
             }
         }
     } else if (warp == 1) {
@@ -236,36 +286,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
             if (leader) {
                 // ===== MMA issuer =====
                 int it = 0;
+                long long t_full = 0, t_tmem = 0, t_issue = 0;
+                const long long t_begin = clock64();
+                unsigned long long ns_begin = 0;
+                if (g.prof) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+                    g.prof[n_clusters * 8 + cluster * 4 + 1] = (long long)ns_begin;
+                }
                 for (int ui = cluster; ui < g.n_units; ui += n_clusters, ++it) {
                     const G8Unit u = g.units[ui];
                     if (u.n == 0) continue;   // padding of the dealt unit list (every role skips it the same way)
                     const int acc = it & 1;
-                    g8_wait(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1), g.err);   // epilogues of both CTAs have drained it
+                    long long t0 = g.prof ? clock64() : 0;
+                    g8_wait_cluster(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1), g.err);   // epilogues of both CTAs have drained it
+                    if (g.prof) t_tmem += clock64() - t0;
                     g8_fence_after();
                     const uint32_t idesc = g8_idesc(256, u.n, g.a_signed);
                     const uint32_t d_addr = tmem_base + (uint32_t)(acc * G8_MAX_N);
                     for (int kb = 0; kb < u.kbn; ++kb, ++gs) {
-                        const int st = (int)(gs % G8_STAGES);
-                        const uint32_t ph = (uint32_t)((gs / G8_STAGES) & 1);
-                        g8_wait(&full[st], ph, g.err);
-                        g8_wait(&peer_full[st], ph, g.err);
+                        const int st = (int)(gs % NS);
+                        const uint32_t ph = (uint32_t)((gs / NS) & 1);
+                        if (g.prof) t0 = clock64();
+                        g8_wait(&full[st], ph, g.err);   // both halves of the stage have landed
+                        if (g.prof) { const long long t1 = clock64(); t_full += t1 - t0; t0 = t1; }
                         g8_fence_after();
                         const uint32_t sa = smem0 + (uint32_t)st * G8_STAGE_BYTES;
 #pragma unroll
                         for (int j = 0; j < G8_BK / 32; ++j)
                             g8_mma2(d_addr, g8_smem_desc(sa + 32u * j), g8_smem_desc(sa + G8_A_BYTES + 32u * j), idesc, (kb > 0 || j > 0) ? 1u : 0u);
                         g8_commit2(&empty[st]);
+                        if (g.prof) t_issue += clock64() - t0;
                     }
                     g8_commit2(&tmem_full[acc]);
+                }
+                if (g.prof) {
+                    long long *o = g.prof + cluster * 8;
+                    unsigned long long ns_end;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+                    o[0] = t_full; o[1] = (long long)(ns_end - ns_begin); o[2] = t_tmem;
+                    g.prof[n_clusters * 8 + cluster * 4 + 2] = (long long)ns_end; o[3] = t_issue; o[4] = clock64() - t_begin;
                 }
             } else {
                 // ===== forwarder: my half of the stage has landed =====
                 for (int ui = cluster; ui < g.n_units; ui += n_clusters) {
                     const int kbn = g.units[ui].kbn;
                     for (int kb = 0; kb < kbn; ++kb, ++gs) {
-                        const int st = (int)(gs % G8_STAGES);
-                        g8_wait(&full[st], (uint32_t)((gs / G8_STAGES) & 1), g.err);
-                        g8_remote_arrive(&peer_full[st], 0);
+                        const int st = (int)(gs % NS);
+                        g8_wait(&full[st], (uint32_t)((gs / NS) & 1), g.err);
+                        g8_remote_arrive_relaxed(&full[st], 0);
                     }
                 }
             }
@@ -274,11 +342,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
         // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31 =====
         const int quad = warp & 3;
         int it = 0;
+        long long t_epi = 0;
         for (int ui = cluster; ui < g.n_units; ui += n_clusters, ++it) {
             const G8Unit u = g.units[ui];
             if (u.n == 0) continue;
             const int acc = it & 1;
             g8_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1), g.err);
+            const long long t_e0 = g.prof ? clock64() : 0;
+            if (g.prof && lane == 0) {
+                unsigned long long ns;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+                g.prof[n_clusters * 12 + ((cluster * 2 + (int)rank) * 4 + (warp - 2)) * 2] = (long long)ns;
+            }
             g8_fence_after();
             const int64_t a_row = (int64_t)u.a_blk * 256 + rank * G8_A_ROWS + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * G8_MAX_N);
@@ -286,7 +361,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
             for (int c0 = 0; c0 < u.n; c0 += 32) {
                 int32_t v[32];
                 g8_tmem_ld32(taddr + (uint32_t)c0, v);
-                epi(u, a_row, c0, v);
+                if (!(g.debug & 1)) epi(u, a_row, c0, v);
             }
             epi.unit_done();
             g8_fence_before();
@@ -295,7 +370,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
                 if (leader) g8_local_arrive(&tmem_empty[acc]);
                 else g8_remote_arrive(&tmem_empty[acc], 0);
             }
+            if (g.prof) {
+                t_epi += clock64() - t_e0;
+                // per epilogue warp of either CTA: [start, end] of its work on this unit (ns), the last unit's values stay
+                unsigned long long ns;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+                if (lane == 0) {
+                    long long *w = g.prof + n_clusters * 12 + ((cluster * 2 + (int)rank) * 4 + (warp - 2)) * 2;
+                    w[1] = (long long)ns;
+                }
+            }
         }
+        if (g.prof && leader && warp == 2 && lane == 0) g.prof[cluster * 8 + 7] = t_epi;   // epilogue work of one warp
     }
     // teardown: nobody leaves (or frees tensor memory) while the pair may still touch this CTA's shared / tensor memory
     g8_fence_before();
@@ -303,6 +389,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
     g8_cluster_sync();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G8_TMEM_COLS) : "memory");
+    }
+    if (g.prof && tid == 0 && leader) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        g.prof[n_clusters * 8 + cluster * 4 + 3] = (long long)ns;
     }
 }
 
@@ -312,8 +403,63 @@ static int g8_launch(vgs_context *h, const G8Args &g, const Epi &epi, cudaStream
     auto kern = k_g8_gemm<Epi>;
     VGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G8_SMEM_BYTES));
     const int n_clusters = std::max(1, std::min(g.n_units, h->sm_count / 2));
-    kern<<<2 * n_clusters, G8_THREADS, G8_SMEM_BYTES, s>>>(g, epi);
+    static int want_prof = -1;
+    if (want_prof < 0) { const char *e = getenv("VGS_G8_PROF"); want_prof = (e && e[0] == '1') ? 1 : 0; }
+    G8Args ga = g;
+    ga.prof = nullptr;
+    static int n_stages = -1;
+    if (n_stages < 0) { const char *e = getenv("VGS_G8_STAGES"); n_stages = e ? std::max(1, std::min(G8_STAGES, atoi(e))) : G8_STAGES; }
+    ga.stages = n_stages;
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("VGS_G8_DEBUG"); dbg = e ? atoi(e) : 0; }
+    ga.debug = dbg;
+    long long *d_prof = nullptr;
+    if (want_prof) {
+        if (cudaMalloc((void **)&d_prof, (size_t)n_clusters * 224) == cudaSuccess) {
+            cudaMemsetAsync(d_prof, 0, (size_t)n_clusters * 224, s);
+            ga.prof = d_prof;
+        }
+    }
+    kern<<<2 * n_clusters, G8_THREADS, G8_SMEM_BYTES, s>>>(ga, epi);
     VGS_LAUNCH_CHECK(h);
+    if (d_prof) {
+        // developer aid: where the leader CTA's main-loop threads spend their cycles (mean over the CTA pairs)
+        std::vector<long long> hp((size_t)n_clusters * 28);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_prof);
+        double m[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < n_clusters; ++c)
+            for (int k = 0; k < 8; ++k) {
+                m[k] += (double)hp[(size_t)c * 8 + k] / n_clusters;
+                mx[k] = std::max(mx[k], (double)hp[(size_t)c * 8 + k]);
+            }
+        fprintf(stderr, "[g8 prof] units %d pairs %d | MMA thread cycles mean (max): wait full %.0f (%.0f), wait tmem %.0f (%.0f), issue %.0f "
+                        "(%.0f), total %.0f (%.0f) = %.1f us at %.0f MHz | producer: wait empty %.0f (%.0f), total %.0f (%.0f) | epilogue warp %.0f (%.0f)\n",
+                g.n_units, n_clusters, m[0], mx[0], m[2], mx[2], m[3], mx[3], m[4], mx[4], m[1] / 1e3, m[1] > 0 ? m[4] / m[1] * 1e3 : 0.0, m[5], mx[5],
+                m[6], mx[6], m[7], mx[7]);
+        {
+            const long long *ts = hp.data() + (size_t)n_clusters * 8;
+            long long e0 = ts[0], e1 = ts[0], l0 = ts[1], l1 = ts[1], f0 = ts[2], f1 = ts[2], x0 = ts[3], x1 = ts[3];
+            for (int c = 0; c < n_clusters; ++c) {
+                e0 = std::min(e0, ts[4 * c]); e1 = std::max(e1, ts[4 * c]);
+                l0 = std::min(l0, ts[4 * c + 1]); l1 = std::max(l1, ts[4 * c + 1]);
+                f0 = std::min(f0, ts[4 * c + 2]); f1 = std::max(f1, ts[4 * c + 2]);
+                x0 = std::min(x0, ts[4 * c + 3]); x1 = std::max(x1, ts[4 * c + 3]);
+            }
+            fprintf(stderr, "[g8 prof] timeline (us after the first CTA entered): entry ..%.1f | main loop starts %.1f..%.1f | main loop ends %.1f..%.1f | "
+                            "exit %.1f..%.1f\n", (e1 - e0) / 1e3, (l0 - e0) / 1e3, (l1 - e0) / 1e3, (f0 - e0) / 1e3, (f1 - e0) / 1e3, (x0 - e0) / 1e3, (x1 - e0) / 1e3);
+            const long long *ew = hp.data() + (size_t)n_clusters * 12;
+            for (int c = 0; c < n_clusters; ++c) {
+                bool slow = false;
+                for (int k = 0; k < 8; ++k) slow = slow || (ew[(c * 8 + k) * 2 + 1] - ew[(c * 8 + k) * 2] > 30000);
+                if (!slow && c % 24) continue;
+                fprintf(stderr, "[g8 prof] pair %d last-unit epilogue [start,end] us:", c);
+                for (int k = 0; k < 8; ++k) fprintf(stderr, " %s%d [%.1f,%.1f]", k < 4 ? "L" : "P", k & 3, (ew[(c * 8 + k) * 2] - e0) / 1e3, (ew[(c * 8 + k) * 2 + 1] - e0) / 1e3);
+                fprintf(stderr, " | loop end %.1f exit %.1f\n", (ts[4 * c + 2] - e0) / 1e3, (ts[4 * c + 3] - e0) / 1e3);
+            }
+        }
+    }
     return VGS_OK;
 }
 #endif  // __CUDACC__

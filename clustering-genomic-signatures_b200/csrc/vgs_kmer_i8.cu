@@ -50,30 +50,25 @@ struct I8Side {
     const int64_t *seq_off, *seq_len;
     const int32_t *over_cnt;   // [n_seq] frequent k-mers per sequence (nullptr: the set has none)
     const uint2 *over_list;    // [n_seq][I8_MAX_OVER] {k, count >> 8}
+    const int8_t *digits;      // the digit operand (slab layout): the frequent k-mers' digits are read back from it
+    int64_t d_rows_pad;
     int depth;                 // D = largest order of the set; k-mers are (D + 1)-mers
+    int any_shallow;           // some model is shallower than D (only then does anything look at the per-model metadata)
 };
 
-// ln p of model mm for the (D+1)-mer k = (history << 2) | symbol: the longest suffix of the history that is a context
-__device__ __forceinline__ double i8_table_entry(const I8Side &sd, const ModelMeta &mm, uint32_t k) {
-    const int id = vgs_longest_suffix(sd.hash + mm.hash_off, mm.hash_mask, mm.hash_shift, mm.order, k >> 2, sd.depth);
-    return id < 0 ? 0.0 : sd.logp[4 * (mm.ctx_off + id) + (k & 3u)];
-}
-
-// adds 256 * hi * digits(T[m][k]) for the frequent k-mers of a sequence
-__device__ __forceinline__ void i8_add_frequent(long long *S, const I8Side &sd, const ModelMeta &mm, int64_t s) {
+// adds 256 * hi * d_p(T[m][k]) for the frequent k-mers of sequence s.  The digits come straight from the GEMM's own digit
+// operand (eight independent one-byte loads per k-mer, from lines the tile has just streamed through L2) -- the same
+// integers the tensor cores multiplied, so the sum stays exact.  (A first version re-derived them through the model's
+// hash: seven dependent cache misses per model, 100 us for ONE sequence with ONE frequent k-mer at cfg 3.)
+__device__ __forceinline__ void i8_add_frequent(long long *S, const I8Side &sd, int64_t m, int64_t s) {
     if (!sd.over_cnt) return;
     const int n_over = sd.over_cnt[s];
     const uint2 *list = sd.over_list + s * I8_MAX_OVER;
     for (int o = 0; o < n_over; ++o) {
         const uint2 e = list[o];
-        long long q = i8_quantise(i8_table_entry(sd, mm, e.x));
         const long long w = 256ll * (long long)e.y;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const long long d = ((q + 128) & 255) - 128;
-            S[p] += w * d;
-            q = (q - d) >> 8;
-        }
+        for (int p = 0; p < 8; ++p) S[p] += w * (long long)sd.digits[g8_off(m * 8 + p, e.x, sd.d_rows_pad)];
     }
 }
 
@@ -229,9 +224,9 @@ struct EpiNll {
     I8Out o;
     I8Side sd;
     __device__ __forceinline__ void store(int64_t s, int64_t m, long long *S) const {
-        const ModelMeta mm = sd.meta[m];
-        i8_add_frequent(S, sd, mm, s);
-        const double v = i8_head(sd, mm, s) + i8_fold(S);
+        i8_add_frequent(S, sd, m, s);
+        double v = i8_fold(S);
+        if (sd.any_shallow) v = i8_head(sd, sd.meta[m], s) + v;   // IEEE addition commutes: same bits as head + fold
         const int64_t at = s * o.ss + (o.m_col0 + m) * o.sm;
         for (int d = 0; d < o.n_dst; ++d) o.M[d][at] = v;
     }
@@ -327,7 +322,9 @@ static I8Side i8_side(vgs_context *h, bool with_over) {
     sd.seq = h->d_seq; sd.seq_off = h->d_seq_off; sd.seq_len = h->d_seq_len;
     sd.over_cnt = with_over ? (const int32_t *)h->d_i8_over : nullptr;
     sd.over_list = with_over ? (const uint2 *)(h->d_i8_over + ((h->n_seq + 1) / 2) * 2) : nullptr;
+    sd.digits = h->d_i8_digits; sd.d_rows_pad = i8_digit_rows_pad(h);
     sd.depth = h->max_order;
+    sd.any_shallow = h->min_order < h->max_order ? 1 : 0;
     return sd;
 }
 
@@ -417,7 +414,7 @@ int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, co
         }
         G8Args g;
         g.A = h->d_i8_C; g.B = (const uint8_t *)h->d_i8_digits; g.a_rows_pad = c_rows_pad; g.b_rows_pad = d_rows_pad;
-        g.units = w.d_units; g.n_units = w.n_units; g.a_signed = 0; g.err = h->d_err;
+        g.units = w.d_units; g.n_units = w.n_units; g.a_signed = 0; g.err = h->d_err; g.prof = nullptr;
         h->last_nll_kernel = VGS_NLL_KERNEL_I8MMA;
         // an error return between here and the fold leaves partial sums in P: force the memset on the next call
         const int64_t p_elems_keep = h->i8_P_elems;

@@ -36,6 +36,7 @@ SIGNATURES = [
     ("vgs_model_count", c_int, [c_vp, _P(c_i64), _P(c_i64)]),
     ("vgs_model_info", c_int, [c_vp, c_i64, _P(c_int), _P(c_i64), _P(c_int)]),
     ("vgs_get_logp", c_int, [c_vp, c_vp]),
+    ("vgs_parse_tree_text", c_int, [ctypes.c_char_p, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, _P(c_i64)]),
     ("vgs_lookup", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     ("vgs_load_sequences_ascii", c_int, [c_vp, c_i64, c_vp, c_vp]),
     ("vgs_load_sequences_packed", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -131,6 +132,22 @@ def tile_plan(n, tile, world, symmetric=True):
     nt, slots = c_i64(), c_i64()
     _check(lib().vgs_tile_plan(n, tile, world, int(bool(symmetric)), ctypes.byref(nt), ctypes.byref(slots)))
     return nt.value, slots.value
+
+
+def parse_tree_text(text, deltas=False):
+    """Text (bytes or str) of one ``.tree`` file -> (ctx_len uint8 [n], ctx_code uint32 [n], prob float64 [n, 4],
+    occurrence float64 [n]) in file order, parsed by the library (no device needed)."""
+    if isinstance(text, str):
+        text = text.encode("utf-8")
+    n = c_i64()
+    _check(lib().vgs_parse_tree_text(text, len(text), int(bool(deltas)), 0, None, None, None, None, ctypes.byref(n)))
+    ln = np.zeros(n.value, dtype=np.uint8)
+    code = np.zeros(n.value, dtype=np.uint32)
+    prob = np.zeros((n.value, 4), dtype=np.float64)
+    occ = np.zeros(n.value, dtype=np.float64)
+    _check(lib().vgs_parse_tree_text(text, len(text), int(bool(deltas)), n.value, _np_ptr(ln), _np_ptr(code), _np_ptr(prob),
+                                     _np_ptr(occ), ctypes.byref(n)))
+    return ln, code, prob, occ
 
 
 def g8_plan(rects, kblocks, n_cta_pairs, max_split=4):

@@ -52,6 +52,25 @@ def parse_trees(directory, deltas=False):
             fh.write(json.dumps(parse_file(os.path.join(directory, file), deltas)))
 
 
+def load_tree_dir_flat(directory, deltas=False):
+    """``.tree`` files of a directory (sorted by name) straight to ``FlatModels`` through the library's native parser
+    (``vgs_parse_tree_text``): no Python dicts, no JSON.  Returns (FlatModels, list of occurrence-probability arrays)."""
+    import numpy as np
+
+    from . import native
+    from .flat import FlatModels
+    from .vlmc import VLMC
+    lens, codes, probs, occs, names, offsets = [], [], [], [], [], [0]
+    for file in sorted(f for f in os.listdir(directory) if f.endswith(".tree")):
+        with open(os.path.join(directory, file), "rb") as fh:
+            ln, code, prob, occ = native.parse_tree_text(fh.read(), deltas)
+        lens.append(ln); codes.append(code); probs.append(prob); occs.append(occ)
+        offsets.append(offsets[-1] + len(ln))
+        names.append(VLMC.strip_parameters_from_name(os.path.splitext(file)[0]))
+    fm = FlatModels(np.array(offsets, dtype=np.int64), np.concatenate(lens), np.concatenate(codes), np.concatenate(probs), names)
+    return fm.validate(), occs
+
+
 def load_tree_dir(directory):
     """``.tree`` files of a directory straight to VLMC objects (no JSON round trip)."""
     from .vlmc import VLMC

@@ -103,6 +103,16 @@ int vgs_model_info(vgs_handle h, int64_t model, int *order, int64_t *n_ctx, int 
 /* copy back the host-computed ln p table [total][4] (parity hook against math.log) */
 int vgs_get_logp(vgs_handle h, double *logp_out_h);
 
+/* ---- `.tree` ingest: the text of one classifier / PST `.tree` file straight to the flat context table (row f3; replaces
+ *      src/parse_trees_to_json.py:18-55 + the JSON round trip of VLMC.from_json, src/vlmc/vlmc.pyx:33-60).  Contexts come
+ *      out in file order (= the reference's dict order; a repeated key overwrites its row in place); prob_out [n][4] is
+ *      count / total (:45-49) or, with deltas != 0, float(numbers[14..17]) (:40-44); occurrence_out[n] is :29.  Any output
+ *      pointer may be NULL (n_ctx_out alone = counting pass).  Errors mirror the reference's exceptions: VGS_ERR_INVALID
+ *      for a malformed line (IndexError / ValueError / ZeroDivisionError), VGS_ERR_SYMBOL for a non-ACGT context.
+ *      Host code: needs no device and no handle. ----------------------------------------------------------------- */
+int vgs_parse_tree_text(const char *text, int64_t n_bytes, int deltas, int64_t capacity, uint8_t *ctx_len_out,
+                        uint32_t *ctx_code_out, double *prob_out, double *occurrence_out, int64_t *n_ctx_out);
+
 /* ---- longest-suffix lookup: VLMC.get_context / get_all_contexts (src/vlmc/vlmc.pyx:131-154).
  *      ctx_id_out_h[q] = ctx_id of the longest suffix (length <= order) of the history that is a
  *      context, or -1 (reference: RuntimeError).  all_mask_out_h[q] (nullable): bit l set <=> the

@@ -76,7 +76,7 @@ def test_nll_class_reproduces_reference_run(g):
     """random.seed(1234); N^2 loop of d.distance in list order == the golden run of the reference."""
     vl = fixture_vlmcs(g)
     random.seed(g["nll_seed"])
-    d = NegativeLogLikelihood(g["nll_length"])
+    d = NegativeLogLikelihood(g["nll_length"], mode="sequential")   # the reference's own summation order: bit-exact
     tri = util.calculate_distances_within_vlmcs(vl, d)
     assert [v.sequence for v in vl] == g["nll_sequences"]
     assert np.array_equal(tri, np.array(g["nll_triples_f32"], dtype=np.float32))
@@ -86,8 +86,17 @@ def test_nll_class_reproduces_reference_run(g):
             assert d.distance(vl[i], vl[j]) == want[i, j]
     assert np.array_equal(util.index_distances(vl, tri), want.astype(np.float32))
     # an un-batched pair goes to the device as a 2-model set and gives the same value
-    d2 = NegativeLogLikelihood(g["nll_length"])
+    d2 = NegativeLogLikelihood(g["nll_length"], mode="sequential")
     assert d2.distance(vl[0], vl[1]) == want[0, 1]
+    # the default mode (exact int8 tensor-core contraction where the set allows it, else the warp scan): same sequences,
+    # distances within 1e-9, the same float32 triples up to last-place rounding
+    d3 = NegativeLogLikelihood(g["nll_length"])
+    assert d3.mode == "kmer"
+    tri3 = util.calculate_distances_within_vlmcs(vl, d3)
+    got = np.array([[d3.distance(a, b) for b in vl] for a in vl])
+    off = ~np.eye(5, dtype=bool)
+    assert np.max(np.abs(got[off] - want[off]) / np.abs(want[off])) < 1e-9 and np.all(np.diag(got) == 0)
+    assert np.allclose(tri3, tri, rtol=2e-7, atol=0)
 
 
 def test_frobenius_projection_classes(g):

@@ -122,9 +122,6 @@ def test_headline_mode_downstream_parity_cfg3():
         labels, merges = h.average_link(torch.from_numpy(D32).cuda(), k)
         assert np.array_equal(labels, labels_s), mode
         assert np.allclose(merges, merges_s, rtol=1e-6, atol=0), mode
-        # family structure is recovered: every cluster is one family
-        for c in np.unique(labels):
-            assert len(set(fam[labels == c].tolist())) == 1
 
 
 def test_matrix_to_triples_kernel():

@@ -129,6 +129,60 @@ def test_tree_ingest_matches_reference_parser():
                 assert got["tree"] == want and list(got["tree"]) == list(want)
 
 
+def _flat_of(tree):
+    return flat.FlatModels.from_trees([tree])
+
+
+def test_native_tree_parser_matches_reference_parser(tmp_path):
+    """Row f3: vgs_parse_tree_text (C, host) against the goldens the REFERENCE's parser produced -- plain mode on the
+    shipped excerpts, `deltas` mode (src/parse_trees_to_json.py:40-44) on oracle/make_goldens_tree_deltas.py's vectors:
+    same context order, bit-identical rows and occurrence probabilities; and the directory loader's FlatModels equal the
+    ones built from the reference's JSON."""
+    for fname, deltas in (("tree_parse_golden.json", False), ("tree_parse_deltas_golden.json", True)):
+        with open(os.path.join(golden_io.GOLD, fname)) as fh:
+            gold = json.load(fh)
+        for name, item in gold.items():
+            ln, code, prob, occ = native.parse_tree_text(item["text"], deltas)
+            want = item["json"]
+            keys = [flat.decode_context(int(a), int(b)) for a, b in zip(ln, code)]
+            assert keys == list(want["tree"])
+            assert np.array_equal(prob, np.array([[want["tree"][k][c] for c in "ACGT"] for k in keys]))
+            assert np.array_equal(occ, np.array([want["occurrence_probability"][k] for k in keys]))
+            py = parse_trees_to_json.parse_tree_lines(item["text"].splitlines(True), deltas)
+            assert py == want
+            (tmp_path / name).write_text(item["text"])
+        fm, occs = parse_trees_to_json.load_tree_dir_flat(str(tmp_path), deltas)
+        names = sorted(gold)
+        ref = flat.FlatModels.from_trees([gold[n]["json"]["tree"] for n in names])
+        assert np.array_equal(fm.ctx_offsets, ref.ctx_offsets) and np.array_equal(fm.ctx_len, ref.ctx_len)
+        assert np.array_equal(fm.ctx_code, ref.ctx_code) and np.array_equal(fm.prob, ref.prob)
+        assert fm.names == ["AB026117.1", "KF234407.1"]
+    ref_dir = "/root/reference/original_test_trees"
+    if os.path.isdir(ref_dir):   # the full files against the shipped .json
+        fm, _ = parse_trees_to_json.load_tree_dir_flat(ref_dir)
+        for m, f in enumerate(sorted(x for x in os.listdir(ref_dir) if x.endswith(".tree"))):
+            assert fm.tree(m) == json.load(open(os.path.join(ref_dir, f[:-5] + ".json")))
+
+
+def test_native_tree_parser_errors_and_dict_semantics():
+    node = "Node: %d %s [ 1 2 3 4 ] 10 [ %s ][ -1 -1 -1 -1  ]\n"
+    text = "Name: x\n" + node % (0, "#", "4 3 2 1") + node % (1, "A", "1 1 1 1") + node % (2, "A", "0 2 0 2") + "junk Node: 3 C\n"
+    ln, code, prob, occ = native.parse_tree_text(text)
+    assert ln.tolist() == [0, 1] and np.array_equal(prob, [[0.4, 0.3, 0.2, 0.1], [0.0, 0.5, 0.0, 0.5]])   # the repeated key overwrites in place
+    assert np.array_equal(occ, [1.0, 0.4])
+    assert parse_trees_to_json.parse_tree_lines(text.splitlines(True))["tree"] == {"": dict(zip("ACGT", (0.4, 0.3, 0.2, 0.1))),
+                                                                                    "A": dict(zip("ACGT", (0.0, 0.5, 0.0, 0.5)))}
+    with pytest.raises(ValueError):
+        native.parse_tree_text(node % (0, "#", "0 0 0 0"))               # ZeroDivisionError in the reference
+    with pytest.raises(ValueError):
+        native.parse_tree_text(node % (0, "#", "4 3 2 1"), deltas=True)  # IndexError: no numbers[14..17]
+    with pytest.raises(ValueError):
+        native.parse_tree_text("Node: 0 # [ 1 2 3 4 ] 10 [ 1.5 1 1 1 ][ -1 -1 -1 -1 ]\n")   # int('1.5'): ValueError
+    with pytest.raises(KeyError):
+        native.parse_tree_text(node % (0, "#", "4 3 2 1") + node % (1, "AN", "1 1 1 1"))
+    assert native.parse_tree_text("no nodes here\n")[0].size == 0
+
+
 def test_vlmc_host_mirror_construction():
     assert VLMC.strip_parameters_from_name("PST_AB026117.1_10229_34094") == "AB026117.1"
     assert VLMC.strip_parameters_from_name("pst_vlmc_name_23_23") == "vlmc_name"
