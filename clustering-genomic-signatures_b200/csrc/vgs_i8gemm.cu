@@ -11,27 +11,45 @@ static int64_t g8_count(const std::vector<G8Rect> &rects, int N) {
     return t;
 }
 
+// widest tile a rectangle list gives when cut into pieces of at most N rows, and the number of pieces
+static void g8_shape(const std::vector<G8Rect> &rects, int N, int64_t *count, int *widest) {
+    *count = 0;
+    *widest = 0;
+    for (const G8Rect &r : rects) {
+        const int n_t = (r.b_rows + N - 1) / N, quanta = r.b_rows / 32;
+        *count += n_t;
+        *widest = std::max(*widest, 32 * ((quanta + n_t - 1) / n_t));
+    }
+}
+
 int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters, int max_split, std::vector<G8Unit> *out) {
     out->clear();
     if (rects.empty() || kblocks <= 0) return 1;
     if (n_clusters < 1) n_clusters = 1;
-    int N = G8_MAX_N, split = 1;
-    const int64_t wide = g8_count(rects, G8_MAX_N);
+    int N = G8_UNIT_MAX_N, split = 1;
     static int force_n = -1;   // tuning knob: VGS_G8_FORCE_N = tile width
     if (force_n < 0) { const char *e = getenv("VGS_G8_FORCE_N"); force_n = e ? atoi(e) / 32 * 32 : 0; }
-    if (force_n >= 32 && force_n <= G8_MAX_N) {
+    if (force_n >= 32 && force_n <= G8_UNIT_MAX_N) {
         N = force_n;
-    } else if (wide >= n_clusters) {
-        // enough tiles: the smallest width that still fits the same number of waves -> (almost) every CTA pair gets the
-        // same number of tiles, each a little narrower than 256
-        const int64_t waves = (wide + n_clusters - 1) / n_clusters;
-        for (int cand = 32; cand <= G8_MAX_N; cand += 32)
-            if (g8_count(rects, cand) <= waves * n_clusters) { N = cand; break; }
     } else {
-        // fewer 256-wide tiles than CTA pairs (small sets, one GPU's share of a sharded job): keep the tiles wide (operand
-        // bytes per MAC) and cut the k range instead; the parts are added with integer atomics -- exact, order independent
-        split = (int)std::min<int64_t>(std::min<int64_t>(max_split, n_clusters / std::max<int64_t>(1, wide)), std::max(1, kblocks / 8));
-        if (split < 1) split = 1;
+        // Pick the tile width and the k-split by a small cost model of the kernel (cycles per CTA pair), measured on cfg 3:
+        // a k-block of a w-wide unit costs max(MMA time 2 w, operand delivery 1.73 (256 + w)) + barrier overhead; a unit
+        // adds its epilogue (~30 cycles per column with eight warps); a k-split adds the fold kernel and the atomics.
+        // Fewer, wider tiles move fewer operand bytes; more units fill the CTA pairs evenly -- the model arbitrates.
+        double best = 1e300;
+        for (int cand = 32; cand <= G8_UNIT_MAX_N; cand += 32) {
+            int64_t count;
+            int w;
+            g8_shape(rects, cand, &count, &w);
+            for (int sp = 1; sp <= max_split; ++sp) {
+                if (sp > 1 && kblocks / sp < 8) break;
+                const int64_t units = count * sp, waves = (units + n_clusters - 1) / n_clusters;
+                const int kb_per = (kblocks + sp - 1) / sp;
+                const double t_kb = std::max(2.0 * w, 1.73 * (256 + w)) + 60.0;
+                const double t = (double)waves * (kb_per * t_kb + 30.0 * w + 2500.0) + (sp > 1 ? 12000.0 + 8.0 * w : 0.0);
+                if (t < best * 0.999 || (t < best * 1.001 && cand > N)) { best = t; N = cand; split = sp; }
+            }
+        }
     }
     for (const G8Rect &r : rects) {
         const int n_t = (r.b_rows + N - 1) / N;

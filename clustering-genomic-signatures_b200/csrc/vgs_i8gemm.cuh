@@ -16,15 +16,15 @@
 // copy (TMA, SASS UBLKCP) drops into a 1024-byte aligned stage buffer -- no tensor maps, no layout work in the kernel,
 // and the tile width N can be chosen per launch (multiples of 32) so that the tile count divides the CTA pairs evenly.
 //
-// Kernel: one CTA pair (cluster of 2) per SM pair, persistent over a static list of units (tile x k range); 192 threads:
+// Kernel: one CTA pair (cluster of 2) per SM pair, persistent over a static list of units (tile x k range); 576 threads:
 //   warp 0   producer: per stage one expect_tx + two bulk copies (its 128 A rows, its half of the B rows)
 //   warp 1   leader CTA: the one thread that issues every tcgen05.mma of the pair and commits them to the stage's
 //            "empty" barriers of BOTH CTAs (multicast commit); peer CTA: relays "my half of the stage has landed" to
 //            the leader's "full" barrier (relaxed remote mbarrier arrive: the 1-D bulk copy can only signal a barrier
 //            of the CTA it writes to)
-//   warps 2-5 epilogue: tcgen05.ld of their 32 TMEM lanes, 32 columns at a time, handed to the caller's functor.  The
-//            accumulator is double buffered (2 x 256 of the 512 TMEM columns), so the MMAs of unit t+1 run while unit t
-//            is folded and stored.
+//   warps 2-17 epilogue: tcgen05.ld of their 32 TMEM lanes, 32 columns at a time, handed to the caller's functor (four
+//            warps per lane quadrant take every fourth chunk).  A unit is up to 512 columns wide = both halves of tensor
+//            memory, fed by one A tile (see the kernel's comment).
 #pragma once
 #include <stdio.h>
 #include <stdlib.h>
@@ -32,12 +32,15 @@
 #include "vgs_common.cuh"
 
 #define G8_BK 128                 // k per pipeline stage = bytes per operand row per stage = one swizzle atom
-#define G8_STAGES 7                // 7 x 32 KB = 224 KB of the 227 KB a CTA can have
-#define G8_THREADS 192
+#define G8_STAGES 4               // 4 x 48 KB = 192 KB of the 227 KB a CTA can have
+#define G8_EPI_WARPS 16           // four per TMEM lane quadrant
+#define G8_THREADS (32 * (2 + G8_EPI_WARPS))
 #define G8_A_ROWS 128             // A rows per CTA (256 per pair)
-#define G8_MAX_N 256              // B rows per unit (128 per CTA)
+#define G8_MAX_N 256              // B rows per MMA / accumulator (128 per CTA)
+#define G8_UNIT_MAX_N 512         // B rows per unit: two accumulators
 #define G8_A_BYTES (G8_A_ROWS * G8_BK)
-#define G8_STAGE_BYTES (G8_A_BYTES + (G8_MAX_N / 2) * G8_BK)   // 32 KB
+#define G8_B_BYTES ((G8_MAX_N / 2) * G8_BK)                    // one accumulator's B half-tile per stage and CTA
+#define G8_STAGE_BYTES (G8_A_BYTES + 2 * G8_B_BYTES)           // 48 KB
 #define G8_SMEM_BYTES (G8_STAGES * G8_STAGE_BYTES)
 #define G8_TMEM_COLS 512
 #define G8_WATCHDOG_CYCLES (1ll << 32)   // ~2 s: a lost barrier signal traps instead of hanging the GPU
@@ -45,7 +48,7 @@
 struct G8Unit {
     int32_t a_blk;    // 256-row block of A
     int32_t b_row0;   // first B row, multiple of 8 (16 for the peer's half to stay 8-aligned: n / 2 is a multiple of 16)
-    int32_t n;        // B rows of this unit: multiple of 32, <= 256
+    int32_t n;        // B rows of this unit: multiple of 32, <= 512 (above 256: two accumulators, see g8_first_half)
     int32_t kb0, kbn; // k range in 128-blocks
     int32_t partial;  // != 0: this unit covers part of the k range (the functor accumulates atomically)
 };
@@ -62,6 +65,8 @@ struct G8Args {
     long long *prof;                  // optional [n_clusters][8] cycle counters of the leader CTA (VGS_G8_PROF=1), else nullptr
 };
 
+// a unit wider than 256 B rows is computed as two MMAs per k-slice: the first g8_first_half(n) rows, then the rest
+__host__ __device__ __forceinline__ int g8_first_half(int n) { return n <= 256 ? n : ((n / 2 + 31) / 32) * 32; }
 __host__ __device__ __forceinline__ int64_t g8_off(int64_t row, int64_t k, int64_t rows_pad) {
     return (((k >> 7) * rows_pad + row) << 7) + ((((k >> 4) & 7) ^ (row & 7)) << 4) + (k & 15);
 }
@@ -95,6 +100,11 @@ __device__ __forceinline__ uint64_t g8_smem_desc(uint32_t smem_addr) {
 // bit), B signed (1 at bit 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 __device__ __forceinline__ uint32_t g8_idesc(int m, int n, int a_signed) {
     return (2u << 4) | ((uint32_t)(a_signed ? 1 : 0) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t g8_desc_join(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
 }
 __device__ __forceinline__ void g8_mma2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -210,11 +220,21 @@ __device__ __forceinline__ void g8_tmem_ld32(uint32_t taddr, int32_t (&v)[32]) {
 // ---- the kernel ---------------------------------------------------------------------------------------------
 // Epi: struct with   __device__ void operator()(const G8Unit &u, int64_t a_row, int col0, const int32_t (&v)[32]) const
 //                    __device__ void unit_done() const      (after a thread's last chunk of a unit)
-// operator() is called once per thread (= A row a_row) and 32-column chunk col0 (columns col0 .. col0 + 31 = B rows u.b_row0 + col0 ...)
+//                    __device__ void prefetch(const G8Unit &u, int64_t a_row, int col0) const   (whole warp, before the unit's
+//                                         accumulator is ready: warm the lines the chunk's operator() will read)
+// operator() is called once per thread (= A row a_row) and 32-column chunk: columns col0 .. col0 + 31 of the unit = B rows
+// u.b_row0 + col0 ...
+//
+// A unit is up to 512 B rows wide: two accumulators (TMEM columns 0.. and 256..) fed by the SAME A tile, i.e. a 256 x 512
+// output tile per CTA pair.  The kernel is bound by what L2 can deliver to the SMs (measured: time per k-block follows the
+// operand bytes per k-block, ~37 B/clk/SM, whatever the pipeline depth), so the tile is made as large as tensor memory
+// allows: (256 + n) / (256 n) operand bytes per MAC, 0.0059 at n = 512 against 0.0078 at n = 256.  The price: both
+// accumulators are busy until the unit's epilogue has run, so the epilogue is not overlapped with the next unit's MMAs;
+// it is spread over sixteen warps (four per TMEM lane quadrant) to keep it short.
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_gemm(const G8Args g, const Epi epi) {
     extern __shared__ __align__(1024) uint8_t g8_smem[];
-    __shared__ __align__(8) uint64_t full[G8_STAGES], empty[G8_STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ __align__(8) uint64_t full[G8_STAGES], empty[G8_STAGES], tmem_full, tmem_empty;
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = g8_cta_rank();
@@ -222,11 +242,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
     const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const uint32_t smem0 = vgs_smem_addr(g8_smem);
     const int NS = g.stages;
-    if (g.prof && tid == 0 && leader) {
-        unsigned long long ns;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-        g.prof[(gridDim.x >> 1) * 8 + (blockIdx.x >> 1) * 4 + 0] = (long long)ns;
-    }
+    unsigned long long ns_entry = 0;
+    if (g.prof && tid == 0 && leader) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_entry));
     if (smem0 & 1023u) __trap();   // SWIZZLE_128B operand tiles need 1024-byte aligned stage buffers
 
     if (tid == 0) {
@@ -235,10 +252,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
             vgs_mbar_init(&full[i], leader ? 2 : 1);
             vgs_mbar_init(&empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            vgs_mbar_init(&tmem_full[i], 1);
-            vgs_mbar_init(&tmem_empty[i], 8);   // four epilogue warps in each CTA of the pair
-        }
+        vgs_mbar_init(&tmem_full, 1);
+        vgs_mbar_init(&tmem_empty, 2 * G8_EPI_WARPS);   // the epilogue warps of both CTAs of the pair
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(vgs_smem_addr(&tmem_base_slot)),
@@ -255,24 +270,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
     if (warp == 0) {
         // ===== producer =====
         if (lane == 0) {
-            int64_t gs = 0;   // stage use counter
+            int st = 0;            // pipeline stage and the parity of its current use (counters, no divisions: this thread
+            uint32_t ph = 0;       // and the MMA issuer are the kernel's critical path)
             long long t_wait = 0;
             const long long t_begin = clock64();
             for (int ui = cluster; ui < g.n_units; ui += n_clusters) {
                 const G8Unit u = g.units[ui];
-                const uint32_t b_bytes = (uint32_t)(u.n >> 1) * G8_BK;
+                if (u.n == 0) continue;
+                const int n0 = g8_first_half(u.n), n1 = u.n - n0;
+                const uint32_t b0_bytes = (uint32_t)(n0 >> 1) * G8_BK, b1_bytes = (uint32_t)(n1 >> 1) * G8_BK;
                 const uint8_t *a_src = g.A + (((int64_t)u.kb0 * g.a_rows_pad + (int64_t)u.a_blk * 256 + rank * G8_A_ROWS) << 7);
-                const uint8_t *b_src = g.B + (((int64_t)u.kb0 * g.b_rows_pad + u.b_row0 + rank * (u.n >> 1)) << 7);
+                const uint8_t *b0_src = g.B + (((int64_t)u.kb0 * g.b_rows_pad + u.b_row0 + rank * (n0 >> 1)) << 7);
+                const uint8_t *b1_src = g.B + (((int64_t)u.kb0 * g.b_rows_pad + u.b_row0 + n0 + rank * (n1 >> 1)) << 7);
                 const int64_t a_step = g.a_rows_pad << 7, b_step = g.b_rows_pad << 7;
-                for (int kb = 0; kb < u.kbn; ++kb, ++gs) {
-                    const int st = (int)(gs % NS);
+                for (int kb = 0; kb < u.kbn; ++kb) {
                     const long long t0 = g.prof ? clock64() : 0;
-                    g8_wait(&empty[st], (uint32_t)(((gs / NS) & 1) ^ 1), g.err);
+                    g8_wait(&empty[st], ph ^ 1u, g.err);
                     if (g.prof) t_wait += clock64() - t0;
                     uint8_t *dst = g8_smem + (size_t)st * G8_STAGE_BYTES;
-                    vgs_mbar_expect_tx(&full[st], G8_A_BYTES + b_bytes);
+                    vgs_mbar_expect_tx(&full[st], G8_A_BYTES + b0_bytes + b1_bytes);
                     vgs_bulk_g2s(dst, a_src + kb * a_step, G8_A_BYTES, &full[st]);
-                    vgs_bulk_g2s(dst + G8_A_BYTES, b_src + kb * b_step, b_bytes, &full[st]);
+                    vgs_bulk_g2s(dst + G8_A_BYTES, b0_src + kb * b_step, b0_bytes, &full[st]);
+                    if (n1) vgs_bulk_g2s(dst + G8_A_BYTES + G8_B_BYTES, b1_src + kb * b_step, b1_bytes, &full[st]);
+                    if (++st == NS) { st = 0; ph ^= 1u; }
                 }
             }
             if (g.prof && leader) {
@@ -282,104 +302,100 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            int64_t gs = 0;
+            int st = 0;
+            uint32_t ph = 0;
             if (leader) {
                 // ===== MMA issuer =====
                 int it = 0;
                 long long t_full = 0, t_tmem = 0, t_issue = 0;
+                const uint32_t desc_lo0 = ((smem0 >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1 (bit 46), SWIZZLE_128B (bit 61)
                 const long long t_begin = clock64();
                 unsigned long long ns_begin = 0;
-                if (g.prof) {
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
-                    g.prof[n_clusters * 8 + cluster * 4 + 1] = (long long)ns_begin;
-                }
-                for (int ui = cluster; ui < g.n_units; ui += n_clusters, ++it) {
+                if (g.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+                for (int ui = cluster; ui < g.n_units; ui += n_clusters) {
                     const G8Unit u = g.units[ui];
                     if (u.n == 0) continue;   // padding of the dealt unit list (every role skips it the same way)
-                    const int acc = it & 1;
+                    const int n0 = g8_first_half(u.n), n1 = u.n - n0;
                     long long t0 = g.prof ? clock64() : 0;
-                    g8_wait_cluster(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1), g.err);   // epilogues of both CTAs have drained it
+                    g8_wait_cluster(&tmem_empty, (uint32_t)((it & 1) ^ 1), g.err);   // the previous unit's epilogues (both CTAs) are done
                     if (g.prof) t_tmem += clock64() - t0;
                     g8_fence_after();
-                    const uint32_t idesc = g8_idesc(256, u.n, g.a_signed);
-                    const uint32_t d_addr = tmem_base + (uint32_t)(acc * G8_MAX_N);
-                    for (int kb = 0; kb < u.kbn; ++kb, ++gs) {
-                        const int st = (int)(gs % NS);
-                        const uint32_t ph = (uint32_t)((gs / NS) & 1);
+                    const uint32_t idesc0 = g8_idesc(256, n0, g.a_signed), idesc1 = g8_idesc(256, n1 ? n1 : 32, g.a_signed);
+                    for (int kb = 0; kb < u.kbn; ++kb) {
                         if (g.prof) t0 = clock64();
                         g8_wait(&full[st], ph, g.err);   // both halves of the stage have landed
                         if (g.prof) { const long long t1 = clock64(); t_full += t1 - t0; t0 = t1; }
                         g8_fence_after();
-                        const uint32_t sa = smem0 + (uint32_t)st * G8_STAGE_BYTES;
+                        // descriptors: constant high word, low word = (address >> 4) | leading-byte-offset field
+                        const uint32_t a_lo = desc_lo0 + (uint32_t)st * (G8_STAGE_BYTES >> 4);
 #pragma unroll
-                        for (int j = 0; j < G8_BK / 32; ++j)
-                            g8_mma2(d_addr, g8_smem_desc(sa + 32u * j), g8_smem_desc(sa + G8_A_BYTES + 32u * j), idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        for (int j = 0; j < G8_BK / 32; ++j) {
+                            const uint64_t da = g8_desc_join(a_lo + 2u * j, desc_hi);
+                            const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+                            g8_mma2(tmem_base, da, g8_desc_join(a_lo + (G8_A_BYTES >> 4) + 2u * j, desc_hi), idesc0, acc);
+                            if (n1) g8_mma2(tmem_base + G8_MAX_N, da, g8_desc_join(a_lo + ((G8_A_BYTES + G8_B_BYTES) >> 4) + 2u * j, desc_hi), idesc1, acc);
+                        }
                         g8_commit2(&empty[st]);
+                        if (++st == NS) { st = 0; ph ^= 1u; }
                         if (g.prof) t_issue += clock64() - t0;
                     }
-                    g8_commit2(&tmem_full[acc]);
+                    g8_commit2(&tmem_full);
+                    ++it;
                 }
                 if (g.prof) {
                     long long *o = g.prof + cluster * 8;
                     unsigned long long ns_end;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
-                    o[0] = t_full; o[1] = (long long)(ns_end - ns_begin); o[2] = t_tmem;
-                    g.prof[n_clusters * 8 + cluster * 4 + 2] = (long long)ns_end; o[3] = t_issue; o[4] = clock64() - t_begin;
+                    o[0] = t_full; o[1] = (long long)(ns_end - ns_begin); o[2] = t_tmem; o[3] = t_issue; o[4] = clock64() - t_begin;
+                    g.prof[n_clusters * 8 + cluster * 4 + 1] = (long long)ns_begin;
+                    g.prof[n_clusters * 8 + cluster * 4 + 2] = (long long)ns_end;
                 }
             } else {
-                // ===== forwarder: my half of the stage has landed =====
+                // ===== relay: my half of the stage has landed =====
                 for (int ui = cluster; ui < g.n_units; ui += n_clusters) {
-                    const int kbn = g.units[ui].kbn;
-                    for (int kb = 0; kb < kbn; ++kb, ++gs) {
-                        const int st = (int)(gs % NS);
-                        g8_wait(&full[st], (uint32_t)((gs / NS) & 1), g.err);
+                    const G8Unit u = g.units[ui];
+                    if (u.n == 0) continue;
+                    for (int kb = 0; kb < u.kbn; ++kb) {
+                        g8_wait(&full[st], ph, g.err);
                         g8_remote_arrive_relaxed(&full[st], 0);
+                        if (++st == NS) { st = 0; ph ^= 1u; }
                     }
                 }
             }
         }
     } else {
-        // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31 =====
-        const int quad = warp & 3;
+        // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31; the two warps of a quadrant take alternate chunks =====
+        const int quad = warp & 3, part = (warp - 2) >> 2;   // G8_EPI_WARPS / 4 warps share a quadrant: chunk i goes to warp i % that
         int it = 0;
         long long t_epi = 0;
-        for (int ui = cluster; ui < g.n_units; ui += n_clusters, ++it) {
+        for (int ui = cluster; ui < g.n_units; ui += n_clusters) {
             const G8Unit u = g.units[ui];
             if (u.n == 0) continue;
-            const int acc = it & 1;
-            g8_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1), g.err);
-            const long long t_e0 = g.prof ? clock64() : 0;
-            if (g.prof && lane == 0) {
-                unsigned long long ns;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-                g.prof[n_clusters * 12 + ((cluster * 2 + (int)rank) * 4 + (warp - 2)) * 2] = (long long)ns;
-            }
-            g8_fence_after();
+            const int n0 = g8_first_half(u.n);
             const int64_t a_row = (int64_t)u.a_blk * 256 + rank * G8_A_ROWS + quad * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * G8_MAX_N);
+            // the epilogue warps idle while the unit's MMAs run: let the functor warm whatever its chunks will read
+            for (int c0 = 32 * part; c0 < u.n; c0 += 8 * G8_EPI_WARPS) epi.prefetch(u, a_row, c0);
+            g8_wait(&tmem_full, (uint32_t)(it & 1), g.err);
+            const long long t_e0 = g.prof ? clock64() : 0;
+            g8_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < u.n; c0 += 32) {
+            for (int c0 = 32 * part; c0 < u.n; c0 += 8 * G8_EPI_WARPS) {
                 int32_t v[32];
-                g8_tmem_ld32(taddr + (uint32_t)c0, v);
+                // unit column c0 lives in accumulator 0 (TMEM column c0) or 1 (TMEM column 256 + c0 - n0)
+                g8_tmem_ld32(taddr + (uint32_t)(c0 < n0 ? c0 : G8_MAX_N + c0 - n0), v);
                 if (!(g.debug & 1)) epi(u, a_row, c0, v);
             }
             epi.unit_done();
             g8_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (leader) g8_local_arrive(&tmem_empty[acc]);
-                else g8_remote_arrive(&tmem_empty[acc], 0);
+                if (leader) g8_local_arrive(&tmem_empty);
+                else g8_remote_arrive(&tmem_empty, 0);
             }
-            if (g.prof) {
-                t_epi += clock64() - t_e0;
-                // per epilogue warp of either CTA: [start, end] of its work on this unit (ns), the last unit's values stay
-                unsigned long long ns;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-                if (lane == 0) {
-                    long long *w = g.prof + n_clusters * 12 + ((cluster * 2 + (int)rank) * 4 + (warp - 2)) * 2;
-                    w[1] = (long long)ns;
-                }
-            }
+            if (g.prof) t_epi += clock64() - t_e0;
+            ++it;
         }
         if (g.prof && leader && warp == 2 && lane == 0) g.prof[cluster * 8 + 7] = t_epi;   // epilogue work of one warp
     }
@@ -393,6 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
     if (g.prof && tid == 0 && leader) {
         unsigned long long ns;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        g.prof[n_clusters * 8 + cluster * 4 + 0] = (long long)ns_entry;
         g.prof[n_clusters * 8 + cluster * 4 + 3] = (long long)ns;
     }
 }
@@ -403,28 +420,27 @@ static int g8_launch(vgs_context *h, const G8Args &g, const Epi &epi, cudaStream
     auto kern = k_g8_gemm<Epi>;
     VGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G8_SMEM_BYTES));
     const int n_clusters = std::max(1, std::min(g.n_units, h->sm_count / 2));
-    static int want_prof = -1;
+    static int want_prof = -1, n_stages = -1, dbg = -1;
     if (want_prof < 0) { const char *e = getenv("VGS_G8_PROF"); want_prof = (e && e[0] == '1') ? 1 : 0; }
+    if (n_stages < 0) { const char *e = getenv("VGS_G8_STAGES"); n_stages = e ? std::max(1, std::min(G8_STAGES, atoi(e))) : G8_STAGES; }
+    if (dbg < 0) { const char *e = getenv("VGS_G8_DEBUG"); dbg = e ? atoi(e) : 0; }
     G8Args ga = g;
     ga.prof = nullptr;
-    static int n_stages = -1;
-    if (n_stages < 0) { const char *e = getenv("VGS_G8_STAGES"); n_stages = e ? std::max(1, std::min(G8_STAGES, atoi(e))) : G8_STAGES; }
     ga.stages = n_stages;
-    static int dbg = -1;
-    if (dbg < 0) { const char *e = getenv("VGS_G8_DEBUG"); dbg = e ? atoi(e) : 0; }
     ga.debug = dbg;
     long long *d_prof = nullptr;
     if (want_prof) {
-        if (cudaMalloc((void **)&d_prof, (size_t)n_clusters * 224) == cudaSuccess) {
-            cudaMemsetAsync(d_prof, 0, (size_t)n_clusters * 224, s);
+        if (cudaMalloc((void **)&d_prof, (size_t)n_clusters * 96) == cudaSuccess) {
+            cudaMemsetAsync(d_prof, 0, (size_t)n_clusters * 96, s);
             ga.prof = d_prof;
         }
     }
     kern<<<2 * n_clusters, G8_THREADS, G8_SMEM_BYTES, s>>>(ga, epi);
     VGS_LAUNCH_CHECK(h);
     if (d_prof) {
-        // developer aid: where the leader CTA's main-loop threads spend their cycles (mean over the CTA pairs)
-        std::vector<long long> hp((size_t)n_clusters * 28);
+        // developer aid (VGS_G8_PROF=1): where the leader CTA's main-loop threads spend their cycles, mean (max) over the
+        // CTA pairs, and the kernel's timeline
+        std::vector<long long> hp((size_t)n_clusters * 12);
         cudaStreamSynchronize(s);
         cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost);
         cudaFree(d_prof);
@@ -438,27 +454,19 @@ static int g8_launch(vgs_context *h, const G8Args &g, const Epi &epi, cudaStream
                         "(%.0f), total %.0f (%.0f) = %.1f us at %.0f MHz | producer: wait empty %.0f (%.0f), total %.0f (%.0f) | epilogue warp %.0f (%.0f)\n",
                 g.n_units, n_clusters, m[0], mx[0], m[2], mx[2], m[3], mx[3], m[4], mx[4], m[1] / 1e3, m[1] > 0 ? m[4] / m[1] * 1e3 : 0.0, m[5], mx[5],
                 m[6], mx[6], m[7], mx[7]);
-        {
-            const long long *ts = hp.data() + (size_t)n_clusters * 8;
-            long long e0 = ts[0], e1 = ts[0], l0 = ts[1], l1 = ts[1], f0 = ts[2], f1 = ts[2], x0 = ts[3], x1 = ts[3];
-            for (int c = 0; c < n_clusters; ++c) {
-                e0 = std::min(e0, ts[4 * c]); e1 = std::max(e1, ts[4 * c]);
-                l0 = std::min(l0, ts[4 * c + 1]); l1 = std::max(l1, ts[4 * c + 1]);
-                f0 = std::min(f0, ts[4 * c + 2]); f1 = std::max(f1, ts[4 * c + 2]);
-                x0 = std::min(x0, ts[4 * c + 3]); x1 = std::max(x1, ts[4 * c + 3]);
-            }
-            fprintf(stderr, "[g8 prof] timeline (us after the first CTA entered): entry ..%.1f | main loop starts %.1f..%.1f | main loop ends %.1f..%.1f | "
-                            "exit %.1f..%.1f\n", (e1 - e0) / 1e3, (l0 - e0) / 1e3, (l1 - e0) / 1e3, (f0 - e0) / 1e3, (f1 - e0) / 1e3, (x0 - e0) / 1e3, (x1 - e0) / 1e3);
-            const long long *ew = hp.data() + (size_t)n_clusters * 12;
-            for (int c = 0; c < n_clusters; ++c) {
-                bool slow = false;
-                for (int k = 0; k < 8; ++k) slow = slow || (ew[(c * 8 + k) * 2 + 1] - ew[(c * 8 + k) * 2] > 30000);
-                if (!slow && c % 24) continue;
-                fprintf(stderr, "[g8 prof] pair %d last-unit epilogue [start,end] us:", c);
-                for (int k = 0; k < 8; ++k) fprintf(stderr, " %s%d [%.1f,%.1f]", k < 4 ? "L" : "P", k & 3, (ew[(c * 8 + k) * 2] - e0) / 1e3, (ew[(c * 8 + k) * 2 + 1] - e0) / 1e3);
-                fprintf(stderr, " | loop end %.1f exit %.1f\n", (ts[4 * c + 2] - e0) / 1e3, (ts[4 * c + 3] - e0) / 1e3);
-            }
+        const long long *ts = hp.data() + (size_t)n_clusters * 8;
+        long long e0 = ts[0], e1 = ts[0], l0 = ts[1], l1 = ts[1], f0 = ts[2], f1 = ts[2], x0 = ts[3], x1 = ts[3];
+        for (int c = 0; c < n_clusters; ++c) {
+            e0 = std::min(e0, ts[4 * c]); e1 = std::max(e1, ts[4 * c]);
+            l0 = std::min(l0, ts[4 * c + 1]); l1 = std::max(l1, ts[4 * c + 1]);
+            f0 = std::min(f0, ts[4 * c + 2]); f1 = std::max(f1, ts[4 * c + 2]);
+            x0 = std::min(x0, ts[4 * c + 3]); x1 = std::max(x1, ts[4 * c + 3]);
         }
+        fprintf(stderr, "[g8 prof] timeline (us after the first CTA entered): entry ..%.1f | main loop starts %.1f..%.1f | main loop ends %.1f..%.1f | "
+                        "exit %.1f..%.1f\n", (e1 - e0) / 1e3, (l0 - e0) / 1e3, (l1 - e0) / 1e3, (f0 - e0) / 1e3, (f1 - e0) / 1e3, (x0 - e0) / 1e3, (x1 - e0) / 1e3);
+        for (int c = 0; c < n_clusters; ++c)
+            if (ts[4 * c + 3] - ts[4 * c + 2] > 10000)
+                fprintf(stderr, "[g8 prof]   pair %d: main loop end %.1f, exit %.1f\n", c, (ts[4 * c + 2] - e0) / 1e3, (ts[4 * c + 3] - e0) / 1e3);
     }
     return VGS_OK;
 }
@@ -470,6 +478,7 @@ struct G8Rect {
     int32_t b_row0, b_rows; // B row range: b_row0 multiple of 32; b_rows multiple of 32
 };
 // Units for `rects` over k blocks [0, kblocks): tile widths are chosen so that the unit count is (close to) a multiple of
-// the CTA pairs, largest first; when the tiles do not fill the machine the k range is cut too (at most `max_split`
-// parts, at least 8 k-blocks each) and the units are marked partial.  Returns the split used.
+// the CTA pairs and as wide as that allows (operand bytes per MAC), largest first; when the tiles do not fill the machine
+// the k range is cut too (at most `max_split` parts, at least 8 k-blocks each) and the units are marked partial.  Returns
+// the split used.
 int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters, int max_split, std::vector<G8Unit> *out);

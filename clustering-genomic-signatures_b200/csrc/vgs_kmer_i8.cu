@@ -60,9 +60,7 @@ struct I8Side {
 // operand (eight independent one-byte loads per k-mer, from lines the tile has just streamed through L2) -- the same
 // integers the tensor cores multiplied, so the sum stays exact.  (A first version re-derived them through the model's
 // hash: seven dependent cache misses per model, 100 us for ONE sequence with ONE frequent k-mer at cfg 3.)
-__device__ __forceinline__ void i8_add_frequent(long long *S, const I8Side &sd, int64_t m, int64_t s) {
-    if (!sd.over_cnt) return;
-    const int n_over = sd.over_cnt[s];
+__device__ __forceinline__ void i8_add_frequent(long long *S, const I8Side &sd, int64_t m, int64_t s, int n_over) {
     const uint2 *list = sd.over_list + s * I8_MAX_OVER;
     for (int o = 0; o < n_over; ++o) {
         const uint2 e = list[o];
@@ -223,34 +221,98 @@ struct I8Out {
 struct EpiNll {
     I8Out o;
     I8Side sd;
-    __device__ __forceinline__ void store(int64_t s, int64_t m, long long *S) const {
-        i8_add_frequent(S, sd, m, s);
+    __device__ __forceinline__ int frequent_count(int64_t s) const { return sd.over_cnt ? sd.over_cnt[s] : 0; }
+    // S = the complete exact digit sums of (s, m)
+    __device__ __forceinline__ void store_sums(int64_t s, int64_t m, const long long *S) const {
         double v = i8_fold(S);
         if (sd.any_shallow) v = i8_head(sd, sd.meta[m], s) + v;   // IEEE addition commutes: same bits as head + fold
         const int64_t at = s * o.ss + (o.m_col0 + m) * o.sm;
         for (int d = 0; d < o.n_dst; ++d) o.M[d][at] = v;
     }
+    __device__ __forceinline__ void store(int64_t s, int64_t m, long long *S, int n_over) const {
+        if (n_over) i8_add_frequent(S, sd, m, s, n_over);
+        store_sums(s, m, S);
+    }
     // peer-mapped destinations: the band must have left this GPU before the rank signals the peer barrier
     __device__ __forceinline__ void unit_done() const {
         if (o.n_dst > 1) __threadfence_system();
     }
+    // whole warp, while the unit's MMAs still run: pull the frequent-k-mer lists and the digit lines operator() will read
+    // for this chunk into L2 (prefetch only: no registers held, nothing depends on it)
+    __device__ __forceinline__ void prefetch(const G8Unit &u, int64_t s, int c0) const {
+        if (u.partial || !sd.over_cnt) return;
+        const int lane = threadIdx.x & 31;
+        const int n_over = s < o.n_seq ? sd.over_cnt[s] : 0;
+        unsigned pending = __ballot_sync(0xffffffffu, n_over > 0);
+        while (pending) {
+            const int r = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const long long s_r = __shfl_sync(0xffffffffu, (long long)s, r);
+            const int n_r = __shfl_sync(0xffffffffu, n_over, r);
+            const int64_t row = (int64_t)u.b_row0 + c0 + lane;   // digit row this lane reads in operator()
+            const uint2 *list = sd.over_list + s_r * I8_MAX_OVER;
+            for (int oi = 0; oi < n_r; ++oi) {
+                const uint2 e = list[oi];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sd.digits + g8_off(row, e.x, sd.d_rows_pad)));
+            }
+        }
+    }
+    // called by all 32 lanes of an epilogue warp together (lane = sequence row s, v = 32 columns = 4 models x 8 digits)
     __device__ __forceinline__ void operator()(const G8Unit &u, int64_t s, int c0, const int32_t (&v)[32]) const {
-        if (s >= o.n_seq) return;
+        const bool live = s < o.n_seq;
         const int64_t m0 = (int64_t)(u.b_row0 + c0) >> 3;
+        if (u.partial) {
+            if (!live) return;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t m = m0 + q;
+                if (m >= o.n_models) break;
+                int32_t *dst = o.P + (s * o.n_models + m) * 8;
+#pragma unroll
+                for (int d = 0; d < 8; ++d) atomicAdd(dst + d, v[8 * q + d]);
+            }
+            return;
+        }
+        // Rows with frequent k-mers are finished by the whole warp: lane l fetches digit l & 7 of model m0 + (l >> 3) --
+        // exactly the column the row's owner holds in v[l] -- for every frequent k-mer of the row, and the owner picks
+        // the 32 sums up by shuffle.  (Left to the owner alone, ONE such row at cfg 3 -- 112 dependent-latency loads --
+        // added 18 us to the whole kernel.)
+        const int lane = threadIdx.x & 31;
+        const int n_over = live ? frequent_count(s) : 0;
+        unsigned pending = __ballot_sync(0xffffffffu, n_over > 0);
+        while (pending) {
+            const int r = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const long long s_r = __shfl_sync(0xffffffffu, (long long)s, r);
+            const int n_r = __shfl_sync(0xffffffffu, n_over, r);
+            const int64_t m_l = m0 + (lane >> 3);
+            long long F = 0;
+            if (m_l < o.n_models) {
+                const uint2 *list = sd.over_list + s_r * I8_MAX_OVER;
+                for (int oi = 0; oi < n_r; ++oi) {
+                    const uint2 e = list[oi];
+                    F += 256ll * (long long)e.y * (long long)sd.digits[g8_off(m_l * 8 + (lane & 7), e.x, sd.d_rows_pad)];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                long long S[8];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) S[d] = (long long)v[8 * q + d] + __shfl_sync(0xffffffffu, F, 8 * q + d);
+                const int64_t m = m0 + q;
+                if (lane == r && m < o.n_models && !(o.skip_diag && s == o.m_col0 + m)) store_sums(s, m, S);
+            }
+        }
+        if (!live || n_over) return;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int64_t m = m0 + q;
             if (m >= o.n_models) break;
-            if (u.partial) {
-                int32_t *dst = o.P + (s * o.n_models + m) * 8;
+            if (o.skip_diag && s == o.m_col0 + m) continue;
+            long long S[8];
 #pragma unroll
-                for (int d = 0; d < 8; ++d) atomicAdd(dst + d, v[8 * q + d]);
-            } else if (!(o.skip_diag && s == o.m_col0 + m)) {
-                long long S[8];
-#pragma unroll
-                for (int d = 0; d < 8; ++d) S[d] = (long long)v[8 * q + d];
-                store(s, m, S);
-            }
+            for (int d = 0; d < 8; ++d) S[d] = (long long)v[8 * q + d];
+            store_sums(s, m, S);
         }
     }
 };
@@ -267,7 +329,7 @@ __global__ void __launch_bounds__(128) k_i8_fold(const EpiNll e, const G8Rect *_
         src[1] = make_int4(0, 0, 0, 0);
         if (e.o.skip_diag && s == e.o.m_col0 + m) continue;
         long long S[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        e.store(s, m, S);
+        e.store(s, m, S, e.frequent_count(s));
     }
 }
 
@@ -305,7 +367,7 @@ __global__ void __launch_bounds__(256) k_i8_diag(const EpiNll e, const uint8_t *
             for (int w2 = 0; w2 < 8; ++w2) t += part[w2][q];
             S[q] = (long long)t;
         }
-        e.store(sq, m, S);
+        e.store(sq, m, S, e.frequent_count(sq));
     }
 }
 
