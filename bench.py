@@ -405,7 +405,10 @@ def main():
     d2h = out_h.nbytes
 
     def load_all():
-        h.load_models_raw(fm.n_models, host["off"], host["len"], host["code"], host["prob"], skip_nll=(kind != "nll"))
+        # NLL: the sequences are given, so nothing on the device reads the transition rows themselves -- the same load the
+        # drop-in NegativeLogLikelihood class does when every model already carries its sampled sequence
+        h.load_models_raw(fm.n_models, host["off"], host["len"], host["code"], host["prob"], skip_nll=(kind != "nll"),
+                          nll_only=(kind == "nll"))
         if seqs is not None:
             h.load_sequences_packed(host["words"], host["woff"], host["lens"])
 

@@ -86,6 +86,7 @@ struct I8Work {   // device-resident unit / rectangle lists of one int8 contract
     const G8Rect *d_rects;
     int n_rects;
     int split;
+    int max_rect_models;   // models of the widest rectangle
 };
 
 struct vgs_context {
@@ -102,6 +103,7 @@ struct vgs_context {
     double *h_logp = nullptr;   // pinned staging of the host-computed ln p table
     int64_t h_logp_cap = 0;
     bool nll_ready = false;     // false when loaded with VGS_LOAD_SKIP_NLL
+    bool prob_ready = false;    // false when loaded with VGS_LOAD_NLL_ONLY (no transition rows on the device)
     // derived tables are built on first use by the kernels that need them (a k-mer-mode NLL run needs none of these)
     int dense_state = 0;        // scan tables (tier 1 dense / tier 2-3 two-level): 0 = not built, 1 = built
     bool umap_tried = false;    // universe maps of the pair kernels
@@ -162,8 +164,7 @@ struct vgs_context {
     int8_t *d_i8_digits = nullptr;   // [n_models * 8][K8] balanced base-256 digits of round(ln p * 2^51)
     uint8_t *d_i8_C = nullptr;       // [n_seq][K8] k-mer counts (low bytes)
     int32_t *d_i8_over = nullptr;    // [n_seq] counts of frequent k-mers | [n_seq][64] {k, count >> 8}
-    int32_t *d_i8_P = nullptr;       // k-split launches: exact int32 digit sums [n_seq][n_models * 8], zero between calls
-    int64_t i8_P_elems = 0;
+    int32_t *d_i8_P = nullptr;       // k-split launches: exact int32 digit sums [part][n_models * 8][n_seq padded]
     uint64_t i8_tables_gen = ~0ull;
     bool i8_tables_ok = false;
     int last_nll_kernel = 0;         // VGS_NLL_KERNEL_* of the most recent score launch
@@ -279,6 +280,10 @@ bool vgs_kmer_applicable(vgs_context *h);
 int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s, int64_t nb_m, bool diag_separately,
                     const VgsScoreDst &dst, cudaStream_t s, uint64_t cache_key = 0);
 int vgs_kmer_i8_prepare_tables(vgs_context *h, cudaStream_t s);
+bool vgs_kmer_applicable_orders(vgs_context *h);                          // every order <= 6 (known after the host's planning pass)
+int vgs_kmer_i8_digits_begin(vgs_context *h, cudaStream_t s);              // allocate + clear the digit operand of the current set
+int vgs_kmer_i8_digits_range(vgs_context *h, int64_t m_begin, int64_t m_end, cudaStream_t s);   // digits of models [m_begin, m_end)
+int vgs_kmer_i8_digits_end(vgs_context *h, cudaStream_t s);                // after a synchronisation: record whether the operand is usable
 int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, const VgsScoreDst &dst, cudaStream_t s);
 int vgs_ensure_scan_tables(vgs_context *h, cudaStream_t s);   // tier 1-3 NLL tables of the scan kernels
 int vgs_ensure_umap(vgs_context *h, cudaStream_t s);          // universe maps (shallow sets) of the pair kernels

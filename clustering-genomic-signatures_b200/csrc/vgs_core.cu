@@ -303,6 +303,7 @@ __global__ void k_build_keys(int64_t total, const uint8_t *__restrict__ len, con
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     key[i] = vgs_key(len[i], code[i]);
+    if (!prob) return;   // NLL-only load: no transition rows on the device
     const double *p = prob + 4 * i;
     prob32[i] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);  // round-to-nearest like numpy's float32 store
 }
@@ -729,15 +730,18 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     if ((rc = vgs_reserve(h, &h->d_key, total))) return rc;
     if ((rc = vgs_reserve(h, &h->d_len, total))) return rc;
     if ((rc = vgs_reserve(h, &h->d_code, total))) return rc;
-    if ((rc = vgs_reserve(h, &h->d_prob32, total))) return rc;
-    if ((rc = vgs_reserve(h, &h->d_prob64, total * 4))) return rc;
+    const bool want_nll = !(flags & VGS_LOAD_SKIP_NLL);
+    const bool want_prob = !(flags & VGS_LOAD_NLL_ONLY);
+    VGS_CHECK_ARG(want_nll || want_prob, "vgs_load_models: VGS_LOAD_SKIP_NLL and VGS_LOAD_NLL_ONLY exclude each other");
+    if (want_prob && (rc = vgs_reserve(h, &h->d_prob32, total))) return rc;
+    if (want_prob && (rc = vgs_reserve(h, &h->d_prob64, total * 4))) return rc;
+    h->prob_ready = want_prob;
     if ((rc = vgs_reserve(h, &h->d_hash, hash_slots))) return rc;
     h->hash_slots = hash_slots;
     h->ph_bytes = ph_bytes;
     h->nll_bytes = nll_bytes;
     h->n_models = n_models;
     h->total_ctx = total;
-    const bool want_nll = !(flags & VGS_LOAD_SKIP_NLL);
     h->nll_ready = false;
 
     // 1. upload what the caller gave us (asynchronous when its buffers are pinned) and build everything that
@@ -746,9 +750,10 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     VGS_CUDA(cudaMemcpyAsync(h->d_meta, h->h_meta.data(), sizeof(ModelMeta) * (size_t)n_models, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemcpyAsync(h->d_len, ctx_len_h, (size_t)total, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemcpyAsync(h->d_code, ctx_code_h, sizeof(uint32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
-    VGS_CUDA(cudaMemcpyAsync(h->d_prob64, prob_h, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    if (want_prob) VGS_CUDA(cudaMemcpyAsync(h->d_prob64, prob_h, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemsetAsync(h->d_hash, 0, sizeof(uint2) * (size_t)hash_slots, s));
-    k_build_keys<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(total, h->d_len, h->d_code, h->d_prob64, h->d_key, h->d_prob32);
+    k_build_keys<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(total, h->d_len, h->d_code, want_prob ? h->d_prob64 : nullptr, h->d_key,
+                                                              want_prob ? h->d_prob32 : nullptr);
     VGS_LAUNCH_CHECK(h);
     k_build_hash<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_key, h->d_hash);
     VGS_LAUNCH_CHECK(h);
@@ -774,13 +779,32 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     if (logp_h) memcpy(h->h_logp, logp_h, sizeof(double) * (size_t)total * 4);
     if ((rc = vgs_reserve(h, &h->d_logp, total * 4))) return rc;
     if ((rc = vgs_reserve(h, &h->d_nll, nll_bytes))) return rc;
+    // sets the k-mer contraction covers (every order <= 6): its digit operand is built here, model block by model block
+    // as soon as a block's ln p has been uploaded, so the build hides under the host's ln p pass instead of following it
+    const bool eager_digits = !(flags & VGS_LOAD_LAZY_TABLES) && vgs_kmer_applicable_orders(h);
+    int64_t digits_built = 0;
+    if (eager_digits && (rc = vgs_kmer_i8_digits_begin(h, s))) return rc;
+    auto build_digits_upto = [&](int64_t elems_uploaded, bool final) -> int {
+        if (!eager_digits) return VGS_OK;
+        int64_t m_done = digits_built;
+        while (m_done < n_models && ctx_offsets_h[m_done + 1] * 4 <= elems_uploaded) ++m_done;
+        if (m_done - digits_built >= 64 || (final && m_done > digits_built)) {
+            const int rcd = vgs_kmer_i8_digits_range(h, digits_built, m_done, s);
+            if (rcd) return rcd;
+            digits_built = m_done;
+        }
+        return VGS_OK;
+    };
     if (logp_h) {
         VGS_CUDA(cudaMemcpyAsync(h->d_logp, h->h_logp, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
+        if ((rc = build_digits_upto(total * 4, true))) return rc;
     } else {
         // chunks are claimed with an atomic counter; this thread uploads each chunk as soon as it is complete, so the
         // PCIe transfer of ln p overlaps its computation
         const int64_t n_elem = total * 4;
-        const int64_t chunk = 1 << 16;
+        // small chunks: 31 chunks of 64 K logarithms on 15 threads left ONE chunk for a third round (0.7 ms of a 2.4 ms
+        // load spent with one thread working); 8 K-element chunks balance to within a few microseconds
+        const int64_t chunk = 1 << 13;
         const int64_t n_chunks = (n_elem + chunk - 1) / chunk;
         std::atomic<int64_t> next(0), bad(-1);
         std::vector<std::atomic<int>> done((size_t)n_chunks);
@@ -804,10 +828,11 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         while (sent < n_chunks && ce == cudaSuccess) {
             int64_t upto = sent;
             while (upto < n_chunks && done[(size_t)upto].load(std::memory_order_acquire)) ++upto;
-            if (upto - sent >= 8 || (upto == n_chunks && upto > sent)) {
+            if (upto - sent >= 32 || (upto == n_chunks && upto > sent)) {   // >= 2 MB per copy
                 const int64_t b0 = sent * chunk, e0 = std::min(n_elem, upto * chunk);
                 ce = cudaMemcpyAsync(h->d_logp + b0, out + b0, sizeof(double) * (size_t)(e0 - b0), cudaMemcpyHostToDevice, s);
                 sent = upto;
+                if (ce == cudaSuccess && build_digits_upto(e0, upto == n_chunks) != VGS_OK) ce = cudaErrorUnknown;
             } else {
                 std::this_thread::yield();
             }
@@ -828,6 +853,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     h->nll_ready = true;
     VGS_CUDA(cudaStreamSynchronize(s));
     lap("stream drained");
+    if (eager_digits && (rc = vgs_kmer_i8_digits_end(h, s))) return rc;
     return VGS_OK;
 }
 
@@ -1176,6 +1202,7 @@ __global__ void k_sample(int64_t n_models, const ModelMeta *__restrict__ meta, c
 
 extern "C" int vgs_sample_sequences(vgs_handle h, int64_t length, int64_t pre_sample, uint32_t *mt_state_h) {
     VGS_CHECK_ARG(h && h->n_models > 0, "vgs_sample_sequences: no models loaded");
+    VGS_CHECK_ARG(h->prob_ready, "vgs_sample_sequences: models were loaded with VGS_LOAD_NLL_ONLY: no transition rows on the device");
     VGS_CHECK_ARG(length > 0 && pre_sample >= 0 && mt_state_h, "vgs_sample_sequences: bad arguments");
     VGS_CHECK_ARG(mt_state_h[624] <= 624, "vgs_sample_sequences: bad MT19937 position");
     VGS_CUDA(cudaSetDevice(h->device));

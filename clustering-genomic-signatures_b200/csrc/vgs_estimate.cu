@@ -349,6 +349,7 @@ static int est_tiles_impl(vgs_context *h, const TilePlan &pl, int rank, float *p
 static int check_est(vgs_context *h) {
     VGS_CHECK_ARG(h, "null handle");
     VGS_CHECK_ARG(h->n_models > 0, "no models loaded (vgs_load_models)");
+    VGS_CHECK_ARG(h->prob_ready, "models were loaded with VGS_LOAD_NLL_ONLY: no transition rows on the device");
     VGS_CHECK_ARG(h->n_seq == h->n_models, "EstimateVLMC needs exactly one sequence per model (sequence j sampled from model j)");
     if (h->max_order + 1 > 13) {
         vgs_set_error("EstimateVLMC dense counting supports order <= 12 (got %d)", h->max_order);

@@ -46,7 +46,8 @@ int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters,
                 const int64_t units = count * sp, waves = (units + n_clusters - 1) / n_clusters;
                 const int kb_per = (kblocks + sp - 1) / sp;
                 const double t_kb = std::max(2.0 * w, 1.73 * (256 + w)) + 60.0;
-                const double t = (double)waves * (kb_per * t_kb + 30.0 * w + 2500.0) + (sp > 1 ? 12000.0 + 8.0 * w : 0.0);
+                // a k-split writes 4 bytes per digit sum instead of one fp64 per 8, and runs the fold kernel afterwards
+                const double t = (double)waves * (kb_per * t_kb + (sp > 1 ? 45.0 : 30.0) * w + 2500.0) + (sp > 1 ? 14000.0 : 0.0);
                 if (t < best * 0.999 || (t < best * 1.001 && cand > N)) { best = t; N = cand; split = sp; }
             }
         }
@@ -62,7 +63,7 @@ int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters,
                 u.a_blk = r.a_blk; u.b_row0 = row; u.n = n;
                 u.kb0 = (int)((int64_t)kblocks * p / split);
                 u.kbn = (int)((int64_t)kblocks * (p + 1) / split) - u.kb0;
-                u.partial = split > 1 ? 1 : 0;
+                u.partial = split > 1 ? p + 1 : 0;   // 1-based part number
                 if (n > 0 && u.kbn > 0) out->push_back(u);
             }
             row += n;

@@ -50,7 +50,7 @@ struct G8Unit {
     int32_t b_row0;   // first B row, multiple of 8 (16 for the peer's half to stay 8-aligned: n / 2 is a multiple of 16)
     int32_t n;        // B rows of this unit: multiple of 32, <= 512 (above 256: two accumulators, see g8_first_half)
     int32_t kb0, kbn; // k range in 128-blocks
-    int32_t partial;  // != 0: this unit covers part of the k range (the functor accumulates atomically)
+    int32_t partial;  // != 0: this unit is part (partial - 1) of a k-split (the functor stores its sums to the part's slab)
 };
 
 struct G8Args {

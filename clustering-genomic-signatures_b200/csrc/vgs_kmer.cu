@@ -362,6 +362,7 @@ __global__ void k_kmer_epilogue(const KgEpi p) {
 // ---------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------
+bool vgs_kmer_applicable_orders(vgs_context *h) { return h->max_nll_bytes_t2 == 0 && h->max_nll_bytes_t3 == 0 && h->max_order <= VGS_DENSE_MAX_ORDER; }
 bool vgs_kmer_applicable(vgs_context *h) {
     if (h->max_nll_bytes_t2 > 0 || h->max_nll_bytes_t3 > 0 || h->max_order > VGS_DENSE_MAX_ORDER) return false;
     return true;
@@ -401,7 +402,7 @@ static int kmer_i8_path(vgs_context *h, const std::vector<char> &need, int64_t n
     I8Work w;
     bool diag_covered = false;
     if (WorkCache *wc = vgs_wcache_find(h, key)) {
-        w.n_units = wc->n[0]; w.n_rects = wc->n[1]; diag_covered = wc->n[2] != 0; w.split = wc->split;
+        w.n_units = wc->n[0]; w.n_rects = wc->n[1]; diag_covered = wc->n[2] != 0; w.split = wc->split; w.max_rect_models = wc->n[3];
         w.d_units = (const G8Unit *)wc->dev;
         w.d_rects = (const G8Rect *)((char *)wc->dev + wc->off2);
     } else {
@@ -430,19 +431,21 @@ static int kmer_i8_path(vgs_context *h, const std::vector<char> &need, int64_t n
         std::vector<G8Unit> units;
         const int kblocks = (int)(std::max<int64_t>(G8_BK, (int64_t)1 << (2 * (h->max_order + 1))) / G8_BK);
         static int max_split = -1;
-        if (max_split < 0) { const char *e = getenv("VGS_I8_SPLITK"); max_split = e ? std::max(1, atoi(e)) : 4; }
+        if (max_split < 0) { const char *e = getenv("VGS_I8_SPLITK"); max_split = e ? std::max(1, atoi(e)) : 8; }
         // the int32 partial-sum buffer of the k-split stays below 1 GB
-        const int ms = (h->n_seq * h->n_models * 32 <= ((int64_t)1 << 30)) ? max_split : 1;
+        const int ms = (h->n_seq * h->n_models * 32 * max_split <= ((int64_t)2 << 30)) ? max_split : 1;
         w.split = g8_make_units(rects, kblocks, h->sm_count / 2, ms, &units);
         w.n_units = (int)units.size();
         w.n_rects = (int)rects.size();
+        w.max_rect_models = 0;
+        for (const G8Rect &r : rects) w.max_rect_models = std::max(w.max_rect_models, r.b_rows / 8);
         const int64_t off2 = ((int64_t)units.size() * (int64_t)sizeof(G8Unit) + 127) / 128 * 128;
         const int64_t bytes = off2 + (int64_t)rects.size() * (int64_t)sizeof(G8Rect) + 256;
         char *base = nullptr;
         if (key) {
             WorkCache *wc = vgs_wcache_add(h, key, bytes);
             if (wc) {
-                wc->n[0] = w.n_units; wc->n[1] = w.n_rects; wc->n[2] = diag_covered ? 1 : 0; wc->split = w.split; wc->off2 = off2;
+                wc->n[0] = w.n_units; wc->n[1] = w.n_rects; wc->n[2] = diag_covered ? 1 : 0; wc->n[3] = w.max_rect_models; wc->split = w.split; wc->off2 = off2;
                 base = (char *)wc->dev;
             }
         }

@@ -215,7 +215,9 @@ struct I8Out {
     int64_t m_col0;             // column of local model 0 (model shards: local model m is column m_col0 + m)
     int64_t n_seq, n_models;    // local operand extents
     int skip_diag;
-    int32_t *P;                 // partial units: exact int32 digit sums [n_seq][n_models * 8], zero between calls
+    int32_t *P;                 // k-split launches: exact int32 digit sums of every part, [part][model][digit][sequence]
+    int64_t p_ld;               // sequences per row of P (padded to 32)
+    int n_parts;
 };
 
 struct EpiNll {
@@ -262,14 +264,16 @@ struct EpiNll {
         const bool live = s < o.n_seq;
         const int64_t m0 = (int64_t)(u.b_row0 + c0) >> 3;
         if (u.partial) {
+            // part (u.partial - 1) of a k-split: its digit sums go to the part's own slab with plain stores, coalesced over
+            // the warp's 32 sequences (a first version added them into one buffer with integer atomics: 8 M atomics at
+            // 2 GPUs cost 110 us); k_i8_fold adds the parts -- integers, so the split changes no bit of the result
             if (!live) return;
+            int32_t *dst = o.P + ((int64_t)(u.partial - 1) * o.n_models + m0) * 8 * o.p_ld + s;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int64_t m = m0 + q;
-                if (m >= o.n_models) break;
-                int32_t *dst = o.P + (s * o.n_models + m) * 8;
+                if (m0 + q >= o.n_models) break;
 #pragma unroll
-                for (int d = 0; d < 8; ++d) atomicAdd(dst + d, v[8 * q + d]);
+                for (int d = 0; d < 8; ++d) dst[(8 * q + d) * o.p_ld] = v[8 * q + d];
             }
             return;
         }
@@ -317,20 +321,20 @@ struct EpiNll {
     }
 };
 
-// k-split launches: P -> M for every entry of the computed rectangles, and P back to zero for the next call
-__global__ void __launch_bounds__(128) k_i8_fold(const EpiNll e, const G8Rect *__restrict__ rects) {
-    const G8Rect r = rects[blockIdx.y];
-    const int64_t s = (int64_t)r.a_blk * 256 + blockIdx.x;
-    if (s >= e.o.n_seq) return;
-    for (int64_t m = (r.b_row0 >> 3) + threadIdx.x; m < ((int64_t)(r.b_row0 + r.b_rows) >> 3) && m < e.o.n_models; m += blockDim.x) {
-        int4 *src = (int4 *)(e.o.P + (s * e.o.n_models + m) * 8);
-        const int4 lo = src[0], hi = src[1];
-        src[0] = make_int4(0, 0, 0, 0);
-        src[1] = make_int4(0, 0, 0, 0);
-        if (e.o.skip_diag && s == e.o.m_col0 + m) continue;
-        long long S[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        e.store(s, m, S, e.frequent_count(s));
+// k-split launches: the parts' digit sums -> M for every entry of the computed rectangles (thread = sequence: coalesced)
+__global__ void __launch_bounds__(256) k_i8_fold(const EpiNll e, const G8Rect *__restrict__ rects) {
+    const G8Rect r = rects[blockIdx.z];
+    const int64_t s = (int64_t)r.a_blk * 256 + threadIdx.x;
+    const int64_t m = (r.b_row0 >> 3) + blockIdx.x;
+    if (s >= e.o.n_seq || m >= ((int64_t)(r.b_row0 + r.b_rows) >> 3) || m >= e.o.n_models) return;
+    if (e.o.skip_diag && s == e.o.m_col0 + m) return;
+    long long S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < e.o.n_parts; ++p) {
+        const int32_t *src = e.o.P + ((int64_t)p * e.o.n_models + m) * 8 * e.o.p_ld + s;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) S[d] += (long long)src[d * e.o.p_ld];
     }
+    e.store(s, m, S, e.frequent_count(s));
 }
 
 // diagonal scores M[m][m] with the same arithmetic (one CTA per model): identical bits to the GEMM's entry
@@ -390,10 +394,10 @@ static I8Side i8_side(vgs_context *h, bool with_over) {
     return sd;
 }
 
-// builds (once per model set) the digit operand from the models; returns VGS_OK, an error, or -1 = not applicable
-// (a model without root context, or a table entry that is no log-probability)
-int vgs_kmer_i8_prepare_tables(vgs_context *h, cudaStream_t s) {
-    if (h->i8_tables_gen == h->model_gen) return h->i8_tables_ok ? VGS_OK : -1;
+// the digit operand of the current model set: begin (allocate, clear padding, clear the flag) -> range(s) -> end (after a
+// stream synchronisation: is it usable?).  vgs_load_models drives the three steps itself, block by block behind the ln p
+// upload; vgs_kmer_i8_prepare_tables does them in one go for sets loaded with VGS_LOAD_LAZY_TABLES.
+int vgs_kmer_i8_digits_begin(vgs_context *h, cudaStream_t s) {
     const int64_t K = (int64_t)1 << (2 * (h->max_order + 1));
     const int64_t K8 = i8_k8(h);
     int rc;
@@ -403,17 +407,39 @@ int vgs_kmer_i8_prepare_tables(vgs_context *h, cudaStream_t s) {
         VGS_CUDA(cudaMemsetAsync(h->d_i8_digits, 0, (size_t)(rows_pad * K8), s));
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
     VGS_CUDA(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(int), s));
+    h->i8_tables_gen = ~0ull;
+    return VGS_OK;
+}
+
+int vgs_kmer_i8_digits_range(vgs_context *h, int64_t m_begin, int64_t m_end, cudaStream_t s) {
+    const int64_t K = (int64_t)1 << (2 * (h->max_order + 1));
+    const int64_t K8 = i8_k8(h);
     const I8Side sd = i8_side(h, false);
-    for (int64_t m0 = 0; m0 < h->n_models; m0 += 65535) {
-        dim3 grid((unsigned)std::min<int64_t>(((K8 >> 4) + 127) / 128, 64), (unsigned)std::min<int64_t>(h->n_models - m0, 65535));
-        k_i8_digits<<<grid, 128, 0, s>>>(m0, sd, K, K8, rows_pad, h->d_i8_digits, h->d_counters + 9);
+    for (int64_t m0 = m_begin; m0 < m_end; m0 += 65535) {
+        dim3 grid((unsigned)std::min<int64_t>(((K8 >> 4) + 127) / 128, 64), (unsigned)std::min<int64_t>(m_end - m0, 65535));
+        k_i8_digits<<<grid, 128, 0, s>>>(m0, sd, K, K8, i8_digit_rows_pad(h), h->d_i8_digits, h->d_counters + 9);
         VGS_LAUNCH_CHECK(h);
     }
+    return VGS_OK;
+}
+
+int vgs_kmer_i8_digits_end(vgs_context *h, cudaStream_t s) {
     int flag = 0;
     VGS_CUDA(cudaMemcpyAsync(&flag, h->d_counters + 9, sizeof(int), cudaMemcpyDeviceToHost, s));
     VGS_CUDA(cudaStreamSynchronize(s));
     h->i8_tables_ok = flag == 0;
     h->i8_tables_gen = h->model_gen;
+    return VGS_OK;
+}
+
+// the digit operand when the load did not build it; returns VGS_OK, an error, or -1 = not applicable (a model without root
+// context, or a table entry that is no log-probability)
+int vgs_kmer_i8_prepare_tables(vgs_context *h, cudaStream_t s) {
+    if (h->i8_tables_gen == h->model_gen) return h->i8_tables_ok ? VGS_OK : -1;
+    int rc;
+    if ((rc = vgs_kmer_i8_digits_begin(h, s))) return rc;
+    if ((rc = vgs_kmer_i8_digits_range(h, 0, h->n_models, s))) return rc;
+    if ((rc = vgs_kmer_i8_digits_end(h, s))) return rc;
     return h->i8_tables_ok ? VGS_OK : -1;
 }
 
@@ -462,33 +488,26 @@ int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, co
     for (int d = 0; d < VGS_MAX_PEERS; ++d) e.o.M[d] = d < dst.n_dst ? dst.M[d] : nullptr;
     e.o.n_dst = dst.n_dst; e.o.ss = dst.stride_s; e.o.sm = dst.stride_m; e.o.m_col0 = dst.m_col0;
     e.o.n_seq = h->n_seq; e.o.n_models = h->n_models; e.o.skip_diag = diag_separately ? 1 : 0;
-    e.o.P = nullptr;
+    e.o.P = nullptr; e.o.p_ld = 0; e.o.n_parts = 1;
     if (w.n_units > 0) {
+        e.o.p_ld = (h->n_seq + 31) / 32 * 32;
+        e.o.n_parts = w.split;
         if (w.split > 1) {
-            const int64_t p_elems = h->n_seq * h->n_models * 8;
-            int32_t *before = h->d_i8_P;
-            if ((rc = vgs_reserve(h, &h->d_i8_P, p_elems))) return rc;
-            if (h->d_i8_P != before || h->i8_P_elems != p_elems) {   // fresh, re-shaped or possibly dirty buffer: all zero once
-                VGS_CUDA(cudaMemsetAsync(h->d_i8_P, 0, (size_t)p_elems * 4, s));
-                h->i8_P_elems = p_elems;
-            }
+            if ((rc = vgs_reserve(h, &h->d_i8_P, (int64_t)w.split * h->n_models * 8 * e.o.p_ld))) return rc;
             e.o.P = h->d_i8_P;
         }
         G8Args g;
         g.A = h->d_i8_C; g.B = (const uint8_t *)h->d_i8_digits; g.a_rows_pad = c_rows_pad; g.b_rows_pad = d_rows_pad;
         g.units = w.d_units; g.n_units = w.n_units; g.a_signed = 0; g.err = h->d_err; g.prof = nullptr;
         h->last_nll_kernel = VGS_NLL_KERNEL_I8MMA;
-        // an error return between here and the fold leaves partial sums in P: force the memset on the next call
-        const int64_t p_elems_keep = h->i8_P_elems;
-        if (w.split > 1) h->i8_P_elems = 0;
         vgs_prof_begin(h, VGS_PROF_NLL_SCORES, s);
         rc = g8_launch(h, g, e, s);
         vgs_prof_end(h, VGS_PROF_NLL_SCORES, s);
         if (rc) return rc;
         if (w.split > 1) {
-            k_i8_fold<<<dim3(256, (unsigned)w.n_rects), 128, 0, s>>>(e, w.d_rects);
+            // widest rectangle in models (grid.x covers it; narrower rectangles leave early)
+            k_i8_fold<<<dim3((unsigned)w.max_rect_models, 1, (unsigned)w.n_rects), 256, 0, s>>>(e, w.d_rects);
             VGS_LAUNCH_CHECK(h);
-            h->i8_P_elems = p_elems_keep;
         }
     }
     if (diag_separately) {

@@ -400,6 +400,7 @@ static int pair_tiles_impl(vgs_context *h, int kind, const TilePlan &pl, int ran
 static int check_pair_args(vgs_context *h, int kind) {
     VGS_CHECK_ARG(h, "null handle");
     VGS_CHECK_ARG(h->n_models > 0, "no models loaded (vgs_load_models)");
+    VGS_CHECK_ARG(h->prob_ready, "models were loaded with VGS_LOAD_NLL_ONLY: no transition rows on the device");
     VGS_CHECK_ARG(kind == VGS_PAIR_FROBENIUS_INTERSECTION || kind == VGS_PAIR_FROBENIUS_UNION || kind == VGS_PAIR_PROJECTION,
                   "bad pair-distance kind");
     return VGS_OK;

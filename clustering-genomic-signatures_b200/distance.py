@@ -57,7 +57,7 @@ class _DeviceDistance(object):
         """float32 [N, N] matrix of ``distance(vlmcs[i], vlmcs[j])`` (src/clustering/util.pyx:23-33 layout)."""
         vlmcs = list(vlmcs)
         h = self._get_handle()
-        h.load_models(vlmcs_to_flat(vlmcs), skip_nll=not self.needs_nll_tables)
+        h.load_models(vlmcs_to_flat(vlmcs), skip_nll=not self.needs_nll_tables, nll_only=self._nll_only(vlmcs))
         D32, D64 = self._compute(h, vlmcs)
         self._D32, self._D64 = D32, D64
         self._vlmcs = vlmcs
@@ -67,6 +67,11 @@ class _DeviceDistance(object):
 
     def _batch_done(self, vlmcs):
         pass
+
+    def _nll_only(self, vlmcs):
+        """True when the device needs nothing but the log-likelihood tables for these models (NegativeLogLikelihood with
+        every sequence already sampled): the transition rows are then not uploaded at all."""
+        return False
 
     def _row(self, v):
         """Row of ``v`` in the batched matrix, or None.  A hit needs the very same object: the reference reads the
@@ -89,7 +94,7 @@ class _DeviceDistance(object):
         # not batched: this pair alone, still on the device
         pair = [left_vlmc, right_vlmc]
         h = self._get_handle()
-        h.load_models(vlmcs_to_flat(pair), skip_nll=not self.needs_nll_tables)
+        h.load_models(vlmcs_to_flat(pair), skip_nll=not self.needs_nll_tables, nll_only=self._nll_only(pair))
         D32, D64 = self._compute(h, pair, pair_only=True)
         return self._scalar(D32, D64)
 
@@ -125,6 +130,10 @@ class NegativeLogLikelihood(_DeviceDistance):
 
     def _batch_done(self, vlmcs):
         self._seq_ids = {id(v): v.sequence for v in vlmcs}
+
+    def _nll_only(self, vlmcs):
+        # scoring reads ln p only; missing sequences are sampled on a handle of their own (vlmc.sample_missing_sequences)
+        return True
 
     def _still_valid(self, left, right):
         # the reference re-samples when a model's cached sequence was reset or has another length

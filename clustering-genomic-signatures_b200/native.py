@@ -211,21 +211,25 @@ class Handle:
         _check(lib().vgs_poll_error(self._h, c_vp(stream)))
 
     # ---- models
-    def load_models(self, fm, logp=None, skip_nll=False):
+    @staticmethod
+    def _load_flags(skip_nll, nll_only, lazy_tables):
+        return (1 if skip_nll else 0) | (2 if nll_only else 0) | (4 if lazy_tables else 0)
+
+    def load_models(self, fm, logp=None, skip_nll=False, nll_only=False, lazy_tables=False):
         off = np.ascontiguousarray(fm.ctx_offsets, dtype=np.int64)
         ln = np.ascontiguousarray(fm.ctx_len, dtype=np.uint8)
         code = np.ascontiguousarray(fm.ctx_code, dtype=np.uint32)
         prob = np.ascontiguousarray(fm.prob, dtype=np.float64)
         lp = None if logp is None else np.ascontiguousarray(logp, dtype=np.float64)
         _check(lib().vgs_load_models_ex(self._h, fm.n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), _np_ptr(lp),
-                                        1 if skip_nll else 0))
+                                        self._load_flags(skip_nll, nll_only, lazy_tables)))
         self.n_models = fm.n_models
         self.total_contexts = fm.total_contexts
 
-    def load_models_raw(self, n_models, off, ln, code, prob, skip_nll=False):
+    def load_models_raw(self, n_models, off, ln, code, prob, skip_nll=False, nll_only=False, lazy_tables=False):
         """Same as load_models but from already-contiguous (e.g. pinned) arrays; no conversions."""
         _check(lib().vgs_load_models_ex(self._h, n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), None,
-                                        1 if skip_nll else 0))
+                                        self._load_flags(skip_nll, nll_only, lazy_tables)))
         self.n_models = n_models
         self.total_contexts = int(off[-1])
 

@@ -192,7 +192,7 @@ def sample_missing_sequences(vlmcs, sequence_length, pre_sample_length, device=N
     if not uniq:
         return
     h = native.Handle(_default_device() if device is None else device)
-    h.load_models(vlmcs_to_flat(uniq))
+    h.load_models(vlmcs_to_flat(uniq), skip_nll=True)   # the sampler reads the transition rows, not their logarithms
     state, tag = take_mt_state()
     h.sample_sequences(sequence_length, pre_sample_length, state)
     put_mt_state(state, tag)

@@ -95,6 +95,13 @@ int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h
 /* same, with flags: VGS_LOAD_SKIP_NLL skips ln p and the NLL tables (enough for Frobenius / Projection /
  * Estimate / sampling / lookups; the vgs_nll_* entry points then return VGS_ERR_INVALID) */
 #define VGS_LOAD_SKIP_NLL 1
+/* VGS_LOAD_NLL_ONLY: only what the log-likelihood path reads goes to the device (keys, hash, host ln p): the transition rows
+ * themselves are not uploaded (half of the host->device bytes of an NLL run); Frobenius / Projection / Estimate / the
+ * sampler then return VGS_ERR_INVALID.  VGS_LOAD_LAZY_TABLES: do not build the k-mer contraction's digit operand during the
+ * load (default for sets with every order <= 6: built block by block behind the ln p upload); it is then built by the
+ * first k-mer-mode call */
+#define VGS_LOAD_NLL_ONLY 2
+#define VGS_LOAD_LAZY_TABLES 4
 int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h, const uint8_t *ctx_len_h,
                        const uint32_t *ctx_code_h, const double *prob_h, const double *logp_h /* nullable */, int flags);
 int vgs_model_count(vgs_handle h, int64_t *n_models, int64_t *total_contexts);

@@ -14,7 +14,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from clustering_genomic_signatures_b200 import native, synthetic  # noqa: E402
-from clustering_genomic_signatures_b200.engine import MatrixJob  # noqa: E402
+from clustering_genomic_signatures_b200.engine import MatrixJob, ShardedNllJob  # noqa: E402
 from clustering_genomic_signatures_b200.flat import pack_sequences  # noqa: E402
 
 
@@ -57,6 +57,37 @@ def main():
         ok = ok and same and same_ranks
         if rank == 0:
             print("mgpu %-24s world=%d tile=%d bit-identical to 1 GPU: %s, identical on all ranks: %s" % (kind, world, job.tile, same, same_ranks))
+    # model-sharded NLL (each rank holds only its models): peer-memory exchange (GEMM epilogue stores into every rank's
+    # matrix over NVLink + flag barrier) and NCCL all-gather exchange, k-mer / sequential / warp kernels, several steps
+    packed = pack_sequences(seqs)
+    m0, m1 = ShardedNllJob.shard_bounds(n, world)[rank]
+    hs = native.Handle(local)
+    hs.load_models(fm.subset(range(m0, m1)))
+    hs.load_sequences_packed(*packed)
+    for exchange in ("peer", "nccl"):
+        for mode in ("kmer", "sequential", "warp"):
+            try:
+                job = ShardedNllJob(hs, n, L, mode=mode, exchange=exchange)
+            except Exception as exc:
+                if rank == 0:
+                    print("mgpu sharded nll %-10s exchange=%s: setup failed: %s" % (mode, exchange, str(exc)[:200]))
+                ok = False
+                continue
+            ref = torch.empty((n, n), dtype=torch.float32, device="cuda")
+            h.nll_matrix(L, mode, ref, None, stream)
+            h.poll_error(stream)
+            same = True
+            for step in range(3):
+                D = job.run()
+                job.check()
+                same = same and bool(torch.equal(D, ref))
+            flag = torch.tensor([1 if same else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = ok and bool(int(flag.item()))
+            if rank == 0:
+                print("mgpu sharded nll %-10s world=%d exchange=%s (used %s): bit-identical to 1 GPU on every rank, 3 steps: %s"
+                      % (mode, world, exchange, job.exchange, bool(int(flag.item()))))
+            job.close()
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

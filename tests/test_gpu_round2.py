@@ -149,3 +149,29 @@ def test_tensor_peak_probe():
     t1, ms1 = h.tensor_peak_i8(1)
     print("int8 tensor peak probe: cta_group::2 %.0f TOPS (%.3f ms), cta_group::1 %.0f TOPS (%.3f ms)" % (t2, ms2, t1, ms1))
     assert 500.0 < t2 < 6000.0 and 250.0 < t1 < 6000.0
+
+
+def test_nll_only_and_lazy_table_loads():
+    """VGS_LOAD_NLL_ONLY uploads no transition rows (the pair / estimate / sampler entry points then refuse), and the digit
+    operand built during the load (block by block behind the ln p upload) equals the one built on first use."""
+    fm, _ = synthetic.make_family_models(150, 77, 6, 120, 5)
+    seqs = synthetic.sample_sequences(fm, 800, 3)
+    packed = pack_sequences(seqs)
+    outs = []
+    for kw in ({}, {"nll_only": True}, {"lazy_tables": True}, {"nll_only": True, "lazy_tables": True}):
+        h = native.Handle(0)
+        h.load_models(fm, **kw)
+        h.load_sequences_packed(*packed)
+        outs.append((h.nll_matrix_h(800, "kmer")[1], h.nll_matrix_h(800, "sequential")[1]))
+        assert h.last_nll_kernel() == 0
+        if kw.get("nll_only"):
+            with pytest.raises(ValueError, match="NLL_ONLY"):
+                h.pair_matrix_h("frobenius_intersection")
+            with pytest.raises(ValueError, match="NLL_ONLY"):
+                h.estimate_matrix_h()
+            with pytest.raises(ValueError, match="NLL_ONLY"):
+                h.sample_sequences(10, 0, np.zeros(625, dtype=np.uint32))
+        h.close()
+    for k, s in outs[1:]:
+        assert np.array_equal(k, outs[0][0]) and np.array_equal(s, outs[0][1])
+    assert np.array_equal(outs[0][1], c_oracle.COracle(fm).nll_matrix(seqs))
