@@ -169,6 +169,13 @@ struct vgs_context {
     bool i8_tables_ok = false;
     int last_nll_kernel = 0;         // VGS_NLL_KERNEL_* of the most recent score launch
     int i8_counts_state = 0;         // 0 = not checked for this sequence set, 1 = no frequent k-mers, 3 = some, 2 = too many
+    // tensor-core Frobenius / Projection (vgs_pairs_tc.cu): digit operands over the dense universe, raw digit-pair sums
+    int8_t *d_tc_P = nullptr, *d_tc_Q = nullptr, *d_tc_I = nullptr;
+    int32_t *d_tc_model = nullptr, *d_tc_G = nullptr, *d_tc_R = nullptr;
+    uint64_t tc_gen = ~0ull;
+    bool tc_ok = false;
+    int last_pair_kernel = 0;        // 0 = CUDA-core pair kernels, 1 = tensor-core path
+    int pair_path = -1;              // vgs_set_pair_path: -1 = by density, 0 = CUDA cores, 1 = tensor cores where they apply
     float *d_out32 = nullptr;   // staging for the *_h entry points
     double *d_out64 = nullptr;
 
@@ -285,6 +292,8 @@ int vgs_kmer_i8_digits_begin(vgs_context *h, cudaStream_t s);              // al
 int vgs_kmer_i8_digits_range(vgs_context *h, int64_t m_begin, int64_t m_end, cudaStream_t s);   // digits of models [m_begin, m_end)
 int vgs_kmer_i8_digits_end(vgs_context *h, cudaStream_t s);                // after a synchronisation: record whether the operand is usable
 int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, const VgsScoreDst &dst, cudaStream_t s);
+bool vgs_pair_tc_wanted(vgs_context *h, int kind);
+int vgs_pair_tc_matrix(vgs_context *h, int kind, float *D32, double *D64, cudaStream_t s);   // -1: not applicable
 int vgs_ensure_scan_tables(vgs_context *h, cudaStream_t s);   // tier 1-3 NLL tables of the scan kernels
 int vgs_ensure_umap(vgs_context *h, cudaStream_t s);          // universe maps (shallow sets) of the pair kernels
 int vgs_assemble_impl(vgs_context *h, const TilePlan &p, const float *gathered32, const double *gathered64,

@@ -406,6 +406,13 @@ static int check_pair_args(vgs_context *h, int kind) {
     return VGS_OK;
 }
 
+extern "C" int vgs_last_pair_kernel(vgs_handle h) { return h ? h->last_pair_kernel : 0; }
+extern "C" int vgs_set_pair_path(vgs_handle h, int path) {
+    VGS_CHECK_ARG(h && path >= -1 && path <= 1, "vgs_set_pair_path: path is -1 (by density), 0 (CUDA cores) or 1 (tensor cores)");
+    h->pair_path = path;
+    return VGS_OK;
+}
+
 extern "C" int vgs_pair_tiles(vgs_handle h, int kind, int64_t tile, int rank, int world, float *payload_d, void *stream) {
     int rc = check_pair_args(h, kind);
     if (rc) return rc;
@@ -422,6 +429,12 @@ extern "C" int vgs_pair_matrix(vgs_handle h, int kind, float *D32_d, double *D64
     VGS_CHECK_ARG(D32_d, "vgs_pair_matrix: null output");
     VGS_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
+    // dense enough universes (full chains, shallow trees): exact integer GEMMs on the tensor cores (vgs_pairs_tc.cu)
+    if (vgs_pair_tc_wanted(h, kind)) {
+        rc = vgs_pair_tc_matrix(h, kind, D32_d, D64_d, s);
+        if (rc != -1) return rc;
+    }
+    h->last_pair_kernel = 0;
     TilePlan pl;
     const int64_t n = h->n_models;
     // tile edge: 64/128 normally; a few huge models (tables larger than shared memory, read from L2/HBM) need many

@@ -49,6 +49,8 @@ SIGNATURES = [
     ("vgs_nll_matrix_h", c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     ("vgs_pair_matrix", c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
     ("vgs_pair_matrix_h", c_int, [c_vp, c_int, c_vp, c_vp]),
+    ("vgs_last_pair_kernel", c_int, [c_vp]),
+    ("vgs_set_pair_path", c_int, [c_vp, c_int]),
     ("vgs_estimate_matrix", c_int, [c_vp, c_vp, c_vp, c_vp]),
     ("vgs_estimate_matrix_h", c_int, [c_vp, c_vp, c_vp]),
     ("vgs_tile_plan", c_int, [c_i64, c_i64, c_int, c_int, _P(c_i64), _P(c_i64)]),
@@ -205,6 +207,14 @@ class Handle:
     def last_nll_kernel(self):
         """0 scan, 1 fp64 MMA contraction, 2 fp64 FMA contraction, 3 exact int8 tensor-core contraction."""
         return int(lib().vgs_last_nll_kernel(self._h))
+
+    def last_pair_kernel(self):
+        """0 CUDA-core pair kernels, 1 tensor-core (exact integer GEMM) path."""
+        return int(lib().vgs_last_pair_kernel(self._h))
+
+    def set_pair_path(self, path):
+        """-1 by universe density (default), 0 CUDA-core kernels, 1 tensor-core path wherever it applies."""
+        _check(lib().vgs_set_pair_path(self._h, {"auto": -1, "cuda": 0, "tensor": 1}.get(path, path)))
 
     def poll_error(self, stream):
         """Synchronise `stream` and raise what the kernels flagged (RuntimeError / KeyError)."""

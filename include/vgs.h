@@ -167,6 +167,13 @@ int vgs_nll_matrix_h(vgs_handle h, int64_t length, int mode, float *D32_out_h, d
 /* ---- FrobeniusNorm.distance (src/distance/frobenius.pyx:17-53) and Projection.distance
  *      (src/distance/projection.pyx:7-36) for all pairs; `kind` is a VGS_PAIR_* value. ------------- */
 int vgs_pair_matrix(vgs_handle h, int kind, float *D32_d, double *D64_d, void *stream);
+/* which kernels the most recent vgs_pair_matrix[_h] call used: 0 = CUDA-core pair kernels (sparse contexts, any depth),
+ * 1 = exact integer GEMMs on the tcgen05 tensor cores over the dense universe (Frobenius intersection / Projection,
+ * depth <= 7, N <= 4096, contexts filling >= 3 % of the universe; VGS_PAIR_TC=0 / 1 forces the choice) */
+int vgs_last_pair_kernel(vgs_handle h);
+/* path of the following vgs_pair_matrix[_h] calls: -1 (default) chosen by universe density, 0 CUDA cores (<= 1e-9 of the fp64
+ * oracle), 1 tensor cores wherever they apply (|d - d_oracle| <= 1.3e-7 d + 1e-9: rows quantised to 2^-31, exact integers) */
+int vgs_set_pair_path(vgs_handle h, int path);
 int vgs_pair_matrix_h(vgs_handle h, int kind, float *D32_out_h, double *D64_out_h);
 
 /* ---- EstimateVLMC.distance for all (left, right) (src/distance/estimate.pyx:19-108):

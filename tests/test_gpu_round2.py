@@ -175,3 +175,77 @@ def test_nll_only_and_lazy_table_loads():
     for k, s in outs[1:]:
         assert np.array_equal(k, outs[0][0]) and np.array_equal(s, outs[0][1])
     assert np.array_equal(outs[0][1], c_oracle.COracle(fm).nll_matrix(seqs))
+
+
+def _tc_bound_ok(D_tc, D_ref):
+    """Stated bound of the tensor-core variant: |d_tc - d_ref| <= 1.3e-7 d_ref + 1e-9 (rows quantised to 2^-31, the
+    difference of two rows not rounded to float32 before squaring)."""
+    fin = np.isfinite(D_ref)
+    assert np.array_equal(np.isnan(D_tc), np.isnan(D_ref))
+    return bool(np.all(np.abs(D_tc[fin] - D_ref[fin]) <= 1.3e-7 * np.abs(D_ref[fin]) + 1e-9))
+
+
+@pytest.mark.parametrize("shape", ["chains4", "chains6", "trees6", "trees7_sparse_forced", "tiny"])
+def test_tensor_core_frobenius_projection(shape):
+    """K5: Frobenius (intersection) and Projection as exact integer GEMMs on the tensor cores against the fp64 oracle
+    (stated bound) and the CUDA-core path (1e-9 of the oracle); symmetric, exact zero diagonal, exact zero between
+    duplicates, NaN for an empty intersection; the dispatcher picks the path by universe density."""
+    if shape == "chains4":
+        fm, _ = synthetic.make_full_chains(150, 3, 4)
+    elif shape == "chains6":
+        fm, _ = synthetic.make_full_chains(70, 4, 6)
+    elif shape == "trees6":
+        fm, _ = synthetic.make_family_models(200, 5, 6, 400, 8)
+    elif shape == "trees7_sparse_forced":
+        fm, _ = synthetic.make_family_models(90, 6, 7, 120, 5)
+    else:
+        fm, _ = synthetic.make_family_models(3, 7, 2, 9, 1)
+    n = fm.n_models
+    dup = fm.subset(list(range(n)) + [0, n - 1])     # two duplicates at the end
+    h = native.Handle(0)
+    h.load_models(dup, skip_nll=True)
+    co = c_oracle.COracle(dup)
+    for kind, mode in (("frobenius_intersection", "intersection"), ("projection", "projection")):
+        want = co.pair_matrix(mode)
+        h.set_pair_path("cuda")
+        Dc = h.pair_matrix_h(kind)[1]
+        assert h.last_pair_kernel() == 0
+        assert rel_err(Dc, want) < 1e-9
+        h.set_pair_path("tensor")
+        D32, Dt = h.pair_matrix_h(kind)
+        assert h.last_pair_kernel() == 1
+        assert _tc_bound_ok(Dt, want), (shape, kind, float(np.nanmax(np.abs(Dt - want) / np.maximum(np.abs(want), 1e-30))))
+        assert np.array_equal(Dt, Dt.T) and np.all(np.diag(Dt) == 0) and np.array_equal(D32, Dt.astype(np.float32))
+        assert Dt[0, n] == 0.0 and Dt[n - 1, n + 1] == 0.0 and Dt[n, 0] == 0.0
+        h.set_pair_path("auto")
+        h.pair_matrix_h(kind)
+        dense = fm.total_contexts >= 0.03 * n * ((4 ** (int(fm.orders().max()) + 1) - 1) // 3) and dup.n_models >= 64
+        assert h.last_pair_kernel() == (1 if dense else 0), shape
+    # the union stays on the CUDA cores whatever the setting
+    h.set_pair_path("tensor")
+    h.pair_matrix_h("frobenius_union")
+    assert h.last_pair_kernel() == 0
+
+
+def test_tensor_core_pair_edge_cases():
+    from clustering_genomic_signatures_b200.flat import FlatModels
+    U = dict(zip("ACGT", (0.25, 0.25, 0.25, 0.25)))
+    a = {"A": dict(zip("ACGT", (0.1, 0.2, 0.3, 0.4))), "": U}
+    b = {"C": dict(zip("ACGT", (0.4, 0.3, 0.2, 0.1))), "G": U}
+    c = {"T": U, "": dict(zip("ACGT", (1.0, 0.0, 0.0, 0.0)))}
+    fm = FlatModels.from_trees([a, b, c])
+    h = native.Handle(0)
+    h.load_models(fm, skip_nll=True)
+    h.set_pair_path("tensor")
+    D = h.pair_matrix_h("frobenius_intersection")[1]
+    assert h.last_pair_kernel() == 1
+    assert np.isnan(D[0, 1]) and np.isnan(D[1, 2]) and D[0, 0] == 0.0 and np.isfinite(D[0, 2])
+    co = c_oracle.COracle(fm)
+    assert _tc_bound_ok(D, co.pair_matrix("intersection"))
+    P = h.pair_matrix_h("projection")[1]
+    assert np.all(np.isfinite(P)) and _tc_bound_ok(P, co.pair_matrix("projection"))
+    # rows that are no probabilities (the `deltas` ingest can produce them) have no fixed-point form: CUDA cores
+    d = {"": dict(zip("ACGT", (1.5, -0.5, 0.0, 0.0)))}
+    h.load_models(FlatModels.from_trees([a, d, c]), skip_nll=True)
+    h.pair_matrix_h("projection")
+    assert h.last_pair_kernel() == 0
