@@ -143,11 +143,15 @@ class NegativeLogLikelihood(_DeviceDistance):
 class FrobeniusNorm(_DeviceDistance):
     """||P_l - P_r||_F / sqrt(#C) over the shared (default) or united context set, src/distance/frobenius.pyx:21-36."""
 
-    def __init__(self, use_union=False):
+    def __init__(self, use_union=False, path="auto"):
         super().__init__()
         self.use_union = use_union
+        # "auto": sets that fill >= 3 % of their universe (depth <= 7) go to the exact integer tensor-core GEMMs (within
+        # 1.3e-7 d + 1e-9 of the fp64 result), the rest to the CUDA-core kernels (1e-9); "cuda" / "tensor" force one
+        self.path = path
 
     def _compute(self, h, vlmcs, pair_only=False):
+        h.set_pair_path(self.path)
         return h.pair_matrix_h("frobenius_union" if self.use_union else "frobenius_intersection")
 
 
@@ -155,11 +159,12 @@ class Projection(_DeviceDistance):
     """Euclidean distance between the models embedded over the union of all context sets,
     src/distance/projection.pyx:7-36.  ``distance`` returns ``numpy.float32`` like the reference."""
 
-    def __init__(self):
+    def __init__(self, path="auto"):
         super().__init__()
         self.vlmcs = None
         self.dimension = 0
         self.context_transition_to_array_index = None
+        self.path = path   # see FrobeniusNorm
 
     def set_vlmcs(self, vlmcs):
         self.vlmcs = list(vlmcs)
@@ -172,6 +177,7 @@ class Projection(_DeviceDistance):
         self.distance_matrix(self.vlmcs)
 
     def _compute(self, h, vlmcs, pair_only=False):
+        h.set_pair_path(self.path)
         return h.pair_matrix_h("projection")
 
     def _value(self, i, j):

@@ -271,9 +271,21 @@ def test_full_size_properties():
     co = c_oracle.COracle(fm.subset(range(k)))
     M = h.nll_scores_h(native.SKIP_ORDER, "sequential")
     assert np.array_equal(M[:k, :k], co.score_matrix(seqs[:k]))
-    F32, F64 = h.pair_matrix_h("frobenius_intersection")
+    F32, F64 = h.pair_matrix_h("frobenius_intersection")   # cfg 2 fills 9 % of its universe: the tensor-core path
+    assert h.last_pair_kernel() == 1
     assert np.array_equal(F64, F64.T) and np.all(np.diag(F64) == 0)
-    assert np.allclose(F64[:k, :k], co.pair_matrix("intersection"), rtol=1e-9, atol=0)
+    want = co.pair_matrix("intersection")
+    assert np.all(np.abs(F64[:k, :k] - want) <= 1.3e-7 * want + 1e-9)
+    h.set_pair_path("cuda")
+    F32c, F64c = h.pair_matrix_h("frobenius_intersection")
+    assert h.last_pair_kernel() == 0 and np.array_equal(F64c, F64c.T) and np.all(np.diag(F64c) == 0)
+    assert np.allclose(F64c[:k, :k], want, rtol=1e-9, atol=0)
+    # downstream: both paths give the same average-link clusters
+    import torch
+    kf = int(fam.max()) + 1
+    la, ma = h.average_link(torch.from_numpy(F32).cuda(), kf)
+    lb, mb = h.average_link(torch.from_numpy(F32c).cuda(), kf)
+    assert np.array_equal(la, lb) and np.allclose(ma, mb, rtol=1e-6)
     # same-family pairs are closer than cross-family pairs on average (the set clusters)
     same = fam[:, None] == fam[None, :]
     assert F64[same & off].mean() < 0.5 * F64[~same].mean()

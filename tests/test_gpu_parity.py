@@ -215,9 +215,18 @@ def test_against_c_oracle_medium(n, depth, ctx, L):
     D32k, D64k = h.nll_matrix_h(L, "kmer")
     assert rel_err(D64k, D_or) < RTOL and np.all(np.diag(D64k) == 0) and np.array_equal(D64k, D64k.T)
     for kind, mode in (("frobenius_intersection", "intersection"), ("frobenius_union", "union"), ("projection", "projection")):
+        h.set_pair_path("cuda")          # fp64-accumulating CUDA-core kernels: the 1e-9 bar
         D32, D64 = h.pair_matrix_h(kind)
-        assert rel_err(D64, co.pair_matrix(mode)) < RTOL
+        assert h.last_pair_kernel() == 0
+        want = co.pair_matrix(mode)
+        assert rel_err(D64, want) < RTOL
         assert np.allclose(D64, D64.T, rtol=1e-14, atol=0)
+        h.set_pair_path("auto")          # dense enough sets go to the tensor cores: their stated bound
+        D32a, D64a = h.pair_matrix_h(kind)
+        if h.last_pair_kernel() == 1:
+            assert np.all(np.abs(D64a - want) <= 1.3e-7 * np.abs(want) + 1e-9) and np.array_equal(D64a, D64a.T)
+        else:
+            assert np.array_equal(D64a, D64)
     if depth <= 9:
         k = 12
         sub = fm.subset(range(k))

@@ -1,11 +1,11 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-{
-timeout 600 python -m pytest tests/test_gpu_round2.py -x -q -k "tensor_core" 2>&1 | tail -15
-timeout 300 python tools/pair_tune.py trees 1000 6 500
-timeout 300 python tools/pair_tune.py chains 1000 6
-timeout 300 python tools/pair_tune.py chains 400 7
-timeout 300 python tools/pair_tune.py trees 1000 7 500
-} > gpurun_out/b_tune.log 2>&1
-cat gpurun_out/b_tune.log | cut -c1-300
+timeout 1500 python tests/large_cfg5.py > gpurun_out/r2_cfg5_sweep_1gpu.jsonl 2> gpurun_out/cfg5.err
+echo "cfg5 exit $?"; tail -3 gpurun_out/cfg5.err; python - <<'PY'
+import json
+for l in open('gpurun_out/r2_cfg5_sweep_1gpu.jsonl'):
+    d=json.loads(l)
+    ft=d.get('frobenius_tensor')
+    print(d['arm'],d['depth'],d['n_models'],'ctx %.0f'%d['mean_contexts'],'fill %.3f'%d['universe_fill'],'| frob cuda %.3f ms ok=%s'%(d['frobenius_cuda']['ms'],d['frobenius_cuda']['corner_within_bound_of_c_oracle']),'| tensor',('%.3f ms ok=%s'%(ft['ms'],ft['corner_within_bound_of_c_oracle']) if ft else None),'| picks',d['dispatcher_picks'],'| nll %.3f ms %s ok=%s'%(d['nll']['ms'],d['nll']['kernel'][:6],d['nll']['within_1e-9']))
+PY
