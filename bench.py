@@ -420,9 +420,12 @@ def main():
     if kind == "nll" and args.mode == "kmer":
         tile = max(128, tile // 128 * 128)
     job = None
+    replicated = False
     if sharded:
         job = ShardedNllJob(h, n, L, mode=args.mode, exchange=args.exchange)
         D32 = job.D32
+    elif world > 1 and kind in native.PAIR_KINDS and h.pair_kernel_choice(kind) == 1:
+        replicated = True   # tensor-core pair path: every rank computes the whole (cheap) matrix, nothing to shard
     elif world > 1:
         nt, slots = native.tile_plan(n, tile, world, symmetric)
         payload = torch.zeros(slots * tile * tile, dtype=torch.float32, device=dev)
@@ -432,7 +435,7 @@ def main():
         if sharded:
             job.mode = args.mode
             job.run()
-        elif world == 1:
+        elif world == 1 or replicated:
             if kind == "nll":
                 h.nll_matrix(L, args.mode, D32, None, stream)
             elif kind == "estimate":
@@ -519,6 +522,7 @@ def main():
     ms_step, tb, te = timed(device_step, args.steps, 0, True)
     launches = h.launch_count() - l0
     nll_kernel = h.last_nll_kernel() if kind == "nll" else -1   # which score kernel the timed steps used
+    pair_tc = kind not in ("nll", "estimate") and h.last_pair_kernel() == 1
     k_ms, k_n = h.profile_read(prof_id)
     h.profile_enable(False)
     clocks = sampler.stop(tb, te) if rank == 0 else None
@@ -527,7 +531,7 @@ def main():
     # ---- end to end through the host-buffer C-ABI
     e2e_ms, _, _ = timed(e2e_step, max(3, args.steps // 4), 1, False)
 
-    if args.breakdown and world > 1 and not sharded:
+    if args.breakdown and world > 1 and not sharded and not replicated:
         def ev():
             return torch.cuda.Event(enable_timing=True)
         acc = np.zeros(3)
@@ -606,7 +610,7 @@ def main():
         probe = scale_probe(args, world, rank, local_rank, dev, bit_checksum)
 
     i8_peak = None
-    if nll_kernel == 3 and rank == 0:
+    if (nll_kernel == 3 or pair_tc) and rank == 0:
         i8_peak = {"cta_group_2_tops": h.tensor_peak_i8(2)[0], "cta_group_1_tops": h.tensor_peak_i8(1)[0]}
 
     exchange_used = None
@@ -632,8 +636,9 @@ def main():
     k_avg_ms = k_ms / max(k_n, 1)
     launches_per_step = max(1, k_n // args.steps)
     achieved = alg_bytes_rank / launches_per_step / (k_avg_ms / 1000.0) / 1e9 if k_avg_ms > 0 else None
-    kernel_name = {0: {3: "k_kmer_i8mma", 1: "k_kmer_dmma", 2: "k_kmer_gemm"}.get(nll_kernel, "k_nll_scores") if kind == "nll" else "",
-                   1: "k_pair_partials", 2: "k_est_pairs"}[prof_id]
+    kernel_name = {0: {3: "k_g8_gemm<EpiNll> (int8 tcgen05 contraction)", 1: "k_kmer_dmma", 2: "k_kmer_gemm"}.get(nll_kernel, "k_nll_scores")
+                   if kind == "nll" else "", 1: "k_g8_gemm<EpiRaw> (int8 tcgen05, a.a digit GEMM)" if pair_tc else "k_pair_partials",
+                   2: "k_est_pairs"}[prof_id]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": (achieved / peak_gbs) if achieved else None, "traffic": None,
                 "kernel": kernel_name,
@@ -675,6 +680,45 @@ def main():
                                  "one fp64-equivalent MAC per 8 executed int8 MACs"})
         for k in ("algorithmic_bytes_per_step", "algorithmic_bytes_formula"):
             roofline.pop(k, None)   # SURVEY 8d's scan-bytes model does not describe a contraction
+    elif pair_tc and k_avg_ms > 0:
+        # Frobenius (intersection) / Projection on the tensor cores: the dominant kernel is the a.a digit GEMM over the dense
+        # universe: 4 digit rows per model on either side, upper triangle of 256-row blocks, K = 4 x universe (padded to 128)
+        D_ = int(orders.max())
+        U_ = (4 ** (D_ + 1) - 1) // 3
+        K8 = (4 * U_ + 127) // 128 * 128
+        rows = 4 * n
+        g_ld = (rows + 31) // 32 * 32
+        macs = sum(256.0 * (g_ld - 256 * a) * K8 for a in range((rows + 255) // 256))
+        ops = 2.0 * macs
+        a_tops = ops / (k_avg_ms / 1e3) / 1e12
+        probe_peak = (i8_peak or {}).get("cta_group_2_tops") or 0.0
+        peak_bf16 = float(peaks.get("bf16_tflops", 1590.0))
+        peak_used = probe_peak if probe_peak > 0 else 2.0 * peak_bf16
+        roofline.update({"bound": "tensor", "achieved": a_tops, "peak": peak_used, "unit": "TFLOP/s", "frac": a_tops / peak_used,
+                         "peak_source": "int8 tensor-pipe peak measured in this run by vgs_tensor_peak_i8 (of measured)" if probe_peak > 0
+                         else "2 x MEASURED_PEAKS.json bf16_tflops (probe unavailable)",
+                         "int8_peak_probe": i8_peak, "frac_of_2x_bf16_burst": a_tops / (2.0 * peak_bf16), "ops_per_launch": ops,
+                         "ops_formula": "2 x sum over 256-row blocks a of 256 x (4N - 256 a) x (4 x universe): the executed int8 MACs of the a.a "
+                                        "digit GEMM (16 digit pairs per model pair, upper triangle)",
+                         "note": "second GEMM (sq.n, 9 x N x N x universe MACs) and the 128-bit recombination follow; the CUDA-core "
+                                 "kernel k_pair_partials runs the same matrix in the time profiles/r2_cfg5_sweep_1gpu.jsonl lists"})
+        for k in ("algorithmic_bytes_per_step", "algorithmic_bytes_formula"):
+            roofline.pop(k, None)
+    elif kind != "nll" and k_avg_ms > 0:
+        # CUDA-core pair kernels / Estimate: the tables are staged in shared memory (or live in L2) and reused for many pairs,
+        # so SURVEY 8d's per-pair bytes are NOT DRAM traffic and their rate is not bounded by HBM (it exceeded the peak in
+        # round 1).  The roofline entry is therefore the kernel's measured DRAM traffic (ncu, profiles/traffic.json) against
+        # HBM -- a small fraction: the kernel is bound by shared-memory gathers and issue slots (ncu: XU pipe 45-55 %,
+        # shared-memory wavefronts 60 %, profiles/r2_ncu_full_pairs_tc_vs_cuda_core.txt) -- and the algorithmic rate is kept
+        # beside it, labelled as what it is.
+        tr = roofline.get("traffic")
+        roofline["algorithmic_rate_GBps_not_a_roofline"] = achieved
+        if tr:
+            a_dram = tr / (k_avg_ms / 1e3) / 1e9
+            roofline.update({"achieved": a_dram, "frac": a_dram / peak_gbs})
+        else:
+            roofline.update({"achieved": None, "frac": None})
+        roofline["binding_resource"] = "shared-memory gathers + issue slots (not HBM): see profiles/r2_ncu_full_pairs_tc_vs_cuda_core.txt"
     elif kind == "nll" and nll_kernel in (1, 2) and k_avg_ms > 0:
         # the contraction is an fp64 MMA kernel: report it against the fp64 pipe as well
         # (64 fp64 FMA lanes per SM: 2 * 64 * SMs * max SM clock)
@@ -684,6 +728,14 @@ def main():
                             "frac": flops / (k_avg_ms / 1e3) / 1e12 / peak64,
                             "peak_source": "64 fp64 FMA lanes/SM x %d SMs x sm_max_mhz" % sm_count}
 
+    if kind == "nll" and nll_kernel == 0 and k_avg_ms > 0:
+        # scan kernel: one random 8-byte shared-memory gather per scored base.  Conflict-free that is 16 gathers per clock and
+        # SM (128 B/clk); random 8-byte addresses from a half-warp collide on the 16 bank pairs 3.1 x on average (measured 6.36
+        # wavefronts per warp-wide LDS.64 against 2.04 ideal), so the reachable rate is ~5.2 gathers per clock and SM
+        gathers = float(n) * n * L / world
+        per_clk_sm = gathers / (k_avg_ms / 1e3) / (sm_count * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6)
+        roofline["smem_gather"] = {"gathers_per_clk_per_sm": per_clk_sm, "conflict_free_peak": 16.0, "random_address_expectation": 5.2,
+                                   "frac_of_random_address_expectation": per_clk_sm / 5.2}
     line = {
         "metric": "pair-distances/sec", "value": pairs / (ms_step / 1000.0), "unit": unit, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -696,7 +748,8 @@ def main():
                    "parallelism": ("models sharded over ranks (each rank loads / tabulates its own), sequences replicated; score bands "
                                    + ("stored into every rank's matrix by the GEMM epilogue over NVLink peer memory + flag barrier"
                                       if exchange_used == "peer" else "all-gathered with NCCL") + "; local combine") if sharded else
-                                  ("tile-sharded upper triangle + NCCL all-gather" if world > 1 else "single GPU"),
+                                  ("replicas: the tensor-core pair path computes the whole matrix on every rank (N <= 4096, nothing to shard)"
+                                   if replicated else "tile-sharded upper triangle + NCCL all-gather" if world > 1 else "single GPU"),
                    "exchange": exchange_used,
                    "sm_count": sm_count},
         "e2e": {"value": pairs / (e2e_ms / 1000.0), "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),

@@ -72,8 +72,13 @@ class VgsPool {
 
 static VgsPool *get_pool(vgs_context *h) {
     if (!h->pool) {
+        // one process per GPU (torchrun) means several handles share the host's cores: split them, or N x 15 threads on 16
+        // cores make every rank's ln p pass N times slower (e2e at 8 GPUs).  VGS_HOST_THREADS overrides.
         unsigned hc = std::thread::hardware_concurrency();
-        int n = (int)std::max(1u, std::min(hc > 2 ? hc - 1 : 1u, 24u));
+        unsigned share = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(e));
+        int n = (int)std::max(1u, std::min((hc > 2 ? hc - 1 : 1u) / share, 24u));
+        if (const char *e = getenv("VGS_HOST_THREADS")) n = std::max(1, std::min(64, atoi(e)));
         h->pool = new VgsPool(n);
     }
     return (VgsPool *)h->pool;

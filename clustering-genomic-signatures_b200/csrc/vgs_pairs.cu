@@ -407,6 +407,12 @@ static int check_pair_args(vgs_context *h, int kind) {
 }
 
 extern "C" int vgs_last_pair_kernel(vgs_handle h) { return h ? h->last_pair_kernel : 0; }
+// which kernels vgs_pair_matrix would use for `kind` on the loaded set (the tile entry points always use the CUDA cores)
+extern "C" int vgs_pair_kernel_choice(vgs_handle h, int kind) {
+    if (!h || h->n_models <= 0 || !h->prob_ready) return 0;
+    if (!vgs_pair_tc_wanted(h, kind)) return 0;
+    return (h->tc_gen == h->model_gen && !h->tc_ok) ? 0 : 1;
+}
 extern "C" int vgs_set_pair_path(vgs_handle h, int path) {
     VGS_CHECK_ARG(h && path >= -1 && path <= 1, "vgs_set_pair_path: path is -1 (by density), 0 (CUDA cores) or 1 (tensor cores)");
     h->pair_path = path;

@@ -199,7 +199,10 @@ class MatrixJob(object):
         self.device = torch.device("cuda", handle.device)
         self.D32 = torch.empty((n, n), dtype=torch.float32, device=self.device)
         self.tile = tile or default_tile(n, self.world)
-        if self.world > 1:
+        # dense-universe Frobenius / Projection sets go to the tensor cores (N <= 4096, a fraction of a millisecond): every
+        # rank computes the whole matrix itself -- nothing to shard, and the same bits as on one GPU
+        self.replicated = self.world > 1 and kind in native.PAIR_KINDS and handle.pair_kernel_choice(kind) == 1
+        if self.world > 1 and not self.replicated:
             n_tiles, slots = native.tile_plan(n, self.tile, self.world, self.symmetric)
             self.n_tiles, self.slots = n_tiles, slots
             self.payload = torch.zeros(slots * self.tile * self.tile, dtype=torch.float32, device=self.device)
@@ -218,7 +221,7 @@ class MatrixJob(object):
         import torch
         import torch.distributed as dist
         stream = torch.cuda.current_stream().cuda_stream
-        if self.world == 1:
+        if self.world == 1 or self.replicated:
             if self.kind == "nll":
                 self.h.nll_matrix(self.length, self.mode, self.D32, None, stream)
             elif self.kind == "estimate":

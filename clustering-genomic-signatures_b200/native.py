@@ -51,6 +51,7 @@ SIGNATURES = [
     ("vgs_pair_matrix_h", c_int, [c_vp, c_int, c_vp, c_vp]),
     ("vgs_last_pair_kernel", c_int, [c_vp]),
     ("vgs_set_pair_path", c_int, [c_vp, c_int]),
+    ("vgs_pair_kernel_choice", c_int, [c_vp, c_int]),
     ("vgs_estimate_matrix", c_int, [c_vp, c_vp, c_vp, c_vp]),
     ("vgs_estimate_matrix_h", c_int, [c_vp, c_vp, c_vp]),
     ("vgs_tile_plan", c_int, [c_i64, c_i64, c_int, c_int, _P(c_i64), _P(c_i64)]),
@@ -211,6 +212,10 @@ class Handle:
     def last_pair_kernel(self):
         """0 CUDA-core pair kernels, 1 tensor-core (exact integer GEMM) path."""
         return int(lib().vgs_last_pair_kernel(self._h))
+
+    def pair_kernel_choice(self, kind):
+        """Which kernels pair_matrix would use for this kind on the loaded set: 0 CUDA cores, 1 tensor cores."""
+        return int(lib().vgs_pair_kernel_choice(self._h, PAIR_KINDS[kind]))
 
     def set_pair_path(self, path):
         """-1 by universe density (default), 0 CUDA-core kernels, 1 tensor-core path wherever it applies."""

@@ -171,6 +171,10 @@ int vgs_pair_matrix(vgs_handle h, int kind, float *D32_d, double *D64_d, void *s
  * 1 = exact integer GEMMs on the tcgen05 tensor cores over the dense universe (Frobenius intersection / Projection,
  * depth <= 7, N <= 4096, contexts filling >= 3 % of the universe; VGS_PAIR_TC=0 / 1 forces the choice) */
 int vgs_last_pair_kernel(vgs_handle h);
+/* the kernels vgs_pair_matrix WOULD use for `kind` on the loaded set (same 0 / 1).  A set the tensor-core path takes is cheap
+ * enough (N <= 4096) that a multi-GPU job computes it on every rank instead of sharding its tiles -- the engine asks here,
+ * so that one model set gives the same bits on 1, 2, 4 or 8 GPUs */
+int vgs_pair_kernel_choice(vgs_handle h, int kind);
 /* path of the following vgs_pair_matrix[_h] calls: -1 (default) chosen by universe density, 0 CUDA cores (<= 1e-9 of the fp64
  * oracle), 1 tensor cores wherever they apply (|d - d_oracle| <= 1.3e-7 d + 1e-9: rows quantised to 2^-31, exact integers) */
 int vgs_set_pair_path(vgs_handle h, int path);

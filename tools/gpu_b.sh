@@ -1,11 +1,16 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 1500 python tests/large_cfg5.py > gpurun_out/r2_cfg5_sweep_1gpu.jsonl 2> gpurun_out/cfg5.err
-echo "cfg5 exit $?"; tail -3 gpurun_out/cfg5.err; python - <<'PY'
-import json
-for l in open('gpurun_out/r2_cfg5_sweep_1gpu.jsonl'):
-    d=json.loads(l)
-    ft=d.get('frobenius_tensor')
-    print(d['arm'],d['depth'],d['n_models'],'ctx %.0f'%d['mean_contexts'],'fill %.3f'%d['universe_fill'],'| frob cuda %.3f ms ok=%s'%(d['frobenius_cuda']['ms'],d['frobenius_cuda']['corner_within_bound_of_c_oracle']),'| tensor',('%.3f ms ok=%s'%(ft['ms'],ft['corner_within_bound_of_c_oracle']) if ft else None),'| picks',d['dispatcher_picks'],'| nll %.3f ms %s ok=%s'%(d['nll']['ms'],d['nll']['kernel'][:6],d['nll']['within_1e-9']))
+{
+timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -6
+timeout 120 python tools/i8_tune.py 10
+} > gpurun_out/b_tune.log 2>&1
+cat gpurun_out/b_tune.log | cut -c1-300
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/b_launches.csv python tools/i8_tune.py 2 > /dev/null 2>&1
+python - <<'PY'
+import csv
+rows=list(csv.reader(open('gpurun_out/b_launches.csv')))
+hdr=[i for i,r in enumerate(rows) if r and r[0]=='ID'][0]
+cols=rows[hdr]; ki=cols.index('Kernel Name'); vi=cols.index('Metric Value')
+for r in rows[hdr+1:][-8:]: print('%-60s %8.1f us'%(r[ki][:60], float(r[vi].replace(',',''))/1000))
 PY
