@@ -294,6 +294,7 @@ int vgs_kmer_i8_digits_end(vgs_context *h, cudaStream_t s);                // af
 int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, const VgsScoreDst &dst, cudaStream_t s);
 bool vgs_pair_tc_wanted(vgs_context *h, int kind);
 int vgs_pair_tc_matrix(vgs_context *h, int kind, float *D32, double *D64, cudaStream_t s);   // -1: not applicable
+int vgs_peer_barrier_impl(vgs_context *h, uint32_t *const *flags_h, int rank, int world, uint32_t epoch, cudaStream_t stream);
 int vgs_ensure_scan_tables(vgs_context *h, cudaStream_t s);   // tier 1-3 NLL tables of the scan kernels
 int vgs_ensure_umap(vgs_context *h, cudaStream_t s);          // universe maps (shallow sets) of the pair kernels
 int vgs_assemble_impl(vgs_context *h, const TilePlan &p, const float *gathered32, const double *gathered64,

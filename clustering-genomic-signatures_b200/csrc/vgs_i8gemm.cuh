@@ -418,7 +418,11 @@ template <class Epi>
 static int g8_launch(vgs_context *h, const G8Args &g, const Epi &epi, cudaStream_t s) {
     if (g.n_units <= 0) return VGS_OK;
     auto kern = k_g8_gemm<Epi>;
-    VGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G8_SMEM_BYTES));
+    static bool attr_set[64] = {false};   // per device (one entry per template instance): not on every launch
+    if (!attr_set[h->device & 63]) {
+        VGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G8_SMEM_BYTES));
+        attr_set[h->device & 63] = true;
+    }
     const int n_clusters = std::max(1, std::min(g.n_units, h->sm_count / 2));
     static int want_prof = -1, n_stages = -1, dbg = -1;
     if (want_prof < 0) { const char *e = getenv("VGS_G8_PROF"); want_prof = (e && e[0] == '1') ? 1 : 0; }

@@ -720,6 +720,26 @@ extern "C" int vgs_nll_scores_band(vgs_handle h, int mode, int64_t m_col0, int64
     return nll_scores_band_impl(h, mode, m_col0, ld, Mt_dsts_h, n_dst, (cudaStream_t)stream);
 }
 
+// one step of the model-sharded job in ONE call (three kernels' worth of host work, one trip through the binding): the band
+// into every destination, the peer barrier (when the destinations are peer-mapped), the local combine
+extern "C" int vgs_nll_sharded_step(vgs_handle h, int mode, int64_t m_col0, int64_t n_total, double *const *Mt_dsts_h, int n_dst,
+                                    uint32_t *const *flags_h, int rank, int world, uint32_t epoch, int64_t length, float *D32_d,
+                                    void *stream) {
+    int rc = vgs_nll_scores_band(h, mode, m_col0, n_total, Mt_dsts_h, n_dst, stream);
+    if (rc) return rc;
+    VGS_CHECK_ARG(length > 0 && D32_d, "vgs_nll_sharded_step: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_dst > 1) {
+        VGS_CHECK_ARG(flags_h && n_dst == world, "vgs_nll_sharded_step: peer stores need every rank's matrix and flag array");
+        if ((rc = vgs_peer_barrier_impl(h, flags_h, rank, world, epoch, s))) return rc;
+    }
+    const unsigned g = (unsigned)((n_total + 31) / 32);
+    VGS_CHECK_ARG(g <= 65535, "vgs_nll_sharded_step: matrix too large");
+    k_nll_combine_full<<<dim3(g, g), 256, 0, s>>>(n_total, Mt_dsts_h[0], n_total, (double)length, D32_d, nullptr, h->d_err, 1);
+    VGS_LAUNCH_CHECK(h);
+    return VGS_OK;
+}
+
 extern "C" int vgs_nll_combine(vgs_handle h, int64_t n, const double *Mt_d, int64_t ld, int64_t length, float *D32_d, double *D64_d,
                                void *stream) {
     VGS_CHECK_ARG(h && n > 0 && Mt_d && ld >= n && length > 0 && D32_d, "vgs_nll_combine: bad arguments");

@@ -79,13 +79,19 @@ __global__ void k_peer_barrier(PeerFlags pf, int rank, int world, uint32_t epoch
     }
 }
 
+int vgs_peer_barrier_impl(vgs_context *h, uint32_t *const *flags_h, int rank, int world, uint32_t epoch, cudaStream_t stream);
 extern "C" int vgs_peer_barrier(vgs_handle h, uint32_t *const *flags_h, int rank, int world, uint32_t epoch, void *stream) {
-    VGS_CHECK_ARG(h && flags_h && world >= 1 && world <= VGS_MAX_PEERS && rank >= 0 && rank < world, "vgs_peer_barrier: bad arguments");
+    VGS_CHECK_ARG(h, "null handle");
     VGS_CUDA(cudaSetDevice(h->device));
+    return vgs_peer_barrier_impl(h, flags_h, rank, world, epoch, (cudaStream_t)stream);
+}
+
+int vgs_peer_barrier_impl(vgs_context *h, uint32_t *const *flags_h, int rank, int world, uint32_t epoch, cudaStream_t stream) {
+    VGS_CHECK_ARG(h && flags_h && world >= 1 && world <= VGS_MAX_PEERS && rank >= 0 && rank < world, "vgs_peer_barrier: bad arguments");
     PeerFlags pf;
     for (int r = 0; r < VGS_MAX_PEERS; ++r) pf.flags[r] = r < world ? flags_h[r] : nullptr;
     for (int r = 0; r < world; ++r) VGS_CHECK_ARG(pf.flags[r] != nullptr, "vgs_peer_barrier: null flag array");
-    k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(pf, rank, world, epoch, h->d_err);
+    k_peer_barrier<<<1, 32, 0, stream>>>(pf, rank, world, epoch, h->d_err);
     VGS_LAUNCH_CHECK(h);
     return VGS_OK;
 }

@@ -138,9 +138,10 @@ class ShardedNllJob(object):
         if self.exchange == "peer":
             self.epoch += 1
             off = (self.epoch & 1) * self._mt_bytes
-            mt = self.mt_ptr + off
-            self.h.nll_scores_band(self.mode, self.m0, self.n, [p + off for p in self._dsts], stream)
-            self.h.peer_barrier(self._flags, self.rank, self.epoch, stream)
+            # peer order for the library: destination 0 = this rank's matrix; the flag arrays stay in rank order
+            self.h.nll_sharded_step(self.mode, self.m0, self.n, [p + off for p in self._dsts], self._flags, self.rank, self.world,
+                                    self.epoch, self.length, self.D32, stream)
+            return self.D32
         else:
             self.h.nll_scores_band(self.mode, self.m0, self.n, [self.mt_ptr], stream)
             if self.world > 1:

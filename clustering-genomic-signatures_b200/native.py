@@ -61,6 +61,7 @@ SIGNATURES = [
     ("vgs_assemble", c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     ("vgs_nll_scores_band", c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp]),
     ("vgs_nll_combine", c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    ("vgs_nll_sharded_step", c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_int, c_int, ctypes.c_uint32, c_i64, c_vp, c_vp]),
     ("vgs_peer_alloc", c_int, [c_vp, c_i64, _P(c_vp), c_vp]),
     ("vgs_peer_open", c_int, [c_vp, c_vp, _P(c_vp)]),
     ("vgs_peer_close", c_int, [c_vp, c_vp]),
@@ -394,6 +395,13 @@ class Handle:
         """dst_ptrs: device addresses (ints) of the transposed score matrices to write, this GPU's first."""
         arr = (c_vp * len(dst_ptrs))(*[c_vp(int(p)) for p in dst_ptrs])
         _check(lib().vgs_nll_scores_band(self._h, NLL_MODES[mode], m_col0, ld, arr, len(dst_ptrs), c_vp(stream)))
+
+    def nll_sharded_step(self, mode, m_col0, n_total, dst_ptrs, flag_ptrs, rank, world, epoch, length, D32, stream):
+        """band -> (peer barrier) -> combine in one library call; dst_ptrs / flag_ptrs: device addresses (ints)."""
+        dsts = (c_vp * len(dst_ptrs))(*[c_vp(int(p)) for p in dst_ptrs])
+        flags = (c_vp * len(flag_ptrs))(*[c_vp(int(p)) for p in flag_ptrs]) if flag_ptrs else None
+        _check(lib().vgs_nll_sharded_step(self._h, NLL_MODES[mode], m_col0, n_total, dsts, len(dst_ptrs), flags, rank, world,
+                                          epoch & 0xFFFFFFFF, length, _dev_ptr(D32), c_vp(stream)))
 
     def nll_combine(self, n, Mt, ld, length, D32, D64, stream):
         _check(lib().vgs_nll_combine(self._h, n, _dev_ptr(Mt), ld, length, _dev_ptr(D32), _dev_ptr(D64), c_vp(stream)))

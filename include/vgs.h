@@ -209,6 +209,12 @@ int vgs_assemble(vgs_handle h, int64_t n, int64_t tile, int world, int symmetric
  *      optionally fp64) [n][n] distance matrix; entry (i, j) needs Mt[j][i], Mt[i][j] and both diagonal scores. ------- */
 int vgs_nll_scores_band(vgs_handle h, int mode, int64_t m_col0, int64_t ld, double *const *Mt_dsts_h, int n_dst, void *stream);
 int vgs_nll_combine(vgs_handle h, int64_t n, const double *Mt_d, int64_t ld, int64_t length, float *D32_d, double *D64_d, void *stream);
+/* one whole step of the model-sharded job in a single call: vgs_nll_scores_band into Mt_dsts_h (leading dimension n_total),
+ * vgs_peer_barrier when there are peer destinations (n_dst == world; flags_h as for vgs_peer_barrier), vgs_nll_combine of
+ * Mt_dsts_h[0] into D32_d */
+int vgs_nll_sharded_step(vgs_handle h, int mode, int64_t m_col0, int64_t n_total, double *const *Mt_dsts_h, int n_dst,
+                         uint32_t *const *flags_h /* nullable when n_dst == 1 */, int rank, int world, uint32_t epoch, int64_t length,
+                         float *D32_d, void *stream);
 
 /* ---- peer memory over NVLink (one process per GPU): vgs_peer_alloc returns a zeroed device buffer and its 64-byte CUDA
  *      IPC handle; the other ranks map it with vgs_peer_open (and unmap with vgs_peer_close); the owner frees it with

@@ -249,3 +249,58 @@ def test_tensor_core_pair_edge_cases():
     h.load_models(FlatModels.from_trees([a, d, c]), skip_nll=True)
     h.pair_matrix_h("projection")
     assert h.last_pair_kernel() == 0
+
+
+def test_tree_files_to_device_tables(tmp_path):
+    """Row f3 end to end: `.tree` text -> native parser (vgs_parse_tree_text) -> FlatModels -> device tables: lookups and the
+    NLL matrix bit-exact against the oracle built from the REFERENCE parser's JSON of the same files; the `deltas` ingest
+    (src/parse_trees_to_json.py:40-44) gives the same rows as the reference's JSON and loads for the pair distances."""
+    import json
+    import os
+
+    import golden_io
+    from clustering_genomic_signatures_b200 import parse_trees_to_json
+    from clustering_genomic_signatures_b200.flat import FlatModels, encode_history
+    with open(os.path.join(golden_io.GOLD, "tree_parse_golden.json")) as fh:
+        gold = json.load(fh)
+    for name, item in gold.items():
+        (tmp_path / name).write_text(item["text"])
+    fm, occ = parse_trees_to_json.load_tree_dir_flat(str(tmp_path))
+    names = sorted(gold)
+    trees = [gold[k]["json"]["tree"] for k in names]
+    ref_fm = FlatModels.from_trees(trees)
+    assert np.array_equal(fm.prob, ref_fm.prob) and np.array_equal(fm.ctx_code, ref_fm.ctx_code)
+    h = native.Handle(0)
+    h.load_models(fm)
+    # lookups: every context is found as itself; a random longer history resolves to the oracle's longest suffix
+    rng = np.random.default_rng(5)
+    models, codes, lens, want = [], [], [], []
+    for m, t in enumerate(trees):
+        keys = list(t)
+        for i, c in enumerate(keys):
+            ln, code = encode_history(c)
+            models.append(m); codes.append(code); lens.append(ln); want.append(i)
+        for _ in range(200):
+            hist = "".join(rng.choice(list("ACGT"), size=int(rng.integers(0, 12))))
+            ln, code = encode_history(hist)
+            models.append(m); codes.append(code); lens.append(ln)
+            want.append(keys.index(O.get_context(t, O.order_of(t), hist)))
+    got = h.lookup(models, codes, lens)
+    assert np.array_equal(got, np.array(want, dtype=np.int32))
+    seqs = synthetic.sample_sequences(fm, 700, 3)
+    h.load_sequences_packed(*pack_sequences(seqs))
+    D = h.nll_matrix_h(700, "sequential")[1]
+    assert np.array_equal(D, c_oracle.COracle(ref_fm).nll_matrix(seqs))
+    # deltas mode
+    with open(os.path.join(golden_io.GOLD, "tree_parse_deltas_golden.json")) as fh:
+        gold_d = json.load(fh)
+    d_dir = tmp_path / "deltas"
+    d_dir.mkdir()
+    for name, item in gold_d.items():
+        (d_dir / name).write_text(item["text"])
+    fmd, _ = parse_trees_to_json.load_tree_dir_flat(str(d_dir), deltas=True)
+    ref_d = FlatModels.from_trees([gold_d[k]["json"]["tree"] for k in sorted(gold_d)])
+    assert np.array_equal(fmd.prob, ref_d.prob)
+    h.load_models(fmd, skip_nll=True)
+    F = h.pair_matrix_h("frobenius_intersection")[1]
+    assert rel_err(F, c_oracle.COracle(ref_d).pair_matrix("intersection")) < 1e-9
