@@ -11,11 +11,16 @@ sec at 1/2/4/8 B200" is quoted on.  ``--workload frobenius`` is BASELINE configs
 
 A step = one full N x N float32 distance matrix:
   value  tables and packed sequences already resident in HBM -> matrix resident on every GPU
-         (N > 1: upper-triangular tile space sharded over ranks, NCCL all-gather, local assemble);
+         (N > 1, NLL: models sharded over ranks, score bands stored into every rank's matrix by the GEMM epilogue over NVLink
+         peer memory + flag barrier -- or NCCL all-gather --, local combine; other kinds: upper-triangular tile space sharded
+         over ranks, NCCL all-gather, local assemble);
   e2e    the same matrix through the C-ABI with HOST buffers: H2D of the flat model tables and packed
          sequences (pinned), table construction, kernels, D2H of the float32 matrix (pinned).
 Timing: CUDA events on the launching stream, one pair per step, L2 flushed (256 MiB memset) between
 steps outside the timed pairs, barrier + synchronize on both sides, max over ranks.
+Extra keys: `matrix_checksum` (exact int64 sum of the float32 bit patterns: equal across GPU counts iff the matrices are),
+`parity_check` (N > 1: this rank's matrix == the single-GPU matrix of the unsharded set, min over ranks), `scale_probe` (a cfg-4
+slice, N = 8000 depth 9: Frobenius with sharded tiles and NLL with sharded models at this GPU count; `--probe-models 0` skips).
 """
 import argparse
 import json
@@ -742,7 +747,7 @@ def main():
         # scan kernel: one random 8-byte shared-memory gather per scored base.  Conflict-free that is 16 gathers per clock and
         # SM (128 B/clk); random 8-byte addresses from a half-warp collide on the 16 bank pairs 3.1 x on average (measured 6.36
         # wavefronts per warp-wide LDS.64 against 2.04 ideal), so the reachable rate is ~5.2 gathers per clock and SM
-        gathers = float(n) * n * L / world
+        gathers = float(n) * n * L / world * (2.0 if orders.max() > 6 else 1.0)   # deep sets: first-level map + row
         per_clk_sm = gathers / (k_avg_ms / 1e3) / (sm_count * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6)
         roofline["smem_gather"] = {"gathers_per_clk_per_sm": per_clk_sm, "conflict_free_peak": 16.0, "random_address_expectation": 5.2,
                                    "frac_of_random_address_expectation": per_clk_sm / 5.2}
