@@ -77,7 +77,9 @@ static VgsPool *get_pool(vgs_context *h) {
         unsigned hc = std::thread::hardware_concurrency();
         unsigned share = 1;
         if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(e));
-        int n = (int)std::max(1u, std::min((hc > 2 ? hc - 1 : 1u) / share, 24u));
+        // alone: all cores but one (this thread feeds the copy engine); shared: an equal slice of all cores (the feeding
+        // thread sleeps between polls, see the upload loop)
+        int n = (int)std::max(1u, std::min(share > 1 ? hc / share : (hc > 2 ? hc - 1 : 1u), 24u));
         if (const char *e = getenv("VGS_HOST_THREADS")) n = std::max(1, std::min(64, atoi(e)));
         h->pool = new VgsPool(n);
     }
@@ -839,7 +841,8 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
                 sent = upto;
                 if (ce == cudaSuccess && build_digits_upto(e0, upto == n_chunks) != VGS_OK) ce = cudaErrorUnknown;
             } else {
-                std::this_thread::yield();
+                if (getenv("LOCAL_WORLD_SIZE")) std::this_thread::sleep_for(std::chrono::microseconds(5));   // other ranks' workers may need this core
+                else std::this_thread::yield();
             }
         }
         pool->wait();
