@@ -1,20 +1,14 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-{
-timeout 600 python -m pytest tests/test_gpu_round2.py -x -q -k "tree_files" 2>&1 | tail -8
-for W in frobenius frobenius_union projection estimate nll_deep frobenius_deep; do
-  timeout 600 python bench.py --workload $W --probe-models 0 --no-cpu-baseline --steps 10 > gpurun_out/r2_bench_$W.json 2> gpurun_out/r2_bench_$W.err || tail -5 gpurun_out/r2_bench_$W.err
-  python -c "
-import json,sys
-d=json.loads(open('gpurun_out/r2_bench_$W.json').read())
-r=d['roofline']
-print('$W','step ms %.3f'%d['ms_per_step'],'e2e ms %.3f'%d['e2e']['ms_per_step'],'| kernel',r['kernel'][:40],'ms %.3f'%r['kernel_ms_per_launch'],'bound',r['bound'],'frac',r['frac'],'| alg rate',r.get('algorithmic_rate_GBps_not_a_roofline'))
-"
+for W in 8 4 2; do
+python tools/shard_tune.py $W 10
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/b_launches.csv python tools/shard_tune.py $W 2 > /dev/null 2>&1
+python - <<'PY'
+import csv
+rows=list(csv.reader(open('gpurun_out/b_launches.csv')))
+hdr=[i for i,r in enumerate(rows) if r and r[0]=='ID'][0]
+cols=rows[hdr]; ki=cols.index('Kernel Name'); vi=cols.index('Metric Value'); gi=cols.index('Grid Size')
+for r in rows[hdr+1:][-5:]: print('   %-56s %-16s %8.1f us'%(r[ki][:56], r[gi], float(r[vi].replace(',',''))/1000))
+PY
 done
-timeout 600 python bench.py --mode sequential --probe-models 0 --no-cpu-baseline --no-mode-sweep --steps 5 > gpurun_out/r2_bench_nll_sequential.json 2>/dev/null
-python -c "
-import json
-d=json.loads(open('gpurun_out/r2_bench_nll_sequential.json').read()); print('nll sequential', d['ms_per_step'], d['roofline'].get('smem_gather'), d['roofline']['frac'])"
-} > gpurun_out/b_tune.log 2>&1
-cat gpurun_out/b_tune.log | cut -c1-400
