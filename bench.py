@@ -668,7 +668,8 @@ def main():
         # figure, so the peak is measured live by the library's probe (the same instruction back to back from resident
         # shared memory on every SM pair, vgs_tensor_peak_i8); 2 x the measured cuBLAS bf16 burst is reported beside it.
         K8 = max(128.0, 4.0 ** (orders.max() + 1))
-        ops = 2.0 * n * (8.0 * n) * K8 / world
+        nd, frac_bits = h.kmer_digit_info()   # digit rows per model of the operand as built (6 / 7 / 8), fraction bits of ln p
+        ops = 2.0 * n * (float(nd) * n) * K8 / world
         peak_bf16 = float(peaks.get("bf16_tflops", 1590.0))
         a_tops = ops / (k_avg_ms / 1e3) / 1e12
         probe_peak = (i8_peak or {}).get("cta_group_2_tops") or 0.0
@@ -681,10 +682,14 @@ def main():
                          "int8_peak_probe": i8_peak,
                          "frac_of_2x_bf16_burst": a_tops / (2.0 * peak_bf16),
                          "two_x_bf16_burst_tflops": 2.0 * peak_bf16,
-                         "ops_per_step": ops * world, "ops_formula": "2 x N_seq x (8 x N_models) x max(128, 4^(D+1)) int8 ops",
+                         "ops_per_step": ops * world,
+                         "ops_formula": "2 x N_seq x (%d digit rows x N_models) x max(128, 4^(D+1)) int8 ops (real rows only: "
+                                        "padding of the 256 x N tiles is not counted)" % nd,
+                         "digit_rows_per_model": nd, "ln_p_fraction_bits": frac_bits,
                          "useful_fp64_equivalent_macs_per_s": n * n * K8 / world / (k_avg_ms / 1e3),
-                         "note": "8 of every 8 int8 MACs carry one base-256 digit of a 61-bit fixed-point ln p: the useful rate is "
-                                 "one fp64-equivalent MAC per 8 executed int8 MACs"})
+                         "note": "every int8 MAC carries one base-256 digit of round(ln p x 2^%d) (%d digits: this set has "
+                                 "%s): the useful rate is one fp64-equivalent MAC per %d executed int8 MACs"
+                                 % (frac_bits, nd, "p = 0 entries / probabilities below e^-16" if nd > 6 else "no probability below e^-16", nd)})
         for k in ("algorithmic_bytes_per_step", "algorithmic_bytes_formula"):
             roofline.pop(k, None)   # SURVEY 8d's scan-bytes model does not describe a contraction
     elif pair_tc and k_avg_ms > 0:
@@ -755,7 +760,7 @@ def main():
         "metric": "pair-distances/sec", "value": pairs / (ms_step / 1000.0), "unit": unit, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": ("int8 x int8 -> int32 exact fixed point (ln p quantised to 2^-51), f64 result" if nll_kernel == 3 else
+        "dtype": ("int8 x int8 -> int32 exact fixed point (ln p quantised to 2^-%d), f64 result" % h.kmer_digit_info()[1] if nll_kernel == 3 else
                   "f64" if kind in ("nll", "estimate") else "f32 rows, f64 accumulate"), "data": "synthetic",
         "config": {"workload": desc, "n_models": n, "seq_len": L, "pairs_per_step": pairs, "total_contexts": fm_full.total_contexts,
                    "nll_mode": args.mode if kind == "nll" else None, "nll_kernel": kernel_name if kind == "nll" else None, "tile": tile if world > 1 else None,

@@ -161,10 +161,12 @@ struct vgs_context {
     double *d_kmer_T = nullptr, *d_kmer_C = nullptr, *d_kmer_partial = nullptr;
     bool kmer_tables_ready = false, kmer_counts_ready = false, kmer_has_nan = false;
     // exact int8 tensor-core contraction (vgs_kmer_i8.cu)
-    int8_t *d_i8_digits = nullptr;   // [n_models * 8][K8] balanced base-256 digits of round(ln p * 2^51)
+    int8_t *d_i8_digits = nullptr;   // [n_models * i8_nd][K8] balanced base-256 digits of round(ln p * 2^i8_frac_bits)
+    int i8_frac_bits = 43;           // fraction bits of the fixed-point ln p (vgs_set_kmer_fraction_bits, VGS_I8_FRAC_BITS)
+    int i8_nd = 8;                   // digit rows per model of the operand as built (6, 7 or 8)
     uint8_t *d_i8_C = nullptr;       // [n_seq][K8] k-mer counts (low bytes)
     int32_t *d_i8_over = nullptr;    // [n_seq] counts of frequent k-mers | [n_seq][64] {k, count >> 8}
-    int32_t *d_i8_P = nullptr;       // k-split launches: exact int32 digit sums [part][n_models * 8][n_seq padded]
+    int32_t *d_i8_P = nullptr;       // k-split launches: exact int32 digit sums [part][n_models * i8_nd][n_seq padded]
     uint64_t i8_tables_gen = ~0ull;
     bool i8_tables_ok = false;
     int last_nll_kernel = 0;         // VGS_NLL_KERNEL_* of the most recent score launch
@@ -288,10 +290,12 @@ int vgs_kmer_scores(vgs_context *h, const std::vector<char> &need, int64_t nb_s,
                     const VgsScoreDst &dst, cudaStream_t s, uint64_t cache_key = 0);
 int vgs_kmer_i8_prepare_tables(vgs_context *h, cudaStream_t s);
 bool vgs_kmer_applicable_orders(vgs_context *h);                          // every order <= 6 (known after the host's planning pass)
-int vgs_kmer_i8_digits_begin(vgs_context *h, cudaStream_t s);              // allocate + clear the digit operand of the current set
+int vgs_kmer_i8_digits_begin(vgs_context *h, bool wide, cudaStream_t s);   // choose the digit count, allocate + clear the operand of the current set
+double vgs_kmer_i8_narrow_limit(vgs_context *h);                           // |ln p| below this fits the narrow digit count
 int vgs_kmer_i8_digits_range(vgs_context *h, int64_t m_begin, int64_t m_end, cudaStream_t s);   // digits of models [m_begin, m_end)
 int vgs_kmer_i8_digits_end(vgs_context *h, cudaStream_t s);                // after a synchronisation: record whether the operand is usable
 int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, const VgsScoreDst &dst, cudaStream_t s);
+int vgs_kmer_i8_gran(vgs_context *h);   // unit granule (B rows) of the operand as built
 bool vgs_pair_tc_wanted(vgs_context *h, int kind);
 int vgs_pair_tc_matrix(vgs_context *h, int kind, float *D32, double *D64, cudaStream_t s);   // -1: not applicable
 int vgs_peer_barrier_impl(vgs_context *h, uint32_t *const *flags_h, int rank, int world, uint32_t epoch, cudaStream_t stream);

@@ -20,6 +20,15 @@
 
 #include "vgs_common.cuh"
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#define VGS_STREAM_STORE_F64(ptr, v) _mm_stream_si64((long long *)(ptr), __builtin_bit_cast(long long, (double)(v)))
+#define VGS_STREAM_FENCE() _mm_sfence()
+#else
+#define VGS_STREAM_STORE_F64(ptr, v) (*(ptr) = (v))
+#define VGS_STREAM_FENCE() std::atomic_thread_fence(std::memory_order_release)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // small persistent host thread pool (per handle): the host side of vgs_load_models (validation, ln p) runs on it
 class VgsPool {
@@ -217,6 +226,7 @@ extern "C" int vgs_create(int device, vgs_handle *out) {
     VGS_CUDA(cudaMalloc((void **)&h->d_err, sizeof(int)));
     VGS_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
     VGS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    if (const char *e = getenv("VGS_I8_FRAC_BITS")) h->i8_frac_bits = std::max(35, std::min(51, atoi(e)));
     *out = h;
     return VGS_OK;
 }
@@ -608,6 +618,9 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
                                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     };
     free_models(h);
+    // developer aid (VGS_LOAD_TIMING=1): device-side timestamps of the load's stream, relative to the first enqueued operation
+    cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (load_timing) for (auto &e : ev_t) cudaEventCreate(&e);
     const int64_t total = ctx_offsets_h[n_models];
     VGS_CHECK_ARG(ctx_offsets_h[0] == 0 && total > 0, "vgs_load_models: ctx_offsets must start at 0");
     VGS_CHECK_ARG(total < (int64_t)1 << 31, "vgs_load_models: more than 2^31 contexts in one set");
@@ -754,6 +767,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     // 1. upload what the caller gave us (asynchronous when its buffers are pinned) and build everything that
     //    does not need ln p: keys, fp32 rows, hashes, universe maps
     cudaStream_t s = h->own_stream;
+    if (load_timing) cudaEventRecord(ev_t[0], s);
     VGS_CUDA(cudaMemcpyAsync(h->d_meta, h->h_meta.data(), sizeof(ModelMeta) * (size_t)n_models, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemcpyAsync(h->d_len, ctx_len_h, (size_t)total, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemcpyAsync(h->d_code, ctx_code_h, sizeof(uint32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
@@ -764,6 +778,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     VGS_LAUNCH_CHECK(h);
     k_build_hash<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_key, h->d_hash);
     VGS_LAUNCH_CHECK(h);
+    if (load_timing) cudaEventRecord(ev_t[1], s);
     lap("enqueued: uploads + keys/hash");
     h->dense_state = 0;
     h->umap_tried = false;
@@ -790,19 +805,42 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     // as soon as a block's ln p has been uploaded, so the build hides under the host's ln p pass instead of following it
     const bool eager_digits = !(flags & VGS_LOAD_LAZY_TABLES) && vgs_kmer_applicable_orders(h);
     int64_t digits_built = 0;
-    if (eager_digits && (rc = vgs_kmer_i8_digits_begin(h, s))) return rc;
+    // The operand's digit count (= the GEMM's work) follows from the range of ln p, and the operand is laid out for it.  The
+    // workers of the ln p pass note a value outside the narrow range (p == 0 or p < e^-16); the count is fixed when the first
+    // block is built, from what has been seen by then -- a set with such values shows them early -- and a late surprise
+    // costs one rebuild (vgs_kmer_i8_digits_end).
+    std::atomic<int> wide_seen(0);
+    bool digits_begun = false;
+    const double narrow_limit = vgs_kmer_i8_narrow_limit(h);
+    std::vector<cudaEvent_t> ev_batch;
+    std::vector<double> ev_host;
     auto build_digits_upto = [&](int64_t elems_uploaded, bool final) -> int {
+        if (load_timing) {
+            cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev_batch.push_back(e);
+            ev_host.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+        }
         if (!eager_digits) return VGS_OK;
         int64_t m_done = digits_built;
         while (m_done < n_models && ctx_offsets_h[m_done + 1] * 4 <= elems_uploaded) ++m_done;
         if (m_done - digits_built >= 64 || (final && m_done > digits_built)) {
+            if (!digits_begun) {
+                const int rcb = vgs_kmer_i8_digits_begin(h, wide_seen.load() != 0, s);
+                if (rcb) return rcb;
+                digits_begun = true;
+            }
             const int rcd = vgs_kmer_i8_digits_range(h, digits_built, m_done, s);
             if (rcd) return rcd;
             digits_built = m_done;
         }
+        if (load_timing) {
+            cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev_batch.push_back(e);
+            ev_host.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+        }
         return VGS_OK;
     };
     if (logp_h) {
+        for (int64_t i = 0; i < total * 4 && !wide_seen.load(std::memory_order_relaxed); ++i)
+            if (!(fabs(logp_h[i]) < narrow_limit)) wide_seen.store(1);
         VGS_CUDA(cudaMemcpyAsync(h->d_logp, h->h_logp, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
         if ((rc = build_digits_upto(total * 4, true))) return rc;
     } else {
@@ -814,6 +852,13 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         const int64_t chunk = 1 << 13;
         const int64_t n_chunks = (n_elem + chunk - 1) / chunk;
         std::atomic<int64_t> next(0), bad(-1);
+        // The logarithms go to the pinned staging buffer with streaming (non-temporal) stores: written through the caches,
+        // the last 2-3 MB were still dirty in the cores' caches when the copy engine came for them and that copy ran at
+        // 8-10 GB/s instead of 37 (the load's stream drained 0.45 ms after the host had finished; now 0.08).
+        // VGS_LOAD_NT=0 restores plain stores.
+        static int nt_stores = -1;
+        if (nt_stores < 0) { const char *e = getenv("VGS_LOAD_NT"); nt_stores = (e && e[0] == '0') ? 0 : 1; }
+        const int batch_chunks = 32;
         std::vector<std::atomic<int>> done((size_t)n_chunks);
         for (auto &d : done) d.store(0);
         double *out = h->h_logp;
@@ -822,11 +867,17 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
                 const int64_t c = next.fetch_add(1);
                 if (c >= n_chunks) break;
                 const int64_t b0 = c * chunk, e0 = std::min(n_elem, b0 + chunk);
+                bool wide = false;
                 for (int64_t i = b0; i < e0; ++i) {
                     const double p = prob_h[i];
                     if (p < 0) { int64_t expect = -1; bad.compare_exchange_strong(expect, i); }
-                    out[i] = (p == 0) ? -1000.0 : log(p);
+                    const double lg = (p == 0) ? -1000.0 : log(p);
+                    wide |= !(fabs(lg) < narrow_limit);
+                    if (nt_stores) VGS_STREAM_STORE_F64(out + i, lg);
+                    else out[i] = lg;
                 }
+                if (nt_stores) VGS_STREAM_FENCE();
+                if (wide) wide_seen.store(1, std::memory_order_relaxed);
                 done[(size_t)c].store(1, std::memory_order_release);
             }
         });
@@ -835,7 +886,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         while (sent < n_chunks && ce == cudaSuccess) {
             int64_t upto = sent;
             while (upto < n_chunks && done[(size_t)upto].load(std::memory_order_acquire)) ++upto;
-            if (upto - sent >= 32 || (upto == n_chunks && upto > sent)) {   // >= 2 MB per copy
+            if (upto - sent >= batch_chunks || (upto == n_chunks && upto > sent)) {   // >= 2 MB per copy
                 const int64_t b0 = sent * chunk, e0 = std::min(n_elem, upto * chunk);
                 ce = cudaMemcpyAsync(h->d_logp + b0, out + b0, sizeof(double) * (size_t)(e0 - b0), cudaMemcpyHostToDevice, s);
                 sent = upto;
@@ -854,6 +905,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         }
     }
 
+    if (load_timing) cudaEventRecord(ev_t[2], s);
     lap("host: ln p computed + streamed");
     // 3. the NLL tables of the scan kernels, the digit operand of the k-mer contraction and the universe maps of the pair
     //    kernels are derived on first use (vgs_ensure_scan_tables, vgs_kmer_i8_prepare_tables, vgs_ensure_umap): a run
@@ -861,6 +913,21 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     h->nll_ready = true;
     VGS_CUDA(cudaStreamSynchronize(s));
     lap("stream drained");
+    if (load_timing) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ev_t[0], ev_t[1]);
+        cudaEventElapsedTime(&b, ev_t[0], ev_t[2]);
+        for (size_t i = 0; i + 1 < ev_batch.size(); i += 2) {
+            float u = 0.f, d = 0.f;
+            cudaEventElapsedTime(&u, ev_t[0], ev_batch[i]);
+            cudaEventElapsedTime(&d, ev_t[0], ev_batch[i + 1]);
+            fprintf(stderr, "[vgs_load_models]   batch %2zu: host enqueued at %.3f ms; device: upload done %.3f, digits done %.3f ms after the first copy began\n",
+                    i / 2, ev_host[i], u, d);
+        }
+        for (auto &e : ev_batch) cudaEventDestroy(e);
+        fprintf(stderr, "[vgs_load_models] device: keys/hash done %.3f ms, last ln p upload + digits done %.3f ms after the first copy began\n", a, b);
+        for (auto &e : ev_t) cudaEventDestroy(e);
+    }
     if (eager_digits && (rc = vgs_kmer_i8_digits_end(h, s))) return rc;
     return VGS_OK;
 }

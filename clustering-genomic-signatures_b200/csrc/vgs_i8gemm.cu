@@ -12,35 +12,36 @@ static int64_t g8_count(const std::vector<G8Rect> &rects, int N) {
 }
 
 // widest tile a rectangle list gives when cut into pieces of at most N rows, and the number of pieces
-static void g8_shape(const std::vector<G8Rect> &rects, int N, int64_t *count, int *widest) {
+static void g8_shape(const std::vector<G8Rect> &rects, int N, int gran, int64_t *count, int *widest) {
     *count = 0;
     *widest = 0;
     for (const G8Rect &r : rects) {
-        const int n_t = (r.b_rows + N - 1) / N, quanta = r.b_rows / 32;
+        const int n_t = (r.b_rows + N - 1) / N, quanta = r.b_rows / gran;
         *count += n_t;
-        *widest = std::max(*widest, 32 * ((quanta + n_t - 1) / n_t));
+        *widest = std::max(*widest, gran * ((quanta + n_t - 1) / n_t));
     }
 }
 
-int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters, int max_split, std::vector<G8Unit> *out) {
+int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters, int max_split, int gran, std::vector<G8Unit> *out) {
     out->clear();
     if (rects.empty() || kblocks <= 0) return 1;
     if (n_clusters < 1) n_clusters = 1;
-    int N = G8_UNIT_MAX_N, split = 1;
+    const int unit_max = 2 * g8_max_acc(gran);   // two accumulators, each a whole number of granules
+    int N = unit_max, split = 1;
     static int force_n = -1;   // tuning knob: VGS_G8_FORCE_N = tile width
-    if (force_n < 0) { const char *e = getenv("VGS_G8_FORCE_N"); force_n = e ? atoi(e) / 32 * 32 : 0; }
-    if (force_n >= 32 && force_n <= G8_UNIT_MAX_N) {
-        N = force_n;
+    if (force_n < 0) { const char *e = getenv("VGS_G8_FORCE_N"); force_n = e ? atoi(e) : 0; }
+    if (force_n >= gran && force_n <= unit_max) {
+        N = force_n / gran * gran;
     } else {
         // Pick the tile width and the k-split by a small cost model of the kernel (cycles per CTA pair), measured on cfg 3:
         // a k-block of a w-wide unit costs max(MMA time 2 w, operand delivery 1.73 (256 + w)) + barrier overhead; a unit
         // adds its epilogue (~30 cycles per column with eight warps); a k-split adds the fold kernel and the atomics.
         // Fewer, wider tiles move fewer operand bytes; more units fill the CTA pairs evenly -- the model arbitrates.
         double best = 1e300;
-        for (int cand = 32; cand <= G8_UNIT_MAX_N; cand += 32) {
+        for (int cand = gran; cand <= unit_max; cand += gran) {
             int64_t count;
             int w;
-            g8_shape(rects, cand, &count, &w);
+            g8_shape(rects, cand, gran, &count, &w);
             for (int sp = 1; sp <= max_split; ++sp) {
                 if (sp > 1 && kblocks / sp < 8) break;
                 const int64_t units = count * sp, waves = (units + n_clusters - 1) / n_clusters;
@@ -54,10 +55,10 @@ int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters,
     }
     for (const G8Rect &r : rects) {
         const int n_t = (r.b_rows + N - 1) / N;
-        const int quanta = r.b_rows / 32, q = quanta / n_t, rem = quanta % n_t;
+        const int quanta = r.b_rows / gran, q = quanta / n_t, rem = quanta % n_t;
         int row = r.b_row0;
         for (int t = 0; t < n_t; ++t) {
-            const int n = 32 * (q + (t < rem ? 1 : 0));
+            const int n = gran * (q + (t < rem ? 1 : 0));
             for (int p = 0; p < split; ++p) {
                 G8Unit u;
                 u.a_blk = r.a_blk; u.b_row0 = row; u.n = n;
@@ -98,16 +99,22 @@ int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters,
 
 extern "C" int vgs_g8_plan(const int32_t *rects_h, int n_rects, int kblocks, int n_cta_pairs, int max_split, int32_t *units_out_h,
                            int capacity, int *n_units_out, int *split_out) {
+    return vgs_g8_plan_gran(rects_h, n_rects, kblocks, n_cta_pairs, max_split, 32, units_out_h, capacity, n_units_out, split_out);
+}
+
+extern "C" int vgs_g8_plan_gran(const int32_t *rects_h, int n_rects, int kblocks, int n_cta_pairs, int max_split, int gran,
+                                int32_t *units_out_h, int capacity, int *n_units_out, int *split_out) {
     VGS_CHECK_ARG(rects_h && n_rects >= 0 && kblocks > 0 && n_cta_pairs > 0 && max_split >= 1 && n_units_out, "vgs_g8_plan: bad arguments");
+    VGS_CHECK_ARG(gran >= 32 && gran % 32 == 0 && gran <= G8_MAX_N, "vgs_g8_plan: the granule is a multiple of 32, at most 256");
     std::vector<G8Rect> rects;
     for (int i = 0; i < n_rects; ++i) {
         G8Rect r;
         r.a_blk = rects_h[3 * i]; r.b_row0 = rects_h[3 * i + 1]; r.b_rows = rects_h[3 * i + 2];
-        VGS_CHECK_ARG(r.a_blk >= 0 && r.b_row0 >= 0 && r.b_row0 % 32 == 0 && r.b_rows > 0 && r.b_rows % 32 == 0, "vgs_g8_plan: rows must be multiples of 32");
+        VGS_CHECK_ARG(r.a_blk >= 0 && r.b_row0 >= 0 && r.b_row0 % gran == 0 && r.b_rows > 0 && r.b_rows % gran == 0, "vgs_g8_plan: rows must be multiples of the granule");
         rects.push_back(r);
     }
     std::vector<G8Unit> units;
-    const int split = g8_make_units(rects, kblocks, n_cta_pairs, max_split, &units);
+    const int split = g8_make_units(rects, kblocks, n_cta_pairs, max_split, gran, &units);
     if (split_out) *split_out = split;
     *n_units_out = (int)units.size();
     if (units_out_h) {
@@ -130,7 +137,7 @@ extern "C" int vgs_g8_plan(const int32_t *rects_h, int n_rects, int kblocks, int
 #define PK_STAGE_BYTES (G8_A_BYTES + G8_MAX_N * G8_BK)
 #define PK_SMEM_BYTES (4 * PK_STAGE_BYTES)   // 192 KB (two stages used): one CTA per SM, like the GEMM
 template <int CG>
-__global__ void __launch_bounds__(128, 1) k_g8_peak(int iters, int *err) {
+__global__ void __launch_bounds__(128, 1) k_g8_peak(int iters, int n_cols, int *err) {
     extern __shared__ __align__(1024) uint8_t pk_smem[];
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t tmem_slot;
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(128, 1) k_g8_peak(int iters, int *err) {
     const bool issuer = threadIdx.x == 32 && (CG == 1 || g8_cta_rank() == 0);
     if (issuer) {
         const uint32_t sa = vgs_smem_addr(pk_smem);
-        const uint32_t idesc = g8_idesc(CG == 2 ? 256 : 128, 256, 0);
+        const uint32_t idesc = g8_idesc(CG == 2 ? 256 : 128, n_cols, 0);
         for (int it = 0; it < iters; ++it) {
             const uint32_t st = sa + (uint32_t)(it & 1) * PK_STAGE_BYTES;
 #pragma unroll
@@ -180,7 +187,13 @@ __global__ void __launch_bounds__(128, 1) k_g8_peak(int iters, int *err) {
 }
 
 extern "C" int vgs_tensor_peak_i8(vgs_handle h, int cta_group, double *tops_out, double *ms_out) {
-    VGS_CHECK_ARG(h && (cta_group == 1 || cta_group == 2) && tops_out, "vgs_tensor_peak_i8: bad arguments");
+    return vgs_tensor_rate_i8(h, cta_group, 256, tops_out, ms_out);
+}
+
+// the same probe at another instruction width N (multiple of 16, <= 256): how the tensor pipe's time per MMA depends on N
+extern "C" int vgs_tensor_rate_i8(vgs_handle h, int cta_group, int n_cols, double *tops_out, double *ms_out) {
+    VGS_CHECK_ARG(h && (cta_group == 1 || cta_group == 2) && tops_out, "vgs_tensor_rate_i8: bad arguments");
+    VGS_CHECK_ARG(n_cols >= 16 && n_cols <= 256 && n_cols % 16 == 0, "vgs_tensor_rate_i8: N is a multiple of 16, at most 256");
     VGS_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->own_stream;
     const int iters = 2048;   // x 4 MMAs of 256 x 256 x 32 (pair) / 128 x 256 x 32 (single CTA)
@@ -200,10 +213,10 @@ extern "C" int vgs_tensor_peak_i8(vgs_handle h, int cta_group, double *tops_out,
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            VGS_CUDA(cudaLaunchKernelEx(&cfg, k_g8_peak<2>, iters, h->d_err));
+            VGS_CUDA(cudaLaunchKernelEx(&cfg, k_g8_peak<2>, iters, n_cols, h->d_err));
         } else {
             VGS_CUDA(cudaFuncSetAttribute(k_g8_peak<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            k_g8_peak<1><<<n_cta, 128, smem, s>>>(iters, h->d_err);
+            k_g8_peak<1><<<n_cta, 128, smem, s>>>(iters, n_cols, h->d_err);
         }
         VGS_LAUNCH_CHECK(h);
         VGS_CUDA(cudaEventRecord(e1, s));
@@ -215,7 +228,7 @@ extern "C" int vgs_tensor_peak_i8(vgs_handle h, int cta_group, double *tops_out,
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     const double units = cta_group == 2 ? (double)(n_cta / 2) : (double)n_cta;
-    const double ops = 2.0 * units * (double)iters * 4.0 * (cta_group == 2 ? 256.0 : 128.0) * 256.0 * 32.0;
+    const double ops = 2.0 * units * (double)iters * 4.0 * (cta_group == 2 ? 256.0 : 128.0) * (double)n_cols * 32.0;
     *tops_out = ops / ((double)best * 1e-3) / 1e12;
     if (ms_out) *ms_out = (double)best;
     return VGS_OK;

@@ -32,7 +32,8 @@
 #include "vgs_common.cuh"
 
 #define G8_BK 128                 // k per pipeline stage = bytes per operand row per stage = one swizzle atom
-#define G8_STAGES 4               // 4 x 48 KB = 192 KB of the 227 KB a CTA can have
+#define G8_STAGES 4               // stages at the widest units (4 x 48 KB = 192 KB of the 227 KB a CTA can have)
+#define G8_MAX_STAGES 8           // barrier slots: narrower granules / units leave room for more, smaller stages
 #define G8_EPI_WARPS 16           // four per TMEM lane quadrant
 #define G8_THREADS (32 * (2 + G8_EPI_WARPS))
 #define G8_A_ROWS 128             // A rows per CTA (256 per pair)
@@ -42,13 +43,15 @@
 #define G8_B_BYTES ((G8_MAX_N / 2) * G8_BK)                    // one accumulator's B half-tile per stage and CTA
 #define G8_STAGE_BYTES (G8_A_BYTES + 2 * G8_B_BYTES)           // 48 KB
 #define G8_SMEM_BYTES (G8_STAGES * G8_STAGE_BYTES)
+#define G8_SMEM_LIMIT (226 * 1024)   // dynamic shared memory the kernel may ask for (227 KB per CTA minus its static 1 KB)
 #define G8_TMEM_COLS 512
 #define G8_WATCHDOG_CYCLES (1ll << 32)   // ~2 s: a lost barrier signal traps instead of hanging the GPU
 
 struct G8Unit {
     int32_t a_blk;    // 256-row block of A
     int32_t b_row0;   // first B row, multiple of 8 (16 for the peer's half to stay 8-aligned: n / 2 is a multiple of 16)
-    int32_t n;        // B rows of this unit: multiple of 32, <= 512 (above 256: two accumulators, see g8_first_half)
+    int32_t n;        // B rows of this unit: multiple of the launch's granule (32 unless the functor's chunks are narrower),
+                      // <= 512 (more than one accumulator's worth: two accumulators, see g8_first_half)
     int32_t kb0, kbn; // k range in 128-blocks
     int32_t partial;  // != 0: this unit is part (partial - 1) of a k-split (the functor stores its sums to the part's slab)
 };
@@ -61,12 +64,23 @@ struct G8Args {
     int a_signed;                     // A operand: 0 = unsigned 8 bit, 1 = signed
     int *err;                         // device error word (bit 2: watchdog)
     int debug;                        // developer knob VGS_G8_DEBUG: bit 0 = skip the epilogue functor (timing experiments only)
-    int stages;                       // pipeline stages in use (<= G8_STAGES; tuning knob VGS_G8_STAGES)
+    int stages;                       // pipeline stages in use (set by g8_launch; tuning knob VGS_G8_STAGES caps it)
+    int b_bytes;                      // bytes of one accumulator's B half-tile in a stage = (largest accumulator / 2) rows x 128
+    int stage_bytes;                  // A tile + two B half-tiles: 16 KB + 2 b_bytes (a multiple of 1024)
+    int gran;                         // granule of the unit widths (multiple of 32 and of the functor's chunk width)
     long long *prof;                  // optional [n_clusters][8] cycle counters of the leader CTA (VGS_G8_PROF=1), else nullptr
 };
 
-// a unit wider than 256 B rows is computed as two MMAs per k-slice: the first g8_first_half(n) rows, then the rest
-__host__ __device__ __forceinline__ int g8_first_half(int n) { return n <= 256 ? n : ((n / 2 + 31) / 32) * 32; }
+// a unit wider than one accumulator (the largest multiple of the granule <= 256 B rows) is computed as two MMAs per
+// k-slice: the first g8_first_half(n, gran) rows, then the rest -- both multiples of the granule, so that no chunk of the
+// epilogue functor straddles the two accumulators
+__host__ __device__ __forceinline__ int g8_max_acc(int gran) { return (G8_MAX_N / gran) * gran; }
+__host__ __device__ __forceinline__ int g8_first_half(int n, int gran) {
+    const int max_acc = g8_max_acc(gran);
+    if (n <= max_acc) return n;
+    const int half = ((n / 2 + gran - 1) / gran) * gran;
+    return half < max_acc ? half : max_acc;
+}
 __host__ __device__ __forceinline__ int64_t g8_off(int64_t row, int64_t k, int64_t rows_pad) {
     return (((k >> 7) * rows_pad + row) << 7) + ((((k >> 4) & 7) ^ (row & 7)) << 4) + (k & 15);
 }
@@ -205,7 +219,8 @@ __device__ __forceinline__ void g8_wait_t(uint64_t *bar, uint32_t parity, int *e
 }
 __device__ __forceinline__ void g8_wait(uint64_t *bar, uint32_t parity, int *err) { g8_wait_t<false>(bar, parity, err); }
 __device__ __forceinline__ void g8_wait_cluster(uint64_t *bar, uint32_t parity, int *err) { g8_wait_t<true>(bar, parity, err); }
-__device__ __forceinline__ void g8_tmem_ld32(uint32_t taddr, int32_t (&v)[32]) {
+// this warp's 32 TMEM lanes x W consecutive columns -> registers (no wait: g8_tmem_ld ends a chunk's loads with one)
+__device__ __forceinline__ void g8_tmem_ld_x32(uint32_t taddr, int32_t *v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
         "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -214,16 +229,41 @@ __device__ __forceinline__ void g8_tmem_ld32(uint32_t taddr, int32_t (&v)[32]) {
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
+}
+__device__ __forceinline__ void g8_tmem_ld_x8(uint32_t taddr, int32_t *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void g8_tmem_ld_x4(uint32_t taddr, int32_t *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+// W columns (multiple of 4, <= 32) starting at taddr: one x32, or 8- and 4-column pieces, then ONE wait
+template <int W>
+__device__ __forceinline__ void g8_tmem_ld(uint32_t taddr, int32_t (&v)[W]) {
+    static_assert(W % 4 == 0 && W >= 4 && W <= 32, "chunk width");
+    if (W == 32) {
+        g8_tmem_ld_x32(taddr, v);
+    } else {
+#pragma unroll
+        for (int c = 0; c + 8 <= W; c += 8) g8_tmem_ld_x8(taddr + (uint32_t)c, v + c);
+        if (W % 8) g8_tmem_ld_x4(taddr + (uint32_t)(W - 4), v + (W - 4));
+    }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------
-// Epi: struct with   __device__ void operator()(const G8Unit &u, int64_t a_row, int col0, const int32_t (&v)[32]) const
+// Epi: struct with   static constexpr int CHUNK = columns per operator() call (multiple of 4, <= 32; the launch's granule is a
+//                                         multiple of it)
+//                    struct State;  __device__ State prepare(const G8Unit &u, int64_t a_row) const   (whole warp, while the unit's
+//                                         MMAs still run: every global load the chunks' operator() would otherwise wait for -- the
+//                                         epilogue is exposed time, a dependent L2 round trip per chunk in it cost 13 of 93 us)
+//                    __device__ void prefetch(const G8Unit &u, int64_t a_row, int col0, const State &) const   (whole warp, before
+//                                         the accumulator is ready: warm the lines the chunk's operator() will read)
+//                    __device__ void operator()(const G8Unit &u, int64_t a_row, int col0, const int32_t (&v)[CHUNK], const State &) const
 //                    __device__ void unit_done() const      (after a thread's last chunk of a unit)
-//                    __device__ void prefetch(const G8Unit &u, int64_t a_row, int col0) const   (whole warp, before the unit's
-//                                         accumulator is ready: warm the lines the chunk's operator() will read)
-// operator() is called once per thread (= A row a_row) and 32-column chunk: columns col0 .. col0 + 31 of the unit = B rows
-// u.b_row0 + col0 ...
+// operator() is called once per thread (= A row a_row) and CHUNK-column chunk: columns col0 .. col0 + CHUNK - 1 of the unit
+// = B rows u.b_row0 + col0 ...
 //
 // A unit is up to 512 B rows wide: two accumulators (TMEM columns 0.. and 256..) fed by the SAME A tile, i.e. a 256 x 512
 // output tile per CTA pair.  The kernel is bound by what L2 can deliver to the SMs (measured: time per k-block follows the
@@ -234,7 +274,7 @@ __device__ __forceinline__ void g8_tmem_ld32(uint32_t taddr, int32_t (&v)[32]) {
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_gemm(const G8Args g, const Epi epi) {
     extern __shared__ __align__(1024) uint8_t g8_smem[];
-    __shared__ __align__(8) uint64_t full[G8_STAGES], empty[G8_STAGES], tmem_full, tmem_empty;
+    __shared__ __align__(8) uint64_t full[G8_MAX_STAGES], empty[G8_MAX_STAGES], tmem_full, tmem_empty;
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = g8_cta_rank();
@@ -247,7 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
     if (smem0 & 1023u) __trap();   // SWIZZLE_128B operand tiles need 1024-byte aligned stage buffers
 
     if (tid == 0) {
-        for (int i = 0; i < G8_STAGES; ++i) {
+        for (int i = 0; i < G8_MAX_STAGES; ++i) {
             // leader: its own copies (one expect_tx arrival + the bytes) and the peer's relay arrival; peer: its own copies
             vgs_mbar_init(&full[i], leader ? 2 : 1);
             vgs_mbar_init(&empty[i], 1);
@@ -277,7 +317,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
             for (int ui = cluster; ui < g.n_units; ui += n_clusters) {
                 const G8Unit u = g.units[ui];
                 if (u.n == 0) continue;
-                const int n0 = g8_first_half(u.n), n1 = u.n - n0;
+                const int n0 = g8_first_half(u.n, g.gran), n1 = u.n - n0;
                 const uint32_t b0_bytes = (uint32_t)(n0 >> 1) * G8_BK, b1_bytes = (uint32_t)(n1 >> 1) * G8_BK;
                 const uint8_t *a_src = g.A + (((int64_t)u.kb0 * g.a_rows_pad + (int64_t)u.a_blk * 256 + rank * G8_A_ROWS) << 7);
                 const uint8_t *b0_src = g.B + (((int64_t)u.kb0 * g.b_rows_pad + u.b_row0 + rank * (n0 >> 1)) << 7);
@@ -287,11 +327,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
                     const long long t0 = g.prof ? clock64() : 0;
                     g8_wait(&empty[st], ph ^ 1u, g.err);
                     if (g.prof) t_wait += clock64() - t0;
-                    uint8_t *dst = g8_smem + (size_t)st * G8_STAGE_BYTES;
+                    uint8_t *dst = g8_smem + (size_t)st * g.stage_bytes;
                     vgs_mbar_expect_tx(&full[st], G8_A_BYTES + b0_bytes + b1_bytes);
                     vgs_bulk_g2s(dst, a_src + kb * a_step, G8_A_BYTES, &full[st]);
                     vgs_bulk_g2s(dst + G8_A_BYTES, b0_src + kb * b_step, b0_bytes, &full[st]);
-                    if (n1) vgs_bulk_g2s(dst + G8_A_BYTES + G8_B_BYTES, b1_src + kb * b_step, b1_bytes, &full[st]);
+                    if (n1) vgs_bulk_g2s(dst + G8_A_BYTES + g.b_bytes, b1_src + kb * b_step, b1_bytes, &full[st]);
                     if (++st == NS) { st = 0; ph ^= 1u; }
                 }
             }
@@ -316,7 +356,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
                 for (int ui = cluster; ui < g.n_units; ui += n_clusters) {
                     const G8Unit u = g.units[ui];
                     if (u.n == 0) continue;   // padding of the dealt unit list (every role skips it the same way)
-                    const int n0 = g8_first_half(u.n), n1 = u.n - n0;
+                    const int n0 = g8_first_half(u.n, g.gran), n1 = u.n - n0;
                     long long t0 = g.prof ? clock64() : 0;
                     g8_wait_cluster(&tmem_empty, (uint32_t)((it & 1) ^ 1), g.err);   // the previous unit's epilogues (both CTAs) are done
                     if (g.prof) t_tmem += clock64() - t0;
@@ -328,13 +368,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
                         if (g.prof) { const long long t1 = clock64(); t_full += t1 - t0; t0 = t1; }
                         g8_fence_after();
                         // descriptors: constant high word, low word = (address >> 4) | leading-byte-offset field
-                        const uint32_t a_lo = desc_lo0 + (uint32_t)st * (G8_STAGE_BYTES >> 4);
+                        const uint32_t a_lo = desc_lo0 + (uint32_t)st * (uint32_t)(g.stage_bytes >> 4);
 #pragma unroll
                         for (int j = 0; j < G8_BK / 32; ++j) {
                             const uint64_t da = g8_desc_join(a_lo + 2u * j, desc_hi);
                             const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
                             g8_mma2(tmem_base, da, g8_desc_join(a_lo + (G8_A_BYTES >> 4) + 2u * j, desc_hi), idesc0, acc);
-                            if (n1) g8_mma2(tmem_base + G8_MAX_N, da, g8_desc_join(a_lo + ((G8_A_BYTES + G8_B_BYTES) >> 4) + 2u * j, desc_hi), idesc1, acc);
+                            if (n1) g8_mma2(tmem_base + G8_MAX_N, da, g8_desc_join(a_lo + (uint32_t)((G8_A_BYTES + g.b_bytes) >> 4) + 2u * j, desc_hi), idesc1, acc);
                         }
                         g8_commit2(&empty[st]);
                         if (++st == NS) { st = 0; ph ^= 1u; }
@@ -372,20 +412,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
         for (int ui = cluster; ui < g.n_units; ui += n_clusters) {
             const G8Unit u = g.units[ui];
             if (u.n == 0) continue;
-            const int n0 = g8_first_half(u.n);
+            const int n0 = g8_first_half(u.n, g.gran);
             const int64_t a_row = (int64_t)u.a_blk * 256 + rank * G8_A_ROWS + quad * 32 + lane;
-            // the epilogue warps idle while the unit's MMAs run: let the functor warm whatever its chunks will read
-            for (int c0 = 32 * part; c0 < u.n; c0 += 8 * G8_EPI_WARPS) epi.prefetch(u, a_row, c0);
+            // the epilogue warps idle while the unit's MMAs run: let the functor load / warm whatever its chunks will read
+            const typename Epi::State est = epi.prepare(u, a_row);
+            constexpr int CH = Epi::CHUNK, CH_STEP = (G8_EPI_WARPS / 4) * Epi::CHUNK;
+            for (int c0 = CH * part; c0 < u.n; c0 += CH_STEP) epi.prefetch(u, a_row, c0, est);
             g8_wait(&tmem_full, (uint32_t)(it & 1), g.err);
             const long long t_e0 = g.prof ? clock64() : 0;
             g8_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 32 * part; c0 < u.n; c0 += 8 * G8_EPI_WARPS) {
-                int32_t v[32];
+            for (int c0 = CH * part; c0 < u.n; c0 += CH_STEP) {
+                int32_t v[CH];
                 // unit column c0 lives in accumulator 0 (TMEM column c0) or 1 (TMEM column 256 + c0 - n0)
-                g8_tmem_ld32(taddr + (uint32_t)(c0 < n0 ? c0 : G8_MAX_N + c0 - n0), v);
-                if (!(g.debug & 1)) epi(u, a_row, c0, v);
+                g8_tmem_ld<CH>(taddr + (uint32_t)(c0 < n0 ? c0 : G8_MAX_N + c0 - n0), v);
+                if (!(g.debug & 1)) epi(u, a_row, c0, v, est);
             }
             epi.unit_done();
             g8_fence_before();
@@ -420,18 +462,31 @@ static int g8_launch(vgs_context *h, const G8Args &g, const Epi &epi, cudaStream
     auto kern = k_g8_gemm<Epi>;
     static bool attr_set[64] = {false};   // per device (one entry per template instance): not on every launch
     if (!attr_set[h->device & 63]) {
-        VGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G8_SMEM_BYTES));
+        VGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G8_SMEM_LIMIT));
         attr_set[h->device & 63] = true;
     }
     const int n_clusters = std::max(1, std::min(g.n_units, h->sm_count / 2));
     static int want_prof = -1, n_stages = -1, dbg = -1;
     if (want_prof < 0) { const char *e = getenv("VGS_G8_PROF"); want_prof = (e && e[0] == '1') ? 1 : 0; }
-    if (n_stages < 0) { const char *e = getenv("VGS_G8_STAGES"); n_stages = e ? std::max(1, std::min(G8_STAGES, atoi(e))) : G8_STAGES; }
+    if (n_stages < 0) { const char *e = getenv("VGS_G8_STAGES"); n_stages = e ? std::max(1, std::min(G8_MAX_STAGES, atoi(e))) : G8_MAX_STAGES; }
     if (dbg < 0) { const char *e = getenv("VGS_G8_DEBUG"); dbg = e ? atoi(e) : 0; }
     G8Args ga = g;
     ga.prof = nullptr;
-    ga.stages = n_stages;
     ga.debug = dbg;
+    if (ga.gran < 32 || ga.gran % 32 || ga.gran % Epi::CHUNK || ga.gran > G8_MAX_N) {
+        vgs_set_error("int8 GEMM: unit granule %d does not fit the functor's %d-column chunks", ga.gran, Epi::CHUNK);
+        return VGS_ERR_INVALID;
+    }
+    // stage = this CTA's A rows + its halves of two accumulators' B rows; an accumulator is at most g8_max_acc(gran) rows
+    // wide, so granules that do not divide 256 leave room for a deeper pipeline (the kernel is bound by how many operand
+    // bytes each SM keeps in flight against the L2 round trip: 5 x 40 KB instead of 4 x 48 KB)
+    ga.b_bytes = (g8_max_acc(ga.gran) / 2) * G8_BK;
+    ga.stage_bytes = G8_A_BYTES + 2 * ga.b_bytes;
+    ga.stages = std::max(1, std::min(std::min(n_stages, G8_MAX_STAGES), G8_SMEM_LIMIT / ga.stage_bytes));
+    if (ga.stage_bytes % 1024) {
+        vgs_set_error("int8 GEMM: stage of %d bytes is not 1024-byte aligned", ga.stage_bytes);
+        return VGS_ERR_INVALID;
+    }
     long long *d_prof = nullptr;
     if (want_prof) {
         if (cudaMalloc((void **)&d_prof, (size_t)n_clusters * 96) == cudaSuccess) {
@@ -439,7 +494,7 @@ static int g8_launch(vgs_context *h, const G8Args &g, const Epi &epi, cudaStream
             ga.prof = d_prof;
         }
     }
-    kern<<<2 * n_clusters, G8_THREADS, G8_SMEM_BYTES, s>>>(ga, epi);
+    kern<<<2 * n_clusters, G8_THREADS, (size_t)ga.stages * ga.stage_bytes, s>>>(ga, epi);
     VGS_LAUNCH_CHECK(h);
     if (d_prof) {
         // developer aid (VGS_G8_PROF=1): where the leader CTA's main-loop threads spend their cycles, mean (max) over the
@@ -479,10 +534,11 @@ static int g8_launch(vgs_context *h, const G8Args &g, const Epi &epi, cudaStream
 // ---- host: cutting rectangles of the output into units -------------------------------------------------------
 struct G8Rect {
     int32_t a_blk;          // 256-row block of A
-    int32_t b_row0, b_rows; // B row range: b_row0 multiple of 32; b_rows multiple of 32
+    int32_t b_row0, b_rows; // B row range: multiples of the granule
 };
 // Units for `rects` over k blocks [0, kblocks): tile widths are chosen so that the unit count is (close to) a multiple of
 // the CTA pairs and as wide as that allows (operand bytes per MAC), largest first; when the tiles do not fill the machine
 // the k range is cut too (at most `max_split` parts, at least 8 k-blocks each) and the units are marked partial.  Returns
 // the split used.
-int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters, int max_split, std::vector<G8Unit> *out);
+// `gran`: granule of the unit widths and of the rectangles' row ranges (32, or the multiple of 32 the functor needs).
+int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters, int max_split, int gran, std::vector<G8Unit> *out);

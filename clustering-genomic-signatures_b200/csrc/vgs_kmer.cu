@@ -398,7 +398,8 @@ static int kmer_i8_path(vgs_context *h, const std::vector<char> &need, int64_t n
                         const VgsScoreDst &dst, cudaStream_t s, uint64_t cache_key) {
     int rc = vgs_kmer_i8_prepare_tables(h, s);
     if (rc != VGS_OK) return rc;
-    const uint64_t key = cache_key ? vgs_mix(cache_key, 0x6938) : 0;
+    const int nd = h->i8_nd, gran = vgs_kmer_i8_gran(h);   // digit rows per model; granule of the unit widths
+    const uint64_t key = cache_key ? vgs_mix(cache_key, 0x6938 + (uint64_t)nd) : 0;
     I8Work w;
     bool diag_covered = false;
     if (WorkCache *wc = vgs_wcache_find(h, key)) {
@@ -408,7 +409,7 @@ static int kmer_i8_path(vgs_context *h, const std::vector<char> &need, int64_t n
     } else {
         std::vector<G8Rect> rects;
         const int64_t nb_a = (nb_s + 1) / 2;   // 256-sequence blocks
-        const int64_t rows_total = (h->n_models * 8 + 31) / 32 * 32;
+        const int64_t rows_total = (h->n_models * nd + gran - 1) / gran * gran;
         for (int64_t a = 0; a < nb_a; ++a) {
             int64_t mb = 0;
             while (mb < nb_m) {
@@ -420,8 +421,8 @@ static int kmer_i8_path(vgs_context *h, const std::vector<char> &need, int64_t n
                 while (e < nb_m && needed(e)) ++e;
                 G8Rect r;
                 r.a_blk = (int32_t)a;
-                r.b_row0 = (int32_t)(mb * 1024);   // 128 models x 8 digit rows
-                r.b_rows = (int32_t)(std::min<int64_t>(e * 1024, rows_total) - r.b_row0);
+                r.b_row0 = (int32_t)(mb * 128 * nd);   // 128 models x nd digit rows: a whole number of granules
+                r.b_rows = (int32_t)(std::min<int64_t>(e * 128 * nd, rows_total) - r.b_row0);
                 if (r.b_rows > 0) rects.push_back(r);
                 mb = e;
             }
@@ -433,12 +434,12 @@ static int kmer_i8_path(vgs_context *h, const std::vector<char> &need, int64_t n
         static int max_split = -1;
         if (max_split < 0) { const char *e = getenv("VGS_I8_SPLITK"); max_split = e ? std::max(1, atoi(e)) : 8; }
         // the int32 partial-sum buffer of the k-split stays below 1 GB
-        const int ms = (h->n_seq * h->n_models * 32 * max_split <= ((int64_t)2 << 30)) ? max_split : 1;
-        w.split = g8_make_units(rects, kblocks, h->sm_count / 2, ms, &units);
+        const int ms = (h->n_seq * h->n_models * 4 * nd * max_split <= ((int64_t)2 << 30)) ? max_split : 1;
+        w.split = g8_make_units(rects, kblocks, h->sm_count / 2, ms, gran, &units);
         w.n_units = (int)units.size();
         w.n_rects = (int)rects.size();
         w.max_rect_models = 0;
-        for (const G8Rect &r : rects) w.max_rect_models = std::max(w.max_rect_models, r.b_rows / 8);
+        for (const G8Rect &r : rects) w.max_rect_models = std::max(w.max_rect_models, (r.b_rows + nd - 1) / nd);
         const int64_t off2 = ((int64_t)units.size() * (int64_t)sizeof(G8Unit) + 127) / 128 * 128;
         const int64_t bytes = off2 + (int64_t)rects.size() * (int64_t)sizeof(G8Rect) + 256;
         char *base = nullptr;

@@ -81,11 +81,14 @@ __global__ void k_tc_model_of_ctx(int64_t n_models, const ModelMeta *__restrict_
 
 // GEMM epilogue: the raw int32 digit-pair sums, row-major [A row][B row]
 struct EpiRaw {
+    static constexpr int CHUNK = 32;
     int32_t *out;
     int64_t ld, a_rows;
-    __device__ __forceinline__ void prefetch(const G8Unit &, int64_t, int) const {}
+    struct State {};
+    __device__ __forceinline__ State prepare(const G8Unit &, int64_t) const { return State(); }
+    __device__ __forceinline__ void prefetch(const G8Unit &, int64_t, int, const State &) const {}
     __device__ __forceinline__ void unit_done() const {}
-    __device__ __forceinline__ void operator()(const G8Unit &u, int64_t a_row, int c0, const int32_t (&v)[32]) const {
+    __device__ __forceinline__ void operator()(const G8Unit &u, int64_t a_row, int c0, const int32_t (&v)[32], const State &) const {
         if (a_row >= a_rows) return;
         int4 *dst = (int4 *)(out + a_row * ld + u.b_row0 + c0);
 #pragma unroll
@@ -150,7 +153,7 @@ static int tc_units(vgs_context *h, uint64_t key, const std::vector<G8Rect> &rec
         return VGS_OK;
     }
     std::vector<G8Unit> units;
-    g8_make_units(rects, kblocks, h->sm_count / 2, 1, &units);
+    g8_make_units(rects, kblocks, h->sm_count / 2, 1, 32, &units);
     const int64_t bytes = (int64_t)units.size() * (int64_t)sizeof(G8Unit) + 64;
     WorkCache *wc = vgs_wcache_add(h, key, bytes);
     void *dev;
@@ -232,7 +235,7 @@ int vgs_pair_tc_matrix(vgs_context *h, int kind, float *D32, double *D64, cudaSt
             }
         G8Args g;
         g.A = (const uint8_t *)h->d_tc_P; g.B = (const uint8_t *)h->d_tc_P; g.a_rows_pad = p_rows_pad; g.b_rows_pad = p_rows_pad;
-        g.a_signed = 1; g.err = h->d_err; g.prof = nullptr; g.stages = G8_STAGES; g.debug = 0;
+        g.a_signed = 1; g.err = h->d_err; g.prof = nullptr; g.stages = G8_STAGES; g.debug = 0; g.gran = 32;
         if ((rc = tc_units(h, vgs_mix(key, 1), rects, (int)(K8 / G8_BK), &g.units, &g.n_units, s))) return rc;
         EpiRaw e;
         e.out = h->d_tc_G; e.ld = g_ld; e.a_rows = p_rows;
@@ -252,7 +255,7 @@ int vgs_pair_tc_matrix(vgs_context *h, int kind, float *D32, double *D64, cudaSt
             }
         G8Args g;
         g.A = (const uint8_t *)h->d_tc_Q; g.B = (const uint8_t *)h->d_tc_I; g.a_rows_pad = q_rows_pad; g.b_rows_pad = i_rows_pad;
-        g.a_signed = 1; g.err = h->d_err; g.prof = nullptr; g.stages = G8_STAGES; g.debug = 0;
+        g.a_signed = 1; g.err = h->d_err; g.prof = nullptr; g.stages = G8_STAGES; g.debug = 0; g.gran = 32;
         if ((rc = tc_units(h, vgs_mix(key, 2), rects, (int)(KQ8 / G8_BK), &g.units, &g.n_units, s))) return rc;
         EpiRaw e;
         e.out = h->d_tc_R; e.ld = r_ld; e.a_rows = q_rows;

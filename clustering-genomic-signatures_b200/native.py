@@ -68,7 +68,11 @@ SIGNATURES = [
     ("vgs_peer_free", c_int, [c_vp, c_vp]),
     ("vgs_peer_barrier", c_int, [c_vp, c_vp, c_int, c_int, ctypes.c_uint32, c_vp]),
     ("vgs_tensor_peak_i8", c_int, [c_vp, c_int, _P(ctypes.c_double), _P(ctypes.c_double)]),
+    ("vgs_tensor_rate_i8", c_int, [c_vp, c_int, c_int, _P(ctypes.c_double), _P(ctypes.c_double)]),
     ("vgs_g8_plan", c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, _P(c_int), _P(c_int)]),
+    ("vgs_g8_plan_gran", c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, _P(c_int), _P(c_int)]),
+    ("vgs_set_kmer_fraction_bits", c_int, [c_vp, c_int]),
+    ("vgs_kmer_digit_info", c_int, [c_vp, _P(c_int), _P(c_int)]),
     ("vgs_matrix_to_triples", c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     ("vgs_last_nll_kernel", c_int, [c_vp]),
     ("vgs_average_link", c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, _P(c_i64)]),
@@ -154,14 +158,16 @@ def parse_tree_text(text, deltas=False):
     return ln, code, prob, occ
 
 
-def g8_plan(rects, kblocks, n_cta_pairs, max_split=4):
-    """Unit list of the int8 GEMM for output rectangles [(a_blk, b_row0, b_rows), ...] (host only).
+def g8_plan(rects, kblocks, n_cta_pairs, max_split=4, gran=32):
+    """Unit list of the int8 GEMM for output rectangles [(a_blk, b_row0, b_rows), ...] (host only); ``gran`` = granule of the
+    row ranges and unit widths (32; 96 / 224 for the NLL contraction with 6 / 7 digit rows per model).
     Returns (units int32 [n, 6] = a_blk, b_row0, n, kb0, kbn, partial; split)."""
     rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 3)
     cap = 64 + 16 * max_split * int(sum(-(-int(r[2]) // 32) for r in rects))
     out = np.zeros((cap, 6), dtype=np.int32)
     n, split = c_int(), c_int()
-    _check(lib().vgs_g8_plan(_np_ptr(rects), len(rects), kblocks, n_cta_pairs, max_split, _np_ptr(out), cap, ctypes.byref(n), ctypes.byref(split)))
+    _check(lib().vgs_g8_plan_gran(_np_ptr(rects), len(rects), kblocks, n_cta_pairs, max_split, gran, _np_ptr(out), cap, ctypes.byref(n),
+                                  ctypes.byref(split)))
     return out[: n.value].copy(), split.value
 
 
@@ -209,6 +215,16 @@ class Handle:
     def last_nll_kernel(self):
         """0 scan, 1 fp64 MMA contraction, 2 fp64 FMA contraction, 3 exact int8 tensor-core contraction."""
         return int(lib().vgs_last_nll_kernel(self._h))
+
+    def set_kmer_fraction_bits(self, bits):
+        """Fraction bits f of the fixed-point ln p in the k-mer contraction (35..51, default 43): |d distance| <= 2^-f."""
+        _check(lib().vgs_set_kmer_fraction_bits(self._h, int(bits)))
+
+    def kmer_digit_info(self):
+        """(digit rows per model of the int8 operand as built -- 0 when not built --, fraction bits)."""
+        nd, f = c_int(), c_int()
+        _check(lib().vgs_kmer_digit_info(self._h, ctypes.byref(nd), ctypes.byref(f)))
+        return nd.value, f.value
 
     def last_pair_kernel(self):
         """0 CUDA-core pair kernels, 1 tensor-core (exact integer GEMM) path."""
@@ -432,6 +448,12 @@ class Handle:
         """(TOPS, ms) of back-to-back tcgen05.mma kind::i8 from resident shared memory on every SM."""
         tops, ms = ctypes.c_double(), ctypes.c_double()
         _check(lib().vgs_tensor_peak_i8(self._h, cta_group, ctypes.byref(tops), ctypes.byref(ms)))
+        return tops.value, ms.value
+
+    def tensor_rate_i8(self, n_cols, cta_group=2):
+        """(TOPS, ms) of the same probe at instruction width N = n_cols (multiple of 16, <= 256)."""
+        tops, ms = ctypes.c_double(), ctypes.c_double()
+        _check(lib().vgs_tensor_rate_i8(self._h, cta_group, int(n_cols), ctypes.byref(tops), ctypes.byref(ms)))
         return tops.value, ms.value
 
     def matrix_to_triples(self, n, D32, triples, stream):

@@ -153,6 +153,12 @@ int vgs_sample_sequences(vgs_handle h, int64_t length, int64_t pre_sample, uint3
 #define VGS_NLL_KERNEL_FMA 2    /* k_kmer_gemm: fp64 FMA contraction (VGS_KMER_GEMM=fma)                    */
 #define VGS_NLL_KERNEL_I8MMA 3  /* k_kmer_i8mma: exact int8 contraction on tcgen05 tensor cores (default)   */
 int vgs_last_nll_kernel(vgs_handle h);
+/* k-mer contraction: ln p enters as the fixed-point integer round(ln p * 2^f) in 6..8 base-256 digit rows per model (the
+ * GEMM's work is proportional to the digit count).  f = 43 by default (environment VGS_I8_FRAC_BITS): |d score| <=
+ * L * 2^-44, |d distance| <= 2^-43 against the exact sum, below the fp64 scan's own rounding noise; 51 reproduces the
+ * scan to 2e-14.  vgs_kmer_digit_info: the digit rows per model of the operand as built (0: not built) and f. */
+int vgs_set_kmer_fraction_bits(vgs_handle h, int bits /* 35..51 */);
+int vgs_kmer_digit_info(vgs_handle h, int *digits_out /* nullable */, int *fraction_bits_out /* nullable */);
 
 int vgs_nll_scores(vgs_handle h, int64_t s_begin, int64_t s_end, int64_t m_begin, int64_t m_end, int skip_mode,
                    int mode, double *M_d, int64_t ld, void *stream);
@@ -231,10 +237,15 @@ int vgs_peer_barrier(vgs_handle h, uint32_t *const *flags_h, int rank, int world
  *      of back-to-back tcgen05.mma kind::i8 M256 N256 K32 (cta_group 2) or M128 N256 K32 (cta_group 1) from resident
  *      shared memory on every SM: the measured tensor-pipe ceiling of the contraction's own instruction.
  *      vgs_g8_plan: the unit list the int8 GEMM would run for the given output rectangles {256-row A block, first B row,
- *      B rows} (host only; rows in multiples of 32): units_out[i] = {a_blk, b_row0, n, kb0, kbn, partial}. -------------- */
+ *      B rows} (host only; rows in multiples of the granule: 32, or vgs_g8_plan_gran's `gran` -- the NLL contraction
+ *      with 6 / 7 digit rows per model uses 96 / 224): units_out[i] = {a_blk, b_row0, n, kb0, kbn, partial}. ------------ */
 int vgs_tensor_peak_i8(vgs_handle h, int cta_group, double *tops_out, double *ms_out /* nullable */);
+/* the same probe at instruction width N (multiple of 16, <= 256): the tensor pipe's rate as a function of N */
+int vgs_tensor_rate_i8(vgs_handle h, int cta_group, int n_cols, double *tops_out, double *ms_out /* nullable */);
 int vgs_g8_plan(const int32_t *rects_h /* [n_rects][3] */, int n_rects, int kblocks, int n_cta_pairs, int max_split,
                 int32_t *units_out_h /* [capacity][6] */, int capacity, int *n_units_out, int *split_out);
+int vgs_g8_plan_gran(const int32_t *rects_h /* [n_rects][3] */, int n_rects, int kblocks, int n_cta_pairs, int max_split, int gran,
+                     int32_t *units_out_h /* [capacity][6] */, int capacity, int *n_units_out, int *split_out);
 
 /* ---- matrix hand-off layouts of src/clustering/util.pyx:6-21: float32 [N*N][3] rows (i, j, d) ---- */
 int vgs_matrix_to_triples(vgs_handle h, int64_t n, const float *D32_d, float *triples_d, void *stream);

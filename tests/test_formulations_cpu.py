@@ -7,54 +7,63 @@ import numpy as np
 
 import vlmc_oracle as O
 
-SCALE = 2 ** 51
+import pytest
 
 
-def digits_of(q):
-    """Eight balanced base-256 digits of a Python int, as k_i8_digits computes them."""
+def digits_of(q, nd):
+    """nd balanced base-256 digits of a Python int, as k_i8_digits computes them (a remainder flags 'does not fit')."""
     out = []
-    for _ in range(8):
+    for _ in range(nd):
         d = ((q + 128) & 255) - 128
         out.append(d)
         q = (q - d) >> 8
-    assert q == 0
-    return out
+    return out, q == 0
 
 
-def fold(S):
-    """i8_fold: two int64 halves, one fp64 rounding each, exact power-of-two scaling."""
+def fold(S, scale):
+    """i8_fold: two int64 halves, exact power-of-two scaling."""
     lo = S[0] + S[1] * 256 + S[2] * 65536 + S[3] * 16777216
-    hi = S[4] + S[5] * 256 + S[6] * 65536 + S[7] * 16777216
+    hi = 0
+    for p in range(len(S) - 1, 3, -1):
+        hi = hi * 256 + S[p]
     assert abs(lo) < 2 ** 63 and abs(hi) < 2 ** 63
     v = float(np.float64(hi)) * 4294967296.0 + float(np.float64(lo))   # fma(hi, 2^32, lo): both products exact here
-    return v / SCALE
+    return v / scale
 
 
-def test_fixed_point_contraction_is_exact():
+@pytest.mark.parametrize("frac_bits,nd,with_zero_p", [(43, 6, False), (43, 7, True), (51, 7, False), (51, 8, True)])
+def test_fixed_point_contraction_is_exact(frac_bits, nd, with_zero_p):
+    """round(ln p * 2^f) in nd digits: six hold |ln p| < 16 at the default f = 43, seven the -1000 of p = 0 as well."""
+    SCALE = 2 ** frac_bits
     rng = np.random.Generator(np.random.PCG64(1))
     K = 4096
     p = rng.dirichlet([0.3, 0.3, 0.3, 0.3], size=K // 4).ravel()
-    T = np.where(rng.random(K) < 0.02, -1000.0, np.log(np.maximum(p, 1e-300)))   # includes the p == 0 marker
+    T = np.log(np.maximum(p, 2e-7))
+    if with_zero_p:
+        T = np.where(rng.random(K) < 0.02, -1000.0, T)                             # includes the p == 0 marker
     C = rng.integers(0, 4, size=K)
     C[rng.integers(0, K, 7)] += rng.integers(300, 40000, 7)                        # frequent k-mers: above one byte
     q = [int(np.rint(t * SCALE)) for t in T]
-    assert max(abs(x) for x in q) < 2 ** 61
-    D = np.array([digits_of(x) for x in q])                                        # [K, 8]
+    dg = [digits_of(x, nd) for x in q]
+    assert all(ok for _, ok in dg)
+    if with_zero_p:
+        assert not all(digits_of(x, nd - 1)[1] for x in q)                         # ... and one digit fewer would not do
+    D = np.array([d for d, _ in dg])                                               # [K, nd]
     assert D.min() >= -128 and D.max() <= 127
-    assert all(sum(int(D[k, j]) * 256 ** j for j in range(8)) == q[k] for k in range(0, K, 97))
+    assert all(sum(int(D[k, j]) * 256 ** j for j in range(nd)) == q[k] for k in range(0, K, 97))
     # tensor-core part: low bytes, int32 sums; epilogue part: 256 * (count >> 8) for the frequent k-mers
     lo, hi = C & 255, C >> 8
-    S_lo = [int(np.dot(lo.astype(np.int64), D[:, j].astype(np.int64))) for j in range(8)]
+    S_lo = [int(np.dot(lo.astype(np.int64), D[:, j].astype(np.int64))) for j in range(nd)]
     assert max(abs(x) for x in S_lo) < 2 ** 31
-    S_hi = [int(sum(256 * int(hi[k]) * int(D[k, j]) for k in np.nonzero(hi)[0])) for j in range(8)]
-    got = fold(S_lo) + fold(S_hi)
+    S_hi = [int(sum(256 * int(hi[k]) * int(D[k, j]) for k in np.nonzero(hi)[0])) for j in range(nd)]
+    got = fold([a + b for a, b in zip(S_lo, S_hi)], SCALE)
     exact = Fraction(sum(int(C[k]) * q[k] for k in range(K)), SCALE)                # exact sum of the quantised terms
-    assert abs(Fraction(got) - exact) <= Fraction(2, 2 ** 52) * abs(exact)          # two fp64 roundings
-    # against the real-number sum: only the 2^-52 quantisation of each ln p
+    assert abs(Fraction(got) - exact) <= Fraction(3, 2 ** 53) * abs(exact)          # the fold's fp64 roundings
+    # against the real-number sum: only the 2^-(f+1) quantisation of each ln p
     real = sum(Fraction(int(C[k])) * Fraction(float(T[k])) for k in range(K))
-    assert abs(exact - real) <= Fraction(int(C.sum()), 2 ** 52)
-    # and an fp64 dot product in any order is no closer
-    assert abs(got - float(np.dot(C.astype(np.float64), T))) <= 1e-12 * abs(got)
+    assert abs(exact - real) <= Fraction(int(C.sum()), 2 ** (frac_bits + 1))
+    # and an fp64 dot product in any order is no closer than the stated bound
+    assert abs(got - float(np.dot(C.astype(np.float64), T))) <= max(1e-12, 2.0 ** -(frac_bits + 1) / 1.0) * abs(got)
 
 
 def test_projection_one_direction_identity():

@@ -314,25 +314,30 @@ def test_shard_bounds_cover_the_models():
             assert all(a == min(n, r * per) for r, (a, e) in enumerate(b))
 
 
-@pytest.mark.parametrize("rects,kblocks,pairs", [([(a, 0, 8000) for a in range(4)], 128, 74), ([(a, 0, 1024) for a in range(4)], 128, 74),
-                                                 ([(0, 0, 64)], 1, 74), ([(0, 0, 32)], 128, 74), ([(a, 0, 16000) for a in range(8)], 128, 74),
-                                                 ([(0, 0, 2400), (1, 1024, 1024)], 16, 74), ([(0, 32, 160032 - 32)], 4, 3)])
-def test_int8_gemm_unit_plan(rects, kblocks, pairs):
-    """The unit list of the CTA-pair int8 GEMM (host planner behind vgs_g8_plan): every (256-row block, 32-row quantum,
-    k block) of the requested rectangles is covered exactly once, widths are multiples of 32 up to 512, k-splits only
-    where they pay, and the dealt load per CTA pair stays close to the mean."""
-    units, split = native.g8_plan(rects, kblocks, pairs)
+@pytest.mark.parametrize("rects,kblocks,pairs,gran", [
+    ([(a, 0, 8000) for a in range(4)], 128, 74, 32), ([(a, 0, 1024) for a in range(4)], 128, 74, 32),
+    ([(0, 0, 64)], 1, 74, 32), ([(0, 0, 32)], 128, 74, 32), ([(a, 0, 16000) for a in range(8)], 128, 74, 32),
+    ([(0, 0, 2400), (1, 1024, 1024)], 16, 74, 32), ([(0, 32, 160032 - 32)], 4, 3, 32),
+    # the NLL contraction with 6 / 7 digit rows per model: granules of 16 / 32 models
+    ([(a, 0, 6048) for a in range(4)], 128, 74, 96), ([(a, 0, 768) for a in range(4)], 128, 74, 96), ([(0, 768, 96)], 2, 74, 96),
+    ([(a, 0, 7168) for a in range(4)], 128, 74, 224), ([(0, 0, 224), (3, 896, 1792)], 16, 5, 224)])
+def test_int8_gemm_unit_plan(rects, kblocks, pairs, gran):
+    """The unit list of the CTA-pair int8 GEMM (host planner behind vgs_g8_plan): every (256-row block, granule of rows,
+    k block) of the requested rectangles is covered exactly once, widths are whole granules of at most two accumulators
+    (each the largest multiple of the granule <= 256), k-splits only where they pay, and the dealt load per CTA pair
+    stays close to the mean."""
+    units, split = native.g8_plan(rects, kblocks, pairs, gran=gran)
     live = units[units[:, 2] > 0]
     seen = set()
     for a, b0, n, k0, kn, part in live:
-        assert n % 32 == 0 and 0 < n <= 512 and kn > 0 and b0 % 32 == 0
+        assert n % gran == 0 and 0 < n <= 2 * (256 // gran) * gran and kn > 0 and b0 % gran == 0
         assert (part != 0) == (split > 1)
-        for r in range(b0, b0 + n, 32):
+        for r in range(b0, b0 + n, gran):
             for k in range(k0, k0 + kn):
                 assert (a, r, k) not in seen
                 seen.add((a, r, k))
-    assert len(seen) == sum((r[2] // 32) * kblocks for r in rects)
-    assert all((a, r, k) in seen for a, b0, rows in rects for r in range(b0, b0 + rows, 32) for k in range(kblocks))
+    assert len(seen) == sum((r[2] // gran) * kblocks for r in rects)
+    assert all((a, r, k) in seen for a, b0, rows in rects for r in range(b0, b0 + rows, gran) for k in range(kblocks))
     load = np.zeros(pairs)
     for i, (a, b0, n, k0, kn, part) in enumerate(units):
         load[i % pairs] += n * kn
