@@ -413,7 +413,7 @@ def main():
         # NLL: the sequences are given, so nothing on the device reads the transition rows themselves -- the same load the
         # drop-in NegativeLogLikelihood class does when every model already carries its sampled sequence
         h.load_models_raw(fm.n_models, host["off"], host["len"], host["code"], host["prob"], skip_nll=(kind != "nll"),
-                          nll_only=(kind == "nll"))
+                          nll_only=(kind == "nll"), device_log=(kind == "nll" and args.mode == "kmer"))
         if seqs is not None:
             h.load_sequences_packed(host["words"], host["woff"], host["lens"])
 
@@ -590,7 +590,7 @@ def main():
     parity_check = None
     if world > 1:
         h1 = native.Handle(local_rank)
-        h1.load_models(fm_full, skip_nll=(kind != "nll"))
+        h1.load_models(fm_full, skip_nll=(kind != "nll"), device_log=(kind == "nll" and args.mode == "kmer"))
         if seqs is not None:
             h1.load_sequences_packed(*pack_sequences(seqs))
         ref = torch.empty((n, n), dtype=torch.float32, device=dev)

@@ -120,6 +120,9 @@ struct vgs_context {
     float4 *d_prob32 = nullptr;
     double *d_prob64 = nullptr;
     double *d_logp = nullptr;
+    double *d_logp_dev = nullptr;   // VGS_LOAD_DEVICE_LOG: the device's own ln p (read by the k-mer contraction only)
+    bool logp_exact = true;         // d_logp holds libm's ln p (false after a VGS_LOAD_DEVICE_LOG load until a bit-exact mode asks)
+    bool logp_device = false;       // the current set was loaded with VGS_LOAD_DEVICE_LOG
     double *d_invp = nullptr;   // Estimate: 1 / p, built on first use per model set
     uint64_t invp_gen = ~0ull;
     uint2 *d_hash = nullptr;
@@ -295,6 +298,7 @@ double vgs_kmer_i8_narrow_limit(vgs_context *h);                           // |l
 int vgs_kmer_i8_digits_range(vgs_context *h, int64_t m_begin, int64_t m_end, cudaStream_t s);   // digits of models [m_begin, m_end)
 int vgs_kmer_i8_digits_end(vgs_context *h, cudaStream_t s);                // after a synchronisation: record whether the operand is usable
 int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, const VgsScoreDst &dst, cudaStream_t s);
+int vgs_ensure_exact_logp(vgs_context *h, cudaStream_t s);   // libm's ln p in h->d_logp (no-op unless VGS_LOAD_DEVICE_LOG)
 int vgs_kmer_i8_gran(vgs_context *h);   // unit granule (B rows) of the operand as built
 bool vgs_pair_tc_wanted(vgs_context *h, int kind);
 int vgs_pair_tc_matrix(vgs_context *h, int kind, float *D32, double *D64, cudaStream_t s);   // -1: not applicable

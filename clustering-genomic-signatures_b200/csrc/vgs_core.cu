@@ -600,6 +600,47 @@ static int log2_ceil_pow2(int64_t v, int64_t *cap_out) {
     return lg;
 }
 
+// VGS_LOAD_DEVICE_LOG: ln p from the transition rows on the device (src/vlmc/vlmc.pyx:94-99: -1000 where p == 0; a negative
+// probability is the reference's "math domain error")
+__global__ void k_device_logp(int64_t n, const double *__restrict__ prob, double *__restrict__ logp, int *__restrict__ neg_flag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double p = prob[i];
+        if (p < 0) atomicOr(neg_flag, 1);
+        logp[i] = (p == 0) ? -1000.0 : log(p);
+    }
+}
+
+// libm's ln p on the device (h->d_logp) for the bit-exact consumers of a set that was loaded with VGS_LOAD_DEVICE_LOG: the
+// transition rows come back from the device, the host pool takes the logarithms, the result goes up.  Once per model set;
+// the k-mer contraction keeps using the device's own ln p (h->d_logp_dev), so its results do not depend on whether a
+// bit-exact mode ran in between.
+int vgs_ensure_exact_logp(vgs_context *h, cudaStream_t s) {
+    if (h->logp_exact) return VGS_OK;
+    const int64_t n_elem = h->total_ctx * 4;
+    int rc;
+    if (h->h_logp_cap < n_elem) {
+        if (h->h_logp) cudaFreeHost(h->h_logp);
+        h->h_logp = nullptr;
+        h->h_logp_cap = 0;
+        VGS_CUDA(cudaHostAlloc((void **)&h->h_logp, sizeof(double) * (size_t)n_elem, cudaHostAllocDefault));
+        h->h_logp_cap = n_elem;
+    }
+    if ((rc = vgs_reserve(h, &h->d_logp, n_elem))) return rc;
+    VGS_CUDA(cudaStreamSynchronize(s));
+    VGS_CUDA(cudaMemcpy(h->h_logp, h->d_prob64, sizeof(double) * (size_t)n_elem, cudaMemcpyDeviceToHost));
+    VgsPool *pool = get_pool(h);
+    const int nt = pool->size();
+    double *v = h->h_logp;
+    pool->start([&, nt](int tid) {
+        const int64_t b0 = n_elem * tid / nt, e0 = n_elem * (tid + 1) / nt;
+        for (int64_t i = b0; i < e0; ++i) v[i] = (v[i] == 0) ? -1000.0 : log(v[i]);
+    });
+    pool->wait();
+    VGS_CUDA(cudaMemcpy(h->d_logp, h->h_logp, sizeof(double) * (size_t)n_elem, cudaMemcpyHostToDevice));
+    h->logp_exact = true;
+    return VGS_OK;
+}
+
 extern "C" int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h, const uint8_t *ctx_len_h,
                                const uint32_t *ctx_code_h, const double *prob_h, const double *logp_h) {
     return vgs_load_models_ex(h, n_models, ctx_offsets_h, ctx_len_h, ctx_code_h, prob_h, logp_h, 0);
@@ -624,6 +665,24 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     const int64_t total = ctx_offsets_h[n_models];
     VGS_CHECK_ARG(ctx_offsets_h[0] == 0 && total > 0, "vgs_load_models: ctx_offsets must start at 0");
     VGS_CHECK_ARG(total < (int64_t)1 << 31, "vgs_load_models: more than 2^31 contexts in one set");
+    const bool want_nll = !(flags & VGS_LOAD_SKIP_NLL);
+    const bool want_prob = !(flags & VGS_LOAD_NLL_ONLY);
+    VGS_CHECK_ARG(want_nll || want_prob, "vgs_load_models: VGS_LOAD_SKIP_NLL and VGS_LOAD_NLL_ONLY exclude each other");
+    // VGS_LOAD_DEVICE_LOG: ln p is taken on the device (CUDA's log(), <= 1 ulp from libm's) for the k-mer contraction -- its
+    // fixed-point quantisation is 64 times coarser than that -- so the load is one pass over PCIe with no host arithmetic.
+    // The bit-exact modes still get libm's ln p: vgs_ensure_exact_logp computes it on first need.
+    bool device_log = (flags & VGS_LOAD_DEVICE_LOG) && want_nll && !logp_h;
+    int rc;
+    cudaStream_t s = h->own_stream;
+    // the caller's arrays start crossing PCIe before anything else happens; every return below drains the stream first
+    struct Drain { cudaStream_t st; ~Drain() { cudaStreamSynchronize(st); } } drain{s};
+    if ((rc = vgs_reserve(h, &h->d_len, total))) return rc;
+    if ((rc = vgs_reserve(h, &h->d_code, total))) return rc;
+    if ((want_prob || device_log) && (rc = vgs_reserve(h, &h->d_prob64, total * 4))) return rc;
+    if (load_timing) cudaEventRecord(ev_t[0], s);
+    VGS_CUDA(cudaMemcpyAsync(h->d_len, ctx_len_h, (size_t)total, cudaMemcpyHostToDevice, s));
+    VGS_CUDA(cudaMemcpyAsync(h->d_code, ctx_code_h, sizeof(uint32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    if (want_prob || device_log) VGS_CUDA(cudaMemcpyAsync(h->d_prob64, prob_h, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
 
     h->h_ctx_off.assign(ctx_offsets_h, ctx_offsets_h + n_models + 1);
     h->h_meta.assign((size_t)n_models, ModelMeta());
@@ -745,16 +804,11 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     }
 
     lap("host: validate + plan");
-    int rc;
+    // sets the contraction does not cover (deeper than 6) are scored by the scan, which wants libm's ln p: the host pass below
+    if (device_log && !vgs_kmer_applicable_orders(h)) device_log = false;
     if ((rc = vgs_reserve(h, &h->d_meta, n_models))) return rc;
     if ((rc = vgs_reserve(h, &h->d_key, total))) return rc;
-    if ((rc = vgs_reserve(h, &h->d_len, total))) return rc;
-    if ((rc = vgs_reserve(h, &h->d_code, total))) return rc;
-    const bool want_nll = !(flags & VGS_LOAD_SKIP_NLL);
-    const bool want_prob = !(flags & VGS_LOAD_NLL_ONLY);
-    VGS_CHECK_ARG(want_nll || want_prob, "vgs_load_models: VGS_LOAD_SKIP_NLL and VGS_LOAD_NLL_ONLY exclude each other");
     if (want_prob && (rc = vgs_reserve(h, &h->d_prob32, total))) return rc;
-    if (want_prob && (rc = vgs_reserve(h, &h->d_prob64, total * 4))) return rc;
     h->prob_ready = want_prob;
     if ((rc = vgs_reserve(h, &h->d_hash, hash_slots))) return rc;
     h->hash_slots = hash_slots;
@@ -764,14 +818,9 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     h->total_ctx = total;
     h->nll_ready = false;
 
-    // 1. upload what the caller gave us (asynchronous when its buffers are pinned) and build everything that
-    //    does not need ln p: keys, fp32 rows, hashes, universe maps
-    cudaStream_t s = h->own_stream;
-    if (load_timing) cudaEventRecord(ev_t[0], s);
+    // 1. behind the uploads of the caller's arrays (enqueued at the top; asynchronous when its buffers are pinned): everything
+    //    that does not need ln p -- keys, fp32 rows, hashes
     VGS_CUDA(cudaMemcpyAsync(h->d_meta, h->h_meta.data(), sizeof(ModelMeta) * (size_t)n_models, cudaMemcpyHostToDevice, s));
-    VGS_CUDA(cudaMemcpyAsync(h->d_len, ctx_len_h, (size_t)total, cudaMemcpyHostToDevice, s));
-    VGS_CUDA(cudaMemcpyAsync(h->d_code, ctx_code_h, sizeof(uint32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
-    if (want_prob) VGS_CUDA(cudaMemcpyAsync(h->d_prob64, prob_h, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemsetAsync(h->d_hash, 0, sizeof(uint2) * (size_t)hash_slots, s));
     k_build_keys<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(total, h->d_len, h->d_code, want_prob ? h->d_prob64 : nullptr, h->d_key,
                                                               want_prob ? h->d_prob32 : nullptr);
@@ -782,6 +831,8 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     lap("enqueued: uploads + keys/hash");
     h->dense_state = 0;
     h->umap_tried = false;
+    h->logp_exact = !device_log;
+    h->logp_device = device_log;
     if (!want_nll) {
         // negative probabilities pass here as they do in the reference, which only fails on them when it takes their
         // logarithm at scoring time (src/vlmc/vlmc.pyx:99): the NLL load below reports that "math domain error"
@@ -789,6 +840,32 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         return VGS_OK;
     }
 
+    if (device_log) {
+        // 2'. ln p on the device, then (sets the contraction covers) its digit operand; nothing for the host to do
+        if ((rc = vgs_reserve(h, &h->d_logp_dev, total * 4))) return rc;
+        if ((rc = vgs_reserve(h, &h->d_nll, nll_bytes))) return rc;
+        if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
+        VGS_CUDA(cudaMemsetAsync(h->d_counters + 12, 0, sizeof(int), s));
+        k_device_logp<<<std::min<int64_t>(8 * h->sm_count, (total * 4 + 255) / 256), 256, 0, s>>>(total * 4, h->d_prob64, h->d_logp_dev, h->d_counters + 12);
+        VGS_LAUNCH_CHECK(h);
+        int neg = 0;
+        VGS_CUDA(cudaMemcpyAsync(&neg, h->d_counters + 12, sizeof(int), cudaMemcpyDeviceToHost, s));
+        h->nll_ready = true;
+        const bool eager = !(flags & VGS_LOAD_LAZY_TABLES) && vgs_kmer_applicable_orders(h);
+        if (eager) {
+            // (k_i8_range + the digit builder; its own synchronisation also delivers `neg`)
+            rc = vgs_kmer_i8_prepare_tables(h, s);
+            if (rc > 0) return rc;
+        } else {
+            VGS_CUDA(cudaStreamSynchronize(s));
+        }
+        lap("device ln p + digits: stream drained");
+        if (neg) {
+            vgs_set_error("math domain error: negative transition probability");
+            return VGS_ERR_INVALID;
+        }
+        return VGS_OK;
+    }
     // 2. meanwhile on the host: ln p with libm (bit-identical to CPython's math.log on this host), threaded,
     //    into a pinned staging buffer
     if (h->h_logp_cap < total * 4) {
@@ -934,6 +1011,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
 
 int vgs_ensure_scan_tables(vgs_context *h, cudaStream_t s) {
     if (h->dense_state) return VGS_OK;
+    { const int rce = vgs_ensure_exact_logp(h, s); if (rce) return rce; }
     const int64_t n_models = h->n_models;
     if (h->max_nll_bytes_t1 > 0) {
         // grid.x covers up to 4^6 histories with 256-thread blocks
@@ -1030,6 +1108,7 @@ extern "C" int vgs_get_logp(vgs_handle h, double *logp_out_h) {
     VGS_CHECK_ARG(h && logp_out_h && h->n_models > 0, "vgs_get_logp: no models loaded");
     VGS_CHECK_ARG(h->nll_ready, "vgs_get_logp: models were loaded with VGS_LOAD_SKIP_NLL");
     VGS_CUDA(cudaSetDevice(h->device));
+    { const int rce = vgs_ensure_exact_logp(h, h->own_stream); if (rce) return rce; }
     // read back from the device so the test sees what the kernels see
     VGS_CUDA(cudaMemcpy(logp_out_h, h->d_logp, sizeof(double) * (size_t)h->total_ctx * 4, cudaMemcpyDeviceToHost));
     return VGS_OK;

@@ -373,6 +373,7 @@ static int ensure_kmer_tables(vgs_context *h, cudaStream_t s) {
     const int64_t K = std::max<int64_t>(KD_BK, (int64_t)1 << (2 * (D + 1)));  // row stride, padded to one MMA k-stage
     if (h->kmer_tables_ready) return VGS_OK;
     int rc;
+    if ((rc = vgs_ensure_exact_logp(h, s))) return rc;
     if ((rc = vgs_reserve(h, &h->d_kmer_T, h->n_models * K))) return rc;
     if (K != ((int64_t)1 << (2 * (D + 1)))) VGS_CUDA(cudaMemsetAsync(h->d_kmer_T, 0, sizeof(double) * (size_t)(h->n_models * K), s));
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;

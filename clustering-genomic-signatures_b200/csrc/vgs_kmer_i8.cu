@@ -465,7 +465,7 @@ static int i8_digits_for(int frac_bits, int int_bits) { return std::max(6, std::
 
 static I8Side i8_side(vgs_context *h, bool with_over) {
     I8Side sd;
-    sd.meta = h->d_meta; sd.hash = h->d_hash; sd.logp = h->d_logp;
+    sd.meta = h->d_meta; sd.hash = h->d_hash; sd.logp = h->logp_device ? h->d_logp_dev : h->d_logp;
     sd.seq = h->d_seq; sd.seq_off = h->d_seq_off; sd.seq_len = h->d_seq_len;
     sd.over_cnt = with_over ? (const int32_t *)h->d_i8_over : nullptr;
     sd.over_list = with_over ? (const uint2 *)(h->d_i8_over + ((h->n_seq + 1) / 2) * 2) : nullptr;
@@ -551,7 +551,7 @@ int vgs_kmer_i8_prepare_tables(vgs_context *h, cudaStream_t s) {
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
     int wide = 0;
     VGS_CUDA(cudaMemsetAsync(h->d_counters + 11, 0, sizeof(int), s));
-    k_i8_range<<<std::min(4 * h->sm_count, (int)((h->total_ctx * 4 + 255) / 256)), 256, 0, s>>>(h->total_ctx * 4, h->d_logp, vgs_kmer_i8_narrow_limit(h), h->d_counters + 11);
+    k_i8_range<<<std::min(4 * h->sm_count, (int)((h->total_ctx * 4 + 255) / 256)), 256, 0, s>>>(h->total_ctx * 4, h->logp_device ? h->d_logp_dev : h->d_logp, vgs_kmer_i8_narrow_limit(h), h->d_counters + 11);
     VGS_LAUNCH_CHECK(h);
     VGS_CUDA(cudaMemcpyAsync(&wide, h->d_counters + 11, sizeof(int), cudaMemcpyDeviceToHost, s));
     VGS_CUDA(cudaStreamSynchronize(s));

@@ -57,7 +57,8 @@ class _DeviceDistance(object):
         """float32 [N, N] matrix of ``distance(vlmcs[i], vlmcs[j])`` (src/clustering/util.pyx:23-33 layout)."""
         vlmcs = list(vlmcs)
         h = self._get_handle()
-        h.load_models(vlmcs_to_flat(vlmcs), skip_nll=not self.needs_nll_tables, nll_only=self._nll_only(vlmcs))
+        h.load_models(vlmcs_to_flat(vlmcs), skip_nll=not self.needs_nll_tables, nll_only=self._nll_only(vlmcs),
+                      device_log=self._device_log())
         D32, D64 = self._compute(h, vlmcs)
         self._D32, self._D64 = D32, D64
         self._vlmcs = vlmcs
@@ -71,6 +72,10 @@ class _DeviceDistance(object):
     def _nll_only(self, vlmcs):
         """True when the device needs nothing but the log-likelihood tables for these models (NegativeLogLikelihood with
         every sequence already sampled): the transition rows are then not uploaded at all."""
+        return False
+
+    def _device_log(self):
+        """True when ln p may be taken on the device (VGS_LOAD_DEVICE_LOG): only the k-mer contraction reads it."""
         return False
 
     def _row(self, v):
@@ -94,7 +99,8 @@ class _DeviceDistance(object):
         # not batched: this pair alone, still on the device
         pair = [left_vlmc, right_vlmc]
         h = self._get_handle()
-        h.load_models(vlmcs_to_flat(pair), skip_nll=not self.needs_nll_tables, nll_only=self._nll_only(pair))
+        h.load_models(vlmcs_to_flat(pair), skip_nll=not self.needs_nll_tables, nll_only=self._nll_only(pair),
+                      device_log=self._device_log())
         D32, D64 = self._compute(h, pair, pair_only=True)
         return self._scalar(D32, D64)
 
@@ -134,6 +140,11 @@ class NegativeLogLikelihood(_DeviceDistance):
     def _nll_only(self, vlmcs):
         # scoring reads ln p only; missing sequences are sampled on a handle of their own (vlmc.sample_missing_sequences)
         return True
+
+    def _device_log(self):
+        # the contraction quantises ln p to 2^-43: the device's log() (<= 1 ulp from libm's) is 64 times finer than that.  The
+        # library ignores the flag for sets the contraction does not cover; "sequential" / "warp" always take libm's ln p
+        return self.mode == "kmer"
 
     def _still_valid(self, left, right):
         # the reference re-samples when a model's cached sequence was reset or has another length

@@ -244,24 +244,26 @@ class Handle:
 
     # ---- models
     @staticmethod
-    def _load_flags(skip_nll, nll_only, lazy_tables):
-        return (1 if skip_nll else 0) | (2 if nll_only else 0) | (4 if lazy_tables else 0)
+    def _load_flags(skip_nll, nll_only, lazy_tables, device_log=False):
+        return (1 if skip_nll else 0) | (2 if nll_only else 0) | (4 if lazy_tables else 0) | (8 if device_log else 0)
 
-    def load_models(self, fm, logp=None, skip_nll=False, nll_only=False, lazy_tables=False):
+    def load_models(self, fm, logp=None, skip_nll=False, nll_only=False, lazy_tables=False, device_log=False):
+        """``device_log``: VGS_LOAD_DEVICE_LOG -- ln p for the k-mer contraction is taken on the device (no host arithmetic in the
+        load); the bit-exact modes still get libm's ln p on first use."""
         off = np.ascontiguousarray(fm.ctx_offsets, dtype=np.int64)
         ln = np.ascontiguousarray(fm.ctx_len, dtype=np.uint8)
         code = np.ascontiguousarray(fm.ctx_code, dtype=np.uint32)
         prob = np.ascontiguousarray(fm.prob, dtype=np.float64)
         lp = None if logp is None else np.ascontiguousarray(logp, dtype=np.float64)
         _check(lib().vgs_load_models_ex(self._h, fm.n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), _np_ptr(lp),
-                                        self._load_flags(skip_nll, nll_only, lazy_tables)))
+                                        self._load_flags(skip_nll, nll_only, lazy_tables, device_log)))
         self.n_models = fm.n_models
         self.total_contexts = fm.total_contexts
 
-    def load_models_raw(self, n_models, off, ln, code, prob, skip_nll=False, nll_only=False, lazy_tables=False):
+    def load_models_raw(self, n_models, off, ln, code, prob, skip_nll=False, nll_only=False, lazy_tables=False, device_log=False):
         """Same as load_models but from already-contiguous (e.g. pinned) arrays; no conversions."""
         _check(lib().vgs_load_models_ex(self._h, n_models, _np_ptr(off), _np_ptr(ln), _np_ptr(code), _np_ptr(prob), None,
-                                        self._load_flags(skip_nll, nll_only, lazy_tables)))
+                                        self._load_flags(skip_nll, nll_only, lazy_tables, device_log)))
         self.n_models = n_models
         self.total_contexts = int(off[-1])
 

@@ -102,6 +102,12 @@ int vgs_load_models(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h
  * first k-mer-mode call */
 #define VGS_LOAD_NLL_ONLY 2
 #define VGS_LOAD_LAZY_TABLES 4
+/* VGS_LOAD_DEVICE_LOG (with the NLL tables, without logp_h): ln p is taken on the device (CUDA's log(), at most 1 ulp from
+ * libm's) for the k-mer contraction, whose fixed-point quantisation of ln p (2^-43) is 64 times coarser -- the load is one pass
+ * over PCIe with no host arithmetic.  The bit-exact modes (sequential / warp scan, vgs_get_logp) still see libm's ln p: it is
+ * computed from the resident transition rows the first time one of them runs, and the contraction keeps its own, so no result
+ * depends on the order of calls. */
+#define VGS_LOAD_DEVICE_LOG 8
 int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t *ctx_offsets_h, const uint8_t *ctx_len_h,
                        const uint32_t *ctx_code_h, const double *prob_h, const double *logp_h /* nullable */, int flags);
 int vgs_model_count(vgs_handle h, int64_t *n_models, int64_t *total_contexts);

@@ -177,6 +177,59 @@ def test_nll_only_and_lazy_table_loads():
     assert np.array_equal(outs[0][1], c_oracle.COracle(fm).nll_matrix(seqs))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_zeros", [False, True])
+def test_device_log_load(with_zeros):
+    """VGS_LOAD_DEVICE_LOG: the contraction takes ln p from the device's log() -- scores within the mode's bound of the oracle
+    (6 digit rows when every probability exceeds e^-16, 7 when the set has p = 0 entries) --, the bit-exact modes still see
+    libm's ln p (computed on first need), and no kmer result depends on whether a bit-exact mode ran in between.  Sets the
+    contraction does not cover ignore the flag; a negative probability is the reference's math domain error."""
+    fm, _ = synthetic.make_family_models(90, 31, 6, 100, 4)
+    if with_zeros:
+        assert (fm.prob == 0).any()
+    else:
+        fm.prob[:] = np.maximum(fm.prob, 1e-3)
+        fm.prob[:] /= fm.prob.sum(axis=1, keepdims=True)
+        assert fm.prob.min() > 2e-7
+    seqs = synthetic.sample_sequences(fm, 900, 3)
+    packed = pack_sequences(seqs)
+    co = c_oracle.COracle(fm)
+    M_or = co.score_matrix(seqs)
+    h = native.Handle(0)
+    h.load_models(fm, nll_only=True, device_log=True)
+    h.load_sequences_packed(*packed)
+    Mk = h.nll_scores_h(native.SKIP_ORDER, "kmer")
+    assert h.last_nll_kernel() == 3
+    nd, f = h.kmer_digit_info()
+    assert f == 43 and nd == (7 if with_zeros else 6)
+    assert rel_err(Mk, M_or) < 1e-12
+    Dk = h.nll_matrix_h(900, "kmer")[1]
+    assert rel_err(Dk, co.nll_from_scores(M_or, 900)) < 1e-9 and np.array_equal(Dk, Dk.T) and np.all(np.diag(Dk) == 0)
+    # bit-exact modes on the same handle: libm's ln p arrives on first need
+    assert np.array_equal(h.nll_scores_h(native.SKIP_ORDER, "sequential"), M_or)
+    import math
+    want_lp = np.array([-1000.0 if p == 0 else math.log(p) for p in fm.prob.ravel()]).reshape(fm.prob.shape)   # libm, not numpy's SIMD log
+    assert np.array_equal(h.get_logp(), want_lp)
+    assert np.array_equal(h.nll_scores_h(native.SKIP_ORDER, "kmer"), Mk)       # ... and the contraction keeps its own
+    # host-log load of the same set: the same scores to the mode's bound (not necessarily the same bits)
+    h2 = native.Handle(0)
+    h2.load_models(fm)
+    h2.load_sequences_packed(*packed)
+    assert rel_err(h2.nll_scores_h(native.SKIP_ORDER, "kmer"), Mk) < 1e-13
+    h2.close()
+    # a set deeper than the contraction reaches ignores the flag (host ln p, scan)
+    fd, _ = synthetic.make_family_models(12, 5, 8, 300, 2)
+    sd = synthetic.sample_sequences(fd, 400, 2)
+    h.load_models(fd, nll_only=True, device_log=True)
+    h.load_sequences_packed(*pack_sequences(sd))
+    assert np.array_equal(h.nll_scores_h(native.SKIP_ORDER, "sequential"), c_oracle.COracle(fd).score_matrix(sd))
+    bad = fm.subset(range(3))
+    bad.prob[1, 2] = -0.25
+    with pytest.raises(ValueError, match="math domain error"):
+        h.load_models(bad, device_log=True)
+    h.close()
+
+
 def _tc_bound_ok(D_tc, D_ref):
     """Stated bound of the tensor-core variant: |d_tc - d_ref| <= 1.3e-7 d_ref + 1e-9 (rows quantised to 2^-31, the
     difference of two rows not rounded to float32 before squaring)."""

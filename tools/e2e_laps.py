@@ -16,7 +16,7 @@ words, woff, lens = pack_sequences(seqs)
 for name, arr in (("words", words), ("woff", woff), ("lens", lens)):
     t, a = pinned(arr); keep.append(t); arrs[name] = a
 out_t = torch.empty((1000, 1000), dtype=torch.float32).pin_memory(); out = out_t.numpy()
-for kw in ({"nll_only": True}, {"nll_only": True, "lazy_tables": True}, {}):
+for kw in ({"nll_only": True}, {"nll_only": True, "device_log": True}, {"nll_only": True, "lazy_tables": True}, {}):
     for rep in range(4):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
