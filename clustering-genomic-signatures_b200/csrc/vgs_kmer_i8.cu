@@ -108,24 +108,45 @@ __device__ __forceinline__ double i8_head(const I8Side &sd, const ModelMeta &mm,
 }
 
 // ---- operand builders ----------------------------------------------------------------------------------------
-// digits[slab(m * ND + p, k)] = p-th balanced base-256 digit of round(ln p_m(k) * 2^f); one thread per 16 k-mers
-// (= 4 histories x 4 symbols) of one model.  flag bit 0: an entry is not a log-probability (|T| > 1000 or NaN);
-// bit 1: a history has no context at all (model without root context: the scan raises the reference's RuntimeError);
-// bit 2: a value does not fit ND digits (the host rebuilds the operand with more)
-__global__ void k_i8_digits(int64_t m_base, I8Side sd, int64_t K, int64_t K8, int64_t rows_pad, int8_t *__restrict__ digits,
-                            int *__restrict__ flag) {
-    const int64_t m = m_base + blockIdx.y;
+// digits[slab(m * ND + p, k)] = p-th balanced base-256 digit of round(ln p_m(k) * 2^f).  One CTA per model.
+// First the context of EVERY history up to the set's depth D, level by level in shared memory: a history of length k is its
+// own context if the model has it (one hash probe), otherwise it inherits the context of its suffix of length k - 1 -- the
+// longest-suffix rule (src/vlmc/vlmc.pyx:131-141) with (4^(D+1) - 1) / 3 probes per model instead of a walk of up to D + 1
+// probes for each of the 4^D histories (1000 models of depth 6: 150 -> 35 us).  Then one thread per 16 k-mers (= 4 histories
+// x 4 symbols) quantises and splits the digits.
+// flag bit 0: an entry is not a log-probability (|T| > 1000 or NaN); bit 1: a history has no context at all (model without
+// root context: the scan raises the reference's RuntimeError); bit 2: a value does not fit ND digits (the host rebuilds the
+// operand with more)
+__global__ void __launch_bounds__(256) k_i8_digits(int64_t m_base, I8Side sd, int64_t K, int64_t K8, int64_t rows_pad,
+                                                   int8_t *__restrict__ digits, int *__restrict__ flag) {
+    extern __shared__ uint16_t ctx_of[];   // levels 0 .. D one after the other: level k starts at (4^k - 1) / 3
+    const int64_t m = m_base + blockIdx.x;
     const ModelMeta mm = sd.meta[m];
     const uint2 *slots = sd.hash + mm.hash_off;
-    for (int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < (K8 >> 4); ch += (int64_t)gridDim.x * blockDim.x) {
+    const int D = sd.depth;
+    if (threadIdx.x == 0) {
+        const int id = vgs_hash_find(slots, mm.hash_mask, mm.hash_shift, vgs_key(0, 0u));
+        ctx_of[0] = id < 0 ? (uint16_t)0xFFFFu : (uint16_t)id;
+    }
+    __syncthreads();
+    for (int k = 1; k <= D; ++k) {
+        const uint32_t n_k = 1u << (2 * k), off_k = (n_k - 1u) / 3u, off_prev = (n_k / 4u - 1u) / 3u, mask_prev = n_k / 4u - 1u;
+        for (uint32_t hc = threadIdx.x; hc < n_k; hc += blockDim.x) {
+            const int id = k <= mm.order ? vgs_hash_find(slots, mm.hash_mask, mm.hash_shift, vgs_key(k, hc)) : -1;
+            ctx_of[off_k + hc] = id >= 0 ? (uint16_t)id : ctx_of[off_prev + (hc & mask_prev)];   // newest symbol in the low bits
+        }
+        __syncthreads();
+    }
+    const uint16_t *ctx_D = ctx_of + (((1u << (2 * D)) - 1u) / 3u);
+    for (int64_t ch = threadIdx.x; ch < (K8 >> 4); ch += blockDim.x) {
         long long q[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int64_t hc = 4 * ch + i;   // history code
             double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
             if (16 * ch + 4 * i < K) {
-                const int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, (uint32_t)hc, sd.depth);
-                if (id >= 0) {
+                const uint32_t id = ctx_D[hc];
+                if (id != 0xFFFFu) {
                     const double *r = sd.logp + 4 * (mm.ctx_off + id);
                     v = make_double4(r[0], r[1], r[2], r[3]);
                 } else {
@@ -139,22 +160,34 @@ __global__ void k_i8_digits(int64_t m_base, I8Side sd, int64_t K, int64_t K8, in
                 else q[4 * i + x] = i8_quantise(t4[x], sd.scale);
             }
         }
+        // balanced base-256 digits of all 16 values at once: adding 0x80 to every digit position (with the carries of an
+        // ordinary 64-bit addition) turns the balanced digits into the sum's plain bytes minus 128, i.e. its bytes with the
+        // top bit flipped.  (Digit by digit in 64-bit arithmetic this loop was 3/4 of the kernel's instructions.)
+        const unsigned long long bias = sd.nd >= 8 ? 0x8080808080808080ull : ((0x8080808080808080ull) >> (8 * (8 - sd.nd)));
+        uint32_t lo[16], hi[16];
+        long long left = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const long long biased = q[j] + (long long)bias;            // |q| < 2^61: no overflow
+            if (sd.nd < 8) left |= biased >> (8 * sd.nd);              // what does not fit nd digits (0 when all of it does)
+            const unsigned long long dg = (unsigned long long)biased ^ bias;
+            lo[j] = (uint32_t)dg;
+            hi[j] = (uint32_t)(dg >> 32);
+        }
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
             if (p < sd.nd) {
-                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                uint32_t w[4];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const long long d = ((q[j] + 128) & 255) - 128;
-                    w[j >> 2] |= ((uint32_t)d & 255u) << (8 * (j & 3));
-                    q[j] = (q[j] - d) >> 8;
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t *src = p < 4 ? lo : hi;
+                    const uint32_t sel = (uint32_t)((p & 3) | (((p & 3) + 4) << 4));   // byte p of either operand
+                    const uint32_t t0 = __byte_perm(src[4 * g], src[4 * g + 1], sel), t1 = __byte_perm(src[4 * g + 2], src[4 * g + 3], sel);
+                    w[g] = __byte_perm(t0, t1, 0x5410);
                 }
                 *(uint4 *)(digits + g8_off(m * sd.nd + p, 16 * ch, rows_pad)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
-        long long left = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) left |= q[j];
         if (left) atomicOr(flag, 4);
     }
 }
@@ -488,8 +521,11 @@ static int i8_digits_begin_nd(vgs_context *h, int nd, cudaStream_t s) {
     int rc;
     const int64_t rows_pad = i8_digit_rows_pad(h);
     if ((rc = vgs_reserve(h, &h->d_i8_digits, rows_pad * K8))) return rc;
-    if (rows_pad != h->n_models * nd || K8 != K)   // rows beyond the set / columns beyond 4^(D+1): zero
-        VGS_CUDA(cudaMemsetAsync(h->d_i8_digits, 0, (size_t)(rows_pad * K8), s));
+    // zero what the builder does not write: the rows beyond the set (per 128-byte k-block slab the rows lie one after the
+    // other, so they are one strided region) -- the builder itself writes zeros for the columns beyond 4^(D+1)
+    if (rows_pad != h->n_models * nd)
+        VGS_CUDA(cudaMemset2DAsync(h->d_i8_digits + h->n_models * nd * G8_BK, (size_t)(rows_pad * G8_BK), 0,
+                                   (size_t)((rows_pad - h->n_models * nd) * G8_BK), (size_t)(K8 / G8_BK), s));
     if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
     VGS_CUDA(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(int), s));
     h->i8_tables_gen = ~0ull;
@@ -516,11 +552,10 @@ int vgs_kmer_i8_digits_range(vgs_context *h, int64_t m_begin, int64_t m_end, cud
     const int64_t K = (int64_t)1 << (2 * (h->max_order + 1));
     const int64_t K8 = i8_k8(h);
     const I8Side sd = i8_side(h, false);
-    for (int64_t m0 = m_begin; m0 < m_end; m0 += 65535) {
-        dim3 grid((unsigned)std::min<int64_t>(((K8 >> 4) + 127) / 128, 64), (unsigned)std::min<int64_t>(m_end - m0, 65535));
-        k_i8_digits<<<grid, 128, 0, s>>>(m0, sd, K, K8, i8_digit_rows_pad(h), h->d_i8_digits, h->d_counters + 9);
-        VGS_LAUNCH_CHECK(h);
-    }
+    const int smem = (int)(((((int64_t)1 << (2 * (h->max_order + 1))) - 1) / 3) * sizeof(uint16_t));   // <= 10.7 KB at depth 6
+    if (m_end > m_begin)
+        k_i8_digits<<<(unsigned)(m_end - m_begin), 256, smem, s>>>(m_begin, sd, K, K8, i8_digit_rows_pad(h), h->d_i8_digits, h->d_counters + 9);
+    VGS_LAUNCH_CHECK(h);
     return VGS_OK;
 }
 

@@ -66,6 +66,24 @@ def test_fixed_point_contraction_is_exact(frac_bits, nd, with_zero_p):
     assert abs(got - float(np.dot(C.astype(np.float64), T))) <= max(1e-12, 2.0 ** -(frac_bits + 1) / 1.0) * abs(got)
 
 
+def test_byte_parallel_digit_split_equals_the_digit_loop():
+    """k_i8_digits splits all digits of a value at once: q + 0x80..80 (nd bytes) has the balanced digits, plus 128, as its plain
+    bytes; what is left above nd bytes tells whether q fits."""
+    rng = np.random.Generator(np.random.PCG64(7))
+    for nd in (6, 7, 8):
+        bias = 0x8080808080808080 >> (8 * (8 - nd))
+        for e in range(1, 61):
+            for q in [int(x) for x in rng.integers(-2 ** e, 2 ** e, size=200)] + [2 ** e - 1, -2 ** e, 2 ** (e - 1), -2 ** (e - 1) - 1]:
+                want, fits = digits_of(q, nd)
+                b = q + bias
+                left = (b >> (8 * nd)) if nd < 8 else 0
+                dg = (b & (2 ** 64 - 1)) ^ bias
+                got = [((dg >> (8 * p)) & 255) - (256 if (dg >> (8 * p)) & 128 else 0) for p in range(nd)]
+                assert (left == 0) == fits
+                if fits:
+                    assert got == want
+
+
 def test_projection_one_direction_identity():
     rng = np.random.Generator(np.random.PCG64(2))
     ctx = ["", "A", "C", "G", "T", "AA", "CA", "GT", "TT", "ACG", "TTA"]
