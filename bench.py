@@ -15,7 +15,8 @@ A step = one full N x N float32 distance matrix:
          peer memory + flag barrier -- or NCCL all-gather --, local combine; other kinds: upper-triangular tile space sharded
          over ranks, NCCL all-gather, local assemble);
   e2e    the same matrix through the C-ABI with HOST buffers: H2D of the flat model tables and packed
-         sequences (pinned), table construction, kernels, D2H of the float32 matrix (pinned).
+         sequences (pinned), ln p (k-mer mode: on the device, VGS_LOAD_DEVICE_LOG; scan modes: libm on the host, streamed),
+         table construction, kernels, D2H of the float32 matrix (pinned).
 Timing: CUDA events on the launching stream, one pair per step, L2 flushed (256 MiB memset) between
 steps outside the timed pairs, barrier + synchronize on both sides, max over ranks.
 Extra keys: `matrix_checksum` (exact int64 sum of the float32 bit patterns: equal across GPU counts iff the matrices are),
@@ -57,7 +58,7 @@ def parse_args():
     ap.add_argument("--n-models", type=int, default=0)
     ap.add_argument("--seq-len", type=int, default=0)
     ap.add_argument("--mode", default="kmer", choices=["sequential", "warp", "kmer"],
-                    help="NLL kernel: kmer = k-mer histogram + exact int8 tcgen05 contraction (ln p in 2^-51 fixed point, "
+                    help="NLL kernel: kmer = k-mer histogram + exact int8 tcgen05 contraction (ln p in 2^-43 fixed point, "
                          "<= 1e-9 rel.), sequential = bit-exact scan, warp = warp-per-pair scan")
     ap.add_argument("--no-mode-sweep", action="store_true", help="skip the short timings of the other NLL modes")
     ap.add_argument("--tile", type=int, default=0)
@@ -774,8 +775,10 @@ def main():
                    "sm_count": sm_count},
         "e2e": {"value": pairs / (e2e_ms / 1000.0), "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h),
-                "includes": "vgs_load_models (H2D + host ln p; N > 1: this rank's model shard), vgs_load_sequences_packed, device table "
-                            "builds, kernels, exchange, D2H of the float32 matrix"},
+                "includes": "vgs_load_models (H2D of the flat model arrays -- N > 1: this rank's model shard --, ln p "
+                            + ("on the device (VGS_LOAD_DEVICE_LOG: the k-mer contraction quantises it to 2^-43)" if kind == "nll" and args.mode == "kmer"
+                               else "on the host (libm, streamed)" if kind == "nll" else "not needed") +
+                            "), vgs_load_sequences_packed, device table builds, kernels, exchange, D2H of the float32 matrix"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
         "matrix_checksum": matrix_checksum, "parity_check": parity_check, "scale_probe": probe,
     }
