@@ -230,6 +230,32 @@ def test_device_log_load(with_zeros):
     h.close()
 
 
+@pytest.mark.gpu
+def test_kmer_fraction_bits():
+    """The precision of the contraction is a parameter: f fraction bits of ln p -> |d score| <= L * 2^-(f+1); the digit rows per
+    model (the GEMM's work) follow f and the range of the set's ln p; a change takes effect with the next operand build."""
+    fm, _ = synthetic.make_family_models(60, 17, 5, 80, 3)
+    fm.prob[:] = np.maximum(fm.prob, 1e-3)
+    fm.prob[:] /= fm.prob.sum(axis=1, keepdims=True)
+    L = 1500
+    seqs = synthetic.sample_sequences(fm, L, 4)
+    M_or = c_oracle.COracle(fm).score_matrix(seqs)
+    h = native.Handle(0)
+    h.load_models(fm)
+    h.load_sequences_packed(*pack_sequences(seqs))
+    errs = {}
+    for f, nd_want in ((35, 6), (43, 6), (51, 7)):
+        h.set_kmer_fraction_bits(f)
+        Mk = h.nll_scores_h(native.SKIP_ORDER, "kmer")
+        assert h.last_nll_kernel() == 3 and h.kmer_digit_info() == (nd_want, f)
+        errs[f] = float(np.abs(Mk - M_or).max())
+        assert errs[f] <= L * 2.0 ** -(f + 1) + 1e-10          # the stated bound (+ the fp64 scan's own rounding noise)
+    assert errs[35] > errs[51]
+    with pytest.raises(ValueError):
+        h.set_kmer_fraction_bits(60)
+    h.close()
+
+
 def _tc_bound_ok(D_tc, D_ref):
     """Stated bound of the tensor-core variant: |d_tc - d_ref| <= 1.3e-7 d_ref + 1e-9 (rows quantised to 2^-31, the
     difference of two rows not rounded to float32 before squaring)."""
