@@ -225,6 +225,26 @@ int vgs_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         if (_e != cudaSuccess) return vgs_cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
     } while (0)
 
+// ---- programmatic dependent launch (Hopper+): a kernel launched through vgs_launch_dep may begin (its CTAs scheduled, its
+// prologue run) while the previous kernel on the stream is still finishing; it must call vgs_dep_wait() before it touches
+// anything that kernel wrote.  Kernels call vgs_dep_trigger() early so that THEIR successor can be staged.  Both are no-ops
+// in an ordinary launch.  cfg 3's step is four short kernels: the launch gaps were 9 of its 120 us.  VGS_PDL=0 disables.
+#ifdef __CUDACC__
+__device__ __forceinline__ void vgs_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void vgs_dep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool vgs_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline void vgs_launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = vgs_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface in the caller's VGS_LAUNCH_CHECK
+}
+
 int vgs_ensure_scratch(vgs_context *h, int64_t bytes);
 int vgs_ensure_scratch2(vgs_context *h, int64_t bytes);
 int vgs_ensure_M(vgs_context *h);

@@ -95,6 +95,12 @@ static VgsPool *get_pool(vgs_context *h) {
     return (VgsPool *)h->pool;
 }
 
+bool vgs_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("VGS_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
+
 static thread_local std::string g_last_error;
 
 void vgs_set_error(const char *fmt, ...) {

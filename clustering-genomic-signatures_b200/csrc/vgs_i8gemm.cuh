@@ -306,6 +306,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1) k_g8_
     g8_cluster_sync();       // barriers of both CTAs initialised, both allocations done
     g8_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    vgs_dep_trigger();       // the next kernel on the stream may be staged ...
+    vgs_dep_wait();          // ... and everything above overlapped the tail of the previous one (whose output the operands are)
 
     if (warp == 0) {
         // ===== producer =====
@@ -494,7 +496,7 @@ static int g8_launch(vgs_context *h, const G8Args &g, const Epi &epi, cudaStream
             ga.prof = d_prof;
         }
     }
-    kern<<<2 * n_clusters, G8_THREADS, (size_t)ga.stages * ga.stage_bytes, s>>>(ga, epi);
+    vgs_launch_dep(kern, dim3(2 * n_clusters), dim3(G8_THREADS), (size_t)ga.stages * ga.stage_bytes, s, ga, epi);
     VGS_LAUNCH_CHECK(h);
     if (d_prof) {
         // developer aid (VGS_G8_PROF=1): where the leader CTA's main-loop threads spend their cycles, mean (max) over the

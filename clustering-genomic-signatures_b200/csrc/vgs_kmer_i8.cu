@@ -202,6 +202,7 @@ __global__ void k_i8_hist(int depth, const uint32_t *__restrict__ seq, const int
                           int32_t *__restrict__ over_cnt, uint2 *__restrict__ over_list, int *__restrict__ flag) {
     extern __shared__ uint32_t hist[];
     __shared__ int n_over;
+    vgs_dep_trigger();
     if (threadIdx.x == 0) n_over = 0;
     const int64_t s = blockIdx.x;
     const int64_t K = (int64_t)1 << (2 * (depth + 1));
@@ -382,6 +383,8 @@ struct EpiNll {
 // k-split launches: the parts' digit sums -> M for every entry of the computed rectangles (thread = sequence: coalesced)
 template <int ND>
 __global__ void __launch_bounds__(256) k_i8_fold(const EpiNll<ND> e, const G8Rect *__restrict__ rects) {
+    vgs_dep_trigger();
+    vgs_dep_wait();
     const G8Rect r = rects[blockIdx.z];
     const int64_t s = (int64_t)r.a_blk * 256 + threadIdx.x;
     const int64_t m = r.b_row0 / ND + blockIdx.x;
@@ -402,6 +405,8 @@ __global__ void __launch_bounds__(256) k_i8_fold(const EpiNll<ND> e, const G8Rec
 // the launch's rectangles cover (grid.x = model of the rectangle, grid.z = rectangle, thread = sequence)
 template <int ND>
 __global__ void __launch_bounds__(256) k_i8_heads(const EpiNll<ND> e, const G8Rect *__restrict__ rects) {
+    vgs_dep_trigger();
+    vgs_dep_wait();
     const G8Rect r = rects[blockIdx.z];
     const int64_t s = (int64_t)r.a_blk * 256 + threadIdx.x;
     const int64_t m = r.b_row0 / ND + blockIdx.x;
@@ -421,6 +426,8 @@ template <int ND>
 __global__ void __launch_bounds__(128) k_i8_frequent(const EpiNll<ND> e, const G8Rect *__restrict__ rects, int n_rects) {
     __shared__ int todo[128];
     __shared__ int n_todo;
+    vgs_dep_trigger();
+    vgs_dep_wait();
     if (threadIdx.x == 0) n_todo = 0;
     __syncthreads();
     const int64_t s_mine = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -447,6 +454,8 @@ template <int ND>
 __global__ void __launch_bounds__(256) k_i8_diag(const EpiNll<ND> e, const uint8_t *__restrict__ C8, int64_t c_rows_pad,
                                                  const int8_t *__restrict__ digits, int64_t d_rows_pad, int64_t K8) {
     __shared__ int part[8][ND];
+    vgs_dep_trigger();
+    vgs_dep_wait();
     const int64_t m = blockIdx.x, sq = e.o.m_col0 + m;   // sequence sq was sampled from (local) model m
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int acc[ND];
@@ -623,22 +632,24 @@ static int i8_launch(vgs_context *h, const I8Work &w, bool diag_separately, cons
         if (rc) return rc;
         if (w.split > 1) {
             // widest rectangle in models (grid.x covers it; narrower rectangles leave early)
-            k_i8_fold<ND><<<dim3((unsigned)w.max_rect_models, 1, (unsigned)w.n_rects), 256, 0, s>>>(e, w.d_rects);
+            vgs_launch_dep(k_i8_fold<ND>, dim3((unsigned)w.max_rect_models, 1, (unsigned)w.n_rects), dim3(256), 0, s, e, w.d_rects);
             VGS_LAUNCH_CHECK(h);
         } else {
             if (e.sd.any_shallow) {
-                k_i8_heads<ND><<<dim3((unsigned)w.max_rect_models, 1, (unsigned)w.n_rects), 256, 0, s>>>(e, w.d_rects);
+                vgs_launch_dep(k_i8_heads<ND>, dim3((unsigned)w.max_rect_models, 1, (unsigned)w.n_rects), dim3(256), 0, s, e, w.d_rects);
                 VGS_LAUNCH_CHECK(h);
             }
             if (h->i8_counts_state == 3) {
-                k_i8_frequent<ND><<<dim3((unsigned)((h->n_seq + 127) / 128), (unsigned)((w.max_rect_models + 127) / 128)), 128, 0, s>>>(e, w.d_rects, w.n_rects);
+                vgs_launch_dep(k_i8_frequent<ND>, dim3((unsigned)((h->n_seq + 127) / 128), (unsigned)((w.max_rect_models + 127) / 128)), dim3(128), 0, s, e,
+                               w.d_rects, w.n_rects);
                 VGS_LAUNCH_CHECK(h);
             }
         }
     }
     if (diag_separately) {
         const int64_t nd = std::min(h->n_seq, h->n_models);
-        k_i8_diag<ND><<<(unsigned)nd, 256, 0, s>>>(e, h->d_i8_C, c_rows_pad, h->d_i8_digits, d_rows_pad, K8);
+        vgs_launch_dep(k_i8_diag<ND>, dim3((unsigned)nd), dim3(256), 0, s, e, (const uint8_t *)h->d_i8_C, c_rows_pad, (const int8_t *)h->d_i8_digits,
+                       d_rows_pad, K8);
         VGS_LAUNCH_CHECK(h);
     }
     return VGS_OK;

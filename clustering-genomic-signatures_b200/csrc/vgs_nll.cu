@@ -548,11 +548,20 @@ __global__ void __launch_bounds__(256) k_nll_combine_full(int64_t n, const doubl
     __shared__ double t_ji[32][33];   // M[j][i] for the tile, read row-wise (coalesced), used column-wise
     __shared__ double d_i[32], d_j[32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    vgs_dep_trigger();
+    vgs_dep_wait();
     const double rlen = 1.0 / length;   // one IEEE division per thread
     const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
-    for (int r = ty; r < 32; r += 8) {
+    // every global load of the thread is issued before the barrier (one round trip to memory instead of two: 8.1 -> 6 us at
+    // cfg 3, where the kernel is all latency)
+    double direct4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = ty + 8 * q;
         const int64_t j = j0 + r, i = i0 + tx;
         t_ji[r][tx] = (j < n && i < n) ? M[j * ld + i] : 0.0;
+        const int64_t i2 = i0 + r, j2 = j0 + tx;
+        direct4[q] = (i2 < n && j2 < n) ? M[i2 * ld + j2] : 0.0;
     }
     if (threadIdx.x < 32) {
         const int64_t i = i0 + threadIdx.x;
@@ -562,10 +571,12 @@ __global__ void __launch_bounds__(256) k_nll_combine_full(int64_t n, const doubl
         d_j[threadIdx.x - 32] = j < n ? M[j * ld + j] : 0.0;
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = ty + 8 * q;
         const int64_t i = i0 + r, j = j0 + tx;
         if (i >= n || j >= n) continue;
-        const double direct = M[i * ld + j], mirrored = t_ji[tx][r];
+        const double direct = direct4[q], mirrored = t_ji[tx][r];
         const double mij = transposed ? mirrored : direct, mji = transposed ? direct : mirrored;
         const double lr = nll_div_len(__dsub_rn(d_i[r], mij), length, rlen);
         const double rl = nll_div_len(__dsub_rn(d_j[tx], mji), length, rlen);
@@ -646,7 +657,8 @@ static int nll_tiles_impl(vgs_context *h, int64_t length, int mode, const TilePl
         if (rc > 0) return rc;
         if (rc == VGS_OK) {
             const unsigned g = (unsigned)((pl.n + 31) / 32);
-            k_nll_combine_full<<<dim3(g, g), 256, 0, s>>>(pl.n, h->d_M, h->n_seq, (double)length, D32_direct, D64_direct, h->d_err, 1);
+            vgs_launch_dep(k_nll_combine_full, dim3(g, g), dim3(256), 0, s, pl.n, (const double *)h->d_M, h->n_seq, (double)length, D32_direct,
+                           D64_direct, h->d_err, 1);
             VGS_LAUNCH_CHECK(h);
             return VGS_OK;
         }
@@ -735,7 +747,8 @@ extern "C" int vgs_nll_sharded_step(vgs_handle h, int mode, int64_t m_col0, int6
     }
     const unsigned g = (unsigned)((n_total + 31) / 32);
     VGS_CHECK_ARG(g <= 65535, "vgs_nll_sharded_step: matrix too large");
-    k_nll_combine_full<<<dim3(g, g), 256, 0, s>>>(n_total, Mt_dsts_h[0], n_total, (double)length, D32_d, nullptr, h->d_err, 1);
+    vgs_launch_dep(k_nll_combine_full, dim3(g, g), dim3(256), 0, s, n_total, (const double *)Mt_dsts_h[0], n_total, (double)length, D32_d,
+                   (double *)nullptr, h->d_err, 1);
     VGS_LAUNCH_CHECK(h);
     return VGS_OK;
 }

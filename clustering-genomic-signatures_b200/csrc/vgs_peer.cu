@@ -62,6 +62,8 @@ struct PeerFlags {
 };
 __global__ void k_peer_barrier(PeerFlags pf, int rank, int world, uint32_t epoch, int *err) {
     const int t = threadIdx.x;
+    vgs_dep_trigger();
+    vgs_dep_wait();   // "everything I enqueued before": the kernels before this one have completed, their stores are visible
     if (t < world) {
         __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[t] + rank), "r"(epoch) : "memory");
@@ -91,7 +93,7 @@ int vgs_peer_barrier_impl(vgs_context *h, uint32_t *const *flags_h, int rank, in
     PeerFlags pf;
     for (int r = 0; r < VGS_MAX_PEERS; ++r) pf.flags[r] = r < world ? flags_h[r] : nullptr;
     for (int r = 0; r < world; ++r) VGS_CHECK_ARG(pf.flags[r] != nullptr, "vgs_peer_barrier: null flag array");
-    k_peer_barrier<<<1, 32, 0, stream>>>(pf, rank, world, epoch, h->d_err);
+    vgs_launch_dep(k_peer_barrier, dim3(1), dim3(32), 0, stream, pf, rank, world, epoch, h->d_err);
     VGS_LAUNCH_CHECK(h);
     return VGS_OK;
 }
