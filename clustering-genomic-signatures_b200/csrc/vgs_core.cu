@@ -196,6 +196,10 @@ int vgs_read_error_flag(vgs_context *h, cudaStream_t s) {
         vgs_set_error("sequence holds a symbol outside A,C,G,T");
         return VGS_ERR_SYMBOL;
     }
+    if (flag & 8) {
+        vgs_set_error("Total of weights must be greater than zero");  // random.choices' ValueError (src/vlmc/vlmc.pyx:177)
+        return VGS_ERR_INVALID;
+    }
     if (flag & 1) {
         vgs_set_error("get_context vlmc.pyx");  // the reference's RuntimeError text (src/vlmc/vlmc.pyx:141)
         return VGS_ERR_NO_CONTEXT;
@@ -1349,6 +1353,7 @@ __global__ void k_sample(int64_t n_models, const ModelMeta *__restrict__ meta, c
         double c1 = __dadd_rn(c0, p[1]);
         double c2 = __dadd_rn(c1, p[2]);
         double c3 = __dadd_rn(c2, p[3]);
+        if (!(c3 > 0.0)) { atomicOr(err, 8); return; }   // random.choices: "Total of weights must be greater than zero"
         double x = __dmul_rn(u[t], __dadd_rn(c3, 0.0));
         uint32_t sym = (x < c0) ? 0u : (x < c1) ? 1u : (x < c2) ? 2u : 3u;
         if (t >= pre) {

@@ -150,6 +150,19 @@ def test_sampler_reproduces_reference_stream(fx, g):
     assert np.array_equal(st, np.array(random.getstate()[1], dtype=np.uint32))
 
 
+def test_sampler_zero_weight_row_raises_like_random_choices():
+    # random.choices raises ValueError("Total of weights must be greater than zero") on an all-zero row (vlmc.pyx:177)
+    tree = {"": {"A": 0.0, "C": 0.0, "G": 0.0, "T": 0.0}}
+    fm = FlatModels.from_trees([tree], ["z"])
+    h = native.Handle(0)
+    h.load_models(fm, skip_nll=True)
+    random.seed(5)
+    st = np.array(random.getstate()[1], dtype=np.uint32)
+    with pytest.raises(ValueError, match="Total of weights"):
+        h.sample_sequences(20, 5, st)
+    h.close()
+
+
 def test_missing_root_raises_runtime_error():
     # a tree without "": histories that match nothing make the reference raise RuntimeError (vlmc.pyx:141)
     tree = {"A": {"A": 0.25, "C": 0.25, "G": 0.25, "T": 0.25}, "CA": {"A": 0.1, "C": 0.2, "G": 0.3, "T": 0.4}}
