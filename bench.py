@@ -691,6 +691,10 @@ def main():
                          "ops_formula": "2 x N_seq x (%d digit rows x N_models) x max(128, 4^(D+1)) int8 ops (real rows only: "
                                         "padding of the 256 x N tiles is not counted)" % nd,
                          "digit_rows_per_model": nd, "ln_p_fraction_bits": frac_bits,
+                         "binding_resource": "the SM's shared-memory data pipe, shared by the bulk-copy writes of the operand stages and the "
+                                             "MMAs' operand reads (ncu, profiles/r2_ncu_full_k_g8_gemm_nll_cfg3.txt: integer tensor pipe and "
+                                             "sm__mem_tensor active 89 % of the working SMs' cycles; 104 KB per 128-byte k-block at 128 B/clk = 812 of "
+                                             "the ~915 cycles it takes, MMA floor 784); at cfg 3 the 4 x 16 units occupy 64 of the 74 CTA pairs",
                          "useful_fp64_equivalent_macs_per_s": n * n * K8 / world / (k_avg_ms / 1e3),
                          "note": "every int8 MAC carries one base-256 digit of round(ln p x 2^%d) (%d digits: this set has "
                                  "%s): the useful rate is one fp64-equivalent MAC per %d executed int8 MACs"
