@@ -35,7 +35,7 @@ int g8_make_units(const std::vector<G8Rect> &rects, int kblocks, int n_clusters,
     } else {
         // Pick the tile width and the k-split by a small cost model of the kernel (cycles per CTA pair), measured on cfg 3:
         // a k-block of a w-wide unit costs max(MMA time 2 w, operand delivery 1.73 (256 + w)) + barrier overhead; a unit
-        // adds its epilogue (~30 cycles per column with eight warps); a k-split adds the fold kernel and the atomics.
+        // adds its epilogue (~30 cycles per column with eight warps); a k-split adds the fold kernel.
         // Fewer, wider tiles move fewer operand bytes; more units fill the CTA pairs evenly -- the model arbitrates.
         double best = 1e300;
         for (int cand = gran; cand <= unit_max; cand += gran) {

@@ -17,7 +17,7 @@
 // 4^(D+1) is below ~10 L (64 fp64 FMA lanes per SM vs ~4.6 gathers per SM per clock).  This file holds the fp64
 // forms (mma.sync DMMA and a plain-FMA kernel): the counts are exact small integers but ln p needs all 53 bits, so no
 // floating-point tensor-core format applies.  The default is the exact int8 tensor-core form of vgs_kmer_i8.cu (ln p
-// as fixed point in eight base-256 digits); the fp64 kernels remain as its fallback and cross-check.
+// as fixed point in six to eight base-256 digits); the fp64 kernels remain as its fallback and cross-check.
 // Summation order differs from the reference's left-to-right order (parity: <= 1e-12 relative on scores);
 // the bit-exact path remains VGS_NLL_SEQUENTIAL.
 #include <stdlib.h>

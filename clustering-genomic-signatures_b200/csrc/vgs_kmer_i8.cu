@@ -72,7 +72,7 @@ struct I8Side {
 };
 
 // adds 256 * hi * d_p(T[m][k]) for the frequent k-mers of sequence s.  The digits come straight from the GEMM's own digit
-// operand (eight independent one-byte loads per k-mer, from lines the tile has just streamed through L2) -- the same
+// operand (one independent one-byte load per digit and k-mer, from lines the tile has just streamed through L2) -- the same
 // integers the tensor cores multiplied, so the sum stays exact.  (A first version re-derived them through the model's
 // hash: seven dependent cache misses per model, 100 us for ONE sequence with ONE frequent k-mer at cfg 3.)
 template <int ND>

@@ -122,7 +122,7 @@ class NegativeLogLikelihood(_DeviceDistance):
         super().__init__()
         self.generated_sequence_length = sequence_length
         # "kmer" (default): the exact int8 tensor-core contraction bench.py times -- within 1e-9 of the reference's
-        # fp64 sum (2e-14 measured), identical clusters downstream; sets deeper than 6 take the "warp" scan.
+        # fp64 sum (ln p in 2^-43 fixed point: |d distance| <= 1.1e-13), identical clusters downstream; sets deeper than 6 take the "warp" scan.
         # "sequential": one lane per pair, the reference's own summation order, bit-identical fp64.
         self.mode = mode
         self._seq_ids = None

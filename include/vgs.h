@@ -55,7 +55,7 @@ typedef enum {
 #define VGS_NLL_SEQUENTIAL 0 /* one lane per (sequence, model), strictly left-to-right fp64: bit-exact */
 #define VGS_NLL_WARP 1       /* one warp per (sequence, model), 128-bit loads, shuffle reduction     */
 #define VGS_NLL_KMER 2       /* (order+1)-mer histogram per sequence x dense tables as an exact int8 contraction
-                                on the tcgen05 tensor cores (ln p in 2^-51 fixed point; fp64 MMA fallback); sets
+                                on the tcgen05 tensor cores (ln p in 2^-43 fixed point, vgs_set_kmer_fraction_bits; fp64 MMA fallback); sets
                                 with every order <= 6 and a root context, else falls back to WARP; the tile edge
                                 of vgs_nll_tiles must then be a multiple of 128                           */
 
