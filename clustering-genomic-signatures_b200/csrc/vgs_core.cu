@@ -1335,17 +1335,21 @@ struct HostMT {
 
 __global__ void k_sample(int64_t n_models, const ModelMeta *__restrict__ meta, const uint2 *__restrict__ hash,
                          const double *__restrict__ prob64, const double *__restrict__ uniforms, int64_t length,
-                         int64_t pre, const int64_t *__restrict__ word_off, uint32_t *__restrict__ words, int *__restrict__ err) {
+                         int64_t pre, const int64_t *__restrict__ word_off, uint32_t *__restrict__ words, int *__restrict__ err,
+                         uint32_t init_code, int init_len) {
     int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_models) return;
     const ModelMeta mm = meta[m];
     const uint2 *slots = hash + mm.hash_off;
     const double *u = uniforms + m * (length + pre);
     uint32_t *out = words + word_off[m];
-    uint32_t hist = 0, omask = vgs_lowmask(mm.order);
+    // generate_sequence_from(length, context): the chain starts from the caller's context; only its last `order`
+    // symbols are ever read (vlmc.pyx:168: generated_sequence[-self.order:])
+    const uint32_t omask = vgs_lowmask(mm.order);
+    uint32_t hist = init_code & omask;
     uint32_t cur = 0;
     for (int64_t t = 0; t < length + pre; ++t) {
-        int hl = t < mm.order ? (int)t : mm.order;
+        int hl = t + init_len < mm.order ? (int)t + init_len : mm.order;
         int id = vgs_longest_suffix(slots, mm.hash_mask, mm.hash_shift, mm.order, hist, hl);
         if (id < 0) { atomicOr(err, 1); return; }
         const double *p = prob64 + 4 * (mm.ctx_off + id);
@@ -1366,7 +1370,19 @@ __global__ void k_sample(int64_t n_models, const ModelMeta *__restrict__ meta, c
 }
 
 extern "C" int vgs_sample_sequences(vgs_handle h, int64_t length, int64_t pre_sample, uint32_t *mt_state_h) {
+    return vgs_sample_sequences_from(h, length, pre_sample, mt_state_h, nullptr, 0);
+}
+
+extern "C" int vgs_sample_sequences_from(vgs_handle h, int64_t length, int64_t pre_sample, uint32_t *mt_state_h,
+                                         const uint8_t *context_codes_h, int64_t context_len) {
     VGS_CHECK_ARG(h && h->n_models > 0, "vgs_sample_sequences: no models loaded");
+    VGS_CHECK_ARG(context_len >= 0 && (context_len == 0 || context_codes_h), "vgs_sample_sequences_from: bad context");
+    uint32_t init_code = 0;
+    const int init_len = (int)std::min<int64_t>(context_len, VGS_MAX_ORDER);
+    for (int64_t t = context_len - init_len; t < context_len; ++t) {
+        VGS_CHECK_ARG(context_codes_h[t] < 4, "vgs_sample_sequences_from: context symbol outside 0..3");
+        init_code = (init_code << 2) | context_codes_h[t];
+    }
     VGS_CHECK_ARG(h->prob_ready, "vgs_sample_sequences: models were loaded with VGS_LOAD_NLL_ONLY: no transition rows on the device");
     VGS_CHECK_ARG(length > 0 && pre_sample >= 0 && mt_state_h, "vgs_sample_sequences: bad arguments");
     VGS_CHECK_ARG(mt_state_h[624] <= 624, "vgs_sample_sequences: bad MT19937 position");
@@ -1389,7 +1405,7 @@ extern "C" int vgs_sample_sequences(vgs_handle h, int64_t length, int64_t pre_sa
     VGS_CUDA(cudaMemcpyAsync(h->d_seq_len, h->h_seq_len.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemsetAsync(h->d_seq, 0, 4 * (size_t)(h->total_words + 4), s));
     k_sample<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, h->d_meta, h->d_hash, h->d_prob64, (const double *)h->d_scratch,
-                                                     length, pre_sample, h->d_seq_off, h->d_seq, h->d_err);
+                                                     length, pre_sample, h->d_seq_off, h->d_seq, h->d_err, init_code, init_len);
     VGS_LAUNCH_CHECK(h);
     rc = vgs_read_error_flag(h, s);
     if (rc) return rc;

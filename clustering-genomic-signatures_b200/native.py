@@ -43,6 +43,7 @@ SIGNATURES = [
     ("vgs_sequence_count", c_int, [c_vp, _P(c_i64), _P(c_i64)]),
     ("vgs_get_sequence", c_int, [c_vp, c_i64, c_vp, c_i64]),
     ("vgs_sample_sequences", c_int, [c_vp, c_i64, c_i64, c_vp]),
+    ("vgs_sample_sequences_from", c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64]),
     ("vgs_nll_scores", c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp]),
     ("vgs_nll_scores_h", c_int, [c_vp, c_int, c_int, c_vp]),
     ("vgs_nll_matrix", c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
@@ -306,10 +307,15 @@ class Handle:
         _check(lib().vgs_get_sequence(self._h, s, _np_ptr(out), length))
         return out
 
-    def sample_sequences(self, length, pre_sample, mt_state):
-        """mt_state: uint32[625] view of random.getstate()[1]; advanced in place."""
+    def sample_sequences(self, length, pre_sample, mt_state, context_codes=None):
+        """mt_state: uint32[625] view of random.getstate()[1]; advanced in place.  ``context_codes`` (uint8 symbol
+        codes, oldest first): the history every chain starts from (generate_sequence_from, vlmc.pyx:165-172)."""
         assert mt_state.dtype == np.uint32 and mt_state.size == 625 and mt_state.flags["C_CONTIGUOUS"]
-        _check(lib().vgs_sample_sequences(self._h, length, pre_sample, _np_ptr(mt_state)))
+        if context_codes is None or len(context_codes) == 0:
+            _check(lib().vgs_sample_sequences(self._h, length, pre_sample, _np_ptr(mt_state)))
+        else:
+            ctx = np.ascontiguousarray(context_codes, dtype=np.uint8)
+            _check(lib().vgs_sample_sequences_from(self._h, length, pre_sample, _np_ptr(mt_state), _np_ptr(ctx), ctx.size))
         self.n_seq = self.n_models
 
     # ---- host-buffer entry points (copies inside)

@@ -22,6 +22,7 @@ from . import native
 from .flat import ALPHABET, FlatModels, decode_context, encode_history, sequences_to_ascii
 
 _CODE_TO_CHAR = np.frombuffer(b"ACGT", dtype=np.uint8)
+_CHAR_TO_CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
 
 
 def _default_device():
@@ -162,14 +163,22 @@ class VLMC(object):
         return self.sequence
 
     def generate_sequence_from(self, sequence_length, context):
-        if context != "":
-            raise NotImplementedError("device sampler starts from the empty history (the only way the hot path calls it)")
-        saved = self.sequence
-        self.sequence = ""
-        try:
-            return self.generate_sequence(sequence_length, 0)
-        finally:
-            self.sequence = saved
+        """``sequence_length`` symbols continuing ``context`` (src/vlmc/vlmc.pyx:165-172); neither the cached
+        ``.sequence`` nor the context is part of the result.  Symbols outside ACGT can never be part of a matching
+        suffix (get_context, :131-141), so the chain effectively starts after the last one."""
+        if sequence_length <= 0:
+            return ""
+        usable = context
+        for pos in range(len(context) - 1, -1, -1):
+            if context[pos] not in _CHAR_TO_CODE:
+                usable = context[pos + 1:]
+                break
+        codes = np.array([_CHAR_TO_CODE[ch] for ch in usable[-15:]], dtype=np.uint8)
+        h = self._device()
+        state, tag = take_mt_state()
+        h.sample_sequences(sequence_length, 0, state, context_codes=codes)
+        put_mt_state(state, tag)  # one random() per symbol, like the reference's loop
+        return _CODE_TO_CHAR[h.get_sequence(0, sequence_length)].tobytes().decode("ascii")
 
     def reset_sequence(self):
         self.sequence = ""

@@ -149,6 +149,12 @@ int vgs_get_sequence(vgs_handle h, int64_t s, uint8_t *codes_out_h, int64_t capa
  *      m-th block of that stream (list order, as the reference's N^2 loop does).  The sampled
  *      sequences replace the handle's sequence set. --------------------------------------------- */
 int vgs_sample_sequences(vgs_handle h, int64_t length, int64_t pre_sample, uint32_t *mt_state_h);
+/* VLMC.generate_sequence_from(sequence_length, context) with a non-empty context (src/vlmc/vlmc.pyx:165-172): every
+ * chain starts from the history `context` (symbol codes 0..3, oldest first; a model reads its last `order` symbols,
+ * :168) instead of the empty one; the context itself is not part of the output.  context_len = 0 is
+ * vgs_sample_sequences. */
+int vgs_sample_sequences_from(vgs_handle h, int64_t length, int64_t pre_sample, uint32_t *mt_state_h,
+                              const uint8_t *context_codes_h, int64_t context_len);
 
 /* ---- log-likelihood scores: VLMC.log_likelihood / log_likelihood_ignore_initial_bias
  *      (src/vlmc/vlmc.pyx:79-101).  M[s * ld + m] for s in [s_begin, s_end), m in [m_begin, m_end);

@@ -137,6 +137,20 @@ def generate_sequence(tree, order, sequence_length, pre_sample_length, rng):
     return s[len(s) - sequence_length:]
 
 
+def generate_sequence_from(tree, order, sequence_length, context, rng):
+    """src/vlmc/vlmc.pyx:165-172: ``sequence_length`` symbols continuing ``context`` (which is not returned); every
+    step hands the last ``order`` symbols of context + output to the longest-suffix lookup (``[-0:]`` is the whole
+    string when order = 0, and then only "" can match)."""
+    generated = context
+    for _ in range(sequence_length):
+        hist = generated[-order:] if order > 0 else generated
+        row = tree[get_context(tree, order, hist)]
+        cum = list(itertools.accumulate(row[c] for c in ALPHABET))
+        total = cum[-1] + 0.0
+        generated += ALPHABET[bisect.bisect(cum, rng.random() * total, 0, 3)]
+    return generated[len(context):]
+
+
 # ----------------------------------------------------------------------------- Frobenius (a8)
 def frobenius_terms(tree_l, order_l, tree_r, order_r, use_union):
     """Context set and the two row lists of src/distance/frobenius.pyx:21-53 (sorted for determinism)."""

@@ -56,3 +56,9 @@ def fixture_estimate():
     z = np.load(os.path.join(GOLD, "fixtures_estimate.npz"))
     seqs = np.stack([unpack(z["seq_words"], z["seq_word_offsets"], z["seq_lens"], i) for i in range(5)])
     return seqs, z["estimate"]
+
+
+def sampler_from_cases():
+    """generate_sequence_from(length, context) outputs of the compiled reference (oracle/make_goldens_sampler_from.py)."""
+    with open(os.path.join(GOLD, "sampler_from_golden.json")) as fh:
+        return json.load(fh)["cases"]

@@ -72,6 +72,22 @@ def test_generate_sequence_consumes_the_python_stream(g):
     assert vl[0].sequence == ""
 
 
+def test_generate_sequence_from_a_context(g):
+    """VLMC.generate_sequence_from with non-empty contexts (src/vlmc/vlmc.pyx:165-172) against the compiled
+    reference's output: same symbols, same position of CPython's MT19937 stream afterwards, cache untouched."""
+    vl = fixture_vlmcs(g)
+    for c in golden_io.sampler_from_cases():
+        v = vl[c["model"]]
+        v.sequence = "kept"
+        random.seed(c["seed"])
+        assert v.generate_sequence_from(c["length"], c["context"]) == c["sequence"]
+        assert random.random() == c["next_random"]
+        assert v.sequence == "kept"
+    random.seed(g["sampler_seed"])
+    assert vl[0].generate_sequence_from(700, "")[-200:] == g["sampler_sequences"][0]
+    assert vl[0].generate_sequence_from(0, "ACG") == ""
+
+
 def test_nll_class_reproduces_reference_run(g):
     """random.seed(1234); N^2 loop of d.distance in list order == the golden run of the reference."""
     vl = fixture_vlmcs(g)

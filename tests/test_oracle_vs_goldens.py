@@ -94,6 +94,16 @@ def test_sampler_stream_exact(g, co):
         assert golden_io.codes_str(co.sample(m, st, 200)) == g["sampler_sequences"][m]
 
 
+def test_sampler_from_a_context_exact(g):
+    """generate_sequence_from with non-empty contexts (shorter / longer than the order, a symbol outside ACGT):
+    goldens from the compiled reference (oracle/make_goldens_sampler_from.py)."""
+    for c in golden_io.sampler_from_cases():
+        m = c["model"]
+        random.seed(c["seed"])
+        assert O.generate_sequence_from(g["trees"][m], g["orders"][m], c["length"], c["context"], random) == c["sequence"]
+        assert random.random() == c["next_random"]
+
+
 def test_estimate(g, co):
     seqs, E = golden_io.fixture_estimate()
     Ec = co.estimate_matrix(seqs)
