@@ -151,6 +151,59 @@ class VLMC(object):
     def log_likelihood(self, sequence):
         return self._score(sequence, native.SKIP_NONE)
 
+    def _history_ids(self, sequence, first, last, exact_length=False):
+        """ctx_id of the longest-suffix context of the history before every position t in [first, last): the last
+        ``order`` symbols before t (``exact_length``: the window sequence[t:t + order] instead).  One device lookup."""
+        codes = np.array([_CHAR_TO_CODE[ch] for ch in sequence], dtype=np.uint32)
+        t = np.arange(first, last, dtype=np.int64)
+        end = t + self.order if exact_length else t
+        lens = np.minimum(end, self.order).astype(np.int64)
+        hist = np.zeros(len(t), dtype=np.uint32)
+        for k in range(self.order, 0, -1):   # oldest symbol first: code = (code << 2) | symbol
+            use = lens >= k
+            sym = codes[np.where(use, end - k, 0)]
+            hist = np.where(use, (hist << np.uint32(2)) | sym, hist).astype(np.uint32)
+        ids = self._device().lookup(np.zeros(len(t), dtype=np.int32), hist, lens.astype(np.uint8))
+        if (ids < 0).any():
+            raise RuntimeError("get_context vlmc.pyx")
+        return ids
+
+    def likelihood(self, sequence):
+        """Product of the transition probabilities along ``sequence``, 0.0 from the first impossible symbol on
+        (src/vlmc/vlmc.pyx:103-118).  The context lookups run on the device; the product is taken left to right."""
+        if len(sequence) == 0:
+            return 1.0
+        for ch in sequence:
+            if ch not in _CHAR_TO_CODE:
+                break
+        else:
+            ch = None
+        stop = sequence.index(ch) if ch is not None else len(sequence)
+        ids = self._history_ids(sequence[:stop], 0, stop) if stop else []
+        likelihood = 1.0
+        for t in range(stop):
+            prob = self.tree[self._keys[int(ids[t])]][sequence[t]]
+            if prob == 0:
+                return 0.0
+            likelihood *= prob
+        if ch is not None:
+            raise KeyError(ch)
+        return likelihood
+
+    def estimated_context_distribution(self, sequence_length):
+        """Relative frequency of the context every ``order``-symbol window of a sampled sequence falls into, keyed in
+        order of first occurrence (src/vlmc/vlmc.pyx:182-206)."""
+        sequence = self.generate_sequence(sequence_length, 500)
+        n = len(sequence) - self.order
+        if n <= 0:
+            return {}
+        ids = self._history_ids(sequence, 0, n, exact_length=True)
+        uniq, first, counts = np.unique(ids, return_index=True, return_counts=True)
+        out = {}
+        for k in np.argsort(first, kind="stable"):
+            out[self._keys[int(uniq[k])]] = int(counts[k]) / sequence_length
+        return out
+
     # ---- sampling (src/vlmc/vlmc.pyx:156-177)
     def generate_sequence(self, sequence_length, pre_sample_length):
         if len(self.sequence) == sequence_length:

@@ -151,6 +151,28 @@ def generate_sequence_from(tree, order, sequence_length, context, rng):
     return generated[len(context):]
 
 
+def likelihood(tree, order, sequence):
+    """src/vlmc/vlmc.pyx:103-118: left-to-right product, 0.0 from the first impossible symbol on."""
+    value = 1.0
+    for t, ch in enumerate(sequence):
+        hist = sequence[:t][-order:] if order > 0 else sequence[:t]
+        prob = tree[get_context(tree, order, hist)][ch]
+        if prob == 0:
+            return 0.0
+        value *= prob
+    return value
+
+
+def context_distribution(tree, order, sequence, sequence_length):
+    """src/vlmc/vlmc.pyx:182-206 for an already sampled ``sequence``: the context of every ``order``-symbol window,
+    counted, in order of first occurrence, divided by the requested length."""
+    counts = {}
+    for i in range(len(sequence) - order):
+        c = get_context(tree, order, sequence[i:i + order])
+        counts[c] = counts.get(c, 0) + 1
+    return {c: n / sequence_length for c, n in counts.items()}
+
+
 # ----------------------------------------------------------------------------- Frobenius (a8)
 def frobenius_terms(tree_l, order_l, tree_r, order_r, use_union):
     """Context set and the two row lists of src/distance/frobenius.pyx:21-53 (sorted for determinism)."""

@@ -58,7 +58,8 @@ def fixture_estimate():
     return seqs, z["estimate"]
 
 
-def sampler_from_cases():
-    """generate_sequence_from(length, context) outputs of the compiled reference (oracle/make_goldens_sampler_from.py)."""
+def sampler_from_cases(section="cases"):
+    """generate_sequence_from(length, context) outputs of the compiled reference (oracle/make_goldens_sampler_from.py);
+    sections "likelihood" and "context_distribution": VLMC.likelihood / estimated_context_distribution."""
     with open(os.path.join(GOLD, "sampler_from_golden.json")) as fh:
-        return json.load(fh)["cases"]
+        return json.load(fh)[section]

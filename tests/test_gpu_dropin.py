@@ -88,6 +88,23 @@ def test_generate_sequence_from_a_context(g):
     assert vl[0].generate_sequence_from(0, "ACG") == ""
 
 
+def test_likelihood_and_context_distribution(g):
+    """VLMC.likelihood (src/vlmc/vlmc.pyx:103-118) and estimated_context_distribution (:182-206): bit-equal to the
+    compiled reference's values, dict in the same order."""
+    vl = fixture_vlmcs(g)
+    for c in golden_io.sampler_from_cases("likelihood"):
+        assert vl[c["model"]].likelihood(c["sequence"]) == c["likelihood"]
+    with pytest.raises(KeyError):
+        vl[0].likelihood("ACGNT")
+    for c in golden_io.sampler_from_cases("context_distribution"):
+        v = vl[c["model"]]
+        random.seed(c["seed"])
+        v.reset_sequence()
+        d = v.estimated_context_distribution(c["length"])
+        assert v.sequence == c["sequence"]
+        assert list(d.keys()) == c["contexts"] and list(d.values()) == c["values"]
+
+
 def test_nll_class_reproduces_reference_run(g):
     """random.seed(1234); N^2 loop of d.distance in list order == the golden run of the reference."""
     vl = fixture_vlmcs(g)

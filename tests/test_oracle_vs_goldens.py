@@ -104,6 +104,19 @@ def test_sampler_from_a_context_exact(g):
         assert random.random() == c["next_random"]
 
 
+def test_likelihood_and_context_distribution_exact(g):
+    for c in golden_io.sampler_from_cases("likelihood"):
+        m = c["model"]
+        assert O.likelihood(g["trees"][m], g["orders"][m], c["sequence"]) == c["likelihood"]
+    for c in golden_io.sampler_from_cases("context_distribution"):
+        m = c["model"]
+        random.seed(c["seed"])
+        seq = O.generate_sequence(g["trees"][m], g["orders"][m], c["length"], 500, random)
+        assert seq == c["sequence"]
+        d = O.context_distribution(g["trees"][m], g["orders"][m], seq, c["length"])
+        assert list(d.keys()) == c["contexts"] and list(d.values()) == c["values"]
+
+
 def test_estimate(g, co):
     seqs, E = golden_io.fixture_estimate()
     Ec = co.estimate_matrix(seqs)
