@@ -155,6 +155,10 @@ struct vgs_context {
     int64_t scratch2_bytes = 0;
     int *d_err = nullptr;       // device error flag (bit 0: no context, bit 1: bad symbol)
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // vgs_load_models: the bulk upload of the transition rows, beside the table builds
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    void *h_meta_pin = nullptr;           // pinned copy of the per-model metadata (goes between the two halves of the rows on the copy stream)
+    int64_t h_meta_pin_bytes = 0;
 
     // capacity of every handle-owned device buffer (keyed by the address of the pointer member):
     // buffers are reused across vgs_load_* calls and only re-allocated when they must grow
@@ -172,6 +176,9 @@ struct vgs_context {
     int32_t *d_i8_P = nullptr;       // k-split launches: exact int32 digit sums [part][n_models * i8_nd][n_seq padded]
     uint64_t i8_tables_gen = ~0ull;
     bool i8_tables_ok = false;
+    bool i8_guess_wide = false;      // device-log loads: digit range the previous set of this handle needed (the next build's guess)
+    uint16_t *d_i8_ctx = nullptr;    // [n_models][4^D] context of every depth-D history, found ahead of ln p by the load
+    uint64_t i8_ctx_gen = ~0ull;     // model set d_i8_ctx belongs to
     int last_nll_kernel = 0;         // VGS_NLL_KERNEL_* of the most recent score launch
     int i8_counts_state = 0;         // 0 = not checked for this sequence set, 1 = no frequent k-mers, 3 = some, 2 = too many
     // tensor-core Frobenius / Projection (vgs_pairs_tc.cu): digit operands over the dense universe, raw digit-pair sums
@@ -316,6 +323,7 @@ bool vgs_kmer_applicable_orders(vgs_context *h);                          // eve
 int vgs_kmer_i8_digits_begin(vgs_context *h, bool wide, cudaStream_t s);   // choose the digit count, allocate + clear the operand of the current set
 double vgs_kmer_i8_narrow_limit(vgs_context *h);                           // |ln p| below this fits the narrow digit count
 int vgs_kmer_i8_digits_range(vgs_context *h, int64_t m_begin, int64_t m_end, cudaStream_t s);   // digits of models [m_begin, m_end)
+int vgs_kmer_i8_contexts_ahead(vgs_context *h, cudaStream_t s);   // the digit builder's context lookups, before ln p exists (hashes only)
 int vgs_kmer_i8_digits_end(vgs_context *h, cudaStream_t s);                // after a synchronisation: record whether the operand is usable
 int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, const VgsScoreDst &dst, cudaStream_t s);
 int vgs_ensure_exact_logp(vgs_context *h, cudaStream_t s);   // libm's ln p in h->d_logp (no-op unless VGS_LOAD_DEVICE_LOG)

@@ -268,8 +268,11 @@ extern "C" int vgs_destroy(vgs_handle h) {
     cudaFree(h->d_scratch2);
     cudaFree(h->d_err);
     if (h->h_logp) cudaFreeHost(h->h_logp);
+    if (h->h_meta_pin) cudaFreeHost(h->h_meta_pin);
     delete (VgsPool *)h->pool;
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto &e : h->ev_copy) if (e) cudaEventDestroy(e);
     delete h;
     return VGS_OK;
 }
@@ -612,12 +615,19 @@ static int log2_ceil_pow2(int64_t v, int64_t *cap_out) {
 
 // VGS_LOAD_DEVICE_LOG: ln p from the transition rows on the device (src/vlmc/vlmc.pyx:94-99: -1000 where p == 0; a negative
 // probability is the reference's "math domain error")
-__global__ void k_device_logp(int64_t n, const double *__restrict__ prob, double *__restrict__ logp, int *__restrict__ neg_flag) {
+// flag[0] |= 1: a negative probability; flag[1] |= 1: some |ln p| >= narrow_limit (the contraction's digit count follows
+// from it: what k_i8_range finds for sets whose ln p came from the host)
+__global__ void k_device_logp(int64_t n, const double *__restrict__ prob, double *__restrict__ logp, int *__restrict__ flag,
+                              double narrow_limit) {
+    bool wide = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double p = prob[i];
-        if (p < 0) atomicOr(neg_flag, 1);
-        logp[i] = (p == 0) ? -1000.0 : log(p);
+        if (p < 0) atomicOr(flag, 1);
+        const double l = (p == 0) ? -1000.0 : log(p);
+        wide |= !(fabs(l) < narrow_limit);
+        logp[i] = l;
     }
+    if (__any_sync(0xffffffffu, wide) && (threadIdx.x & 31) == 0) atomicOr(flag + 1, 1);
 }
 
 // libm's ln p on the device (h->d_logp) for the bit-exact consumers of a set that was loaded with VGS_LOAD_DEVICE_LOG: the
@@ -685,14 +695,33 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
     int rc;
     cudaStream_t s = h->own_stream;
     // the caller's arrays start crossing PCIe before anything else happens; every return below drains the stream first
-    struct Drain { cudaStream_t st; ~Drain() { cudaStreamSynchronize(st); } } drain{s};
+    // A device-log load that keeps no fp32 rows reads the transition rows for ONE thing, ln p: their upload (7/8 of the
+    // bytes) goes to a second stream, and everything that needs only the context lengths / codes -- keys, hashes, the
+    // context lookups of the digit builder -- runs beside it instead of behind it.
+    const bool split_copy = device_log && !want_prob;
+    const int64_t prob_first = (total * 4) / 2;   // elements of the transition rows uploaded ahead of the metadata
+    if (split_copy && !h->copy_stream) {
+        VGS_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        VGS_CUDA(cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming));
+        VGS_CUDA(cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming));
+    }
+    struct Drain { cudaStream_t st, st2; ~Drain() { if (st2) cudaStreamSynchronize(st2); cudaStreamSynchronize(st); } } drain{s, split_copy ? h->copy_stream : nullptr};
     if ((rc = vgs_reserve(h, &h->d_len, total))) return rc;
     if ((rc = vgs_reserve(h, &h->d_code, total))) return rc;
     if ((want_prob || device_log) && (rc = vgs_reserve(h, &h->d_prob64, total * 4))) return rc;
     if (load_timing) cudaEventRecord(ev_t[0], s);
     VGS_CUDA(cudaMemcpyAsync(h->d_len, ctx_len_h, (size_t)total, cudaMemcpyHostToDevice, s));
     VGS_CUDA(cudaMemcpyAsync(h->d_code, ctx_code_h, sizeof(uint32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
-    if (want_prob || device_log) VGS_CUDA(cudaMemcpyAsync(h->d_prob64, prob_h, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    if (split_copy) {
+        // (after the two small arrays on the bus: the builders wait for those)
+        VGS_CUDA(cudaEventRecord(h->ev_copy[0], s));
+        VGS_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_copy[0], 0));
+        // first half now; the second follows the per-model metadata, which the host is about to plan (a copy engine serves
+        // its queue in order: enqueued behind ALL the rows the metadata would arrive with the last of them)
+        VGS_CUDA(cudaMemcpyAsync(h->d_prob64, prob_h, sizeof(double) * (size_t)prob_first, cudaMemcpyHostToDevice, h->copy_stream));
+    } else if (want_prob || device_log) {
+        VGS_CUDA(cudaMemcpyAsync(h->d_prob64, prob_h, sizeof(double) * (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    }
 
     h->h_ctx_off.assign(ctx_offsets_h, ctx_offsets_h + n_models + 1);
     h->h_meta.assign((size_t)n_models, ModelMeta());
@@ -830,13 +859,32 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
 
     // 1. behind the uploads of the caller's arrays (enqueued at the top; asynchronous when its buffers are pinned): everything
     //    that does not need ln p -- keys, fp32 rows, hashes
-    VGS_CUDA(cudaMemcpyAsync(h->d_meta, h->h_meta.data(), sizeof(ModelMeta) * (size_t)n_models, cudaMemcpyHostToDevice, s));
+    if (split_copy) {
+        // copy stream: [first half of the rows] -> metadata -> [second half]; the builders on `s` wait for the metadata only
+        const int64_t mb = (int64_t)sizeof(ModelMeta) * n_models;
+        if (h->h_meta_pin_bytes < mb) {
+            if (h->h_meta_pin) cudaFreeHost(h->h_meta_pin);
+            h->h_meta_pin = nullptr; h->h_meta_pin_bytes = 0;
+            VGS_CUDA(cudaHostAlloc(&h->h_meta_pin, (size_t)mb, cudaHostAllocDefault));
+            h->h_meta_pin_bytes = mb;
+        }
+        memcpy(h->h_meta_pin, h->h_meta.data(), (size_t)mb);
+        VGS_CUDA(cudaMemcpyAsync(h->d_meta, h->h_meta_pin, (size_t)mb, cudaMemcpyHostToDevice, h->copy_stream));
+        VGS_CUDA(cudaEventRecord(h->ev_copy[0], h->copy_stream));
+        VGS_CUDA(cudaMemcpyAsync(h->d_prob64 + prob_first, prob_h + prob_first, sizeof(double) * (size_t)(total * 4 - prob_first), cudaMemcpyHostToDevice,
+                                 h->copy_stream));
+        VGS_CUDA(cudaEventRecord(h->ev_copy[1], h->copy_stream));
+        VGS_CUDA(cudaStreamWaitEvent(s, h->ev_copy[0], 0));
+    } else {
+        VGS_CUDA(cudaMemcpyAsync(h->d_meta, h->h_meta.data(), sizeof(ModelMeta) * (size_t)n_models, cudaMemcpyHostToDevice, s));
+    }
     VGS_CUDA(cudaMemsetAsync(h->d_hash, 0, sizeof(uint2) * (size_t)hash_slots, s));
     k_build_keys<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(total, h->d_len, h->d_code, want_prob ? h->d_prob64 : nullptr, h->d_key,
                                                               want_prob ? h->d_prob32 : nullptr);
     VGS_LAUNCH_CHECK(h);
     k_build_hash<<<(unsigned)n_models, 256, 0, s>>>(h->d_meta, h->d_key, h->d_hash);
     VGS_LAUNCH_CHECK(h);
+
     if (load_timing) cudaEventRecord(ev_t[1], s);
     lap("enqueued: uploads + keys/hash");
     h->dense_state = 0;
@@ -855,21 +903,50 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         if ((rc = vgs_reserve(h, &h->d_logp_dev, total * 4))) return rc;
         if ((rc = vgs_reserve(h, &h->d_nll, nll_bytes))) return rc;
         if ((rc = vgs_reserve(h, &h->d_counters, 16))) return rc;
-        VGS_CUDA(cudaMemsetAsync(h->d_counters + 12, 0, sizeof(int), s));
-        k_device_logp<<<std::min<int64_t>(8 * h->sm_count, (total * 4 + 255) / 256), 256, 0, s>>>(total * 4, h->d_prob64, h->d_logp_dev, h->d_counters + 12);
-        VGS_LAUNCH_CHECK(h);
-        int neg = 0;
-        VGS_CUDA(cudaMemcpyAsync(&neg, h->d_counters + 12, sizeof(int), cudaMemcpyDeviceToHost, s));
-        h->nll_ready = true;
+        VGS_CUDA(cudaMemsetAsync(h->d_counters + 12, 0, 2 * sizeof(int), s));
         const bool eager = !(flags & VGS_LOAD_LAZY_TABLES) && vgs_kmer_applicable_orders(h);
+        // still beside the upload of the rows: the digit builder's context lookups (hashes only)
+        if (eager && split_copy && (rc = vgs_kmer_i8_contexts_ahead(h, s))) return rc;
+        if (load_timing) cudaEventRecord(ev_t[1], s);
+        if (split_copy) VGS_CUDA(cudaStreamWaitEvent(s, h->ev_copy[1], 0));
+        k_device_logp<<<std::min<int64_t>(8 * h->sm_count, (total * 4 + 255) / 256), 256, 0, s>>>(total * 4, h->d_prob64, h->d_logp_dev, h->d_counters + 12,
+                                                                                                  vgs_kmer_i8_narrow_limit(h));
+        VGS_LAUNCH_CHECK(h);
+        if (load_timing) cudaEventRecord(ev_t[2], s);
+        // The digit count follows from the range of ln p, which only the device knows at this point.  No round trip to the
+        // host for it: the operand is built at once for the count the handle's previous set needed (a first load: the
+        // narrow one), and the flags come back with the builder's own -- a wrong guess costs one rebuild.
+        h->nll_ready = true;
         if (eager) {
-            // (k_i8_range + the digit builder; its own synchronisation also delivers `neg`)
-            rc = vgs_kmer_i8_prepare_tables(h, s);
-            if (rc > 0) return rc;
+            if ((rc = vgs_kmer_i8_digits_begin(h, h->i8_guess_wide, s))) return rc;
+            if ((rc = vgs_kmer_i8_digits_range(h, 0, h->n_models, s))) return rc;
+        }
+        int fl[2] = {0, 0};   // negative probability | a value outside the narrow digit range
+        VGS_CUDA(cudaMemcpyAsync(fl, h->d_counters + 12, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (eager) {
+            if ((rc = vgs_kmer_i8_digits_end(h, s))) return rc;   // synchronises; rebuilds wide if a value did not fit
         } else {
             VGS_CUDA(cudaStreamSynchronize(s));
         }
+        const int neg = fl[0];
+        if (eager && !neg && h->i8_guess_wide && !fl[1]) {
+            // guessed wide, narrow would have done (the GEMM's work follows the digit count): once more
+            if ((rc = vgs_kmer_i8_digits_begin(h, false, s))) return rc;
+            if ((rc = vgs_kmer_i8_digits_range(h, 0, h->n_models, s))) return rc;
+            if ((rc = vgs_kmer_i8_digits_end(h, s))) return rc;
+        }
+        if (eager && !neg) h->i8_guess_wide = fl[1] != 0;
         lap("device ln p + digits: stream drained");
+        if (load_timing) {
+            cudaEventRecord(ev_t[3], s);
+            cudaEventSynchronize(ev_t[3]);
+            float a = 0.f, b = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, ev_t[0], ev_t[1]);
+            cudaEventElapsedTime(&b, ev_t[0], ev_t[2]);
+            cudaEventElapsedTime(&c, ev_t[0], ev_t[3]);
+            fprintf(stderr, "[vgs_load_models] device: keys / hashes / contexts done %.3f ms, rows uploaded + ln p done %.3f, digits done %.3f ms after the first copy began\n", a, b, c);
+            for (auto &e : ev_t) cudaEventDestroy(e);
+        }
         if (neg) {
             vgs_set_error("math domain error: negative transition probability");
             return VGS_ERR_INVALID;

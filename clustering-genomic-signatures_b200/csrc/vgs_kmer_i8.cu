@@ -117,13 +117,8 @@ __device__ __forceinline__ double i8_head(const I8Side &sd, const ModelMeta &mm,
 // flag bit 0: an entry is not a log-probability (|T| > 1000 or NaN); bit 1: a history has no context at all (model without
 // root context: the scan raises the reference's RuntimeError); bit 2: a value does not fit ND digits (the host rebuilds the
 // operand with more)
-__global__ void __launch_bounds__(256) k_i8_digits(int64_t m_base, I8Side sd, int64_t K, int64_t K8, int64_t rows_pad,
-                                                   int8_t *__restrict__ digits, int *__restrict__ flag) {
-    extern __shared__ uint16_t ctx_of[];   // levels 0 .. D one after the other: level k starts at (4^k - 1) / 3
-    const int64_t m = m_base + blockIdx.x;
-    const ModelMeta mm = sd.meta[m];
-    const uint2 *slots = sd.hash + mm.hash_off;
-    const int D = sd.depth;
+// the context of every history of length <= D of one model, level by level in shared memory (whole CTA; ends with a barrier)
+__device__ __forceinline__ void i8_contexts_by_level(uint16_t *ctx_of, const ModelMeta &mm, const uint2 *slots, int D) {
     if (threadIdx.x == 0) {
         const int id = vgs_hash_find(slots, mm.hash_mask, mm.hash_shift, vgs_key(0, 0u));
         ctx_of[0] = id < 0 ? (uint16_t)0xFFFFu : (uint16_t)id;
@@ -137,7 +132,32 @@ __global__ void __launch_bounds__(256) k_i8_digits(int64_t m_base, I8Side sd, in
         }
         __syncthreads();
     }
-    const uint16_t *ctx_D = ctx_of + (((1u << (2 * D)) - 1u) / 3u);
+}
+
+// The context half of the digit builder on its own: needs the hashes only, not ln p -- vgs_load_models runs it while the
+// transition rows are still crossing PCIe (VGS_LOAD_DEVICE_LOG) and hands the result (ctx_pre[m][4^D], the deepest level)
+// to k_i8_digits, which is then a pure streaming pass.
+__global__ void __launch_bounds__(256) k_i8_contexts(int64_t m_base, I8Side sd, uint16_t *__restrict__ ctx_pre) {
+    extern __shared__ uint16_t ctx_of[];
+    const int64_t m = m_base + blockIdx.x;
+    const ModelMeta mm = sd.meta[m];
+    const int D = sd.depth;
+    i8_contexts_by_level(ctx_of, mm, sd.hash + mm.hash_off, D);
+    const uint32_t n_D = 1u << (2 * D);
+    const uint16_t *ctx_D = ctx_of + ((n_D - 1u) / 3u);
+    uint16_t *out = ctx_pre + m * (int64_t)n_D;
+    for (uint32_t hc = threadIdx.x; hc < n_D; hc += blockDim.x) out[hc] = ctx_D[hc];
+}
+
+__global__ void __launch_bounds__(256) k_i8_digits(int64_t m_base, I8Side sd, int64_t K, int64_t K8, int64_t rows_pad,
+                                                   int8_t *__restrict__ digits, int *__restrict__ flag,
+                                                   const uint16_t *__restrict__ ctx_pre) {
+    extern __shared__ uint16_t ctx_of[];   // levels 0 .. D one after the other: level k starts at (4^k - 1) / 3
+    const int64_t m = m_base + blockIdx.x;
+    const ModelMeta mm = sd.meta[m];
+    const int D = sd.depth;
+    if (!ctx_pre) i8_contexts_by_level(ctx_of, mm, sd.hash + mm.hash_off, D);
+    const uint16_t *ctx_D = ctx_pre ? ctx_pre + m * ((int64_t)1 << (2 * D)) : ctx_of + (((1u << (2 * D)) - 1u) / 3u);
     for (int64_t ch = threadIdx.x; ch < (K8 >> 4); ch += blockDim.x) {
         long long q[16];
 #pragma unroll
@@ -562,9 +582,25 @@ int vgs_kmer_i8_digits_range(vgs_context *h, int64_t m_begin, int64_t m_end, cud
     const int64_t K8 = i8_k8(h);
     const I8Side sd = i8_side(h, false);
     const int smem = (int)(((((int64_t)1 << (2 * (h->max_order + 1))) - 1) / 3) * sizeof(uint16_t));   // <= 10.7 KB at depth 6
+    // contexts found ahead of time for exactly this model set (vgs_kmer_i8_contexts_ahead): the builder only streams
+    const uint16_t *pre = h->i8_ctx_gen == h->model_gen ? h->d_i8_ctx : nullptr;
     if (m_end > m_begin)
-        k_i8_digits<<<(unsigned)(m_end - m_begin), 256, smem, s>>>(m_begin, sd, K, K8, i8_digit_rows_pad(h), h->d_i8_digits, h->d_counters + 9);
+        k_i8_digits<<<(unsigned)(m_end - m_begin), 256, pre ? 0 : smem, s>>>(m_begin, sd, K, K8, i8_digit_rows_pad(h), h->d_i8_digits,
+                                                                             h->d_counters + 9, pre);
     VGS_LAUNCH_CHECK(h);
+    return VGS_OK;
+}
+
+// the context lookups of the digit builder, ahead of ln p (needs meta + hashes of the current model set on the device)
+int vgs_kmer_i8_contexts_ahead(vgs_context *h, cudaStream_t s) {
+    const int D = h->max_order;
+    int rc;
+    if ((rc = vgs_reserve(h, &h->d_i8_ctx, h->n_models * ((int64_t)1 << (2 * D))))) return rc;
+    const I8Side sd = i8_side(h, false);
+    const int smem = (int)(((((int64_t)1 << (2 * (D + 1))) - 1) / 3) * sizeof(uint16_t));
+    k_i8_contexts<<<(unsigned)h->n_models, 256, smem, s>>>(0, sd, h->d_i8_ctx);
+    VGS_LAUNCH_CHECK(h);
+    h->i8_ctx_gen = h->model_gen;
     return VGS_OK;
 }
 

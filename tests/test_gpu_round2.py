@@ -231,6 +231,40 @@ def test_device_log_load(with_zeros):
 
 
 @pytest.mark.gpu
+def test_device_log_load_digit_count_guess():
+    """A device-log load builds the digit operand before the host has seen the range of ln p, for the digit count the
+    handle's previous set needed; whatever the guess, the operand ends up with the count the set asks for (6 rows without
+    p = 0 entries, 7 with) and the scores are the same bits as on a fresh handle."""
+    wide, _ = synthetic.make_family_models(40, 17, 6, 80, 3)
+    assert (wide.prob == 0).any()
+    narrow, _ = synthetic.make_family_models(40, 17, 6, 80, 3)
+    narrow.prob[:] = np.maximum(narrow.prob, 1e-3)
+    narrow.prob[:] /= narrow.prob.sum(axis=1, keepdims=True)
+    seqs = synthetic.sample_sequences(wide, 700, 5)
+    packed = pack_sequences(seqs)
+
+    def fresh(fm):
+        h = native.Handle(0)
+        h.load_models(fm, nll_only=True, device_log=True)
+        h.load_sequences_packed(*packed)
+        M = h.nll_scores_h(native.SKIP_ORDER, "kmer")
+        nd = h.kmer_digit_info()[0]
+        h.close()
+        return M, nd
+    want = {id(narrow): fresh(narrow), id(wide): fresh(wide)}
+    assert want[id(narrow)][1] == 6 and want[id(wide)][1] == 7
+    h = native.Handle(0)
+    for fm in (narrow, wide, wide, narrow, narrow, wide):
+        h.load_models(fm, nll_only=True, device_log=True)
+        h.load_sequences_packed(*packed)
+        M = h.nll_scores_h(native.SKIP_ORDER, "kmer")
+        assert h.last_nll_kernel() == 3
+        assert h.kmer_digit_info()[0] == want[id(fm)][1]
+        assert np.array_equal(M, want[id(fm)][0])
+    h.close()
+
+
+@pytest.mark.gpu
 def test_kmer_fraction_bits():
     """The precision of the contraction is a parameter: f fraction bits of ln p -> |d score| <= L * 2^-(f+1); the digit rows per
     model (the GEMM's work) follow f and the range of the set's ln p; a change takes effect with the next operand build."""
