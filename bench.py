@@ -16,7 +16,10 @@ A step = one full N x N float32 distance matrix:
          over ranks, NCCL all-gather, local assemble);
   e2e    the same matrix through the C-ABI with HOST buffers: H2D of the flat model tables and packed
          sequences (pinned), ln p (k-mer mode: on the device, VGS_LOAD_DEVICE_LOG; scan modes: libm on the host, streamed),
-         table construction, kernels, D2H of the float32 matrix (pinned).
+         table construction, kernels, D2H of the float32 matrix (pinned).  N > 1: every rank holds the whole matrix in HBM
+         after the exchange; it crosses to the host ONCE, on rank 0 (the process that hands it to the clustering code, as in
+         the reference's single-process pipeline) -- eight ranks each pulling all 4 MB at the same moment measured the host's
+         aggregate PCIe ingest (0.33-0.58 ms per rank at 8 GPUs, tools/e2e_laps_mgpu.py), not the path.
 Timing: CUDA events on the launching stream, one pair per step, L2 flushed (256 MiB memset) between
 steps outside the timed pairs, barrier + synchronize on both sides, max over ranks.
 Extra keys: `matrix_checksum` (exact int64 sum of the float32 bit patterns: equal across GPU counts iff the matrices are),
@@ -469,7 +472,8 @@ def main():
                 h.pair_matrix_h(kind, want_f64=False, out32=out_h)
         else:
             device_step()
-            out_t.copy_(D32, non_blocking=True)
+            if rank == 0:   # the matrix goes to the host once: rank 0 is the process that consumes it (see the docstring)
+                out_t.copy_(D32, non_blocking=True)
             torch.cuda.synchronize()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -786,7 +790,9 @@ def main():
                 "includes": "vgs_load_models (H2D of the flat model arrays -- N > 1: this rank's model shard --, ln p "
                             + ("on the device (VGS_LOAD_DEVICE_LOG: the k-mer contraction quantises it to 2^-43)" if kind == "nll" and args.mode == "kmer"
                                else "on the host (libm, streamed)" if kind == "nll" else "not needed") +
-                            "), vgs_load_sequences_packed, device table builds, kernels, exchange, D2H of the float32 matrix"},
+                            "), vgs_load_sequences_packed, device table builds, kernels, exchange, D2H of the float32 matrix"
+                            + (" (N > 1: once, on rank 0 -- the consuming process; d2h_bytes_per_step is that one copy; every rank's H2D is "
+                               "h2d_bytes_per_step of its own shard)" if world > 1 else "")},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
         "matrix_checksum": matrix_checksum, "parity_check": parity_check, "scale_probe": probe,
     }
