@@ -180,6 +180,9 @@ struct vgs_context {
     uint16_t *d_i8_ctx = nullptr;    // [n_models][4^D] context of every depth-D history, found ahead of ln p by the load
     uint64_t i8_ctx_gen = ~0ull;     // model set d_i8_ctx belongs to
     int last_nll_kernel = 0;         // VGS_NLL_KERNEL_* of the most recent score launch
+    bool i8_defer_check = false;     // set by a host-buffer entry point around its pass: the frequent-k-mer check needs no wait of its own
+    bool i8_check_pending = false;   // ... and its flag is on the way to h_i8_flag (vgs_kmer_i8_settle)
+    int *h_i8_flag = nullptr;        // pinned
     int i8_counts_state = 0;         // 0 = not checked for this sequence set, 1 = no frequent k-mers, 3 = some, 2 = too many
     // tensor-core Frobenius / Projection (vgs_pairs_tc.cu): digit operands over the dense universe, raw digit-pair sums
     int8_t *d_tc_P = nullptr, *d_tc_Q = nullptr, *d_tc_I = nullptr;
@@ -323,6 +326,7 @@ bool vgs_kmer_applicable_orders(vgs_context *h);                          // eve
 int vgs_kmer_i8_digits_begin(vgs_context *h, bool wide, cudaStream_t s);   // choose the digit count, allocate + clear the operand of the current set
 double vgs_kmer_i8_narrow_limit(vgs_context *h);                           // |ln p| below this fits the narrow digit count
 int vgs_kmer_i8_digits_range(vgs_context *h, int64_t m_begin, int64_t m_end, cudaStream_t s);   // digits of models [m_begin, m_end)
+bool vgs_kmer_i8_settle(vgs_context *h);   // after a synchronised pass with i8_defer_check: true = void, redo
 int vgs_kmer_i8_contexts_ahead(vgs_context *h, cudaStream_t s);   // the digit builder's context lookups, before ln p exists (hashes only)
 int vgs_kmer_i8_digits_end(vgs_context *h, cudaStream_t s);                // after a synchronisation: record whether the operand is usable
 int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, const VgsScoreDst &dst, cudaStream_t s);

@@ -269,6 +269,7 @@ extern "C" int vgs_destroy(vgs_handle h) {
     cudaFree(h->d_err);
     if (h->h_logp) cudaFreeHost(h->h_logp);
     if (h->h_meta_pin) cudaFreeHost(h->h_meta_pin);
+    if (h->h_i8_flag) cudaFreeHost(h->h_i8_flag);
     delete (VgsPool *)h->pool;
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -864,6 +865,7 @@ extern "C" int vgs_load_models_ex(vgs_handle h, int64_t n_models, const int64_t 
         const int64_t mb = (int64_t)sizeof(ModelMeta) * n_models;
         if (h->h_meta_pin_bytes < mb) {
             if (h->h_meta_pin) cudaFreeHost(h->h_meta_pin);
+    if (h->h_i8_flag) cudaFreeHost(h->h_i8_flag);
             h->h_meta_pin = nullptr; h->h_meta_pin_bytes = 0;
             VGS_CUDA(cudaHostAlloc(&h->h_meta_pin, (size_t)mb, cudaHostAllocDefault));
             h->h_meta_pin_bytes = mb;

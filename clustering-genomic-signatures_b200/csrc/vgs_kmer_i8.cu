@@ -722,20 +722,47 @@ int vgs_kmer_i8_scores(vgs_context *h, const I8Work &w, bool diag_separately, co
         k_i8_hist<false><<<(unsigned)h->n_seq, hist_threads, hist_smem, s>>>(D, h->d_seq, h->d_seq_off, h->d_seq_len, K8, c_rows_pad, h->d_i8_C,
                                                                     over_cnt, over_list, h->d_counters + 10);
     VGS_LAUNCH_CHECK(h);
+    bool deferred = false;
     if (h->i8_counts_state == 0) {
-        // first call on this sequence set: any frequent k-mers, and few enough per sequence?  (one synchronisation per
-        // loaded set; the histograms of later calls are the same numbers)
-        int flag = 0;
-        VGS_CUDA(cudaMemcpyAsync(&flag, h->d_counters + 10, sizeof(int), cudaMemcpyDeviceToHost, s));
-        VGS_CUDA(cudaStreamSynchronize(s));
-        h->i8_counts_state = (flag & 2) ? 2 : ((flag & 1) ? 3 : 1);   // 1 = no frequent k-mers at all, 3 = some, 2 = too many
+        // first call on this sequence set: any frequent k-mers, and few enough per sequence?  (once per loaded set; the
+        // histograms of later calls are the same numbers)
+        if (h->i8_defer_check) {
+            // a host-buffer entry point waits for its result anyway: no wait here.  The chain is launched as for a set
+            // WITH frequent k-mers (their kernel finds what there is), the flag travels behind it, and the caller settles
+            // the state after its own synchronisation (vgs_kmer_i8_settle: "too many" voids the pass and it is redone)
+            if (!h->h_i8_flag) VGS_CUDA(cudaHostAlloc((void **)&h->h_i8_flag, sizeof(int), cudaHostAllocDefault));
+            h->i8_counts_state = 3;
+            deferred = true;
+        } else {
+            int flag = 0;
+            VGS_CUDA(cudaMemcpyAsync(&flag, h->d_counters + 10, sizeof(int), cudaMemcpyDeviceToHost, s));
+            VGS_CUDA(cudaStreamSynchronize(s));
+            h->i8_counts_state = (flag & 2) ? 2 : ((flag & 1) ? 3 : 1);   // 1 = no frequent k-mers at all, 3 = some, 2 = too many
+        }
     }
     if (h->i8_counts_state == 2) return -1;
     switch (h->i8_nd) {
-    case 6: return i8_launch<6>(h, w, diag_separately, dst, K8, c_rows_pad, d_rows_pad, s);
-    case 7: return i8_launch<7>(h, w, diag_separately, dst, K8, c_rows_pad, d_rows_pad, s);
-    default: return i8_launch<8>(h, w, diag_separately, dst, K8, c_rows_pad, d_rows_pad, s);
+    case 6: rc = i8_launch<6>(h, w, diag_separately, dst, K8, c_rows_pad, d_rows_pad, s); break;
+    case 7: rc = i8_launch<7>(h, w, diag_separately, dst, K8, c_rows_pad, d_rows_pad, s); break;
+    default: rc = i8_launch<8>(h, w, diag_separately, dst, K8, c_rows_pad, d_rows_pad, s); break;
     }
+    if (deferred) {
+        // (behind the whole chain: a copy between the histogram and the GEMM would end their dependent-launch overlap)
+        cudaMemcpyAsync(h->h_i8_flag, h->d_counters + 10, sizeof(int), cudaMemcpyDeviceToHost, s);
+        h->i8_check_pending = true;
+    }
+    return rc;
+}
+
+// after the caller's synchronisation of a pass that ran with i8_defer_check: the frequent-k-mer state of the sequence set.
+// Returns true when the pass is void (a sequence with more frequent k-mers than the side list holds) and must be redone.
+bool vgs_kmer_i8_settle(vgs_context *h) {
+    if (!h->i8_check_pending) return false;
+    h->i8_check_pending = false;
+    if (h->i8_counts_state == 0) return false;   // the sets changed in between: nothing to settle
+    const int flag = *h->h_i8_flag;
+    h->i8_counts_state = (flag & 2) ? 2 : ((flag & 1) ? 3 : 1);
+    return h->i8_counts_state == 2;
 }
 
 // fraction bits f of the fixed-point ln p of the k-mer contraction (35..51; default 43): |d score| <= L * 2^-(f+1),

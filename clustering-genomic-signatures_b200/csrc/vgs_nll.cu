@@ -791,10 +791,18 @@ extern "C" int vgs_nll_matrix_h(vgs_handle h, int64_t length, int mode, float *D
     float *d32 = h->d_out32;
     double *d64 = D64_out_h ? h->d_out64 : nullptr;
     cudaStream_t s = h->own_stream;
-    rc = vgs_nll_matrix(h, length, mode, d32, d64, s);
-    if (!rc) rc = vgs_read_error_flag(h, s);
-    if (!rc && D32_out_h) rc = cudaMemcpyAsync(D32_out_h, d32, 4 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
-    if (!rc && D64_out_h) rc = cudaMemcpyAsync(D64_out_h, d64, 8 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
-    cudaStreamSynchronize(s);
+    // the result starts for the host behind the kernels and the error word is read behind it: ONE wait for all of it (on
+    // an error the caller's buffers hold an unspecified matrix and the call reports the error).  The k-mer contraction's
+    // once-per-sequence-set check rides along (i8_defer_check); in the rare case it voids the pass, the pass is redone.
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        h->i8_defer_check = attempt == 0;
+        rc = vgs_nll_matrix(h, length, mode, d32, d64, s);
+        h->i8_defer_check = false;
+        if (!rc && D32_out_h) rc = cudaMemcpyAsync(D32_out_h, d32, 4 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
+        if (!rc && D64_out_h) rc = cudaMemcpyAsync(D64_out_h, d64, 8 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
+        const int rc_flag = vgs_read_error_flag(h, s);   // synchronises
+        if (!rc) rc = rc_flag;
+        if (!vgs_kmer_i8_settle(h)) break;
+    }
     return rc;
 }

@@ -474,9 +474,10 @@ extern "C" int vgs_pair_matrix_h(vgs_handle h, int kind, float *D32_out_h, doubl
     double *d64 = D64_out_h ? h->d_out64 : nullptr;
     cudaStream_t s = h->own_stream;
     rc = vgs_pair_matrix(h, kind, d32, d64, s);
-    if (!rc) rc = vgs_read_error_flag(h, s);
+    // the result starts for the host behind the kernels and the error word is read behind it: ONE wait for all three (on
+    // an error the caller's buffers hold an unspecified matrix and the call reports the error)
     if (!rc && D32_out_h) rc = cudaMemcpyAsync(D32_out_h, d32, 4 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
     if (!rc && D64_out_h) rc = cudaMemcpyAsync(D64_out_h, d64, 8 * (size_t)(n * n), cudaMemcpyDeviceToHost, s) == cudaSuccess ? VGS_OK : VGS_ERR_CUDA;
-    cudaStreamSynchronize(s);
-    return rc;
+    const int rc_flag = vgs_read_error_flag(h, s);   // synchronises
+    return rc ? rc : rc_flag;
 }

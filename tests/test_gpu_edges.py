@@ -218,3 +218,26 @@ def test_int8_contraction_with_frequent_kmers(L):
     env = dict(os.environ, VGS_KMER_GEMM="dmma")
     subprocess.check_call([sys.executable, "-c", code, out, str(L)], env=env)
     assert rel_err(np.load(out), Mk) < 1e-12
+
+
+def test_too_many_frequent_kmers_voids_the_speculative_pass():
+    """vgs_nll_matrix_h launches the int8 contraction without waiting for the once-per-sequence-set check of the k-mer
+    counts; when a sequence turns out to have more k-mers above 255 counts than the side list holds (order 3, 256 k-mers,
+    all of them counted ~500 times), the pass is void and the call redoes it on the fp64 contraction -- same answer as the
+    oracle, first call and second."""
+    fm, _ = synthetic.make_family_models(12, 4, 3, 60, 2)
+    assert int(fm.orders().max()) == 3
+    fm.prob[:] = 0.25 + 0.3 * (fm.prob - 0.25)         # flattened rows: most 4-mers occur ~ L / 256 = 500 times
+    fm.prob[:] /= fm.prob.sum(axis=1, keepdims=True)
+    L = 130000
+    seqs = synthetic.sample_sequences(fm, L, 9)
+    co = c_oracle.COracle(fm)
+    want = co.nll_from_scores(co.score_matrix(seqs), L)
+    h = native.Handle(0)
+    h.load_models(fm)
+    h.load_sequences_packed(*pack_sequences(seqs))
+    for _ in range(2):
+        D = h.nll_matrix_h(L, "kmer")[1]
+        assert h.last_nll_kernel() == 1, "expected the fp64 contraction after the void int8 pass"
+        assert np.allclose(D, want, rtol=1e-9, atol=1e-13) and np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+    h.close()
