@@ -198,6 +198,48 @@ def test_vlmc_host_mirror_construction():
     assert json.loads(w.to_json())["tree"] == w.tree
 
 
+class _LookupOnly(object):
+    """Stands in for the device handle of ONE model: answers `lookup` the way vgs_lookup does (ctx_id of the longest
+    suffix), from a plain dict walk -- so the host arithmetic of VLMC.likelihood / estimated_context_distribution around
+    the lookups can be checked without a GPU."""
+
+    def __init__(self, tree):
+        self.keys = list(tree.keys())
+        self.order = max(len(k) for k in self.keys)
+
+    def lookup(self, models, codes, lengths, want_all=False):
+        out = np.zeros(len(codes), dtype=np.int32)
+        for i, (c, ln) in enumerate(zip(codes, lengths)):
+            hist = flat.decode_context(int(ln), int(c))
+            out[i] = -1
+            for k in range(min(len(hist), self.order), -1, -1):
+                cand = hist[len(hist) - k:] if k else ""
+                if cand in self.keys:
+                    out[i] = self.keys.index(cand)
+                    break
+        return out
+
+
+def test_vlmc_likelihood_and_context_distribution_host_logic():
+    """The position -> (history code, length) arithmetic of VLMC._history_ids and what likelihood /
+    estimated_context_distribution do with the ids (src/vlmc/vlmc.pyx:103-118, :182-206), against the compiled
+    reference's values; the lookups themselves are the device's job (tests/test_gpu_dropin.py)."""
+    g = golden_io.fixtures()
+    vl = [VLMC(t, n, {}) for t, n in zip(g["trees"], g["names"])]
+    for v in vl:
+        v._handle = _LookupOnly(v.tree)
+        v._keys = list(v.tree.keys())
+    for c in golden_io.sampler_from_cases("likelihood"):
+        assert vl[c["model"]].likelihood(c["sequence"]) == c["likelihood"]
+    with pytest.raises(KeyError):
+        vl[0].likelihood("ACGNT")
+    for c in golden_io.sampler_from_cases("context_distribution"):
+        v = vl[c["model"]]
+        v.sequence = c["sequence"]      # cached while the length matches: no sampling, no device
+        d = v.estimated_context_distribution(c["length"])
+        assert list(d.keys()) == c["contexts"] and list(d.values()) == c["values"]
+
+
 def test_matrix_layouts_host():
     from clustering_genomic_signatures_b200.clustering import util
 
